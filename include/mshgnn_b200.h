@@ -1,0 +1,155 @@
+/* mshgnn_b200.h - C ABI of the B200-native MS-HGNN forward/backward hot path.
+ *
+ * The reference (lunarlab-gatech/MorphSym-HGNN) is pure Python and has no FFI: its
+ * boundary for this path is the Python object protocol of
+ *   src/ms_hgnn/lightning_py/hgnn_k4.py:L10-196      (GRF_HGNN_K4.__init__/forward)
+ *   src/ms_hgnn/lightning_py/hgnn_c2.py:L10-189      (GRF_HGNN_C2)
+ *   src/ms_hgnn/lightning_py/hgnn_k4_com.py:L10-177  (COM_HGNN_K4), hgnn_c2_com.py, hgnn.py
+ *   src/ms_hgnn/lightning_py/gnnLightning.py:L124-151 (loss heads), L258-265 (optimizer)
+ * This library sits under the drop-in Python mirror of those classes
+ * (morphsym-hgnn_b200/ms_hgnn) and is bound with ctypes.
+ *
+ * Conventions: every entry point returns 0 on success and a negative code on error
+ * (text via mshgnn_last_error(), thread-local).  No allocation happens inside compute
+ * calls: the caller passes device buffers (torch-allocated).  All compute calls enqueue
+ * on the caller's CUDA stream (a cudaStream_t passed as void*) and return immediately.
+ * A plan is immutable after creation and may be shared by threads; a workspace may be
+ * used by one call at a time.  There is no CPU fallback: without a CUDA device every
+ * compute call fails with MSHGNN_ERR_CUDA.
+ */
+#ifndef MSHGNN_B200_H
+#define MSHGNN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSHGNN_MAX_NODE_TYPES 4
+#define MSHGNN_MAX_EDGE_TYPES 16
+
+#define MSHGNN_OK              0
+#define MSHGNN_ERR_ARG        -1   /* bad argument / unsupported configuration            */
+#define MSHGNN_ERR_CUDA       -2   /* CUDA runtime error (including "no device")          */
+#define MSHGNN_ERR_WORKSPACE  -3   /* workspace too small                                 */
+
+/* element types of caller buffers */
+#define MSHGNN_F32 0
+#define MSHGNN_F64 1
+#define MSHGNN_I64 2
+
+/* arithmetic modes */
+#define MSHGNN_MODE_FP32   0   /* SIMT fp32 FMA everywhere: <=1e-4 parity mode              */
+#define MSHGNN_MODE_TC     1   /* tcgen05 tensor-core path, split-fp16 operands (3 MMAs), fp32 accumulate */
+#define MSHGNN_MODE_TC_1X  2   /* tcgen05, single fp16 pass (1e-3 on predictions only)      */
+
+/* loss heads (gnnLightning.py:L124-151, gnnLightning_com.py:L96-121) */
+#define MSHGNN_LOSS_MSE 0      /* mean((out - y)^2) over every output element               */
+#define MSHGNN_LOSS_CE2 1      /* per-row 2-way cross-entropy, mean over rows (customMetrics.py:L6-25) */
+
+/* parameter kinds for mshgnn_param_offset; the flat parameter order equals the reference's
+ * named_parameters() order (SURVEY 3.3 state-dict names) */
+#define MSHGNN_P_ENC_W   0     /* encoder.lins.<type>.weight   [H, in]   idx = node type      */
+#define MSHGNN_P_ENC_B   1     /* encoder.lins.<type>.bias     [H]                            */
+#define MSHGNN_P_REL_W   2     /* convs.<l>.convs.<et>.lin_rel.weight [H,H]  idx = edge type  */
+#define MSHGNN_P_REL_B   3     /* convs.<l>.convs.<et>.lin_rel.bias   [H]                     */
+#define MSHGNN_P_ROOT_W  4     /* convs.<l>.convs.<et>.lin_root.weight [H,H]                  */
+#define MSHGNN_P_MLP_W   5     /* base_transform.{0,2}.weight  [H,H]     idx = 0 | 1          */
+#define MSHGNN_P_MLP_B   6     /* base_transform.{0,2}.bias    [H]                            */
+#define MSHGNN_P_DEC_W   7     /* decoder.weight [C, H]                                       */
+#define MSHGNN_P_DEC_B   8     /* decoder.bias   [C]                                          */
+
+typedef struct mshgnn_plan mshgnn_plan;
+
+/* Static description of one model + morphology template.  Everything the reference
+ * derives at construction (hgnn_k4.py:L37-144) or reads from the batch
+ * (edge_index_dict) is given here once; the library compiles it
+ * into constant gather tables, so no edge_index is read on the device afterwards. */
+typedef struct mshgnn_desc {
+    int32_t n_node_types;                                /* <= 4, reference order (base, joint, foot)       */
+    int32_t nodes_per_graph[MSHGNN_MAX_NODE_TYPES];      /* e.g. K4: 4, 12, 4                                */
+    int32_t in_width[MSHGNN_MAX_NODE_TYPES];             /* feature width per type (900/300/900 ...)         */
+    int32_t n_edge_types;                                /* <= 16, metadata order                            */
+    int32_t edge_src_type[MSHGNN_MAX_EDGE_TYPES];
+    int32_t edge_dst_type[MSHGNN_MAX_EDGE_TYPES];
+    int32_t edge_mean[MSHGNN_MAX_EDGE_TYPES];            /* 1: aggr='mean' (gt/gs/center_bb)                 */
+    int32_t edge_count[MSHGNN_MAX_EDGE_TYPES];           /* edges per graph                                  */
+    const int32_t* edge_src[MSHGNN_MAX_EDGE_TYPES];      /* per-graph local source node index, [edge_count]  */
+    const int32_t* edge_dst[MSHGNN_MAX_EDGE_TYPES];      /* per-graph local destination node index           */
+    int32_t hidden;                                      /* H; this build supports 128                       */
+    int32_t num_layers;                                  /* L >= 1                                           */
+    int32_t morph_sym;                                   /* 1: MS-HGNN (shared base MLP + residual), 0: MI-HGNN (ReLU only) */
+    int32_t mlp_type;                                    /* node type that goes through base_transform (morph_sym only) */
+    int32_t decode_type;                                 /* node type the decoder reads (foot or base)       */
+    int32_t out_channels;                                /* decoder width C (1, 2, 3 or 6)                   */
+    const float* in_sign[MSHGNN_MAX_NODE_TYPES];         /* per type [nodes_per_graph*in_width] of +-1, NULL = ones (apply_symmetry) */
+    const float* out_sign;                               /* [nodes_per_graph[decode_type]*C] of +-1, NULL = ones (ms_foot_decoder / morphological_symmetry_decoder) */
+} mshgnn_desc;
+
+/* ---- plan ------------------------------------------------------------------------- */
+int  mshgnn_plan_create(const mshgnn_desc* desc, mshgnn_plan** plan_out);
+void mshgnn_plan_destroy(mshgnn_plan* plan);
+
+/* number of fp32 elements of the flat parameter (and gradient) buffer */
+int64_t mshgnn_param_count(const mshgnn_plan* plan);
+/* offset/numel of one parameter tensor inside the flat buffer */
+int  mshgnn_param_offset(const mshgnn_plan* plan, int32_t kind, int32_t layer, int32_t idx,
+                         int64_t* offset_out, int64_t* numel_out);
+
+/* bytes of device workspace needed for B graphs (train != 0 keeps activations for backward) */
+int64_t mshgnn_workspace_bytes(const mshgnn_plan* plan, int64_t B, int32_t train, int32_t mode);
+/* output rows = B * nodes_per_graph[decode_type], each out_channels wide */
+int64_t mshgnn_out_rows(const mshgnn_plan* plan, int64_t B);
+
+/* ---- compute (device pointers; stream = cudaStream_t) --------------------------------
+ * x[t]: node features of type t, row-major [B*nodes_per_graph[t], in_width[t]], graph-major
+ *       rows (row = g*nodes_per_graph[t] + local), element type x_dtype (F32 or F64).
+ * params: flat fp32 parameters.  out: fp32 [mshgnn_out_rows(B), out_channels].
+ * Replaces: GRF_HGNN_K4.forward hgnn_k4.py:L146-196 and its C2/COM/MI siblings. */
+int mshgnn_forward(const mshgnn_plan* plan, int64_t B,
+                   const void* const* x, int32_t x_dtype,
+                   const float* params, float* out,
+                   void* workspace, int64_t workspace_bytes,
+                   int32_t train, int32_t mode, void* stream);
+
+/* Fused loss head: writes the scalar loss to loss_out[0] and d(loss)/d(out) to dout
+ * (same shape as out; dout may be NULL for evaluation).  labels: MSE -> same element count
+ * as out; CE2 -> one label in {0,1} per output row.  loss_scale multiplies dout (and not
+ * loss_out): pass 1/world_size for data-parallel training with a summed all-reduce.
+ * Replaces: Base_Lightning.calculate_losses_step gnnLightning.py:L124-139. */
+int mshgnn_loss(const mshgnn_plan* plan, int64_t B, int32_t loss_kind,
+                const float* out, const void* labels, int32_t label_dtype,
+                float loss_scale, float* loss_out, float* dout,
+                void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Backward of mshgnn_forward(train=1) on the same workspace: writes d(loss)/d(params)
+ * (every element, zeros for structurally dead branches) into grads[param_count].
+ * Replaces: torch autograd through PyG (SURVEY 3.1 "loss.backward()"). */
+int mshgnn_backward(const mshgnn_plan* plan, int64_t B,
+                    const void* const* x, int32_t x_dtype,
+                    const float* params, const float* dout, float* grads,
+                    void* workspace, int64_t workspace_bytes,
+                    int32_t mode, void* stream);
+
+/* Fused Adam on flat buffers (torch.optim.Adam defaults semantics, gnnLightning.py:L258-265):
+ * step is the 1-based step count after this update. */
+int mshgnn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                     int64_t n, int64_t step, float lr, float beta1, float beta2, float eps,
+                     float weight_decay, void* stream);
+/* plain SGD: p -= lr * g */
+int mshgnn_sgd_step(float* params, const float* grads, int64_t n, float lr, void* stream);
+
+/* JSON summary of the compiled tables (slots, liveness, gather lists); returns the bytes needed
+ * (including the terminating NUL).  Host-only: usable without a GPU. */
+int64_t mshgnn_plan_describe(const mshgnn_plan* plan, char* buf, int64_t cap);
+
+/* number of kernels launched by this library since process start (for gpu_launches accounting) */
+int64_t mshgnn_launch_count(void);
+const char* mshgnn_last_error(void);
+const char* mshgnn_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSHGNN_B200_H */

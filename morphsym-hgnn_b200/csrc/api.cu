@@ -1,0 +1,321 @@
+// C ABI of libmshgnn_b200.so (see include/mshgnn_b200.h): launch sequencing of the hot path.
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "kernels_simt.cuh"
+#include "plan.cuh"
+
+using namespace mshgnn;
+
+struct mshgnn_plan {
+    Plan p;
+};
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                     \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess)                                                             \
+            return fail(MSHGNN_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+#define LAUNCH_CHECK()                                                                     \
+    do {                                                                                   \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                                \
+        cudaError_t _e = cudaGetLastError();                                               \
+        if (_e != cudaSuccess)                                                             \
+            return fail(MSHGNN_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+template <typename T>
+int upload(const std::vector<T>& v, T** d) {
+    *d = nullptr;
+    if (v.empty()) return 0;
+    CUDA_TRY(cudaMalloc((void**)d, v.size() * sizeof(T)));
+    CUDA_TRY(cudaMemcpy(*d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int ensure_uploaded(const Plan& p) {
+    std::lock_guard<std::mutex> lk(p.mu);
+    int dev = -1;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (p.uploaded) {
+        if (dev != p.device) return fail(MSHGNN_ERR_ARG, "plan tables live on device %d but the current device is %d", p.device, dev);
+        return 0;
+    }
+    int rc;
+    if ((rc = upload(p.tiles, &p.d_tiles))) return rc;
+    if ((rc = upload(p.rtasks, &p.d_rtasks))) return rc;
+    if ((rc = upload(p.rpairs, &p.d_rpairs))) return rc;
+    if ((rc = upload(p.groups, &p.d_groups))) return rc;
+    if ((rc = upload(p.derive_ops, &p.d_derive))) return rc;
+    if ((rc = upload(p.signs, &p.d_signs))) return rc;
+    p.device = dev;
+    p.uploaded = true;
+    return 0;
+}
+
+void fill_bufs(const Plan& p, const WsLayout& w, char* ws, BufTable& bt) {
+    memset(&bt, 0, sizeof bt);
+    bt.p[BUF_DERIVED] = ws + w.derived;
+    bt.p[BUF_SIGNS] = p.d_signs;
+    auto at = [&](int64_t off) -> void* { return off < 0 ? nullptr : (void*)(ws + off); };
+    bt.p[BUF_DH0] = at(w.dh[0]); bt.p[BUF_DH1] = at(w.dh[1]);
+    bt.p[BUF_DC0] = at(w.dc[0]); bt.p[BUF_DC1] = at(w.dc[1]);
+    bt.p[BUF_DU] = at(w.du);
+    for (int l = 0; l <= p.L; ++l) bt.p[BUF_H0 + l] = at(w.h[l]);
+    for (int l = 0; l < p.L; ++l) { bt.p[BUF_CT0 + l] = at(w.ct[l]); bt.p[BUF_MASK0 + l] = at(w.mask[l]); }
+}
+
+int launch_rowgemm(const Plan& p, const Launch& L, const BufTable& bt, int64_t B, int64_t Bp, int x_f64, cudaStream_t st) {
+    if (L.count == 0) return 0;
+    dim3 grid((unsigned)(Bp / TILE_M), (unsigned)L.count);
+    k_rowgemm<<<grid, 256, 0, st>>>(p.d_tiles + L.begin, bt, B, Bp, x_f64);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+int check_common(const mshgnn_plan* plan, int64_t B, const void* ws, int64_t ws_bytes, const WsLayout& w) {
+    if (!plan) return fail(MSHGNN_ERR_ARG, "plan is NULL");
+    if (B < 1) return fail(MSHGNN_ERR_ARG, "B must be >= 1 (got %lld)", (long long)B);
+    if (!ws) return fail(MSHGNN_ERR_ARG, "workspace is NULL");
+    if (ws_bytes < w.total) return fail(MSHGNN_ERR_WORKSPACE, "workspace too small: %lld < %lld bytes", (long long)ws_bytes, (long long)w.total);
+    if (reinterpret_cast<uintptr_t>(ws) & 255) return fail(MSHGNN_ERR_ARG, "workspace must be 256-byte aligned");
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mshgnn_plan_create(const mshgnn_desc* desc, mshgnn_plan** plan_out) {
+    if (!plan_out) return fail(MSHGNN_ERR_ARG, "plan_out is NULL");
+    *plan_out = nullptr;
+    mshgnn_plan* pl = new (std::nothrow) mshgnn_plan();
+    if (!pl) return fail(MSHGNN_ERR_ARG, "out of host memory");
+    std::string e = build_plan(desc, pl->p);
+    if (!e.empty()) { delete pl; return fail(MSHGNN_ERR_ARG, "%s", e.c_str()); }
+    *plan_out = pl;
+    return 0;
+}
+
+void mshgnn_plan_destroy(mshgnn_plan* plan) {
+    if (!plan) return;
+    Plan& p = plan->p;
+    if (p.uploaded) {
+        cudaFree(p.d_tiles); cudaFree(p.d_rtasks); cudaFree(p.d_rpairs);
+        cudaFree(p.d_groups); cudaFree(p.d_derive); cudaFree(p.d_signs);
+    }
+    delete plan;
+}
+
+int64_t mshgnn_param_count(const mshgnn_plan* plan) { return plan ? plan->p.n_params : -1; }
+
+int mshgnn_param_offset(const mshgnn_plan* plan, int32_t kind, int32_t layer, int32_t idx, int64_t* off, int64_t* numel) {
+    if (!plan || !off || !numel) return fail(MSHGNN_ERR_ARG, "NULL argument");
+    const Plan& p = plan->p;
+    auto lay_ok = [&]() { return layer >= 0 && layer < p.L && idx >= 0 && idx < p.n_etypes; };
+    switch (kind) {
+        case MSHGNN_P_ENC_W: if (idx < 0 || idx >= p.n_types) break; *off = p.off_enc_w[idx]; *numel = (int64_t)H * p.in_w[idx]; return 0;
+        case MSHGNN_P_ENC_B: if (idx < 0 || idx >= p.n_types) break; *off = p.off_enc_b[idx]; *numel = H; return 0;
+        case MSHGNN_P_REL_W: if (!lay_ok()) break; *off = p.off_rel_w[layer * p.n_etypes + idx]; *numel = H * H; return 0;
+        case MSHGNN_P_REL_B: if (!lay_ok()) break; *off = p.off_rel_b[layer * p.n_etypes + idx]; *numel = H; return 0;
+        case MSHGNN_P_ROOT_W: if (!lay_ok()) break; *off = p.off_root_w[layer * p.n_etypes + idx]; *numel = H * H; return 0;
+        case MSHGNN_P_MLP_W: if (!p.morph_sym || idx < 0 || idx > 1) break; *off = p.off_mlp_w[idx]; *numel = H * H; return 0;
+        case MSHGNN_P_MLP_B: if (!p.morph_sym || idx < 0 || idx > 1) break; *off = p.off_mlp_b[idx]; *numel = H; return 0;
+        case MSHGNN_P_DEC_W: *off = p.off_dec_w; *numel = (int64_t)p.C * H; return 0;
+        case MSHGNN_P_DEC_B: *off = p.off_dec_b; *numel = p.C; return 0;
+        default: break;
+    }
+    return fail(MSHGNN_ERR_ARG, "no such parameter (kind=%d layer=%d idx=%d)", kind, layer, idx);
+}
+
+int64_t mshgnn_workspace_bytes(const mshgnn_plan* plan, int64_t B, int32_t train, int32_t mode) {
+    if (!plan || B < 1) return -1;
+    return ws_layout(plan->p, B, train, mode).total;
+}
+
+int64_t mshgnn_out_rows(const mshgnn_plan* plan, int64_t B) { return plan ? B * plan->p.nodes[plan->p.dec_type] : -1; }
+
+int64_t mshgnn_plan_describe(const mshgnn_plan* plan, char* buf, int64_t cap) {
+    if (!plan) return -1;
+    const std::string s = describe_plan(plan->p);
+    if (buf && cap > 0) {
+        const int64_t n = (int64_t)s.size() < cap - 1 ? (int64_t)s.size() : cap - 1;
+        memcpy(buf, s.data(), n);
+        buf[n] = 0;
+    }
+    return (int64_t)s.size() + 1;
+}
+
+int mshgnn_forward(const mshgnn_plan* plan, int64_t B, const void* const* x, int32_t x_dtype, const float* params,
+                   float* out, void* workspace, int64_t workspace_bytes, int32_t train, int32_t mode, void* stream) {
+    if (!plan) return fail(MSHGNN_ERR_ARG, "plan is NULL");
+    const Plan& p = plan->p;
+    if (mode != MSHGNN_MODE_FP32) return fail(MSHGNN_ERR_ARG, "mode %d is not available in this build", mode);
+    if (x_dtype != MSHGNN_F32 && x_dtype != MSHGNN_F64) return fail(MSHGNN_ERR_ARG, "x_dtype must be F32 or F64");
+    if (!x || !params || !out) return fail(MSHGNN_ERR_ARG, "NULL argument");
+    const WsLayout w = ws_layout(p, B, train, mode);
+    int rc = check_common(plan, B, workspace, workspace_bytes, w);
+    if (rc) return rc;
+    for (int t = 0; t < p.n_types; ++t)
+        if (!x[t]) return fail(MSHGNN_ERR_ARG, "x[%d] is NULL", t);
+    if ((rc = ensure_uploaded(p))) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    BufTable bt;
+    fill_bufs(p, w, (char*)workspace, bt);
+    bt.p[BUF_PARAMS] = (void*)params;
+    for (int t = 0; t < p.n_types; ++t) bt.p[BUF_X0 + t] = (void*)x[t];
+    const int xf64 = x_dtype == MSHGNN_F64;
+
+    {   // derived weights (transposes, root sums, bias sums) from the current parameters
+        dim3 grid(16, (unsigned)p.derive_ops.size());
+        k_derive<<<grid, 256, 0, st>>>(p.d_derive, params, (float*)bt.p[BUF_DERIVED]);
+        LAUNCH_CHECK();
+    }
+    if ((rc = launch_rowgemm(p, p.enc_launch, bt, B, w.Bp, xf64, st))) return rc;
+    for (int l = 0; l < p.L; ++l) {
+        if ((rc = launch_rowgemm(p, train ? p.conv_train[l] : p.conv_infer[l], bt, B, w.Bp, 0, st))) return rc;
+        if ((rc = launch_rowgemm(p, p.mlp1[l], bt, B, w.Bp, 0, st))) return rc;
+        if ((rc = launch_rowgemm(p, p.mlp2[l], bt, B, w.Bp, 0, st))) return rc;
+    }
+    {
+        const int64_t rows = B * p.dec.n_dec;
+        int blocks = (int)((rows + 7) / 8);
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        k_decoder_fwd<<<blocks, 256, 0, st>>>(p.dec, (const float*)bt.p[BUF_H0 + p.L], params, p.d_signs, out, B, w.Bp);
+        LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+int mshgnn_loss(const mshgnn_plan* plan, int64_t B, int32_t loss_kind, const float* out, const void* labels,
+                int32_t label_dtype, float loss_scale, float* loss_out, float* dout, void* workspace,
+                int64_t workspace_bytes, void* stream) {
+    if (!plan) return fail(MSHGNN_ERR_ARG, "plan is NULL");
+    const Plan& p = plan->p;
+    if (!out || !labels || !loss_out || !workspace) return fail(MSHGNN_ERR_ARG, "NULL argument");
+    if (B < 1) return fail(MSHGNN_ERR_ARG, "B must be >= 1");
+    if (label_dtype < 0 || label_dtype > 2) return fail(MSHGNN_ERR_ARG, "bad label_dtype");
+    if (loss_kind == MSHGNN_LOSS_CE2 && p.C != 2) return fail(MSHGNN_ERR_ARG, "CE2 loss needs out_channels == 2");
+    if (loss_kind != MSHGNN_LOSS_CE2 && loss_kind != MSHGNN_LOSS_MSE) return fail(MSHGNN_ERR_ARG, "bad loss_kind");
+    if (workspace_bytes < LOSS_BLOCKS * 8) return fail(MSHGNN_ERR_WORKSPACE, "workspace too small for the loss partials");
+    cudaStream_t st = (cudaStream_t)stream;
+    // the loss partials live in the last 256-aligned LOSS_BLOCKS*8 bytes of the workspace
+    double* partial = (double*)((char*)workspace + ((workspace_bytes - LOSS_BLOCKS * 8) & ~(int64_t)255));
+    const int64_t rows = B * p.dec.n_dec;
+    const int64_t n = loss_kind == MSHGNN_LOSS_MSE ? rows * p.C : rows;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > LOSS_BLOCKS) blocks = LOSS_BLOCKS;
+    k_loss_partial<<<blocks, 256, 0, st>>>(loss_kind, out, labels, label_dtype, n, loss_scale / (float)n, dout, partial);
+    LAUNCH_CHECK();
+    k_loss_final<<<1, 32, 0, st>>>(partial, blocks, 1.0 / (double)n, loss_kind == MSHGNN_LOSS_CE2, loss_out);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+int mshgnn_backward(const mshgnn_plan* plan, int64_t B, const void* const* x, int32_t x_dtype, const float* params,
+                    const float* dout, float* grads, void* workspace, int64_t workspace_bytes, int32_t mode, void* stream) {
+    if (!plan) return fail(MSHGNN_ERR_ARG, "plan is NULL");
+    const Plan& p = plan->p;
+    if (mode != MSHGNN_MODE_FP32) return fail(MSHGNN_ERR_ARG, "mode %d is not available in this build", mode);
+    if (x_dtype != MSHGNN_F32 && x_dtype != MSHGNN_F64) return fail(MSHGNN_ERR_ARG, "x_dtype must be F32 or F64");
+    if (!x || !params || !dout || !grads) return fail(MSHGNN_ERR_ARG, "NULL argument");
+    const WsLayout w = ws_layout(p, B, 1, mode);
+    int rc = check_common(plan, B, workspace, workspace_bytes, w);
+    if (rc) return rc;
+    if ((rc = ensure_uploaded(p))) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    BufTable bt;
+    fill_bufs(p, w, (char*)workspace, bt);
+    bt.p[BUF_PARAMS] = (void*)params;
+    bt.p[BUF_GRADS] = grads;
+    for (int t = 0; t < p.n_types; ++t) { if (!x[t]) return fail(MSHGNN_ERR_ARG, "x[%d] is NULL", t); bt.p[BUF_X0 + t] = (void*)x[t]; }
+    const int xf64 = x_dtype == MSHGNN_F64;
+    char* ws = (char*)workspace;
+    float* part_w = (float*)(ws + w.part_w);
+    float* part_b = (float*)(ws + w.part_b);
+    float* dec_part = (float*)(ws + w.dec_part);
+
+    CUDA_TRY(cudaMemsetAsync(grads, 0, (size_t)p.n_params * 4, st));
+
+    {   // decoder backward: dH_L on the decoded slots (+ masked copy = dc_{L-1}), dW_dec, db_dec
+        const int L = p.L;
+        float* dh = nullptr; float* dc = nullptr; int mk = MK_NONE; const void* mbuf = nullptr;
+        if (p.morph_sym) {
+            dh = (float*)bt.p[BUF_DH0 + (L & 1)];
+            if (p.dec_type != p.mlp_type) { dc = (float*)bt.p[BUF_DC0 + ((L - 1) & 1)]; mk = MK_BITS; mbuf = bt.p[BUF_MASK0 + L - 1]; }
+        } else {
+            dc = (float*)bt.p[BUF_DC0 + ((L - 1) & 1)]; mk = MK_POS; mbuf = bt.p[BUF_H0 + L];
+        }
+        k_decoder_bwd<<<DEC_BLOCKS, 256, 0, st>>>(p.dec, (const float*)bt.p[BUF_H0 + L], params, p.d_signs, dout, dh, dc, mk, mbuf,
+                                                  dec_part, B, w.Bp);
+        LAUNCH_CHECK();
+        k_decoder_bwd_reduce<<<4, 256, 0, st>>>(p.dec, dec_part, DEC_BLOCKS, grads);
+        LAUNCH_CHECK();
+    }
+    auto launch_dw = [&](const Launch& L) -> int {
+        if (L.count == 0) return 0;
+        dim3 grid((unsigned)L.count, (unsigned)w.n_splits);
+        k_reducegemm<<<grid, 256, 0, st>>>(p.d_rtasks, p.d_rpairs, L.begin, bt, B, w.Bp, xf64, w.n_splits, part_w, part_b);
+        LAUNCH_CHECK();
+        return 0;
+    };
+    for (int l = p.L - 1; l >= 0; --l) {
+        if ((rc = launch_rowgemm(p, p.bwd_m1[l], bt, B, w.Bp, 0, st))) return rc;
+        if ((rc = launch_rowgemm(p, p.bwd_m2[l], bt, B, w.Bp, 0, st))) return rc;
+        if ((rc = launch_dw(p.dw_layer[l]))) return rc;
+        if ((rc = launch_rowgemm(p, p.bwd_dx[l], bt, B, w.Bp, 0, st))) return rc;
+    }
+    if ((rc = launch_dw(p.dw_enc))) return rc;
+    if (!p.groups.empty()) {
+        dim3 grid((unsigned)p.groups.size(), 8);
+        k_reduce_partials<<<grid, 256, 0, st>>>(p.d_groups, part_w, part_b, w.n_splits, grads);
+        LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+int mshgnn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, int64_t step,
+                     float lr, float beta1, float beta2, float eps, float weight_decay, void* stream) {
+    if (!params || !grads || !exp_avg || !exp_avg_sq || n < 1 || step < 1) return fail(MSHGNN_ERR_ARG, "bad argument");
+    const float bc1 = 1.f - (float)std::pow((double)beta1, (double)step);
+    const float bc2s = (float)std::sqrt(1.0 - std::pow((double)beta2, (double)step));
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_adam<<<blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2s);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+int mshgnn_sgd_step(float* params, const float* grads, int64_t n, float lr, void* stream) {
+    if (!params || !grads || n < 1) return fail(MSHGNN_ERR_ARG, "bad argument");
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_sgd<<<blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, n, lr);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+int64_t mshgnn_launch_count(void) { return g_launches.load(); }
+const char* mshgnn_last_error(void) { return g_err; }
+const char* mshgnn_version(void) { return "mshgnn_b200 0.1 (sm_100a)"; }
+
+}  // extern "C"

@@ -1,0 +1,104 @@
+// Internal structures shared by the plan builder (host) and the kernels (device).
+//
+// Data layout in HBM ("node-slot-major slabs"): every activation buffer is
+//   slab[slot][row = graph][H]   (fp32, H = 128, rows padded to Bp = multiple of 128)
+// where a slot is one node of the per-graph morphology template (K4 Mini Cheetah: 4 base +
+// 12 joint + 4 foot = 20 slots).  All rows of a 128-row tile therefore belong to the same
+// template node, so the reference's gather / scatter-add over edge_index
+// (torch_geometric GraphConv) becomes "pick which slot tile feeds which weight":
+// a compile-time table, no index tensors, no atomics.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mshgnn {
+
+constexpr int H = 128;
+constexpr int MAX_CHUNKS = 8;
+constexpr int MAX_BUFS = 64;
+constexpr int TILE_M = 128;
+constexpr int DEC_MAXC = 8;     // max decoder width
+
+enum AKind : int { A_SLAB = 0, A_EXT = 1 };
+enum MaskKind : int { MK_NONE = 0, MK_BITS = 1, MK_POS = 2 };
+
+// base pointers resolved per call (buffer id -> device pointer)
+struct BufTable {
+    void* p[MAX_BUFS];
+};
+
+// One K-chunk of a row-GEMM: D[rows,128] += A[rows,K] * Wt[K,128]
+struct Chunk {
+    int a_kind;      // A_SLAB: fp32 slab tile; A_EXT: caller's x tensor (strided rows, f32/f64)
+    int a_buf;       // buffer id
+    int a_slot;      // slab slot (A_SLAB)
+    int K;           // reduction length
+    int lda;         // row stride in elements (A_EXT)
+    int a_off;       // element offset of row 0 (A_EXT: local_node * in_width)
+    int w_buf;       // buffer id of the weight in [K][128] ("k-major") form
+    int w_off;       // float offset inside that buffer
+    int sign_off;    // float offset into BUF_SIGNS of a [K] +-1 vector, or -1
+    int pad;
+};
+
+// One 128-row x 128-col output tile of a row-GEMM launch.
+struct Tile {
+    int n_chunks;
+    int out_buf, out_slot;            // primary fp32 slab output (-1: none)
+    int bias_buf, bias_off;           // bias [128] (-1: none)
+    int relu;                         // relu after bias
+    int posmask_buf, posmask_slot;    // multiply by (slab > 0) after relu (-1: none)
+    int res_buf, res_slot;            // residual add (-1: none)
+    int mask_out_buf;                 // store bitmask of (pre-activation > 0) at out_slot (-1: none)
+    int out2_buf, out2_slot;          // secondary output = result (*) mask (-1: none)
+    int out2_mask_kind, out2_mask_buf, out2_mask_slot;
+    int pad;
+    Chunk chunks[MAX_CHUNKS];
+};
+
+// One (dC, A) pair of a reduce-over-rows GEMM: dW[128, K] += dC[rows,128]^T * A[rows,K]
+struct RPair {
+    int d_buf, d_slot;                // dC slab tile
+    int a_kind, a_buf, a_slot;        // A operand
+    int lda, a_off;                   // A_EXT addressing
+    int sign_off;                     // A_EXT sign vector (-1: none)
+};
+
+struct RTask {
+    int pair_begin, n_pairs;
+    int K;                            // full in-width of the weight
+    int k0;                           // first in-column handled by this task (tile of 128)
+    int want_colsum;                  // also produce column sums of dC (bias gradient)
+    int pad[3];
+};
+
+// Final reduction of split partials into the flat gradient buffer.
+struct OutGroup {
+    int kind;                         // 0: weight tile, 1: bias (colsum)
+    int n_tasks; int tasks[16];       // tasks whose partials are summed
+    int n_outs;  int outs[4];         // float offsets in the gradient buffer that receive the sum
+    int K, k0;                        // weight: row stride K and first column
+    float scale;
+    int pad;
+};
+
+// prep: derived weights (transposes, root sums, bias sums)
+struct DeriveOp {
+    int dst_off;                      // float offset in BUF_DERIVED
+    int rows, cols;                   // shape of each source [rows][cols]
+    int transpose;                    // dst[c][r] (1) or dst[r][c] (0)
+    int n_src; int src_off[8];        // float offsets in params; summed
+    int pad[3];
+};
+
+struct DecoderDesc {
+    int n_dec;                        // decoded nodes per graph
+    int C;                            // output channels
+    int slots[16];                    // slab slot per decoded node
+    int w_off, b_off;                 // params offsets
+    int sign_off;                     // BUF_SIGNS offset of [n_dec*C] or -1
+};
+
+static inline __host__ __device__ int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+}  // namespace mshgnn

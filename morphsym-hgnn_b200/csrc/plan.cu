@@ -1,0 +1,437 @@
+// Plan builder: morphology template + model description -> constant gather tables.
+//
+// What the reference does per step with index tensors (torch_geometric HeteroConv/GraphConv
+// over batch.edge_index_dict, hgnn_k4.py:L102-130,170-172) is resolved here
+// ONCE per (model, template): for every destination node slot the list of (source slot,
+// weight) contributions, which layers/slots are live (the decoder only reads one node type,
+// so last-layer branches into the others are dead), and the transposed pattern
+// for the backward pass.
+#include <cstdio>
+#include <cstring>
+#include <sstream>
+
+#include "plan.cuh"
+
+namespace mshgnn {
+
+static Chunk slab_chunk(int buf, int slot, int w_buf, int64_t w_off) {
+    Chunk c{};
+    c.a_kind = A_SLAB; c.a_buf = buf; c.a_slot = slot; c.K = H; c.lda = H; c.a_off = 0;
+    c.w_buf = w_buf; c.w_off = (int)w_off; c.sign_off = -1;
+    return c;
+}
+
+static Tile empty_tile() {
+    Tile t{};
+    t.n_chunks = 0;
+    t.out_buf = -1; t.out_slot = 0; t.bias_buf = -1; t.bias_off = 0; t.relu = 0;
+    t.posmask_buf = -1; t.posmask_slot = 0; t.res_buf = -1; t.res_slot = 0; t.mask_out_buf = -1;
+    t.out2_buf = -1; t.out2_slot = 0; t.out2_mask_kind = MK_NONE; t.out2_mask_buf = -1; t.out2_mask_slot = 0;
+    return t;
+}
+
+std::string build_plan(const mshgnn_desc* d, Plan& p) {
+    char err[256];
+    if (!d) return "desc is NULL";
+    if (d->hidden != H) { snprintf(err, sizeof err, "hidden=%d unsupported: this build is specialised for H=128", d->hidden); return err; }
+    if (d->n_node_types < 1 || d->n_node_types > MSHGNN_MAX_NODE_TYPES) return "n_node_types out of range";
+    if (d->n_edge_types < 1 || d->n_edge_types > MSHGNN_MAX_EDGE_TYPES) return "n_edge_types out of range";
+    if (d->num_layers < 1 || d->num_layers > MAX_LAYERS) return "num_layers out of range (1..15)";
+    if (d->decode_type < 0 || d->decode_type >= d->n_node_types) return "decode_type out of range";
+    if (d->out_channels < 1 || d->out_channels > 8) return "out_channels out of range (1..8)";
+    if (d->morph_sym && (d->mlp_type < 0 || d->mlp_type >= d->n_node_types)) return "mlp_type out of range";
+
+    p.n_types = d->n_node_types; p.n_etypes = d->n_edge_types; p.L = d->num_layers;
+    p.morph_sym = d->morph_sym ? 1 : 0; p.mlp_type = d->morph_sym ? d->mlp_type : -1;
+    p.dec_type = d->decode_type; p.C = d->out_channels;
+    p.S = 0;
+    for (int t = 0; t < p.n_types; ++t) {
+        if (d->nodes_per_graph[t] < 1 || d->nodes_per_graph[t] > 16) return "nodes_per_graph out of range (1..16)";
+        if (d->in_width[t] < 1) return "in_width must be >= 1";
+        p.nodes[t] = d->nodes_per_graph[t]; p.in_w[t] = d->in_width[t];
+        p.type_base[t] = p.S; p.S += p.nodes[t];
+        for (int n = 0; n < p.nodes[t]; ++n) { p.slot_type.push_back(t); p.slot_local.push_back(n); }
+    }
+    if (p.S > 48) return "too many nodes per graph";
+    p.nm = p.morph_sym ? p.nodes[p.mlp_type] : 0;
+
+    std::vector<char> has_in(p.n_types, 0);
+    for (int e = 0; e < p.n_etypes; ++e) {
+        const int st = d->edge_src_type[e], dt = d->edge_dst_type[e];
+        if (st < 0 || st >= p.n_types || dt < 0 || dt >= p.n_types) return "edge type endpoint out of range";
+        p.e_src_t[e] = st; p.e_dst_t[e] = dt; p.e_mean[e] = d->edge_mean[e] ? 1 : 0;
+        has_in[dt] = 1;
+        if (d->edge_count[e] < 0 || (d->edge_count[e] > 0 && (!d->edge_src[e] || !d->edge_dst[e]))) return "edge list missing";
+        p.e_src[e].assign(d->edge_src[e], d->edge_src[e] + d->edge_count[e]);
+        p.e_dst[e].assign(d->edge_dst[e], d->edge_dst[e] + d->edge_count[e]);
+        std::vector<int> deg(p.nodes[dt], 0);
+        for (int i = 0; i < d->edge_count[e]; ++i) {
+            if (p.e_src[e][i] < 0 || p.e_src[e][i] >= p.nodes[st] || p.e_dst[e][i] < 0 || p.e_dst[e][i] >= p.nodes[dt])
+                return "edge endpoint out of range for its node type";
+            deg[p.e_dst[e][i]]++;
+        }
+        if (p.e_mean[e])
+            for (int n = 0; n < p.nodes[dt]; ++n)
+                if (deg[n] > 1) {
+                    snprintf(err, sizeof err, "edge type %d: aggr='mean' with in-degree %d > 1 is not supported "
+                             "(all reference templates have in-degree 1 on mean relations)", e, deg[n]);
+                    return err;
+                }
+    }
+    for (int t = 0; t < p.n_types; ++t)
+        if (!has_in[t]) return "every node type must be the destination of at least one edge type";
+
+    // ---------------- parameter layout: reference named_parameters() order ----------------
+    int64_t o = 0;
+    for (int t = 0; t < p.n_types; ++t) { p.off_enc_w[t] = o; o += (int64_t)H * p.in_w[t]; p.off_enc_b[t] = o; o += H; }
+    p.off_rel_w.assign(p.L * p.n_etypes, 0); p.off_rel_b = p.off_rel_w; p.off_root_w = p.off_rel_w;
+    for (int l = 0; l < p.L; ++l)
+        for (int e = 0; e < p.n_etypes; ++e) {
+            const int i = l * p.n_etypes + e;
+            p.off_rel_w[i] = o; o += H * H; p.off_rel_b[i] = o; o += H; p.off_root_w[i] = o; o += H * H;
+        }
+    if (p.morph_sym)
+        for (int i = 0; i < 2; ++i) { p.off_mlp_w[i] = o; o += H * H; p.off_mlp_b[i] = o; o += H; }
+    p.off_dec_w = o; o += (int64_t)p.C * H; p.off_dec_b = o; o += p.C;
+    p.n_params = o;
+    if (o > (int64_t)1 << 30) return "parameter count too large";
+
+    // ---------------- derived weights ----------------
+    int64_t q = 0;
+    auto add_op = [&](int64_t dst, int rows, int cols, int tr, std::vector<int64_t> srcs) {
+        DeriveOp op{}; op.dst_off = (int)dst; op.rows = rows; op.cols = cols; op.transpose = tr;
+        op.n_src = (int)srcs.size();
+        for (size_t i = 0; i < srcs.size(); ++i) op.src_off[i] = (int)srcs[i];
+        p.derive_ops.push_back(op);
+    };
+    for (int t = 0; t < p.n_types; ++t) {
+        p.der_encT[t] = q; add_op(q, H, p.in_w[t], 1, {p.off_enc_w[t]}); q += (int64_t)H * p.in_w[t];
+    }
+    p.der_relT.assign(p.L * p.n_etypes, -1);
+    p.der_rootT.assign(p.L * p.n_types, -1); p.der_root = p.der_rootT; p.der_bias = p.der_rootT;
+    for (int l = 0; l < p.L; ++l) {
+        for (int e = 0; e < p.n_etypes; ++e) {
+            p.der_relT[l * p.n_etypes + e] = q; add_op(q, H, H, 1, {p.off_rel_w[l * p.n_etypes + e]}); q += H * H;
+        }
+        for (int t = 0; t < p.n_types; ++t) {
+            std::vector<int64_t> roots, biases;
+            for (int e = 0; e < p.n_etypes; ++e)
+                if (p.e_dst_t[e] == t) { roots.push_back(p.off_root_w[l * p.n_etypes + e]); biases.push_back(p.off_rel_b[l * p.n_etypes + e]); }
+            if (roots.size() > 4) return "more than 4 edge types into one node type is not supported";
+            p.der_rootT[l * p.n_types + t] = q; add_op(q, H, H, 1, roots); q += H * H;
+            p.der_root[l * p.n_types + t] = q;  add_op(q, H, H, 0, roots); q += H * H;
+            p.der_bias[l * p.n_types + t] = q;  add_op(q, 1, H, 0, biases); q += H;
+        }
+    }
+    if (p.morph_sym)
+        for (int i = 0; i < 2; ++i) { p.der_mlpT[i] = q; add_op(q, H, H, 1, {p.off_mlp_w[i]}); q += H * H; }
+    p.n_derived = q;
+
+    // ---------------- signs ----------------
+    p.sign_off_slot.assign(p.S, -1);
+    for (int t = 0; t < p.n_types; ++t) {
+        if (!d->in_sign[t]) continue;
+        for (int n = 0; n < p.nodes[t]; ++n) {
+            p.sign_off_slot[p.slot_of(t, n)] = (int)p.signs.size();
+            for (int k = 0; k < p.in_w[t]; ++k) p.signs.push_back(d->in_sign[t][(int64_t)n * p.in_w[t] + k]);
+            while (p.signs.size() % 4) p.signs.push_back(1.f);
+        }
+    }
+    if (d->out_sign) {
+        p.sign_off_out = (int)p.signs.size();
+        for (int i = 0; i < p.nodes[p.dec_type] * p.C; ++i) p.signs.push_back(d->out_sign[i]);
+    }
+    if (p.signs.empty()) p.signs.push_back(1.f);
+
+    // ---------------- forward contribution lists ----------------
+    // contrib[d] = list of (src slot, edge type); the root term is implicit.
+    struct Contrib { int src, e; };
+    std::vector<std::vector<Contrib>> contrib(p.S);
+    for (int e = 0; e < p.n_etypes; ++e)
+        for (size_t i = 0; i < p.e_src[e].size(); ++i)
+            contrib[p.slot_of(p.e_dst_t[e], p.e_dst[e][i])].push_back({p.slot_of(p.e_src_t[e], p.e_src[e][i]), e});
+    for (int s = 0; s < p.S; ++s)
+        if ((int)contrib[s].size() + 1 > MAX_CHUNKS) return "a node has too many in-edges (max 7)";
+    std::vector<std::vector<Contrib>> outgoing(p.S);   // outgoing[s] = (dst slot, e)
+    for (int dslot = 0; dslot < p.S; ++dslot)
+        for (auto& c : contrib[dslot]) outgoing[c.src].push_back({dslot, c.e});
+    for (int s = 0; s < p.S; ++s)
+        if ((int)outgoing[s].size() + 1 > MAX_CHUNKS) return "a node has too many out-edges (max 7)";
+
+    // ---------------- liveness: need[l][s] <=> h_l[s] influences the output ----------------
+    p.need.assign(p.L + 1, std::vector<char>(p.S, 0));
+    for (int n = 0; n < p.nodes[p.dec_type]; ++n) p.need[p.L][p.slot_of(p.dec_type, n)] = 1;
+    for (int l = p.L - 1; l >= 0; --l)
+        for (int dslot = 0; dslot < p.S; ++dslot) {
+            if (!p.need[l + 1][dslot]) continue;
+            p.need[l][dslot] = 1;                              // root term (and residual)
+            for (auto& c : contrib[dslot]) p.need[l][c.src] = 1;
+        }
+
+    // ---------------- decoder ----------------
+    memset(&p.dec, 0, sizeof p.dec);
+    p.dec.n_dec = p.nodes[p.dec_type]; p.dec.C = p.C;
+    for (int n = 0; n < p.dec.n_dec; ++n) p.dec.slots[n] = p.slot_of(p.dec_type, n);
+    p.dec.w_off = (int)p.off_dec_w; p.dec.b_off = (int)p.off_dec_b; p.dec.sign_off = p.sign_off_out;
+
+    // ---------------- forward tiles ----------------
+    auto push_launch = [&](std::vector<Tile>& v) { Launch L{(int)p.tiles.size(), (int)v.size()}; p.tiles.insert(p.tiles.end(), v.begin(), v.end()); return L; };
+    {
+        std::vector<Tile> v;
+        for (int s = 0; s < p.S; ++s) {
+            if (!p.need[0][s]) continue;
+            const int t = p.slot_type[s], n = p.slot_local[s];
+            Tile T = empty_tile();
+            Chunk c{};
+            c.a_kind = A_EXT; c.a_buf = BUF_X0 + t; c.a_slot = 0; c.K = p.in_w[t]; c.lda = p.nodes[t] * p.in_w[t];
+            c.a_off = n * p.in_w[t]; c.w_buf = BUF_DERIVED; c.w_off = (int)p.der_encT[t]; c.sign_off = p.sign_off_slot[s];
+            T.chunks[T.n_chunks++] = c;
+            T.bias_buf = BUF_PARAMS; T.bias_off = (int)p.off_enc_b[t]; T.relu = 1;
+            T.out_buf = BUF_H0; T.out_slot = s;
+            v.push_back(T);
+        }
+        p.enc_launch = push_launch(v);
+    }
+    for (int l = 0; l < p.L; ++l) {
+        std::vector<Tile> conv, m1, m2;
+        for (int dslot = 0; dslot < p.S; ++dslot) {
+            if (!p.need[l + 1][dslot]) continue;
+            const int t = p.slot_type[dslot], n = p.slot_local[dslot];
+            Tile T = empty_tile();
+            for (auto& c : contrib[dslot])
+                T.chunks[T.n_chunks++] = slab_chunk(BUF_H0 + l, c.src, BUF_DERIVED, p.der_relT[l * p.n_etypes + c.e]);
+            T.chunks[T.n_chunks++] = slab_chunk(BUF_H0 + l, dslot, BUF_DERIVED, p.der_rootT[l * p.n_types + t]);
+            T.bias_buf = BUF_DERIVED; T.bias_off = (int)p.der_bias[l * p.n_types + t];
+            if (p.morph_sym && t == p.mlp_type) {
+                // conv -> c_base ; base_transform: Linear -> ReLU -> Linear ; + residual (hgnn_k4.py:L133-137,175-186)
+                T.relu = 0; T.out_buf = BUF_CT0 + l; T.out_slot = n;
+                conv.push_back(T);
+                Tile A = empty_tile();
+                A.chunks[A.n_chunks++] = slab_chunk(BUF_CT0 + l, n, BUF_DERIVED, p.der_mlpT[0]);
+                A.bias_buf = BUF_PARAMS; A.bias_off = (int)p.off_mlp_b[0]; A.relu = 1;
+                A.out_buf = BUF_CT0 + l; A.out_slot = p.nm + n;
+                m1.push_back(A);
+                Tile Bt = empty_tile();
+                Bt.chunks[Bt.n_chunks++] = slab_chunk(BUF_CT0 + l, p.nm + n, BUF_DERIVED, p.der_mlpT[1]);
+                Bt.bias_buf = BUF_PARAMS; Bt.bias_off = (int)p.off_mlp_b[1]; Bt.relu = 0;
+                Bt.res_buf = BUF_H0 + l; Bt.res_slot = dslot;
+                Bt.out_buf = BUF_H0 + l + 1; Bt.out_slot = dslot;
+                m2.push_back(Bt);
+            } else {
+                T.relu = 1; T.out_buf = BUF_H0 + l + 1; T.out_slot = dslot;
+                if (p.morph_sym) { T.res_buf = BUF_H0 + l; T.res_slot = dslot; }
+                conv.push_back(T);
+            }
+        }
+        // inference copy (no ReLU bitmask), training copy (bitmask for MS joint/foot rows)
+        p.conv_infer.push_back(push_launch(conv));
+        if (p.morph_sym)
+            for (auto& T : conv)
+                if (T.relu) T.mask_out_buf = BUF_MASK0 + l;
+        p.conv_train.push_back(push_launch(conv));
+        p.mlp1.push_back(push_launch(m1));
+        p.mlp2.push_back(push_launch(m2));
+    }
+
+    // ---------------- backward tiles + weight-gradient tasks ----------------
+    p.bwd_m1.resize(p.L); p.bwd_m2.resize(p.L); p.bwd_dx.resize(p.L); p.dw_layer.resize(p.L);
+    std::vector<int> mlp_tasks[2];
+    for (int l = p.L - 1; l >= 0; --l) {
+        const int DHn = BUF_DH0 + ((l + 1) & 1), DHo = BUF_DH0 + (l & 1);
+        const int DCc = BUF_DC0 + (l & 1), DCp = BUF_DC0 + ((l + 1) & 1);   // dc_l lives in DCc, dc_{l-1} goes to DCp
+        std::vector<Tile> b1, b2, dx;
+        if (p.morph_sym)
+            for (int n = 0; n < p.nm; ++n) {
+                const int s = p.slot_of(p.mlp_type, n);
+                if (!p.need[l + 1][s]) continue;
+                Tile A = empty_tile();   // dpre = (du * W2) (*) (t > 0)
+                A.chunks[A.n_chunks++] = slab_chunk(DHn, s, BUF_PARAMS, p.off_mlp_w[1]);
+                A.posmask_buf = BUF_CT0 + l; A.posmask_slot = p.nm + n;
+                A.out_buf = BUF_DU; A.out_slot = n;
+                b1.push_back(A);
+                Tile Bt = empty_tile();  // dc_base = dpre * W1
+                Bt.chunks[Bt.n_chunks++] = slab_chunk(BUF_DU, n, BUF_PARAMS, p.off_mlp_w[0]);
+                Bt.out_buf = DCc; Bt.out_slot = s;
+                b2.push_back(Bt);
+            }
+        for (int s = 0; s < p.S; ++s) {
+            if (!p.need[l][s]) continue;
+            const int t = p.slot_type[s];
+            Tile T = empty_tile();
+            for (auto& og : outgoing[s])
+                if (p.need[l + 1][og.src])   // og.src holds the destination slot here
+                    T.chunks[T.n_chunks++] = slab_chunk(DCc, og.src, BUF_PARAMS, p.off_rel_w[l * p.n_etypes + og.e]);
+            if (p.need[l + 1][s]) {
+                T.chunks[T.n_chunks++] = slab_chunk(DCc, s, BUF_DERIVED, p.der_root[l * p.n_types + t]);
+                if (p.morph_sym) { T.res_buf = DHn; T.res_slot = s; }
+            }
+            if (l == 0) {
+                T.out2_buf = DCp; T.out2_slot = s; T.out2_mask_kind = MK_POS; T.out2_mask_buf = BUF_H0; T.out2_mask_slot = s;
+            } else if (p.morph_sym) {
+                T.out_buf = DHo; T.out_slot = s;
+                if (t != p.mlp_type) {
+                    T.out2_buf = DCp; T.out2_slot = s; T.out2_mask_kind = MK_BITS; T.out2_mask_buf = BUF_MASK0 + l - 1; T.out2_mask_slot = s;
+                }
+            } else {
+                T.out2_buf = DCp; T.out2_slot = s; T.out2_mask_kind = MK_POS; T.out2_mask_buf = BUF_H0 + l; T.out2_mask_slot = s;
+            }
+            dx.push_back(T);
+        }
+        p.bwd_m1[l] = push_launch(b1); p.bwd_m2[l] = push_launch(b2); p.bwd_dx[l] = push_launch(dx);
+
+        // ---- weight-gradient tasks of layer l ----
+        Launch lt{(int)p.rtasks.size(), 0};
+        auto slab_pair = [&](int dbuf, int dslot, int abuf, int aslot) {
+            RPair r{}; r.d_buf = dbuf; r.d_slot = dslot; r.a_kind = A_SLAB; r.a_buf = abuf; r.a_slot = aslot; r.lda = H; r.a_off = 0; r.sign_off = -1;
+            return r;
+        };
+        for (int e = 0; e < p.n_etypes; ++e) {          // lin_rel weights
+            RTask T{}; T.pair_begin = (int)p.rpairs.size(); T.K = H; T.k0 = 0; T.want_colsum = 0;
+            for (size_t i = 0; i < p.e_src[e].size(); ++i) {
+                const int dslot = p.slot_of(p.e_dst_t[e], p.e_dst[e][i]);
+                if (!p.need[l + 1][dslot]) continue;
+                p.rpairs.push_back(slab_pair(DCc, dslot, BUF_H0 + l, p.slot_of(p.e_src_t[e], p.e_src[e][i])));
+            }
+            T.n_pairs = (int)p.rpairs.size() - T.pair_begin;
+            if (!T.n_pairs) continue;
+            OutGroup g{}; g.kind = 0; g.n_tasks = 1; g.tasks[0] = (int)p.rtasks.size(); g.n_outs = 1;
+            g.outs[0] = (int)p.off_rel_w[l * p.n_etypes + e]; g.K = H; g.k0 = 0; g.scale = 1.f;
+            p.groups.push_back(g);
+            p.rtasks.push_back(T);
+        }
+        for (int t = 0; t < p.n_types; ++t) {           // lin_root weights + lin_rel biases (shared by all edge types into t)
+            RTask T{}; T.pair_begin = (int)p.rpairs.size(); T.K = H; T.k0 = 0; T.want_colsum = 1;
+            for (int n = 0; n < p.nodes[t]; ++n) {
+                const int s = p.slot_of(t, n);
+                if (p.need[l + 1][s]) p.rpairs.push_back(slab_pair(DCc, s, BUF_H0 + l, s));
+            }
+            T.n_pairs = (int)p.rpairs.size() - T.pair_begin;
+            if (!T.n_pairs) continue;
+            OutGroup gw{}; gw.kind = 0; gw.n_tasks = 1; gw.tasks[0] = (int)p.rtasks.size(); gw.K = H; gw.k0 = 0; gw.scale = 1.f;
+            OutGroup gb = gw; gb.kind = 1;
+            for (int e = 0; e < p.n_etypes; ++e)
+                if (p.e_dst_t[e] == t) {
+                    gw.outs[gw.n_outs++] = (int)p.off_root_w[l * p.n_etypes + e];
+                    gb.outs[gb.n_outs++] = (int)p.off_rel_b[l * p.n_etypes + e];
+                }
+            p.groups.push_back(gw); p.groups.push_back(gb);
+            p.rtasks.push_back(T);
+        }
+        if (p.morph_sym) {                               // shared base_transform: tasks per layer, one group at the end
+            RTask T1{}; T1.pair_begin = (int)p.rpairs.size(); T1.K = H; T1.k0 = 0; T1.want_colsum = 1;
+            for (int n = 0; n < p.nm; ++n)
+                if (p.need[l + 1][p.slot_of(p.mlp_type, n)]) p.rpairs.push_back(slab_pair(BUF_DU, n, BUF_CT0 + l, n));
+            T1.n_pairs = (int)p.rpairs.size() - T1.pair_begin;
+            if (T1.n_pairs) { mlp_tasks[0].push_back((int)p.rtasks.size()); p.rtasks.push_back(T1); }
+            RTask T2{}; T2.pair_begin = (int)p.rpairs.size(); T2.K = H; T2.k0 = 0; T2.want_colsum = 1;
+            for (int n = 0; n < p.nm; ++n) {
+                const int s = p.slot_of(p.mlp_type, n);
+                if (p.need[l + 1][s]) p.rpairs.push_back(slab_pair(DHn, s, BUF_CT0 + l, p.nm + n));
+            }
+            T2.n_pairs = (int)p.rpairs.size() - T2.pair_begin;
+            if (T2.n_pairs) { mlp_tasks[1].push_back((int)p.rtasks.size()); p.rtasks.push_back(T2); }
+        }
+        lt.count = (int)p.rtasks.size() - lt.begin;
+        p.dw_layer[l] = lt;
+    }
+    if (p.morph_sym)
+        for (int i = 0; i < 2; ++i) {
+            if (mlp_tasks[i].empty()) continue;
+            OutGroup gw{}; gw.kind = 0; gw.K = H; gw.k0 = 0; gw.scale = 1.f; gw.n_outs = 1; gw.outs[0] = (int)p.off_mlp_w[i];
+            for (int tk : mlp_tasks[i]) gw.tasks[gw.n_tasks++] = tk;
+            OutGroup gb = gw; gb.kind = 1; gb.outs[0] = (int)p.off_mlp_b[i];
+            p.groups.push_back(gw); p.groups.push_back(gb);
+        }
+    // ---- encoder weight gradients: dW_enc[t] = sum_slots dpre0[s]^T (x[s] * sign[s]) ----
+    p.dw_enc.begin = (int)p.rtasks.size();
+    for (int t = 0; t < p.n_types; ++t) {
+        std::vector<RPair> prs;
+        for (int n = 0; n < p.nodes[t]; ++n) {
+            const int s = p.slot_of(t, n);
+            if (!p.need[0][s]) continue;
+            RPair r{}; r.d_buf = BUF_DC1; r.d_slot = s; r.a_kind = A_EXT; r.a_buf = BUF_X0 + t; r.a_slot = 0;
+            r.lda = p.nodes[t] * p.in_w[t]; r.a_off = n * p.in_w[t]; r.sign_off = p.sign_off_slot[s];
+            prs.push_back(r);
+        }
+        if (prs.empty()) continue;
+        for (int k0 = 0; k0 < p.in_w[t]; k0 += H) {
+            RTask T{}; T.pair_begin = (int)p.rpairs.size(); T.n_pairs = (int)prs.size(); T.K = p.in_w[t]; T.k0 = k0; T.want_colsum = (k0 == 0);
+            p.rpairs.insert(p.rpairs.end(), prs.begin(), prs.end());
+            OutGroup g{}; g.kind = 0; g.n_tasks = 1; g.tasks[0] = (int)p.rtasks.size(); g.n_outs = 1; g.outs[0] = (int)p.off_enc_w[t];
+            g.K = p.in_w[t]; g.k0 = k0; g.scale = 1.f;
+            p.groups.push_back(g);
+            if (k0 == 0) { OutGroup gb = g; gb.kind = 1; gb.outs[0] = (int)p.off_enc_b[t]; p.groups.push_back(gb); }
+            p.rtasks.push_back(T);
+        }
+    }
+    p.dw_enc.count = (int)p.rtasks.size() - p.dw_enc.begin;
+    return "";
+}
+
+WsLayout ws_layout(const Plan& p, int64_t B, int train, int mode) {
+    (void)mode;
+    WsLayout w{};
+    w.Bp = round_up(B < 1 ? 1 : B, TILE_M);
+    int ns = (int)((B + 1023) / 1024);
+    w.n_splits = ns < 1 ? 1 : (ns > 16 ? 16 : ns);
+    int64_t o = 0;
+    auto take = [&](int64_t bytes) { int64_t at = o; o += round_up(bytes, 256); return at; };
+    const int64_t slab = (int64_t)p.S * w.Bp * H * 4;
+    const int64_t ctb = (int64_t)2 * p.nm * w.Bp * H * 4;
+    w.derived = take(p.n_derived * 4);
+    for (int l = 0; l <= MAX_LAYERS; ++l) w.h[l] = -1;
+    for (int l = 0; l < MAX_LAYERS; ++l) { w.ct[l] = -1; w.mask[l] = -1; }
+    w.dh[0] = w.dh[1] = w.dc[0] = w.dc[1] = w.du = w.part_w = w.part_b = w.dec_part = -1;
+    if (train) {
+        for (int l = 0; l <= p.L; ++l) w.h[l] = take(slab);
+        if (p.morph_sym)
+            for (int l = 0; l < p.L; ++l) { w.ct[l] = take(ctb); w.mask[l] = take((int64_t)p.S * w.Bp * 16); }
+        w.dh[0] = take(slab); w.dh[1] = take(slab); w.dc[0] = take(slab); w.dc[1] = take(slab);
+        if (p.morph_sym) w.du = take((int64_t)p.nm * w.Bp * H * 4);
+        w.part_w = take((int64_t)p.rtasks.size() * w.n_splits * H * H * 4);
+        w.part_b = take((int64_t)p.rtasks.size() * w.n_splits * H * 4);
+        w.dec_part = take((int64_t)DEC_BLOCKS * (DEC_MAXC * H + DEC_MAXC) * 4);
+    } else {
+        const int64_t a = take(slab), b = take(slab);
+        for (int l = 0; l <= p.L; ++l) w.h[l] = (l & 1) ? b : a;
+        if (p.morph_sym) { const int64_t c = take(ctb); for (int l = 0; l < p.L; ++l) w.ct[l] = c; }
+    }
+    w.loss_part = take(LOSS_BLOCKS * 8);
+    w.total = o;
+    return w;
+}
+
+std::string describe_plan(const Plan& p) {
+    std::ostringstream os;
+    os << "{\"S\":" << p.S << ",\"L\":" << p.L << ",\"n_params\":" << p.n_params << ",\"n_derived\":" << p.n_derived
+       << ",\"n_tiles\":" << p.tiles.size() << ",\"n_rtasks\":" << p.rtasks.size() << ",\"n_rpairs\":" << p.rpairs.size()
+       << ",\"n_groups\":" << p.groups.size() << ",\"need\":[";
+    for (int l = 0; l <= p.L; ++l) {
+        os << (l ? "," : "") << "[";
+        for (int s = 0; s < p.S; ++s) os << (s ? "," : "") << (int)p.need[l][s];
+        os << "]";
+    }
+    os << "],\"conv\":[";
+    for (int l = 0; l < p.L; ++l) {
+        os << (l ? "," : "") << "[";
+        const Launch& La = p.conv_infer[l];
+        for (int i = 0; i < La.count; ++i) {
+            const Tile& T = p.tiles[La.begin + i];
+            os << (i ? "," : "") << "{\"out_buf\":" << T.out_buf << ",\"out_slot\":" << T.out_slot << ",\"relu\":" << T.relu
+               << ",\"res\":" << T.res_buf << ",\"src\":[";
+            for (int c = 0; c < T.n_chunks; ++c) os << (c ? "," : "") << "[" << T.chunks[c].a_slot << "," << T.chunks[c].w_off << "]";
+            os << "]}";
+        }
+        os << "]";
+    }
+    os << "],\"mac_rows_fwd\":";
+    int64_t rows = 0;
+    for (int l = 0; l < p.L; ++l) {
+        for (int i = 0; i < p.conv_infer[l].count; ++i) rows += p.tiles[p.conv_infer[l].begin + i].n_chunks;
+        rows += p.mlp1[l].count + p.mlp2[l].count;
+    }
+    os << rows << "}";
+    return os.str();
+}
+
+}  // namespace mshgnn

@@ -1,0 +1,107 @@
+// Host-side plan: compiles the morphology template + model description into constant
+// gather tables (tiles / chunks / reduce tasks) and a workspace layout.
+#pragma once
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/mshgnn_b200.h"
+#include "common.cuh"
+
+namespace mshgnn {
+
+// buffer ids (BufTable slots)
+enum : int {
+    BUF_PARAMS = 0, BUF_DERIVED = 1, BUF_SIGNS = 2, BUF_GRADS = 3,
+    BUF_X0 = 4,                       // +type
+    BUF_DH0 = 8, BUF_DH1 = 9, BUF_DC0 = 10, BUF_DC1 = 11, BUF_DU = 12,
+    BUF_H0 = 16,                      // +layer (0..L)
+    BUF_CT0 = 32,                     // +layer
+    BUF_MASK0 = 48                    // +layer
+};
+constexpr int MAX_LAYERS = 15;
+
+struct Launch { int begin = 0, count = 0; };
+
+struct Plan {
+    // ---- description (deep copy) ----
+    int n_types = 0, n_etypes = 0, L = 0, morph_sym = 0, mlp_type = -1, dec_type = 0, C = 0;
+    int nodes[MSHGNN_MAX_NODE_TYPES] = {0}, in_w[MSHGNN_MAX_NODE_TYPES] = {0};
+    int e_src_t[MSHGNN_MAX_EDGE_TYPES] = {0}, e_dst_t[MSHGNN_MAX_EDGE_TYPES] = {0}, e_mean[MSHGNN_MAX_EDGE_TYPES] = {0};
+    std::vector<int> e_src[MSHGNN_MAX_EDGE_TYPES], e_dst[MSHGNN_MAX_EDGE_TYPES];
+
+    // ---- slots ----
+    int S = 0;                         // slots per graph
+    int type_base[MSHGNN_MAX_NODE_TYPES] = {0};
+    std::vector<int> slot_type, slot_local;
+    int nm = 0;                        // nodes of the MLP type
+
+    // ---- flat parameter layout (reference named_parameters order) ----
+    int64_t n_params = 0;
+    int64_t off_enc_w[MSHGNN_MAX_NODE_TYPES], off_enc_b[MSHGNN_MAX_NODE_TYPES];
+    std::vector<int64_t> off_rel_w, off_rel_b, off_root_w;   // [l * n_etypes + e]
+    int64_t off_mlp_w[2] = {-1, -1}, off_mlp_b[2] = {-1, -1};
+    int64_t off_dec_w = 0, off_dec_b = 0;
+
+    // ---- derived weights layout ----
+    int64_t n_derived = 0;
+    int64_t der_encT[MSHGNN_MAX_NODE_TYPES];
+    std::vector<int64_t> der_relT;                            // [l*n_etypes+e]
+    std::vector<int64_t> der_rootT, der_root, der_bias;       // [l*n_types+t]  (-1 when type has no in-edges)
+    int64_t der_mlpT[2] = {-1, -1};
+    std::vector<DeriveOp> derive_ops;
+
+    // ---- signs ----
+    std::vector<float> signs;          // host copy of BUF_SIGNS
+    std::vector<int> sign_off_slot;    // per slot (-1 none)
+    int sign_off_out = -1;
+
+    // ---- liveness ----
+    std::vector<std::vector<char>> need;   // need[l][slot], l = 0..L
+
+    // ---- compiled tables ----
+    std::vector<Tile> tiles;
+    Launch enc_launch;
+    std::vector<Launch> conv_train, conv_infer, mlp1, mlp2;      // per layer
+    std::vector<Launch> bwd_m1, bwd_m2, bwd_dx;                  // per layer
+    std::vector<RTask> rtasks;
+    std::vector<RPair> rpairs;
+    std::vector<Launch> dw_layer;                                // per layer (task ranges)
+    Launch dw_enc;
+    std::vector<OutGroup> groups;
+    DecoderDesc dec;
+
+    // ---- device copies (lazy) ----
+    mutable std::mutex mu;
+    mutable bool uploaded = false;
+    mutable int device = -1;
+    mutable Tile* d_tiles = nullptr;
+    mutable RTask* d_rtasks = nullptr;
+    mutable RPair* d_rpairs = nullptr;
+    mutable OutGroup* d_groups = nullptr;
+    mutable DeriveOp* d_derive = nullptr;
+    mutable float* d_signs = nullptr;
+
+    int slot_of(int type, int local) const { return type_base[type] + local; }
+};
+
+struct WsLayout {
+    int64_t Bp = 0;
+    int n_splits = 1;
+    int64_t derived = 0;
+    int64_t h[MAX_LAYERS + 1];
+    int64_t ct[MAX_LAYERS];
+    int64_t mask[MAX_LAYERS];
+    int64_t dh[2], dc[2], du = 0;
+    int64_t part_w = 0, part_b = 0, dec_part = 0, loss_part = 0;
+    int64_t total = 0;
+};
+
+constexpr int DEC_BLOCKS = 296;
+constexpr int LOSS_BLOCKS = 592;
+
+std::string build_plan(const mshgnn_desc* d, Plan& p);            // returns error text ("" = ok)
+WsLayout ws_layout(const Plan& p, int64_t B, int train, int mode);
+std::string describe_plan(const Plan& p);
+
+}  // namespace mshgnn

@@ -1,0 +1,132 @@
+"""GPU parity: native CUDA path (through the drop-in modules -> ctypes -> C ABI) vs the fp64 CPU oracle.
+
+Tolerance: 1e-4 norm-wise relative error per tensor (predictions, loss, every gradient tensor) in
+MSHGNN_MODE_FP32 (north_star).  Graph batching / index handling is checked bit-exactly.
+"""
+import pytest
+import torch
+
+from helpers import TOL_FP32, oracle_model, oracle_run, rel_err
+from ms_hgnn import _native as N
+from ms_hgnn.synthetic import CONFIGS, build_model, make_batch
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    ("mini_cheetah-k4-contact", 64, 8), ("mini_cheetah-k4-contact", 200, 8), ("mini_cheetah-k4-contact", 1, 3),
+    ("mini_cheetah-c2-contact", 96, 8), ("a1-c2-grf", 64, 8), ("k4-grf-regression", 130, 8),
+    ("solo12-k4-com", 257, 8), ("solo-c2-com", 33, 4), ("mi-grf", 20, 8), ("mi-contact", 30, 8), ("mi-com", 77, 2),
+]
+
+
+def native_run(cfg, model, batch, x_dtype=torch.float32):
+    dev = torch.device("cuda:0")
+    model = model.to(dev)
+    b = batch.to(dev)
+    x = {k: v.to(x_dtype) for k, v in b.x_dict.items()}
+    model.zero_grad()
+    out = model(x, b.edge_index_dict)
+    B = b.batch_size
+    eng = next(iter(model._engines.values()))
+    kind = N.LOSS_CE2 if cfg.loss == "ce" else N.LOSS_MSE
+    loss, dout = eng.loss(out.detach().float().reshape(-1, eng.spec["out_channels"]).contiguous(), b.y.to(x_dtype), kind)
+    out.backward(dout.view_as(out).to(out.dtype))
+    grads = {n: (p.grad.clone() if p.grad is not None else torch.zeros_like(p)) for n, p in model.named_parameters()}
+    return out.detach(), loss.detach(), grads
+
+
+@pytest.mark.parametrize("name,B,layers", CASES)
+def test_forward_loss_backward_parity(name, B, layers):
+    cfg = CONFIGS[name]
+    batch = make_batch(cfg, B, seed=B)
+    om = oracle_model(cfg, layers=layers, seed=1)
+    nm = build_model(cfg, layers=layers, seed=2)
+    nm.load_state_dict({k: v.float() for k, v in om.state_dict().items()})
+    out_o, loss_o, g_o = oracle_run(cfg, om, batch)
+    out_n, loss_n, g_n = native_run(cfg, nm, batch)
+    assert tuple(out_n.shape) == tuple(out_o.shape)
+    assert rel_err(out_n, out_o) <= TOL_FP32
+    assert abs(loss_n.item() - loss_o.item()) <= TOL_FP32 * abs(loss_o.item())
+    assert set(g_n) == set(g_o)
+    worst = max(((rel_err(g_n[k], g_o[k]), k) for k in g_o), key=lambda t: t[0])
+    for k in g_o:
+        if g_o[k].norm() == 0:     # structurally dead branch: the reference leaves .grad None, we write exact zeros
+            assert g_n[k].abs().max().item() == 0.0, k
+    assert worst[0] <= TOL_FP32, worst
+
+
+def test_float64_inputs_accepted():
+    """The reference feeds float64 everywhere (gnnLightning.py:L1183); features are read as f64 and rounded on load."""
+    cfg = CONFIGS["mini_cheetah-k4-contact"]
+    batch = make_batch(cfg, 48, seed=5, dtype=torch.float64)
+    om = oracle_model(cfg, layers=4, seed=3)
+    nm = build_model(cfg, layers=4, seed=4)
+    nm.load_state_dict({k: v.float() for k, v in om.state_dict().items()})
+    out_o, loss_o, g_o = oracle_run(cfg, om, batch)
+    out_n, loss_n, g_n = native_run(cfg, nm, batch, x_dtype=torch.float64)
+    assert out_n.dtype == torch.float64
+    assert rel_err(out_n, out_o) <= TOL_FP32
+    assert max(rel_err(g_n[k], g_o[k]) for k in g_o) <= TOL_FP32
+
+
+def test_inference_matches_training_forward_and_no_input_mutation():
+    cfg = CONFIGS["mini_cheetah-k4-contact"]
+    batch = make_batch(cfg, 70, seed=9).to("cuda:0")
+    nm = build_model(cfg, layers=8, seed=6).to("cuda:0")
+    x = batch.x_dict
+    keep = {k: v.clone() for k, v in x.items()}
+    with torch.no_grad():
+        o1 = nm(x, batch.edge_index_dict)
+    o2 = nm(x, batch.edge_index_dict)
+    assert torch.equal(o1, o2.detach())                     # ping-pong inference buffers == saved-activation path, bit for bit
+    for k in x:
+        assert torch.equal(x[k], keep[k])                   # the reference mutates its x_dict; we must not
+
+
+def test_batching_rejects_non_template_edges():
+    cfg = CONFIGS["mini_cheetah-k4-contact"]
+    batch = make_batch(cfg, 8, seed=1).to("cuda:0")
+    nm = build_model(cfg, layers=2, seed=1).to("cuda:0")
+    ei = batch.edge_index_dict
+    with torch.no_grad():
+        nm(batch.x_dict, ei)
+    bad = dict(ei)
+    k = ("joint", "connect", "joint")
+    t = bad[k].clone(); t[0, 17] = t[0, 17] + 1; bad[k] = t
+    with pytest.raises(ValueError):
+        nm(batch.x_dict, bad)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        nm({k: v.cpu() for k, v in batch.x_dict.items()}, ei)
+
+
+def test_equivariance_k4_contact():
+    """C2/K4 equivariance protocol of the datasets (LinTzuYaunDataset_Morph.py:L349-408): y(g.x) = y(x)[perm_ls[g]]."""
+    from ms_hgnn import morphology as M
+    cfg = CONFIGS["mini_cheetah-k4-contact"]
+    B, T = 32, 150
+    g = M.GROUPS["mini_cheetah-k4"]
+    gen = torch.Generator().manual_seed(7)
+    joints = torch.randn(B, 2, T, 12, generator=gen)       # (pos, vel) x time x joint
+    feet = torch.randn(B, 2, T, 12, generator=gen)         # (pos, vel) x time x (foot, xyz)
+    base = torch.randn(B, 2, T, 3, generator=gen).repeat(1, 1, 1, 4)   # (lin, ang) tiled over the 4 bases
+
+    def pack(j, f, b):
+        xj = j.permute(0, 3, 1, 2).reshape(B * 12, 2 * T)                               # joint rows: [var][time]
+        xf = f.reshape(B, 2, T, 4, 3).permute(0, 3, 1, 4, 2).reshape(B * 4, 6 * T)      # foot rows: [var][axis][time]
+        xb = b.reshape(B, 2, T, 4, 3).permute(0, 3, 1, 4, 2).reshape(B * 4, 6 * T)
+        return {"base": xb.contiguous(), "joint": xj.contiguous(), "foot": xf.contiguous()}
+
+    def act(arr, perm, refl):
+        return arr[..., perm] * torch.tensor(refl, dtype=arr.dtype)
+
+    nm = build_model(cfg, layers=8, seed=11).to("cuda:0")
+    ei = M.K4_MINI_CHEETAH.edge_index_dict(B, "cuda:0")
+    with torch.no_grad():
+        y0 = nm({k: v.cuda() for k, v in pack(joints, feet, base).items()}, ei).reshape(B, 4, 2)
+        for gi in (0, 1):
+            j2 = act(joints, g["permutation_Q_js"][gi], g["reflection_Q_js"][gi])
+            f2 = act(feet, g["permutation_Q_fs"][gi], g["reflection_Q_fs"][gi])
+            b2 = torch.stack((act(base[:, 0], g["permutation_Q_bs"][gi], g["reflection_Q_bs_lin"][gi]),
+                              act(base[:, 1], g["permutation_Q_bs"][gi], g["reflection_Q_bs_ang"][gi])), dim=1)
+            y1 = nm({k: v.cuda() for k, v in pack(j2, f2, b2).items()}, ei).reshape(B, 4, 2)
+            assert rel_err(y1, y0[:, g["permutation_Q_ls"][gi]]) <= TOL_FP32

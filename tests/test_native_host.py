@@ -1,0 +1,93 @@
+"""CPU checks of the C-ABI library and the host-side plan compiler (no compute calls)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from ms_hgnn import _native as N
+from ms_hgnn import morphology as M
+from ms_hgnn.engine import build_spec
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = N.lib()
+    header = open(os.path.join(ROOT, "include", "mshgnn_b200.h")).read()
+    declared = set(re.findall(r"\b(mshgnn_[a-z_0-9]+)\s*\(", header))
+    assert declared, "no declarations found"
+    assert declared == set(N.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert b"sm_100a" in lib.mshgnn_version()
+
+
+def _spec(tpl, in_w, morph, dec, C, L=8):
+    return build_spec(tpl.node_types, tpl.nodes_per_graph, in_w, tpl.edge_types, tpl.edges, ("gt", "gs", "center_bb"),
+                      128, L, morph, "base" if morph else None, dec, C, {}, None)
+
+
+def test_param_counts_match_reference_models():
+    # parameter counts of the BASELINE configs
+    k4 = N.NativePlan(_spec(M.K4_MINI_CHEETAH, {"base": 900, "joint": 300, "foot": 900}, True, "foot", 2))
+    assert k4.n_params == 2144642
+    c2 = N.NativePlan(_spec(M.C2_MINI_CHEETAH, {"base": 900, "joint": 300, "foot": 900}, True, "foot", 2))
+    assert c2.n_params == 2407810
+    a1 = N.NativePlan(_spec(M.C2_A1, {"base": 900, "joint": 450, "foot": 1}, True, "foot", 3))
+    assert a1.n_params == 2312067
+    com = N.NativePlan(_spec(M.K4_SOLO_COM, {"base": 6, "joint": 2}, True, "base", 6))
+    assert com.n_params == 1350918
+    # the two shipped MI-HGNN checkpoints
+    mi = N.NativePlan(_spec(M.MI_QUADRUPED, {"base": 6, "joint": 3, "foot": 1}, False, "foot", 1))
+    assert mi.n_params == 1317633
+    mi2 = N.NativePlan(_spec(M.MI_QUADRUPED, {"base": 900, "joint": 300, "foot": 900}, False, "foot", 2))
+    assert mi2.n_params == 1585282
+
+
+def test_live_row_gemv_counts():
+    """Live 128x128 row-GEMVs per graph per layer from the compiled gather lists.
+
+    SURVEY 8d counts 64 (K4) / 52 (C2, K4-COM) per full layer and 8 / 24 in the last one.  The compiled lists
+    issue one chunk per (destination node, contributing source), so a thigh (two chain in-edges) costs two
+    chunks instead of one pre-summed one: 60 conv + 8 MLP = 68 = 64 + 4.  Liveness is a cone, not just the
+    last layer: the decoder reads one node type, so layer L-1 only needs its rows, layer L-2 their
+    neighbours, ... (K4: 8, 20, 32, 44 chunks in the last four layers)."""
+    k4 = N.NativePlan(_spec(M.K4_MINI_CHEETAH, {"base": 900, "joint": 300, "foot": 900}, True, "foot", 2)).describe()
+    assert k4["S"] == 20
+    per_layer = [sum(len(t["src"]) for t in layer) for layer in k4["conv"]]
+    assert per_layer == [60, 60, 60, 60, 44, 32, 20, 8]
+    assert k4["need"][8] == [0] * 16 + [1] * 4                      # decoder reads the feet
+    assert k4["need"][7] == [0] * 4 + [0, 0, 1] * 4 + [1] * 4      # calves + feet feed the last layer
+    assert k4["need"][6] == [0] * 4 + [0, 1, 1] * 4 + [1] * 4
+    assert k4["need"][5] == [0] * 4 + [1] * 12 + [1] * 4
+    assert all(k4["need"][l] == [1] * 20 for l in range(5))
+    assert k4["mac_rows_fwd"] == 344 + 8 * 4                         # base MLP only where the base rows are live
+    c2 = N.NativePlan(_spec(M.C2_MINI_CHEETAH, {"base": 900, "joint": 300, "foot": 900}, True, "foot", 2)).describe()
+    assert [sum(len(t["src"]) for t in layer) for layer in c2["conv"]] == [52, 52, 52, 52, 44, 32, 20, 8]
+    com = N.NativePlan(_spec(M.K4_SOLO_COM, {"base": 6, "joint": 2}, True, "base", 6)).describe()
+    assert [sum(len(t["src"]) for t in layer) for layer in com["conv"]] == [48, 48, 48, 48, 48, 40, 28, 16]
+    assert com["need"][8] == [1] * 4 + [0] * 12
+
+
+def test_plan_rejects_unsupported():
+    tpl = M.K4_MINI_CHEETAH
+    spec = _spec(tpl, {"base": 900, "joint": 300, "foot": 900}, True, "foot", 2)
+    spec["hidden"] = 64
+    with pytest.raises(RuntimeError, match="H=128"):
+        N.NativePlan(spec)
+    spec = _spec(tpl, {"base": 900, "joint": 300, "foot": 900}, True, "foot", 2)
+    spec["edges"][2] = (1, 1, True, spec["edges"][2][3], spec["edges"][2][4])   # mean over the joint chain: in-degree 2
+    with pytest.raises(RuntimeError, match="in-degree"):
+        N.NativePlan(spec)
+
+
+def test_compute_call_without_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    plan = N.NativePlan(_spec(M.K4_SOLO_COM, {"base": 6, "joint": 2}, True, "base", 6, L=2))
+    buf = ctypes.create_string_buffer(1 << 20)
+    addr = (ctypes.addressof(buf) + 255) & ~255
+    with pytest.raises(RuntimeError, match="mshgnn_forward failed"):
+        plan.forward(1, [addr, addr], N.F32, addr, addr, addr, plan.workspace_bytes(1, False), False, N.MODE_FP32, None)
