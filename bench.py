@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py - graphs/s of the MS-HGNN train step (and inference) on N B200s.
+
+Contract (one JSON line on rank 0):
+  value      train-step graphs/s, whole job, inputs resident in HBM (fused native step: forward ->
+             loss head -> backward -> [all-reduce of the flat gradient] -> Adam), CUDA events, max over ranks
+  e2e        the same metric through the public API with HOST (pinned) buffers: per step H2D of the
+             batch (features, edge_index, labels), the train step, D2H of the loss
+  inference  no-grad forward graphs/s (device resident)
+  roofline   dominant kernel: algorithmic FLOPs / measured kernel time vs measured peak
+  cpu_baseline  the oracle (CPU restatement of the reference's PyG op sequence) timed on host cores
+`--impl reference` times that oracle alone (the reference's own code cannot be installed: it needs
+torch_geometric / lightning, which are not in this image and there is no network).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (os.path.join(ROOT, "morphsym-hgnn_b200"), os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+WORKLOAD = "mini_cheetah-k4-contact"      # BASELINE.json configs[2]: MS-HGNN K4 Mini Cheetah contact, batch 16384 per GPU
+PER_GPU_BATCH = 16384
+METRIC = "train-step graphs/s (MS-HGNN K4 Mini Cheetah contact, H=128, L=8, fwd+loss+bwd+allreduce+Adam)"
+
+# Algorithmic work per graph, SURVEY 8d (minimum: zero aggregates skipped, roots pre-summed, dead last layer):
+#   MAC: encoder sum n_t*in_t*H ; layers (R*(L-1)+R_last)*H^2 with R=64, R_last=8 ; decoder n_out*H*C
+_ENC_MAC = (4 * 900 + 12 * 300 + 4 * 900) * 128
+_LAY_MAC = (64 * 7 + 8) * 128 * 128
+_DEC_MAC = 4 * 128 * 2
+ALG = {
+    "fwd_flop": 2 * (_ENC_MAC + _LAY_MAC + _DEC_MAC),                      # 17.71 MFLOP
+    "train_flop": 2 * (2 * _ENC_MAC + 3 * _LAY_MAC + 3 * _DEC_MAC),        # 50.36 MFLOP
+    "in_bytes": 43200,                                                     # fp32 features per graph
+    # per kernel kind (names from mshgnn_kernel_kind_name)
+    "encoder_fwd(k_rowgemm)": 2 * _ENC_MAC,
+    "conv_fwd(k_rowgemm)": 2 * (_LAY_MAC - 8 * 7 * 128 * 128),             # layer rows minus the base-MLP rows
+    "base_mlp_fwd(k_rowgemm)": 2 * (8 * 7 * 128 * 128),
+    "dx_bwd(k_rowgemm)": 2 * (_LAY_MAC - 8 * 7 * 128 * 128),
+    "base_mlp_bwd(k_rowgemm)": 2 * (8 * 7 * 128 * 128),
+    "dw_layers(k_reducegemm)": 2 * _LAY_MAC,
+    "dw_encoder(k_reducegemm)": 2 * _ENC_MAC,
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, reasons, mx = [], set(), None
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); mx = float(r[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower() == "active":
+                    reasons.add(name)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def oracle_train_rate(B, steps, warmup, dtype=torch.float64, threads=None):
+    """graphs/s of the CPU oracle train step (fwd + loss + bwd + torch.optim.Adam) on the host cores."""
+    import mshgnn_oracle as O
+    from helpers import oracle_loss
+    from ms_hgnn.synthetic import CONFIGS, build_model, make_batch
+    if threads:
+        torch.set_num_threads(threads)
+    cfg = CONFIGS[WORKLOAD]
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(dtype)
+    try:
+        model = build_model(cfg, 128, 8, 0, module=O)
+        batch = make_batch(cfg, B, seed=1, dtype=dtype)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+        ts = []
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            opt.zero_grad()
+            out = model(batch.x_dict, batch.edge_index_dict)
+            loss = oracle_loss(cfg, out, batch.y, B)
+            loss.backward()
+            opt.step()
+            if i >= warmup:
+                ts.append(time.perf_counter() - t0)
+    finally:
+        torch.set_default_dtype(prev)
+    return B / (sum(ts) / len(ts)), B / min(ts)
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    B = 1024
+    mean_rate, best_rate = oracle_train_rate(B, args.steps, args.warmup)
+    ms = 1e3 * B / mean_rate
+    line = {
+        "impl": "reference", "metric": METRIC, "value": mean_rate, "unit": "graphs/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "per_step_graphs": B, "note": "CPU oracle = pure-PyTorch restatement of the reference's "
+                   "torch_geometric op sequence (the reference itself is not installable offline); fp64 like the reference"},
+        "cpu_baseline": {"value": mean_rate, "unit": "graphs/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{args.steps} train steps of {B} graphs, fp64, torch threads={torch.get_num_threads()}"},
+        "e2e": {"value": mean_rate, "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="graphs per GPU per step")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch.distributed as dist
+    from ms_hgnn import _native as N
+    from ms_hgnn import morphology as M
+    from ms_hgnn.lightning_py.gnnLightning import HGNN_K4_Lightning
+    from ms_hgnn.synthetic import CONFIGS, HeteroBatch, make_batch
+    from ms_hgnn.train import FusedTrainer
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+
+    cfg = CONFIGS[WORKLOAD]
+    B = args.batch
+    K, W = args.steps, args.warmup
+    host = make_batch(cfg, B, seed=100 + rank).pin_memory()
+    torch.manual_seed(2024)
+    module = HGNN_K4_Lightning(128, 8, M.K4_MINI_CHEETAH.metadata, host, "adam", 1e-4, regression=False,
+                               symmetry_mode="MorphSym", group_operator_path=M.cfg_path(cfg.group)).to(dev)
+    module.model.validate_edges = "cached"
+    trainer = FusedTrainer(module)
+    resident = host.to(dev)
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host._x.values()) + \
+        sum(v.numel() * v.element_size() for v in host._edge_index.values()) + host.y.numel() * host.y.element_size()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    # ---------------- train step, device resident ----------------
+    for _ in range(W):
+        trainer.train_step(resident)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    n0 = N.launch_count()
+    train_ms = timed(lambda: trainer.train_step(resident), K)
+    launches = N.launch_count() - n0
+    clocks = sampler.stop() if sampler else {}
+
+    # ---------------- per-kernel times (same steps, events around every launch) ----------------
+    N.profile_enable(True)
+    prof_ms = timed(lambda: trainer.train_step(resident), K)
+    prof = N.profile_read()
+    N.profile_enable(False)
+
+    # ---------------- inference, device resident ----------------
+    for _ in range(W):
+        trainer.infer(resident)
+    infer_ms = timed(lambda: trainer.infer(resident), K)
+
+    # ---------------- end to end: pinned host buffers -> H2D -> train step -> D2H loss ----------------
+    e2e_ms = None
+    if not args.skip_e2e:
+        copy_stream = torch.cuda.Stream(dev)
+        bufs = [host.to(dev), host.to(dev)]
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        done = [torch.cuda.Event(), torch.cuda.Event()]
+        loss_host = torch.empty(K + W, dtype=torch.float32).pin_memory()
+
+        def upload(i):
+            b = bufs[i % 2]
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(done[i % 2])          # the step that last read this buffer has finished
+                for k, v in host._x.items():
+                    b._x[k].copy_(v, non_blocking=True)
+                for k, v in host._edge_index.items():
+                    b._edge_index[k].copy_(v, non_blocking=True)
+                b.y.copy_(host.y, non_blocking=True)
+                ready[i % 2].record(copy_stream)
+
+        def e2e_loop(steps, base):
+            upload(base)
+            for i in range(base, base + steps):
+                if i + 1 < base + steps:
+                    upload(i + 1)
+                torch.cuda.current_stream(dev).wait_event(ready[i % 2])
+                loss = trainer.train_step(bufs[i % 2])
+                done[i % 2].record(torch.cuda.current_stream(dev))
+                loss_host[i:i + 1].copy_(loss, non_blocking=True)
+
+        for e in done:
+            e.record(torch.cuda.current_stream(dev))
+        e2e_loop(W, 0)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        e2e_loop(K, W)
+        e1.record()
+        barrier()
+        e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel ----------------
+    pk = peaks()
+    per_kind = []
+    for name, (ms, cnt) in prof.items():
+        per_step_ms = ms / K
+        flop = ALG.get(name)
+        ent = {"kernel": name, "ms_per_step": per_step_ms, "launches_per_step": cnt / K, "share": ms / (prof_ms if prof_ms else 1)}
+        if flop:
+            ent["achieved_tflops"] = flop * B / (per_step_ms * 1e-3) / 1e12
+            ent["frac_tensor_peak"] = ent["achieved_tflops"] / pk["tflops"]
+        if name.startswith("encoder_fwd") or name.startswith("dw_encoder"):
+            ent["achieved_gbs"] = ALG["in_bytes"] * B / (per_step_ms * 1e-3) / 1e9
+            ent["frac_hbm_peak"] = ent["achieved_gbs"] / pk["hbm_gbs"]
+        per_kind.append(ent)
+    per_kind.sort(key=lambda e: -e["ms_per_step"])
+    dom = next((e for e in per_kind if "achieved_tflops" in e), None)
+    roofline = None
+    if dom:
+        roofline = {"kernel": dom["kernel"], "bound": "tensor", "achieved": dom["achieved_tflops"], "peak": pk["tflops"],
+                    "unit": "TFLOP/s", "frac": dom["frac_tensor_peak"], "traffic": None, "peak_source": pk["src"] + " (bf16 dense, sustained)",
+                    "launches_per_step": dom["launches_per_step"], "ms_per_launch": dom["ms_per_step"] / max(dom["launches_per_step"], 1),
+                    "note": "fp32 SIMT FMA kernel measured against the dense bf16 tensor peak; algorithmic FLOPs per SURVEY 8d"}
+
+    # ---------------- CPU baseline (oracle on host cores), bounded sample ----------------
+    cpu = None
+    if not args.skip_cpu and world == 1:
+        cores = os.cpu_count()
+        torch.set_num_threads(cores)
+        r64, _ = oracle_train_rate(64, 40, 3)             # the reference's own batch size
+        r1k, _ = oracle_train_rate(1024, 6, 1)
+        best = max(r64, r1k)
+        cpu = {"value": best, "unit": "graphs/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"oracle train step fp64: 40 steps of 64 graphs ({r64:.0f} graphs/s), 6 steps of 1024 graphs ({r1k:.0f} graphs/s); best reported"}
+
+    total_graphs = B * world * K
+    line = {
+        "metric": METRIC, "value": total_graphs / (train_ms * 1e-3), "unit": "graphs/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": train_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world, "hidden": 128, "layers": 8,
+                   "parallelism": f"dp{world}", "mode": "fp32-simt", "l2": "inputs (708 MB/step/GPU) exceed the 126 MB L2; no flush needed"},
+        "inference": {"value": total_graphs / (infer_ms * 1e-3), "unit": "graphs/s", "ms_per_step": infer_ms / K},
+        "e2e": None if e2e_ms is None else {"value": total_graphs / (e2e_ms * 1e-3), "unit": "graphs/s", "ms_per_step": e2e_ms / K,
+                                            "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                                            "note": "pinned host batch -> H2D (copy stream, double-buffered) -> train step -> D2H loss"},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": roofline,
+        "kernels": per_kind,
+        "model_flops": {"train_mflop_per_graph": ALG["train_flop"] / 1e6, "fwd_mflop_per_graph": ALG["fwd_flop"] / 1e6,
+                        "train_tflops": ALG["train_flop"] * B * world / (train_ms / K * 1e-3) / 1e12,
+                        "infer_tflops": ALG["fwd_flop"] * B * world / (infer_ms / K * 1e-3) / 1e12},
+        "cpu_baseline": cpu,
+        "profiled_ms_per_step": prof_ms / K,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -144,6 +144,16 @@ int mshgnn_sgd_step(float* params, const float* grads, int64_t n, float lr, void
  * (including the terminating NUL).  Host-only: usable without a GPU. */
 int64_t mshgnn_plan_describe(const mshgnn_plan* plan, char* buf, int64_t cap);
 
+/* ---- per-kernel timing (CUDA events on the launching stream) -----------------------------
+ * While enabled, every kernel launch of this library is bracketed by a pair of CUDA events on the
+ * stream it is launched on.  mshgnn_profile_read synchronises those events, adds the elapsed
+ * milliseconds and launch counts per kernel kind into ms_out / launches_out (n entries each, n >=
+ * MSHGNN_NUM_KERNEL_KINDS) and clears the record.  Used by bench.py for the roofline figures. */
+#define MSHGNN_NUM_KERNEL_KINDS 16
+int mshgnn_profile_enable(int32_t on);
+int mshgnn_profile_read(double* ms_out, int64_t* launches_out, int32_t n);
+const char* mshgnn_kernel_kind_name(int32_t kind);
+
 /* number of kernels launched by this library since process start (for gpu_launches accounting) */
 int64_t mshgnn_launch_count(void);
 const char* mshgnn_last_error(void);

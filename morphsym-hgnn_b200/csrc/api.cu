@@ -4,7 +4,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <new>
+#include <vector>
 
 #include "kernels_simt.cuh"
 #include "plan.cuh"
@@ -34,6 +36,36 @@ int fail(int code, const char* fmt, ...) {
         if (_e != cudaSuccess)                                                             \
             return fail(MSHGNN_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
     } while (0)
+
+// ---- per-kernel event profiling ----
+enum Kind : int { K_DERIVE = 0, K_ENC_FWD, K_CONV_FWD, K_MLP_FWD, K_DEC_FWD, K_LOSS, K_DEC_BWD, K_MLP_BWD, K_DX_BWD,
+                  K_DW_LAYER, K_DW_ENC, K_REDUCE, K_OPTIM, K_MEMSET, K_NKINDS };
+const char* const kKindNames[MSHGNN_NUM_KERNEL_KINDS] = {
+    "derive_weights", "encoder_fwd(k_rowgemm)", "conv_fwd(k_rowgemm)", "base_mlp_fwd(k_rowgemm)", "decoder_fwd", "loss",
+    "decoder_bwd", "base_mlp_bwd(k_rowgemm)", "dx_bwd(k_rowgemm)", "dw_layers(k_reducegemm)", "dw_encoder(k_reducegemm)",
+    "reduce_partials", "optimizer", "memset", "", ""};
+struct ProfRec { int kind; cudaEvent_t a, b; };
+std::mutex g_prof_mu;
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+std::vector<cudaEvent_t> g_prof_pool;
+
+struct ProfScope {
+    cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr; int kind; bool on;
+    ProfScope(int k, cudaStream_t s) : st(s), kind(k), on(g_prof_on) {
+        if (!on) return;
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        auto get = [&]() { cudaEvent_t e; if (!g_prof_pool.empty()) { e = g_prof_pool.back(); g_prof_pool.pop_back(); } else cudaEventCreate(&e); return e; };
+        a = get(); b = get();
+        cudaEventRecord(a, st);
+    }
+    ~ProfScope() {
+        if (!on) return;
+        cudaEventRecord(b, st);
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        g_prof.push_back({kind, a, b});
+    }
+};
 
 #define LAUNCH_CHECK()                                                                     \
     do {                                                                                   \
@@ -84,8 +116,9 @@ void fill_bufs(const Plan& p, const WsLayout& w, char* ws, BufTable& bt) {
     for (int l = 0; l < p.L; ++l) { bt.p[BUF_CT0 + l] = at(w.ct[l]); bt.p[BUF_MASK0 + l] = at(w.mask[l]); }
 }
 
-int launch_rowgemm(const Plan& p, const Launch& L, const BufTable& bt, int64_t B, int64_t Bp, int x_f64, cudaStream_t st) {
+int launch_rowgemm(int kind, const Plan& p, const Launch& L, const BufTable& bt, int64_t B, int64_t Bp, int x_f64, cudaStream_t st) {
     if (L.count == 0) return 0;
+    ProfScope ps(kind, st);
     dim3 grid((unsigned)(Bp / TILE_M), (unsigned)L.count);
     k_rowgemm<<<grid, 256, 0, st>>>(p.d_tiles + L.begin, bt, B, Bp, x_f64);
     LAUNCH_CHECK();
@@ -186,20 +219,22 @@ int mshgnn_forward(const mshgnn_plan* plan, int64_t B, const void* const* x, int
     const int xf64 = x_dtype == MSHGNN_F64;
 
     {   // derived weights (transposes, root sums, bias sums) from the current parameters
+        ProfScope ps(K_DERIVE, st);
         dim3 grid(16, (unsigned)p.derive_ops.size());
         k_derive<<<grid, 256, 0, st>>>(p.d_derive, params, (float*)bt.p[BUF_DERIVED]);
         LAUNCH_CHECK();
     }
-    if ((rc = launch_rowgemm(p, p.enc_launch, bt, B, w.Bp, xf64, st))) return rc;
+    if ((rc = launch_rowgemm(K_ENC_FWD, p, p.enc_launch, bt, B, w.Bp, xf64, st))) return rc;
     for (int l = 0; l < p.L; ++l) {
-        if ((rc = launch_rowgemm(p, train ? p.conv_train[l] : p.conv_infer[l], bt, B, w.Bp, 0, st))) return rc;
-        if ((rc = launch_rowgemm(p, p.mlp1[l], bt, B, w.Bp, 0, st))) return rc;
-        if ((rc = launch_rowgemm(p, p.mlp2[l], bt, B, w.Bp, 0, st))) return rc;
+        if ((rc = launch_rowgemm(K_CONV_FWD, p, train ? p.conv_train[l] : p.conv_infer[l], bt, B, w.Bp, 0, st))) return rc;
+        if ((rc = launch_rowgemm(K_MLP_FWD, p, p.mlp1[l], bt, B, w.Bp, 0, st))) return rc;
+        if ((rc = launch_rowgemm(K_MLP_FWD, p, p.mlp2[l], bt, B, w.Bp, 0, st))) return rc;
     }
     {
         const int64_t rows = B * p.dec.n_dec;
         int blocks = (int)((rows + 7) / 8);
         if (blocks > 148 * 8) blocks = 148 * 8;
+        ProfScope ps(K_DEC_FWD, st);
         k_decoder_fwd<<<blocks, 256, 0, st>>>(p.dec, (const float*)bt.p[BUF_H0 + p.L], params, p.d_signs, out, B, w.Bp);
         LAUNCH_CHECK();
     }
@@ -224,6 +259,7 @@ int mshgnn_loss(const mshgnn_plan* plan, int64_t B, int32_t loss_kind, const flo
     const int64_t n = loss_kind == MSHGNN_LOSS_MSE ? rows * p.C : rows;
     int blocks = (int)((n + 255) / 256);
     if (blocks > LOSS_BLOCKS) blocks = LOSS_BLOCKS;
+    ProfScope ps(K_LOSS, st);
     k_loss_partial<<<blocks, 256, 0, st>>>(loss_kind, out, labels, label_dtype, n, loss_scale / (float)n, dout, partial);
     LAUNCH_CHECK();
     k_loss_final<<<1, 32, 0, st>>>(partial, blocks, 1.0 / (double)n, loss_kind == MSHGNN_LOSS_CE2, loss_out);
@@ -254,7 +290,7 @@ int mshgnn_backward(const mshgnn_plan* plan, int64_t B, const void* const* x, in
     float* part_b = (float*)(ws + w.part_b);
     float* dec_part = (float*)(ws + w.dec_part);
 
-    CUDA_TRY(cudaMemsetAsync(grads, 0, (size_t)p.n_params * 4, st));
+    { ProfScope ps(K_MEMSET, st); CUDA_TRY(cudaMemsetAsync(grads, 0, (size_t)p.n_params * 4, st)); }
 
     {   // decoder backward: dH_L on the decoded slots (+ masked copy = dc_{L-1}), dW_dec, db_dec
         const int L = p.L;
@@ -265,28 +301,31 @@ int mshgnn_backward(const mshgnn_plan* plan, int64_t B, const void* const* x, in
         } else {
             dc = (float*)bt.p[BUF_DC0 + ((L - 1) & 1)]; mk = MK_POS; mbuf = bt.p[BUF_H0 + L];
         }
+        ProfScope ps(K_DEC_BWD, st);
         k_decoder_bwd<<<DEC_BLOCKS, 256, 0, st>>>(p.dec, (const float*)bt.p[BUF_H0 + L], params, p.d_signs, dout, dh, dc, mk, mbuf,
                                                   dec_part, B, w.Bp);
         LAUNCH_CHECK();
         k_decoder_bwd_reduce<<<4, 256, 0, st>>>(p.dec, dec_part, DEC_BLOCKS, grads);
         LAUNCH_CHECK();
     }
-    auto launch_dw = [&](const Launch& L) -> int {
+    auto launch_dw = [&](int kind, const Launch& L) -> int {
         if (L.count == 0) return 0;
+        ProfScope ps(kind, st);
         dim3 grid((unsigned)L.count, (unsigned)w.n_splits);
         k_reducegemm<<<grid, 256, 0, st>>>(p.d_rtasks, p.d_rpairs, L.begin, bt, B, w.Bp, xf64, w.n_splits, part_w, part_b);
         LAUNCH_CHECK();
         return 0;
     };
     for (int l = p.L - 1; l >= 0; --l) {
-        if ((rc = launch_rowgemm(p, p.bwd_m1[l], bt, B, w.Bp, 0, st))) return rc;
-        if ((rc = launch_rowgemm(p, p.bwd_m2[l], bt, B, w.Bp, 0, st))) return rc;
-        if ((rc = launch_dw(p.dw_layer[l]))) return rc;
-        if ((rc = launch_rowgemm(p, p.bwd_dx[l], bt, B, w.Bp, 0, st))) return rc;
+        if ((rc = launch_rowgemm(K_MLP_BWD, p, p.bwd_m1[l], bt, B, w.Bp, 0, st))) return rc;
+        if ((rc = launch_rowgemm(K_MLP_BWD, p, p.bwd_m2[l], bt, B, w.Bp, 0, st))) return rc;
+        if ((rc = launch_dw(K_DW_LAYER, p.dw_layer[l]))) return rc;
+        if ((rc = launch_rowgemm(K_DX_BWD, p, p.bwd_dx[l], bt, B, w.Bp, 0, st))) return rc;
     }
-    if ((rc = launch_dw(p.dw_enc))) return rc;
+    if ((rc = launch_dw(K_DW_ENC, p.dw_enc))) return rc;
     if (!p.groups.empty()) {
         dim3 grid((unsigned)p.groups.size(), 8);
+        ProfScope ps(K_REDUCE, st);
         k_reduce_partials<<<grid, 256, 0, st>>>(p.d_groups, part_w, part_b, w.n_splits, grads);
         LAUNCH_CHECK();
     }
@@ -300,6 +339,7 @@ int mshgnn_adam_step(float* params, const float* grads, float* exp_avg, float* e
     const float bc2s = (float)std::sqrt(1.0 - std::pow((double)beta2, (double)step));
     int blocks = (int)((n + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
+    ProfScope ps(K_OPTIM, (cudaStream_t)stream);
     k_adam<<<blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2s);
     LAUNCH_CHECK();
     return 0;
@@ -309,9 +349,39 @@ int mshgnn_sgd_step(float* params, const float* grads, int64_t n, float lr, void
     if (!params || !grads || n < 1) return fail(MSHGNN_ERR_ARG, "bad argument");
     int blocks = (int)((n + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
+    ProfScope ps(K_OPTIM, (cudaStream_t)stream);
     k_sgd<<<blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, n, lr);
     LAUNCH_CHECK();
     return 0;
+}
+
+int mshgnn_profile_enable(int32_t on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_on = on != 0;
+    return 0;
+}
+
+int mshgnn_profile_read(double* ms_out, int64_t* launches_out, int32_t n) {
+    if (!ms_out || !launches_out || n < MSHGNN_NUM_KERNEL_KINDS) return fail(MSHGNN_ERR_ARG, "bad argument");
+    std::vector<ProfRec> recs;
+    {
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        recs.swap(g_prof);
+    }
+    for (int i = 0; i < n; ++i) { ms_out[i] = 0.0; launches_out[i] = 0; }
+    for (auto& r : recs) {
+        CUDA_TRY(cudaEventSynchronize(r.b));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, r.a, r.b));
+        ms_out[r.kind] += ms; launches_out[r.kind] += 1;
+    }
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (auto& r : recs) { g_prof_pool.push_back(r.a); g_prof_pool.push_back(r.b); }
+    return 0;
+}
+
+const char* mshgnn_kernel_kind_name(int32_t kind) {
+    return (kind >= 0 && kind < MSHGNN_NUM_KERNEL_KINDS) ? kKindNames[kind] : "";
 }
 
 int64_t mshgnn_launch_count(void) { return g_launches.load(); }

@@ -27,7 +27,7 @@ EXPORTS = (
     "mshgnn_plan_create", "mshgnn_plan_destroy", "mshgnn_param_count", "mshgnn_param_offset",
     "mshgnn_workspace_bytes", "mshgnn_out_rows", "mshgnn_forward", "mshgnn_loss", "mshgnn_backward",
     "mshgnn_adam_step", "mshgnn_sgd_step", "mshgnn_plan_describe", "mshgnn_launch_count",
-    "mshgnn_last_error", "mshgnn_version",
+    "mshgnn_last_error", "mshgnn_version", "mshgnn_profile_enable", "mshgnn_profile_read", "mshgnn_kernel_kind_name",
 )
 
 
@@ -91,6 +91,9 @@ def lib() -> C.CDLL:
     L.mshgnn_launch_count.argtypes = []; L.mshgnn_launch_count.restype = i64
     L.mshgnn_last_error.argtypes = []; L.mshgnn_last_error.restype = C.c_char_p
     L.mshgnn_version.argtypes = []; L.mshgnn_version.restype = C.c_char_p
+    L.mshgnn_profile_enable.argtypes = [i32]; L.mshgnn_profile_enable.restype = C.c_int
+    L.mshgnn_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(i64), i32]; L.mshgnn_profile_read.restype = C.c_int
+    L.mshgnn_kernel_kind_name.argtypes = [i32]; L.mshgnn_kernel_kind_name.restype = C.c_char_p
     _lib = L
     return L
 
@@ -98,6 +101,26 @@ def lib() -> C.CDLL:
 def check(rc: int, what: str) -> None:
     if rc != 0:
         raise RuntimeError(f"{what} failed (code {rc}): {lib().mshgnn_last_error().decode()}")
+
+
+NUM_KERNEL_KINDS = 16
+
+
+def profile_enable(on: bool) -> None:
+    check(lib().mshgnn_profile_enable(int(on)), "mshgnn_profile_enable")
+
+
+def profile_read() -> dict:
+    """{kernel kind name: (total ms, launches)} since the last read (synchronises the recorded events)."""
+    ms = (C.c_double * NUM_KERNEL_KINDS)()
+    cnt = (C.c_int64 * NUM_KERNEL_KINDS)()
+    check(lib().mshgnn_profile_read(ms, cnt, NUM_KERNEL_KINDS), "mshgnn_profile_read")
+    out = {}
+    for k in range(NUM_KERNEL_KINDS):
+        name = lib().mshgnn_kernel_kind_name(k).decode()
+        if name and cnt[k]:
+            out[name] = (float(ms[k]), int(cnt[k]))
+    return out
 
 
 def launch_count() -> int:

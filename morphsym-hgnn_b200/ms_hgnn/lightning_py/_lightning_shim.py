@@ -1,0 +1,58 @@
+"""Minimal stand-in for ``lightning.LightningModule`` (lightning is not installed in this image).
+
+Provides what the reference's modules use: ``log``, ``save_hyperparameters``, ``hparams``, ``freeze``,
+``load_from_checkpoint``.  When ``lightning`` is importable the real class is used instead."""
+import inspect
+
+import torch
+from torch import nn
+
+try:  # pragma: no cover - not available offline
+    import lightning as L
+    LightningModule = L.LightningModule
+    HAVE_LIGHTNING = True
+except Exception:
+    HAVE_LIGHTNING = False
+
+    class LightningModule(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.hparams = {}
+            self.logged = {}
+
+        def log(self, name, value, on_step=False, on_epoch=True, **kw):
+            self.logged[name] = value
+
+        def save_hyperparameters(self, *args, **kwargs):
+            frame = inspect.currentframe().f_back
+            names = [p for p in inspect.signature(type(self).__init__).parameters if p != "self"]
+            self.hparams = {n: frame.f_locals[n] for n in names if n in frame.f_locals}
+
+        def freeze(self):
+            for p in self.parameters():
+                p.requires_grad = False
+            self.eval()
+
+        @property
+        def device(self):
+            try:
+                return next(self.parameters()).device
+            except StopIteration:
+                return torch.device("cpu")
+
+        @classmethod
+        def load_from_checkpoint(cls, checkpoint_path, map_location=None, strict=True, **overrides):
+            from ..checkpoint import embedded_batch, load_checkpoint
+            from ..synthetic import HeteroBatch
+            ck = load_checkpoint(checkpoint_path, map_location or "cpu")
+            hp = dict(ck.get("hyper_parameters", {}))
+            eb = embedded_batch(ck)
+            if eb is not None:
+                x, ei, y = eb
+                B = x["base"].shape[0] if "base" in x else 1
+                hp["dummy_batch"] = HeteroBatch(x, ei, y, B)
+            hp.update(overrides)
+            names = [p for p in inspect.signature(cls.__init__).parameters if p != "self"]
+            obj = cls(**{k: v for k, v in hp.items() if k in names})
+            obj.load_state_dict(ck["state_dict"], strict=strict)
+            return obj

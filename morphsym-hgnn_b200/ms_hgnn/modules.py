@@ -173,6 +173,7 @@ class NativeHGNN(nn.Module):
         d["_edge_ok"] = {}
         d["_expected_edges"] = {}
         d["_fwd_token"] = None
+        d.pop("_last_engine", None)
         return d
 
     # ---- reference API ----------------------------------------------------------------
@@ -358,6 +359,7 @@ class NativeHGNN(nn.Module):
         if x0.device.type != "cuda":
             raise RuntimeError("ms_hgnn (B200-native) has no CPU path: move the batch and the model to a CUDA device")
         eng, B = self._engine_for(x_dict, edge_index_dict)
+        self._last_engine = eng
         self._ensure_flat(x0.device)
         xs = [x_dict[t] for t in self.node_types]          # never mutated (the reference mutates its input dict)
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self._flat_params)
@@ -367,3 +369,37 @@ class NativeHGNN(nn.Module):
             out = eng.forward(xs, self._flat, train=False)
         out = self._finish(out, B)
         return out if out.dtype == x0.dtype else out.to(x0.dtype)
+
+
+class _NativeLossFn(torch.autograd.Function):
+    """Fused loss head (value + d loss / d out in one native pass)."""
+
+    @staticmethod
+    def forward(ctx, out2d, labels, kind, engine):
+        loss, dout = engine.loss(out2d, labels, kind, want_grad=True)
+        ctx.save_for_backward(dout)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (dout,) = ctx.saved_tensors
+        return dout * g, None, None, None
+
+
+def native_loss(model: "NativeHGNN", y_pred: torch.Tensor, y: torch.Tensor, kind: int) -> torch.Tensor:
+    """MSE (kind=LOSS_MSE) or per-foot 2-way CE (LOSS_CE2) through the native fused loss kernel.
+
+    ``y_pred`` is the (reshaped) model output; gradients flow back into the native backward pass."""
+    eng = getattr(model, "_last_engine", None)
+    if eng is None:
+        raise RuntimeError("native_loss() needs a preceding forward pass of the model")
+    C = eng.spec["out_channels"]
+    out2d = y_pred.reshape(-1, C)
+    if out2d.dtype != torch.float32:
+        out2d = out2d.float()
+    out2d = out2d.contiguous()
+    labels = y.reshape(-1)
+    if torch.is_grad_enabled() and out2d.requires_grad:
+        return _NativeLossFn.apply(out2d, labels, kind, eng)
+    loss, _ = eng.loss(out2d, labels, kind, want_grad=False)
+    return loss[0]

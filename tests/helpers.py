@@ -44,3 +44,21 @@ def oracle_run(cfg, model, batch):
     loss.backward()
     grads = {n: (p.grad.clone() if p.grad is not None else torch.zeros_like(p)) for n, p in model.named_parameters()}
     return out.detach(), loss.detach(), grads
+
+
+def oracle_fp32_floor(cfg, model, batch, ref_out, ref_grads):
+    """Error of the SAME oracle op sequence run in plain PyTorch float32 against its float64 self.
+
+    ReLU makes the gradient discontinuous in the forward numerics: an fp32 rounding that flips the sign
+    of one pre-activation changes a whole gradient row.  No fp32 implementation (including the
+    reference's own ops in fp32) can be closer to the fp64 oracle than this floor, so the parity bound
+    for gradients is max(1e-4, 2 x floor) per tensor."""
+    import copy
+    m32 = copy.deepcopy(model).float()
+    x = {k: v.float() for k, v in batch.x_dict.items()}
+    m32.zero_grad()
+    out = m32(x, batch.edge_index_dict)
+    loss = oracle_loss(cfg, out, batch.y.float(), batch.batch_size)
+    loss.backward()
+    floor = {n: (rel_err(p.grad, ref_grads[n]) if p.grad is not None else 0.0) for n, p in m32.named_parameters()}
+    return rel_err(out, ref_out), floor

