@@ -285,33 +285,9 @@ k_reducegemm(const RTask* __restrict__ tasks, const RPair* __restrict__ pairs, c
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
     float cs = 0.f;
 
-    // Blocked summation: the register accumulators are flushed into the (CTA-private, L2-resident)
-    // partial tile every RD_FLUSH steps, so no fp32 running sum is longer than RD_FLUSH*16 rows.
-    // Weight gradients are sums over thousands of rows that largely cancel; a single long fp32
-    // running sum loses ~1e-4 of the result there (measured on the K4 COM encoder gradient).
-    constexpr int RD_FLUSH = 8;
+    // Summation accuracy: a task holds at most RD_MAX_PAIRS pairs and a split at most 512 rows, so no fp32
+    // running sum is longer than 2048 terms; the splits are then summed in double (k_reduce_partials).
     float* pw = part_w + ((int64_t)task * n_splits + split) * (H * H);
-    float cs_tot = 0.f;
-    bool first = true;
-    int since = 0;
-    auto flush = [&]() {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int o = ty * 4 + (i & 3) + (i >> 2) * 64;
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-                float4* dst = reinterpret_cast<float4*>(pw + o * H + 64 * hh + tx * 4);
-                float4 cur = first ? make_float4(0.f, 0.f, 0.f, 0.f) : *dst;
-                cur.x += acc[i][hh * 4 + 0]; cur.y += acc[i][hh * 4 + 1];
-                cur.z += acc[i][hh * 4 + 2]; cur.w += acc[i][hh * 4 + 3];
-                *dst = cur;
-                acc[i][hh * 4 + 0] = 0.f; acc[i][hh * 4 + 1] = 0.f; acc[i][hh * 4 + 2] = 0.f; acc[i][hh * 4 + 3] = 0.f;
-            }
-        }
-        cs_tot += cs; cs = 0.f;
-        first = false; since = 0;
-    };
-
     const int64_t total = n_steps_pair * t.n_pairs;
     RdRegs r;
     int64_t step = 0;
@@ -347,10 +323,14 @@ k_reducegemm(const RTask* __restrict__ tasks, const RPair* __restrict__ pairs, c
             for (int k = 0; k < RG_BK; ++k) cs += Ds[k][tid];
         }
         __syncthreads();
-        if (++since == RD_FLUSH) flush();
     }
-    if (since > 0 || first) flush();
-    if (t.want_colsum && tid < H) part_b[((int64_t)task * n_splits + split) * H + tid] = cs_tot;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int o = ty * 4 + (i & 3) + (i >> 2) * 64;
+        *reinterpret_cast<float4*>(pw + o * H + tx * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        *reinterpret_cast<float4*>(pw + o * H + 64 + tx * 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+    }
+    if (t.want_colsum && tid < H) part_b[((int64_t)task * n_splits + split) * H + tid] = cs;
 }
 
 // sum the split partials of a group of tasks into the flat gradient buffer (fixed order => deterministic)

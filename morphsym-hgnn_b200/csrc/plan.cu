@@ -30,6 +30,21 @@ static Tile empty_tile() {
     return t;
 }
 
+constexpr int RD_MAX_PAIRS = 4;
+
+// Emit reduce tasks ("units") of at most RD_MAX_PAIRS pairs each; returns false when more than 16 units result.
+static bool emit_units(Plan& p, const std::vector<RPair>& prs, int K, int k0, int want_colsum, int* ids, int& n_ids) {
+    for (size_t b = 0; b < prs.size(); b += RD_MAX_PAIRS) {
+        const size_t e = b + RD_MAX_PAIRS < prs.size() ? b + RD_MAX_PAIRS : prs.size();
+        RTask T{}; T.pair_begin = (int)p.rpairs.size(); T.n_pairs = (int)(e - b); T.K = K; T.k0 = k0; T.want_colsum = want_colsum;
+        p.rpairs.insert(p.rpairs.end(), prs.begin() + b, prs.begin() + e);
+        if (n_ids >= 16) return false;
+        ids[n_ids++] = (int)p.rtasks.size();
+        p.rtasks.push_back(T);
+    }
+    return true;
+}
+
 std::string build_plan(const mshgnn_desc* d, Plan& p) {
     char err[256];
     if (!d) return "desc is NULL";
@@ -279,35 +294,33 @@ std::string build_plan(const mshgnn_desc* d, Plan& p) {
         }
         p.bwd_m1[l] = push_launch(b1); p.bwd_m2[l] = push_launch(b2); p.bwd_dx[l] = push_launch(dx);
 
-        // ---- weight-gradient tasks of layer l ----
+        // ---- weight-gradient tasks of layer l (units of <= RD_MAX_PAIRS pairs so all CTAs carry equal work) ----
         Launch lt{(int)p.rtasks.size(), 0};
         auto slab_pair = [&](int dbuf, int dslot, int abuf, int aslot) {
             RPair r{}; r.d_buf = dbuf; r.d_slot = dslot; r.a_kind = A_SLAB; r.a_buf = abuf; r.a_slot = aslot; r.lda = H; r.a_off = 0; r.sign_off = -1;
             return r;
         };
         for (int e = 0; e < p.n_etypes; ++e) {          // lin_rel weights
-            RTask T{}; T.pair_begin = (int)p.rpairs.size(); T.K = H; T.k0 = 0; T.want_colsum = 0;
+            std::vector<RPair> prs;
             for (size_t i = 0; i < p.e_src[e].size(); ++i) {
                 const int dslot = p.slot_of(p.e_dst_t[e], p.e_dst[e][i]);
                 if (!p.need[l + 1][dslot]) continue;
-                p.rpairs.push_back(slab_pair(DCc, dslot, BUF_H0 + l, p.slot_of(p.e_src_t[e], p.e_src[e][i])));
+                prs.push_back(slab_pair(DCc, dslot, BUF_H0 + l, p.slot_of(p.e_src_t[e], p.e_src[e][i])));
             }
-            T.n_pairs = (int)p.rpairs.size() - T.pair_begin;
-            if (!T.n_pairs) continue;
-            OutGroup g{}; g.kind = 0; g.n_tasks = 1; g.tasks[0] = (int)p.rtasks.size(); g.n_outs = 1;
-            g.outs[0] = (int)p.off_rel_w[l * p.n_etypes + e]; g.K = H; g.k0 = 0; g.scale = 1.f;
+            if (prs.empty()) continue;
+            OutGroup g{}; g.kind = 0; g.n_outs = 1; g.outs[0] = (int)p.off_rel_w[l * p.n_etypes + e]; g.K = H; g.k0 = 0; g.scale = 1.f;
+            if (!emit_units(p, prs, H, 0, 0, g.tasks, g.n_tasks)) return "too many weight-gradient units for one tensor";
             p.groups.push_back(g);
-            p.rtasks.push_back(T);
         }
         for (int t = 0; t < p.n_types; ++t) {           // lin_root weights + lin_rel biases (shared by all edge types into t)
-            RTask T{}; T.pair_begin = (int)p.rpairs.size(); T.K = H; T.k0 = 0; T.want_colsum = 1;
+            std::vector<RPair> prs;
             for (int n = 0; n < p.nodes[t]; ++n) {
                 const int s = p.slot_of(t, n);
-                if (p.need[l + 1][s]) p.rpairs.push_back(slab_pair(DCc, s, BUF_H0 + l, s));
+                if (p.need[l + 1][s]) prs.push_back(slab_pair(DCc, s, BUF_H0 + l, s));
             }
-            T.n_pairs = (int)p.rpairs.size() - T.pair_begin;
-            if (!T.n_pairs) continue;
-            OutGroup gw{}; gw.kind = 0; gw.n_tasks = 1; gw.tasks[0] = (int)p.rtasks.size(); gw.K = H; gw.k0 = 0; gw.scale = 1.f;
+            if (prs.empty()) continue;
+            OutGroup gw{}; gw.kind = 0; gw.K = H; gw.k0 = 0; gw.scale = 1.f;
+            if (!emit_units(p, prs, H, 0, 1, gw.tasks, gw.n_tasks)) return "too many weight-gradient units for one tensor";
             OutGroup gb = gw; gb.kind = 1;
             for (int e = 0; e < p.n_etypes; ++e)
                 if (p.e_dst_t[e] == t) {
@@ -315,21 +328,23 @@ std::string build_plan(const mshgnn_desc* d, Plan& p) {
                     gb.outs[gb.n_outs++] = (int)p.off_rel_b[l * p.n_etypes + e];
                 }
             p.groups.push_back(gw); p.groups.push_back(gb);
-            p.rtasks.push_back(T);
         }
         if (p.morph_sym) {                               // shared base_transform: tasks per layer, one group at the end
-            RTask T1{}; T1.pair_begin = (int)p.rpairs.size(); T1.K = H; T1.k0 = 0; T1.want_colsum = 1;
-            for (int n = 0; n < p.nm; ++n)
-                if (p.need[l + 1][p.slot_of(p.mlp_type, n)]) p.rpairs.push_back(slab_pair(BUF_DU, n, BUF_CT0 + l, n));
-            T1.n_pairs = (int)p.rpairs.size() - T1.pair_begin;
-            if (T1.n_pairs) { mlp_tasks[0].push_back((int)p.rtasks.size()); p.rtasks.push_back(T1); }
-            RTask T2{}; T2.pair_begin = (int)p.rpairs.size(); T2.K = H; T2.k0 = 0; T2.want_colsum = 1;
+            std::vector<RPair> p1, p2;
             for (int n = 0; n < p.nm; ++n) {
                 const int s = p.slot_of(p.mlp_type, n);
-                if (p.need[l + 1][s]) p.rpairs.push_back(slab_pair(DHn, s, BUF_CT0 + l, p.nm + n));
+                if (!p.need[l + 1][s]) continue;
+                p1.push_back(slab_pair(BUF_DU, n, BUF_CT0 + l, n));
+                p2.push_back(slab_pair(DHn, s, BUF_CT0 + l, p.nm + n));
             }
-            T2.n_pairs = (int)p.rpairs.size() - T2.pair_begin;
-            if (T2.n_pairs) { mlp_tasks[1].push_back((int)p.rtasks.size()); p.rtasks.push_back(T2); }
+            if (!p1.empty()) {
+                int ids[16], n_ids = 0;
+                if (!emit_units(p, p1, H, 0, 1, ids, n_ids)) return "too many weight-gradient units for one tensor";
+                mlp_tasks[0].insert(mlp_tasks[0].end(), ids, ids + n_ids);
+                n_ids = 0;
+                if (!emit_units(p, p2, H, 0, 1, ids, n_ids)) return "too many weight-gradient units for one tensor";
+                mlp_tasks[1].insert(mlp_tasks[1].end(), ids, ids + n_ids);
+            }
         }
         lt.count = (int)p.rtasks.size() - lt.begin;
         p.dw_layer[l] = lt;
@@ -337,6 +352,8 @@ std::string build_plan(const mshgnn_desc* d, Plan& p) {
     if (p.morph_sym)
         for (int i = 0; i < 2; ++i) {
             if (mlp_tasks[i].empty()) continue;
+            // the shared MLP accumulates over layers: chunk the task list into groups of <= 16 that ADD into the output
+            if (mlp_tasks[i].size() > 16) return "base_transform gradient spans more than 16 units";
             OutGroup gw{}; gw.kind = 0; gw.K = H; gw.k0 = 0; gw.scale = 1.f; gw.n_outs = 1; gw.outs[0] = (int)p.off_mlp_w[i];
             for (int tk : mlp_tasks[i]) gw.tasks[gw.n_tasks++] = tk;
             OutGroup gb = gw; gb.kind = 1; gb.outs[0] = (int)p.off_mlp_b[i];
@@ -355,13 +372,10 @@ std::string build_plan(const mshgnn_desc* d, Plan& p) {
         }
         if (prs.empty()) continue;
         for (int k0 = 0; k0 < p.in_w[t]; k0 += H) {
-            RTask T{}; T.pair_begin = (int)p.rpairs.size(); T.n_pairs = (int)prs.size(); T.K = p.in_w[t]; T.k0 = k0; T.want_colsum = (k0 == 0);
-            p.rpairs.insert(p.rpairs.end(), prs.begin(), prs.end());
-            OutGroup g{}; g.kind = 0; g.n_tasks = 1; g.tasks[0] = (int)p.rtasks.size(); g.n_outs = 1; g.outs[0] = (int)p.off_enc_w[t];
-            g.K = p.in_w[t]; g.k0 = k0; g.scale = 1.f;
+            OutGroup g{}; g.kind = 0; g.n_outs = 1; g.outs[0] = (int)p.off_enc_w[t]; g.K = p.in_w[t]; g.k0 = k0; g.scale = 1.f;
+            if (!emit_units(p, prs, p.in_w[t], k0, k0 == 0, g.tasks, g.n_tasks)) return "too many weight-gradient units for one tensor";
             p.groups.push_back(g);
             if (k0 == 0) { OutGroup gb = g; gb.kind = 1; gb.outs[0] = (int)p.off_enc_b[t]; p.groups.push_back(gb); }
-            p.rtasks.push_back(T);
         }
     }
     p.dw_enc.count = (int)p.rtasks.size() - p.dw_enc.begin;
@@ -372,8 +386,8 @@ WsLayout ws_layout(const Plan& p, int64_t B, int train, int mode) {
     (void)mode;
     WsLayout w{};
     w.Bp = round_up(B < 1 ? 1 : B, TILE_M);
-    int ns = (int)((B + 1023) / 1024);
-    w.n_splits = ns < 1 ? 1 : (ns > 16 ? 16 : ns);
+    int ns = (int)((B + 511) / 512);
+    w.n_splits = ns < 1 ? 1 : (ns > 64 ? 64 : ns);
     int64_t o = 0;
     auto take = [&](int64_t bytes) { int64_t at = o; o += round_up(bytes, 256); return at; };
     const int64_t slab = (int64_t)p.S * w.Bp * H * 4;

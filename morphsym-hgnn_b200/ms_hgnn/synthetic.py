@@ -43,6 +43,26 @@ class HeteroBatch:
                            self.y.to(device, non_blocking=non_blocking), self.batch_size,
                            getattr(self, "r_o", None).to(device) if hasattr(self, "r_o") else None)
 
+    def shard(self, rank: int, world: int) -> "HeteroBatch":
+        """Contiguous graph shard for data parallelism: every rank's node rows are a contiguous
+        slice of each x tensor and its edge_index is the same template tiled over the smaller batch."""
+        B = self.batch_size
+        per = (B + world - 1) // world
+        g0, g1 = min(rank * per, B), min((rank + 1) * per, B)
+        nb = g1 - g0
+        if nb <= 0:
+            raise ValueError(f"rank {rank} of {world} gets no graphs out of {B}")
+        x = {}
+        for k, v in self._x.items():
+            n = v.shape[0] // B
+            x[k] = v[g0 * n:g1 * n]
+        ei = {}
+        for k, v in self._edge_index.items():
+            E = v.shape[1] // B
+            ei[k] = v[:, :E * nb]          # the first nb graphs' block IS the template tiled nb times from offset 0
+        w = self.y.numel() // B
+        return HeteroBatch(x, ei, self.y.reshape(-1)[g0 * w:g1 * w], nb)
+
     def pin_memory(self):
         return HeteroBatch({k: v.pin_memory() for k, v in self._x.items()},
                            {k: v.pin_memory() for k, v in self._edge_index.items()},

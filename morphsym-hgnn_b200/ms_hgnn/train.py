@@ -18,6 +18,16 @@ import torch
 from . import _native as N
 
 
+def allreduce_flat_(grads: torch.Tensor, world: int, group=None) -> torch.Tensor:
+    """The one collective of the data-parallel step: sum the flat gradient buffer over the ranks.
+
+    Each rank's loss gradient is pre-scaled by 1/world (``loss_scale``), so the sum equals the gradient of the
+    mean loss over the global batch when the shards have equal size; no post-divide is needed."""
+    if world > 1:
+        torch.distributed.all_reduce(grads, op=torch.distributed.ReduceOp.SUM, group=group)
+    return grads
+
+
 class FusedTrainer:
     def __init__(self, module, optimizer: Optional[str] = None, lr: Optional[float] = None, process_group=None,
                  betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0):
@@ -66,8 +76,7 @@ class FusedTrainer:
         model._fwd_token = object()
         loss, dout = eng.loss(out, batch.y, self._loss_kind(), want_grad=True, loss_scale=1.0 / self.world)
         eng.backward(dout, flat, grads=self.grads)
-        if self.world > 1:
-            torch.distributed.all_reduce(self.grads, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+        allreduce_flat_(self.grads, self.world, self.pg)
         self.step_count += 1
         stream = torch.cuda.current_stream(dev).cuda_stream
         with torch.cuda.device(dev):
