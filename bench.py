@@ -160,6 +160,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="graphs per GPU per step")
+    ap.add_argument("--mode", default="tc", choices=["fp32", "tc", "tc1x"], help="arithmetic mode of the native kernels")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     args = ap.parse_args()
@@ -197,6 +198,7 @@ def main():
     module = HGNN_K4_Lightning(128, 8, M.K4_MINI_CHEETAH.metadata, host, "adam", 1e-4, regression=False,
                                symmetry_mode="MorphSym", group_operator_path=M.cfg_path(cfg.group)).to(dev)
     module.model.validate_edges = "cached"
+    module.model.set_mode(args.mode)
     trainer = FusedTrainer(module)
     resident = host.to(dev)
     h2d_bytes = sum(v.numel() * v.element_size() for v in host._x.values()) + \
@@ -327,10 +329,10 @@ def main():
     total_graphs = B * world * K
     line = {
         "metric": METRIC, "value": total_graphs / (train_ms * 1e-3), "unit": "graphs/s", "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": train_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "ms_per_step": train_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "tc": "f16x2-split (f32 accumulate)", "tc1x": "f16 (f32 accumulate)"}[args.mode],
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world, "hidden": 128, "layers": 8,
-                   "parallelism": f"dp{world}", "mode": "fp32-simt", "l2": "inputs (708 MB/step/GPU) exceed the 126 MB L2; no flush needed"},
+                   "parallelism": f"dp{world}", "mode": {"fp32": "fp32 SIMT FMA", "tc": "tcgen05 split-fp16 x3 (fp32-class accuracy) + SIMT dW/encoder", "tc1x": "tcgen05 fp16 x1"}[args.mode], "l2": "inputs (708 MB/step/GPU) exceed the 126 MB L2; no flush needed"},
         "inference": {"value": total_graphs / (infer_ms * 1e-3), "unit": "graphs/s", "ms_per_step": infer_ms / K},
         "e2e": None if e2e_ms is None else {"value": total_graphs / (e2e_ms * 1e-3), "unit": "graphs/s", "ms_per_step": e2e_ms / K,
                                             "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "kernels_simt.cuh"
+#include "kernels_tc.cuh"
 #include "plan.cuh"
 
 using namespace mshgnn;
@@ -98,6 +99,7 @@ int ensure_uploaded(const Plan& p) {
     if ((rc = upload(p.rpairs, &p.d_rpairs))) return rc;
     if ((rc = upload(p.groups, &p.d_groups))) return rc;
     if ((rc = upload(p.derive_ops, &p.d_derive))) return rc;
+    if ((rc = upload(p.derive16_ops, &p.d_derive16))) return rc;
     if ((rc = upload(p.signs, &p.d_signs))) return rc;
     p.device = dev;
     p.uploaded = true;
@@ -116,11 +118,93 @@ void fill_bufs(const Plan& p, const WsLayout& w, char* ws, BufTable& bt) {
     for (int l = 0; l < p.L; ++l) { bt.p[BUF_CT0 + l] = at(w.ct[l]); bt.p[BUF_MASK0 + l] = at(w.mask[l]); }
 }
 
-int launch_rowgemm(int kind, const Plan& p, const Launch& L, const BufTable& bt, int64_t B, int64_t Bp, int x_f64, cudaStream_t st) {
+void fill_bufs16(const Plan& p, const WsLayout& w, char* ws, BufTable16& bh) {
+    memset(&bh, 0, sizeof bh);
+    auto at = [&](int64_t off) -> __half* { return off < 0 ? nullptr : (__half*)(ws + off); };
+    for (int b = 0; b < 2; ++b) {
+        bh.hi[BUF_DH0 + b] = at(w.dh16[b][0]); bh.lo[BUF_DH0 + b] = at(w.dh16[b][1]);
+        bh.hi[BUF_DC0 + b] = at(w.dc16[b][0]); bh.lo[BUF_DC0 + b] = at(w.dc16[b][1]);
+    }
+    bh.hi[BUF_DU] = at(w.du16[0]); bh.lo[BUF_DU] = at(w.du16[1]);
+    for (int l = 0; l <= p.L; ++l) { bh.hi[BUF_H0 + l] = at(w.h16[l][0]); bh.lo[BUF_H0 + l] = at(w.h16[l][1]); }
+    for (int l = 0; l < p.L; ++l) { bh.hi[BUF_CT0 + l] = at(w.ct16[l][0]); bh.lo[BUF_CT0 + l] = at(w.ct16[l][1]); }
+}
+
+int launch_rowgemm(int kind, const Plan& p, const Launch& L, const BufTable& bt, int64_t B, int64_t Bp, int x_f64, cudaStream_t st,
+                   const BufTable16* bh = nullptr) {
     if (L.count == 0) return 0;
     ProfScope ps(kind, st);
     dim3 grid((unsigned)(Bp / TILE_M), (unsigned)L.count);
-    k_rowgemm<<<grid, 256, 0, st>>>(p.d_tiles + L.begin, bt, B, Bp, x_f64);
+    BufTable16 none;
+    if (!bh) memset(&none, 0, sizeof none);
+    k_rowgemm<<<grid, 256, 0, st>>>(p.d_tiles + L.begin, bt, B, Bp, x_f64, bh ? *bh : none, bh ? 1 : 0);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+// ---- tensor-core launches ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int get_encode_fn(EncodeTiledFn* out) {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || !ptr) return fail(MSHGNN_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+        fn = (EncodeTiledFn)ptr;
+    }
+    *out = fn;
+    return 0;
+}
+
+// [rows, 128] fp16 row-major tensor, box = 128 rows x 64 columns, 128-byte swizzle (the UMMA K-major SW128 layout)
+int make_map16(CUtensorMap* m, const void* base, int64_t rows) {
+    EncodeTiledFn enc;
+    int rc = get_encode_fn(&enc);
+    if (rc) return rc;
+    if (!base || rows < 128) return fail(MSHGNN_ERR_ARG, "internal: bad fp16 tensor for a TMA map");
+    cuuint64_t dims[2] = {(cuuint64_t)H, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)H * 2};
+    cuuint32_t box[2] = {64, 128};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(MSHGNN_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return 0;
+}
+
+int buf_rows(const Plan& p, int buf, int64_t Bp) {
+    if (buf >= BUF_CT0 && buf < BUF_CT0 + MAX_LAYERS) return (int)(2 * p.nm * Bp);
+    if (buf == BUF_DU) return (int)(p.nm * Bp);
+    return (int)(p.S * Bp);
+}
+
+int launch_tc_rowgemm(int kind, const Plan& p, const Launch& L, const BufTable& bt, const BufTable16& bh, const __half* w_hi,
+                      const __half* w_lo, int64_t B, int64_t Bp, int split, cudaStream_t st) {
+    if (L.count == 0) return 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(k_tc_rowgemm, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+        attr_set = true;
+    }
+    const int a_buf = p.tiles[L.begin].chunks[0].a_buf;
+    for (int i = 0; i < L.count; ++i)
+        for (int c = 0; c < p.tiles[L.begin + i].n_chunks; ++c)
+            if (p.tiles[L.begin + i].chunks[c].a_buf != a_buf || p.tiles[L.begin + i].chunks[c].a_kind != A_SLAB)
+                return fail(MSHGNN_ERR_ARG, "internal: a tensor-core launch must read one slab buffer");
+    TcMaps maps;
+    int rc;
+    const int64_t rows = buf_rows(p, a_buf, Bp);
+    if ((rc = make_map16(&maps.a_hi, bh.hi[a_buf], rows))) return rc;
+    if ((rc = make_map16(&maps.a_lo, bh.lo[a_buf], rows))) return rc;
+    if ((rc = make_map16(&maps.w_hi, w_hi, (int64_t)p.n_mats16 * H))) return rc;
+    if ((rc = make_map16(&maps.w_lo, w_lo, (int64_t)p.n_mats16 * H))) return rc;
+    ProfScope ps(kind, st);
+    dim3 grid((unsigned)(Bp / TILE_M), (unsigned)L.count);
+    k_tc_rowgemm<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(maps, p.d_tiles + L.begin, bt, bh, B, Bp, split);
     LAUNCH_CHECK();
     return 0;
 }
@@ -154,7 +238,7 @@ void mshgnn_plan_destroy(mshgnn_plan* plan) {
     Plan& p = plan->p;
     if (p.uploaded) {
         cudaFree(p.d_tiles); cudaFree(p.d_rtasks); cudaFree(p.d_rpairs);
-        cudaFree(p.d_groups); cudaFree(p.d_derive); cudaFree(p.d_signs);
+        cudaFree(p.d_groups); cudaFree(p.d_derive); cudaFree(p.d_derive16); cudaFree(p.d_signs);
     }
     delete plan;
 }
@@ -202,7 +286,7 @@ int mshgnn_forward(const mshgnn_plan* plan, int64_t B, const void* const* x, int
                    float* out, void* workspace, int64_t workspace_bytes, int32_t train, int32_t mode, void* stream) {
     if (!plan) return fail(MSHGNN_ERR_ARG, "plan is NULL");
     const Plan& p = plan->p;
-    if (mode != MSHGNN_MODE_FP32) return fail(MSHGNN_ERR_ARG, "mode %d is not available in this build", mode);
+    if (mode != MSHGNN_MODE_FP32 && mode != MSHGNN_MODE_TC && mode != MSHGNN_MODE_TC_1X) return fail(MSHGNN_ERR_ARG, "unknown mode %d", mode);
     if (x_dtype != MSHGNN_F32 && x_dtype != MSHGNN_F64) return fail(MSHGNN_ERR_ARG, "x_dtype must be F32 or F64");
     if (!x || !params || !out) return fail(MSHGNN_ERR_ARG, "NULL argument");
     const WsLayout w = ws_layout(p, B, train, mode);
@@ -224,11 +308,33 @@ int mshgnn_forward(const mshgnn_plan* plan, int64_t B, const void* const* x, int
         k_derive<<<grid, 256, 0, st>>>(p.d_derive, params, (float*)bt.p[BUF_DERIVED]);
         LAUNCH_CHECK();
     }
-    if ((rc = launch_rowgemm(K_ENC_FWD, p, p.enc_launch, bt, B, w.Bp, xf64, st))) return rc;
-    for (int l = 0; l < p.L; ++l) {
-        if ((rc = launch_rowgemm(K_CONV_FWD, p, train ? p.conv_train[l] : p.conv_infer[l], bt, B, w.Bp, 0, st))) return rc;
-        if ((rc = launch_rowgemm(K_MLP_FWD, p, p.mlp1[l], bt, B, w.Bp, 0, st))) return rc;
-        if ((rc = launch_rowgemm(K_MLP_FWD, p, p.mlp2[l], bt, B, w.Bp, 0, st))) return rc;
+    if (mode == MSHGNN_MODE_FP32) {
+        if ((rc = launch_rowgemm(K_ENC_FWD, p, p.enc_launch, bt, B, w.Bp, xf64, st))) return rc;
+        for (int l = 0; l < p.L; ++l) {
+            if ((rc = launch_rowgemm(K_CONV_FWD, p, train ? p.conv_train[l] : p.conv_infer[l], bt, B, w.Bp, 0, st))) return rc;
+            if ((rc = launch_rowgemm(K_MLP_FWD, p, p.mlp1[l], bt, B, w.Bp, 0, st))) return rc;
+            if ((rc = launch_rowgemm(K_MLP_FWD, p, p.mlp2[l], bt, B, w.Bp, 0, st))) return rc;
+        }
+    } else {
+        // tensor-core path: fp16 (hi, lo) weight images, encoder on the SIMT kernel (it reads the caller's fp32/fp64 rows
+        // and folds the symmetry signs into the load) writing fp32 + (hi, lo) slabs, layers on tcgen05
+        BufTable16 bh;
+        fill_bufs16(p, w, (char*)workspace, bh);
+        __half* w_hi = (__half*)((char*)workspace + w.w16[0]);
+        __half* w_lo = (__half*)((char*)workspace + w.w16[1]);
+        const int split = mode == MSHGNN_MODE_TC;
+        {
+            ProfScope ps(K_DERIVE, st);
+            dim3 grid(8, (unsigned)p.derive16_ops.size());
+            k_derive16<<<grid, 256, 0, st>>>(p.d_derive16, params, w_hi, w_lo);
+            LAUNCH_CHECK();
+        }
+        if ((rc = launch_rowgemm(K_ENC_FWD, p, p.enc_launch, bt, B, w.Bp, xf64, st, &bh))) return rc;
+        for (int l = 0; l < p.L; ++l) {
+            if ((rc = launch_tc_rowgemm(K_CONV_FWD, p, train ? p.conv_train[l] : p.conv_infer[l], bt, bh, w_hi, w_lo, B, w.Bp, split, st))) return rc;
+            if ((rc = launch_tc_rowgemm(K_MLP_FWD, p, p.mlp1[l], bt, bh, w_hi, w_lo, B, w.Bp, split, st))) return rc;
+            if ((rc = launch_tc_rowgemm(K_MLP_FWD, p, p.mlp2[l], bt, bh, w_hi, w_lo, B, w.Bp, split, st))) return rc;
+        }
     }
     {
         const int64_t rows = B * p.dec.n_dec;
@@ -271,7 +377,7 @@ int mshgnn_backward(const mshgnn_plan* plan, int64_t B, const void* const* x, in
                     const float* dout, float* grads, void* workspace, int64_t workspace_bytes, int32_t mode, void* stream) {
     if (!plan) return fail(MSHGNN_ERR_ARG, "plan is NULL");
     const Plan& p = plan->p;
-    if (mode != MSHGNN_MODE_FP32) return fail(MSHGNN_ERR_ARG, "mode %d is not available in this build", mode);
+    if (mode != MSHGNN_MODE_FP32 && mode != MSHGNN_MODE_TC && mode != MSHGNN_MODE_TC_1X) return fail(MSHGNN_ERR_ARG, "unknown mode %d", mode);
     if (x_dtype != MSHGNN_F32 && x_dtype != MSHGNN_F64) return fail(MSHGNN_ERR_ARG, "x_dtype must be F32 or F64");
     if (!x || !params || !dout || !grads) return fail(MSHGNN_ERR_ARG, "NULL argument");
     const WsLayout w = ws_layout(p, B, 1, mode);
@@ -289,6 +395,16 @@ int mshgnn_backward(const mshgnn_plan* plan, int64_t B, const void* const* x, in
     float* part_w = (float*)(ws + w.part_w);
     float* part_b = (float*)(ws + w.part_b);
     float* dec_part = (float*)(ws + w.dec_part);
+    const bool tc = mode != MSHGNN_MODE_FP32;
+    const int split = mode == MSHGNN_MODE_TC;
+    BufTable16 bh;
+    fill_bufs16(p, w, ws, bh);
+    const __half* w_hi = tc ? (const __half*)(ws + w.w16[0]) : nullptr;
+    const __half* w_lo = tc ? (const __half*)(ws + w.w16[1]) : nullptr;
+    // tensor-core modes carry every backward quantity multiplied by a power of two G ~ #output rows so that the
+    // fp16 (hi, lo) images of dL/dh stay in the normal range; the final reductions multiply by 1/G (exact).
+    float G = 1.f;
+    if (tc) { int e = 0; std::frexp((double)(B * p.dec.n_dec), &e); G = (float)std::ldexp(1.0, e - 1); }
 
     { ProfScope ps(K_MEMSET, st); CUDA_TRY(cudaMemsetAsync(grads, 0, (size_t)p.n_params * 4, st)); }
 
@@ -302,10 +418,12 @@ int mshgnn_backward(const mshgnn_plan* plan, int64_t B, const void* const* x, in
             dc = (float*)bt.p[BUF_DC0 + ((L - 1) & 1)]; mk = MK_POS; mbuf = bt.p[BUF_H0 + L];
         }
         ProfScope ps(K_DEC_BWD, st);
+        const int dhb = BUF_DH0 + (L & 1), dcb = BUF_DC0 + ((L - 1) & 1);
         k_decoder_bwd<<<DEC_BLOCKS, 256, 0, st>>>(p.dec, (const float*)bt.p[BUF_H0 + L], params, p.d_signs, dout, dh, dc, mk, mbuf,
-                                                  dec_part, B, w.Bp);
+                                                  dec_part, B, w.Bp, G, (tc && dh) ? bh.hi[dhb] : nullptr, (tc && dh) ? bh.lo[dhb] : nullptr,
+                                                  (tc && dc) ? bh.hi[dcb] : nullptr, (tc && dc) ? bh.lo[dcb] : nullptr);
         LAUNCH_CHECK();
-        k_decoder_bwd_reduce<<<4, 256, 0, st>>>(p.dec, dec_part, DEC_BLOCKS, grads);
+        k_decoder_bwd_reduce<<<4, 256, 0, st>>>(p.dec, dec_part, DEC_BLOCKS, grads, 1.f / G);
         LAUNCH_CHECK();
     }
     auto launch_dw = [&](int kind, const Launch& L) -> int {
@@ -317,16 +435,23 @@ int mshgnn_backward(const mshgnn_plan* plan, int64_t B, const void* const* x, in
         return 0;
     };
     for (int l = p.L - 1; l >= 0; --l) {
-        if ((rc = launch_rowgemm(K_MLP_BWD, p, p.bwd_m1[l], bt, B, w.Bp, 0, st))) return rc;
-        if ((rc = launch_rowgemm(K_MLP_BWD, p, p.bwd_m2[l], bt, B, w.Bp, 0, st))) return rc;
-        if ((rc = launch_dw(K_DW_LAYER, p.dw_layer[l]))) return rc;
-        if ((rc = launch_rowgemm(K_DX_BWD, p, p.bwd_dx[l], bt, B, w.Bp, 0, st))) return rc;
+        if (tc) {
+            if ((rc = launch_tc_rowgemm(K_MLP_BWD, p, p.bwd_m1[l], bt, bh, w_hi, w_lo, B, w.Bp, split, st))) return rc;
+            if ((rc = launch_tc_rowgemm(K_MLP_BWD, p, p.bwd_m2[l], bt, bh, w_hi, w_lo, B, w.Bp, split, st))) return rc;
+            if ((rc = launch_dw(K_DW_LAYER, p.dw_layer[l]))) return rc;
+            if ((rc = launch_tc_rowgemm(K_DX_BWD, p, p.bwd_dx[l], bt, bh, w_hi, w_lo, B, w.Bp, split, st))) return rc;
+        } else {
+            if ((rc = launch_rowgemm(K_MLP_BWD, p, p.bwd_m1[l], bt, B, w.Bp, 0, st))) return rc;
+            if ((rc = launch_rowgemm(K_MLP_BWD, p, p.bwd_m2[l], bt, B, w.Bp, 0, st))) return rc;
+            if ((rc = launch_dw(K_DW_LAYER, p.dw_layer[l]))) return rc;
+            if ((rc = launch_rowgemm(K_DX_BWD, p, p.bwd_dx[l], bt, B, w.Bp, 0, st))) return rc;
+        }
     }
     if ((rc = launch_dw(K_DW_ENC, p.dw_enc))) return rc;
     if (!p.groups.empty()) {
         dim3 grid((unsigned)p.groups.size(), 8);
         ProfScope ps(K_REDUCE, st);
-        k_reduce_partials<<<grid, 256, 0, st>>>(p.d_groups, part_w, part_b, w.n_splits, grads);
+        k_reduce_partials<<<grid, 256, 0, st>>>(p.d_groups, part_w, part_b, w.n_splits, grads, 1.f / G);
         LAUNCH_CHECK();
     }
     return 0;

@@ -8,6 +8,7 @@
 // (torch_geometric GraphConv) becomes "pick which slot tile feeds which weight":
 // a compile-time table, no index tensors, no atomics.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -27,6 +28,12 @@ struct BufTable {
     void* p[MAX_BUFS];
 };
 
+// fp16 (hi, lo) images of the slab buffers (tensor-core modes): v ~= hi + lo with ~22 significant bits
+struct BufTable16 {
+    __half* hi[MAX_BUFS];
+    __half* lo[MAX_BUFS];
+};
+
 // One K-chunk of a row-GEMM: D[rows,128] += A[rows,K] * Wt[K,128]
 struct Chunk {
     int a_kind;      // A_SLAB: fp32 slab tile; A_EXT: caller's x tensor (strided rows, f32/f64)
@@ -38,7 +45,7 @@ struct Chunk {
     int w_buf;       // buffer id of the weight in [K][128] ("k-major") form
     int w_off;       // float offset inside that buffer
     int sign_off;    // float offset into BUF_SIGNS of a [K] +-1 vector, or -1
-    int pad;
+    int w16_row;     // tensor-core path: first row of this weight's 128x128 fp16 image (W for forward, W^T for dX)
 };
 
 // One 128-row x 128-col output tile of a row-GEMM launch.
@@ -89,6 +96,15 @@ struct DeriveOp {
     int transpose;                    // dst[c][r] (1) or dst[r][c] (0)
     int n_src; int src_off[8];        // float offsets in params; summed
     int pad[3];
+};
+
+// fp16 (hi, lo) image of one 128x128 weight for the tensor-core kernels
+struct Derive16Op {
+    int dst_row;          // first row of the 128x128 matrix inside the fp16 weight tensor
+    int transpose;        // dst[n][k] = src[k][n]
+    int n_src;
+    int src_off[4];       // float offsets in params, summed
+    int pad;
 };
 
 struct DecoderDesc {

@@ -19,6 +19,19 @@ __device__ __forceinline__ float ld_x(const void* base, int dtype_f64, int64_t i
     return dtype_f64 ? (float)__ldg((const double*)base + idx) : __ldg((const float*)base + idx);
 }
 
+// (hi, lo) fp16 image of 4 consecutive values: hi = fp16(v), lo = fp16((v - hi) * 2^11)  (see kernels_tc.cuh)
+__device__ __forceinline__ void split_store4(__half* hi, __half* lo, int64_t off, const float (&v)[4]) {
+    __half2 h[2], l[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const __half ha = __float2half_rn(v[2 * j]), hb = __float2half_rn(v[2 * j + 1]);
+        h[j] = __halves2half2(ha, hb);
+        l[j] = __halves2half2(__float2half_rn((v[2 * j] - __half2float(ha)) * 2048.f), __float2half_rn((v[2 * j + 1] - __half2float(hb)) * 2048.f));
+    }
+    *reinterpret_cast<uint2*>(hi + off) = *reinterpret_cast<uint2*>(h);
+    *reinterpret_cast<uint2*>(lo + off) = *reinterpret_cast<uint2*>(l);
+}
+
 // ------------------------------------------------------------------------------------------
 // row-GEMM
 // ------------------------------------------------------------------------------------------
@@ -79,7 +92,8 @@ __device__ __forceinline__ void rg_load(const Tile& t, const BufTable& bt, int c
 }
 
 __global__ void __launch_bounds__(256, 2)
-k_rowgemm(const Tile* __restrict__ tiles, const BufTable bt, const int64_t B, const int64_t Bp, const int x_f64) {
+k_rowgemm(const Tile* __restrict__ tiles, const BufTable bt, const int64_t B, const int64_t Bp, const int x_f64,
+          const BufTable16 bh, const int write16) {
     __shared__ Tile t;
     __shared__ __align__(16) float As[RG_BK][RG_AS];
     __shared__ __align__(16) float Ws[RG_BK][H];
@@ -190,8 +204,9 @@ k_rowgemm(const Tile* __restrict__ tiles, const BufTable bt, const int64_t B, co
                 v[0] += q.x; v[1] += q.y; v[2] += q.z; v[3] += q.w;
             }
             if (t.out_buf >= 0) {
-                *reinterpret_cast<float4*>((float*)bt.p[t.out_buf] + ((int64_t)t.out_slot * Bp + row) * H + col) =
-                    make_float4(v[0], v[1], v[2], v[3]);
+                const int64_t off = ((int64_t)t.out_slot * Bp + row) * H + col;
+                *reinterpret_cast<float4*>((float*)bt.p[t.out_buf] + off) = make_float4(v[0], v[1], v[2], v[3]);
+                if (write16) split_store4(bh.hi[t.out_buf], bh.lo[t.out_buf], off, v);
             }
             if (t.out2_buf >= 0) {
                 if (t.out2_mask_kind == MK_BITS) {
@@ -206,8 +221,9 @@ k_rowgemm(const Tile* __restrict__ tiles, const BufTable bt, const int64_t B, co
                     v[0] = q.x > 0.f ? v[0] : 0.f; v[1] = q.y > 0.f ? v[1] : 0.f;
                     v[2] = q.z > 0.f ? v[2] : 0.f; v[3] = q.w > 0.f ? v[3] : 0.f;
                 }
-                *reinterpret_cast<float4*>((float*)bt.p[t.out2_buf] + ((int64_t)t.out2_slot * Bp + row) * H + col) =
-                    make_float4(v[0], v[1], v[2], v[3]);
+                const int64_t off2 = ((int64_t)t.out2_slot * Bp + row) * H + col;
+                *reinterpret_cast<float4*>((float*)bt.p[t.out2_buf] + off2) = make_float4(v[0], v[1], v[2], v[3]);
+                if (write16) split_store4(bh.hi[t.out2_buf], bh.lo[t.out2_buf], off2, v);
             }
         }
     }
@@ -336,7 +352,7 @@ k_reducegemm(const RTask* __restrict__ tasks, const RPair* __restrict__ pairs, c
 // sum the split partials of a group of tasks into the flat gradient buffer (fixed order => deterministic)
 __global__ void __launch_bounds__(256)
 k_reduce_partials(const OutGroup* __restrict__ groups, const float* __restrict__ part_w,
-                  const float* __restrict__ part_b, const int n_splits, float* __restrict__ grads) {
+                  const float* __restrict__ part_b, const int n_splits, float* __restrict__ grads, const float rscale) {
     const OutGroup g = groups[blockIdx.x];
     if (g.kind == 0) {
         const int per = (H * H) / gridDim.y;
@@ -348,7 +364,7 @@ k_reduce_partials(const OutGroup* __restrict__ groups, const float* __restrict__
                 const float* p = part_w + (int64_t)g.tasks[ti] * n_splits * (H * H) + e;
                 for (int sp = 0; sp < n_splits; ++sp) sd += (double)p[(int64_t)sp * (H * H)];
             }
-            const float s = (float)(sd * (double)g.scale);
+            const float s = (float)(sd * (double)g.scale * (double)rscale);
             for (int oi = 0; oi < g.n_outs; ++oi) grads[(int64_t)g.outs[oi] + (int64_t)o * g.K + g.k0 + i] = s;
         }
     } else {
@@ -359,7 +375,7 @@ k_reduce_partials(const OutGroup* __restrict__ groups, const float* __restrict__
                 const float* p = part_b + (int64_t)g.tasks[ti] * n_splits * H + e;
                 for (int sp = 0; sp < n_splits; ++sp) sd += (double)p[(int64_t)sp * H];
             }
-            const float s = (float)(sd * (double)g.scale);
+            const float s = (float)(sd * (double)g.scale * (double)rscale);
             for (int oi = 0; oi < g.n_outs; ++oi) grads[(int64_t)g.outs[oi] + e] = s;
         }
     }
@@ -422,7 +438,8 @@ __global__ void __launch_bounds__(256)
 k_decoder_bwd(const DecoderDesc dd, const float* __restrict__ hslab, const float* __restrict__ params,
               const float* __restrict__ signs, const float* __restrict__ dout,
               float* __restrict__ dh, float* __restrict__ dc, const int mask_kind, const void* __restrict__ mask_buf,
-              float* __restrict__ part, const int64_t B, const int64_t Bp) {
+              float* __restrict__ part, const int64_t B, const int64_t Bp, const float gscale,
+              __half* __restrict__ dh_hi, __half* __restrict__ dh_lo, __half* __restrict__ dc_hi, __half* __restrict__ dc_lo) {
     __shared__ float red[8][DEC_MAXC][H + 1];
     __shared__ float redb[8][DEC_MAXC];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -447,7 +464,7 @@ k_decoder_bwd(const DecoderDesc dd, const float* __restrict__ hslab, const float
 #pragma unroll
         for (int c = 0; c < DEC_MAXC; ++c) {
             if (c >= dd.C) break;
-            float dv = __ldg(dout + row * dd.C + c);
+            float dv = __ldg(dout + row * dd.C + c) * gscale;
             if (dd.sign_off >= 0) dv *= __ldg(signs + dd.sign_off + j * dd.C + c);
             d.x = fmaf(dv, w[c].x, d.x); d.y = fmaf(dv, w[c].y, d.y);
             d.z = fmaf(dv, w[c].z, d.z); d.w = fmaf(dv, w[c].w, d.w);
@@ -455,7 +472,10 @@ k_decoder_bwd(const DecoderDesc dd, const float* __restrict__ hslab, const float
             gw[c].z = fmaf(dv, h.z, gw[c].z); gw[c].w = fmaf(dv, h.w, gw[c].w);
             gb[c] += dv;
         }
-        if (dh) *reinterpret_cast<float4*>(dh + off) = d;
+        if (dh) {
+            *reinterpret_cast<float4*>(dh + off) = d;
+            if (dh_hi) { const float vv[4] = {d.x, d.y, d.z, d.w}; split_store4(dh_hi, dh_lo, off, vv); }
+        }
         if (dc) {
             if (mask_kind == MK_BITS) {
                 const unsigned wd = *((const unsigned*)mask_buf + ((int64_t)dd.slots[j] * Bp + g) * 4 + (lane >> 3));
@@ -468,6 +488,7 @@ k_decoder_bwd(const DecoderDesc dd, const float* __restrict__ hslab, const float
                 d.z = q.z > 0.f ? d.z : 0.f; d.w = q.w > 0.f ? d.w : 0.f;
             }
             *reinterpret_cast<float4*>(dc + off) = d;
+            if (dc_hi) { const float vv[4] = {d.x, d.y, d.z, d.w}; split_store4(dc_hi, dc_lo, off, vv); }
         }
     }
 #pragma unroll
@@ -494,11 +515,13 @@ k_decoder_bwd(const DecoderDesc dd, const float* __restrict__ hslab, const float
 }
 
 __global__ void __launch_bounds__(256)
-k_decoder_bwd_reduce(const DecoderDesc dd, const float* __restrict__ part, const int n_blocks, float* __restrict__ grads) {
+k_decoder_bwd_reduce(const DecoderDesc dd, const float* __restrict__ part, const int n_blocks, float* __restrict__ grads,
+                     const float scale) {
     for (int e = blockIdx.x * 256 + threadIdx.x; e < dd.C * H + dd.C; e += gridDim.x * 256) {
         const int src = (e < dd.C * H) ? e : (DEC_MAXC * H + (e - dd.C * H));
         float s = 0.f;
         for (int b = 0; b < n_blocks; ++b) s += part[(int64_t)b * (DEC_MAXC * H + DEC_MAXC) + src];
+        s *= scale;
         if (e < dd.C * H) grads[dd.w_off + e] = s; else grads[dd.b_off + (e - dd.C * H)] = s;
     }
 }

@@ -1,0 +1,313 @@
+// tcgen05 tensor-core kernels of the MS-HGNN hot path (MSHGNN_MODE_TC / MSHGNN_MODE_TC_1X), sm_100a only.
+//
+//  k_tc_rowgemm : the same tile/chunk program as k_rowgemm (kernels_simt.cuh) for slab inputs:
+//        D[128 graphs, 128] = sum_chunks A_c[128, 128] * W_c[128, 128]^T + fused epilogue.
+//     * operands are fp16; every activation / weight value v is stored as a pair (hi, lo) with
+//       hi = fp16(v), lo = fp16(v - hi)  (~22 significant bits).  MODE_TC issues three MMAs per chunk
+//       (hi*hi + lo*hi + hi*lo, fp32 accumulation in TMEM) which keeps forward pre-activations at fp32
+//       accuracy - required because ReLU makes the gradient discontinuous in the forward numerics
+//       (DESIGN.md "precision").  MODE_TC_1X issues hi*hi only.
+//     * TMA (cp.async.bulk.tensor, SWIZZLE_128B) stages the slot tile picked by the gather table and the
+//       weight tile straight into the UMMA shared-memory layout: the morphology gather never touches a
+//       register.  One elected thread issues tcgen05.mma; the accumulator lives in TMEM; four epilogue
+//       warps read it back with tcgen05.ld (one thread per graph row) and apply bias / ReLU / mask /
+//       residual, then write the fp32 slab plus its (hi, lo) fp16 images for the next layer's TMA.
+//  warp roles: 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2..5 = epilogue.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace mshgnn {
+
+constexpr int TC_STAGES = 3;
+constexpr int TC_TILE_BYTES = 128 * 128;           // 128 rows x 64 fp16 (one 128B-swizzled K block)
+constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;  // A_hi, A_lo, W_hi, W_lo
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int TC_THREADS = 192;
+constexpr float TC_W_SCALE = 256.f;                // weights are stored as fp16 pairs of (w * 2^8)
+constexpr float TC_W_UNSCALE = 1.f / 256.f;
+// The low halves are stored multiplied by 2^11: lo = fp16((v - hi) * 2048), which is always a NORMAL fp16 when hi
+// is (|lo*2048| <= |v|), so the pair keeps ~22 significant bits over fp16's whole normal range instead of hitting the
+// 2^-24 subnormal floor for |v| < 0.25.  The cross terms therefore accumulate in a second TMEM accumulator (D1) and the
+// epilogue combines D0 + D1 * 2^-11.
+constexpr float TC_LO_SCALE = 2048.f;
+constexpr float TC_LO_UNSCALE = 1.f / 2048.f;
+constexpr uint32_t TC_TMEM_COLS = 256;
+
+struct alignas(64) TcMaps {
+    CUtensorMap a_hi, a_lo, w_hi, w_lo;
+};
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128B-swizzled shared-memory operand: 8-row groups 1024 B apart (SBO), descriptor version 1.
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+    const uint32_t lo = ((saddr & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    return ((uint64_t)hi << 32) | lo;
+}
+// kind::f16, A = B = fp16, D = fp32, both K-major, M = 128, N = 128
+constexpr uint32_t TC_IDESC = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ void split_store(__half* hi, __half* lo, int64_t off, const float (&v)[32]) {
+    // 32 consecutive columns of one row -> 4 x 16-byte stores per image
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        __half2 h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float a = v[q * 8 + 2 * j], b = v[q * 8 + 2 * j + 1];
+            const __half ha = __float2half_rn(a), hb = __float2half_rn(b);
+            h[j] = __halves2half2(ha, hb);
+            l[j] = __halves2half2(__float2half_rn((a - __half2float(ha)) * TC_LO_SCALE), __float2half_rn((b - __half2float(hb)) * TC_LO_SCALE));
+        }
+        *reinterpret_cast<uint4*>(hi + off + q * 8) = *reinterpret_cast<uint4*>(h);
+        *reinterpret_cast<uint4*>(lo + off + q * 8) = *reinterpret_cast<uint4*>(l);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// row-GEMM on tcgen05
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_tc_rowgemm(const __grid_constant__ TcMaps maps, const Tile* __restrict__ tiles, const BufTable bt, const BufTable16 bh,
+             const int64_t B, const int64_t Bp, const int split) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ Tile t;
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + TC_STAGES), accum_bar = smem_u32(bars + 2 * TC_STAGES);
+    const uint32_t smem_base = smem_u32(smem);
+
+    {
+        const int* src = reinterpret_cast<const int*>(tiles + blockIdx.y);
+        int* dst = reinterpret_cast<int*>(&t);
+        for (int i = tid; i < (int)(sizeof(Tile) / 4); i += TC_THREADS) dst[i] = src[i];
+    }
+    if (tid == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), TC_TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    const int row0 = blockIdx.x * TILE_M;
+    const int n_steps = t.n_chunks * 2;   // two 64-wide K blocks per 128-wide chunk
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint32_t tx_bytes = split ? 4 * TC_TILE_BYTES : 2 * TC_TILE_BYTES;
+            for (int i = 0; i < n_steps; ++i) {
+                const int s = i % TC_STAGES;
+                mbar_wait(empty0 + 8 * s, ((i / TC_STAGES) & 1) ^ 1);
+                const Chunk& ch = t.chunks[i >> 1];
+                const int kcol = (i & 1) * 64;
+                const int arow = (int)((int64_t)ch.a_slot * Bp + row0);
+                const uint32_t st = smem_base + s * TC_STAGE_BYTES;
+                const uint32_t fb = full0 + 8 * s;
+                mbar_expect_tx(fb, tx_bytes);
+                tma_load_2d(st, &maps.a_hi, fb, kcol, arow);
+                tma_load_2d(st + 2 * TC_TILE_BYTES, &maps.w_hi, fb, kcol, ch.w16_row);
+                if (split) {
+                    tma_load_2d(st + TC_TILE_BYTES, &maps.a_lo, fb, kcol, arow);
+                    tma_load_2d(st + 3 * TC_TILE_BYTES, &maps.w_lo, fb, kcol, ch.w16_row);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            for (int i = 0; i < n_steps; ++i) {
+                const int s = i % TC_STAGES;
+                mbar_wait(full0 + 8 * s, (i / TC_STAGES) & 1);
+                tc_fence_after();
+                const uint32_t st = smem_base + s * TC_STAGE_BYTES;
+                const uint64_t a_hi = smem_desc_sw128(st), a_lo = smem_desc_sw128(st + TC_TILE_BYTES);
+                const uint64_t w_hi = smem_desc_sw128(st + 2 * TC_TILE_BYTES), w_lo = smem_desc_sw128(st + 3 * TC_TILE_BYTES);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint64_t adv = (uint64_t)(ks * 2);      // +32 bytes (16 fp16) along K inside the swizzle atom
+                    umma_f16(tmem_base, a_hi + adv, w_hi + adv, TC_IDESC, (i | ks) ? 1u : 0u);             // D0 += hi * hi
+                    if (split) {
+                        umma_f16(tmem_base + 128, a_lo + adv, w_hi + adv, TC_IDESC, (i | ks) ? 1u : 0u);   // D1 += lo * hi
+                        umma_f16(tmem_base + 128, a_hi + adv, w_lo + adv, TC_IDESC, 1u);                   // D1 += hi * lo
+                    }
+                }
+                umma_commit(empty0 + 8 * s);          // frees the stage once these MMAs have read it
+            }
+            umma_commit(accum_bar);                   // accumulator complete
+        }
+        __syncwarp();
+    } else {
+        // ---------------- epilogue: one thread per graph row ----------------
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+        const int q = warp & 3;                       // TMEM lane quarter this warp may access
+        const int64_t row = row0 + q * 32 + lane;
+        const bool live = row < B;
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+            uint32_t raw[32], raw1[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + cc * 32, raw);
+            if (split) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + 128 + cc * 32, raw1);
+            if (!live) continue;
+            const int col = cc * 32;
+            float v[32];
+            unsigned mask = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                float x = __uint_as_float(raw[j]);
+                if (split) x = fmaf(__uint_as_float(raw1[j]), TC_LO_UNSCALE, x);
+                x *= TC_W_UNSCALE;
+                if (t.bias_buf >= 0) x += __ldg((const float*)bt.p[t.bias_buf] + t.bias_off + col + j);
+                if (x > 0.f) mask |= 1u << j;
+                if (t.relu) x = fmaxf(x, 0.f);
+                v[j] = x;
+            }
+            if (t.mask_out_buf >= 0)
+                *((unsigned*)bt.p[t.mask_out_buf] + ((int64_t)t.out_slot * Bp + row) * 4 + cc) = mask;
+            if (t.posmask_buf >= 0) {
+                const float4* p = reinterpret_cast<const float4*>((const float*)bt.p[t.posmask_buf] + ((int64_t)t.posmask_slot * Bp + row) * H + col);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 m = p[j];
+                    v[4 * j] = m.x > 0.f ? v[4 * j] : 0.f; v[4 * j + 1] = m.y > 0.f ? v[4 * j + 1] : 0.f;
+                    v[4 * j + 2] = m.z > 0.f ? v[4 * j + 2] : 0.f; v[4 * j + 3] = m.w > 0.f ? v[4 * j + 3] : 0.f;
+                }
+            }
+            if (t.res_buf >= 0) {
+                const float4* p = reinterpret_cast<const float4*>((const float*)bt.p[t.res_buf] + ((int64_t)t.res_slot * Bp + row) * H + col);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 m = p[j];
+                    v[4 * j] += m.x; v[4 * j + 1] += m.y; v[4 * j + 2] += m.z; v[4 * j + 3] += m.w;
+                }
+            }
+            if (t.out_buf >= 0) {
+                const int64_t off = ((int64_t)t.out_slot * Bp + row) * H + col;
+                float4* o = reinterpret_cast<float4*>((float*)bt.p[t.out_buf] + off);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                split_store(bh.hi[t.out_buf], bh.lo[t.out_buf], off, v);
+            }
+            if (t.out2_buf >= 0) {
+                if (t.out2_mask_kind == MK_BITS) {
+                    const unsigned w = *((const unsigned*)bt.p[t.out2_mask_buf] + ((int64_t)t.out2_mask_slot * Bp + row) * 4 + cc);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = ((w >> j) & 1u) ? v[j] : 0.f;
+                } else if (t.out2_mask_kind == MK_POS) {
+                    const float4* p = reinterpret_cast<const float4*>((const float*)bt.p[t.out2_mask_buf] + ((int64_t)t.out2_mask_slot * Bp + row) * H + col);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 m = p[j];
+                        v[4 * j] = m.x > 0.f ? v[4 * j] : 0.f; v[4 * j + 1] = m.y > 0.f ? v[4 * j + 1] : 0.f;
+                        v[4 * j + 2] = m.z > 0.f ? v[4 * j + 2] : 0.f; v[4 * j + 3] = m.w > 0.f ? v[4 * j + 3] : 0.f;
+                    }
+                }
+                const int64_t off = ((int64_t)t.out2_slot * Bp + row) * H + col;
+                float4* o = reinterpret_cast<float4*>((float*)bt.p[t.out2_buf] + off);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                split_store(bh.hi[t.out2_buf], bh.lo[t.out2_buf], off, v);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TC_TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// fp16 (hi, lo) images of the weights the tensor-core kernels read: W (forward) and W^T (backward dX)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_derive16(const Derive16Op* __restrict__ ops, const float* __restrict__ params, __half* __restrict__ w_hi, __half* __restrict__ w_lo) {
+    const Derive16Op op = ops[blockIdx.y];
+    for (int e = blockIdx.x * 256 + threadIdx.x; e < H * H; e += gridDim.x * 256) {
+        const int r = e / H, c = e % H;
+        const int src = op.transpose ? (c * H + r) : e;
+        float s = 0.f;
+        for (int i = 0; i < op.n_src; ++i) s += params[(int64_t)op.src_off[i] + src];
+        s *= TC_W_SCALE;
+        const __half h = __float2half_rn(s);
+        w_hi[(int64_t)op.dst_row * H + e] = h;
+        w_lo[(int64_t)op.dst_row * H + e] = __float2half_rn((s - __half2float(h)) * TC_LO_SCALE);
+    }
+}
+
+}  // namespace mshgnn

@@ -14,11 +14,27 @@
 
 namespace mshgnn {
 
-static Chunk slab_chunk(int buf, int slot, int w_buf, int64_t w_off) {
+static Chunk slab_chunk(int buf, int slot, int w_buf, int64_t w_off, int w16_row) {
     Chunk c{};
     c.a_kind = A_SLAB; c.a_buf = buf; c.a_slot = slot; c.K = H; c.lda = H; c.a_off = 0;
-    c.w_buf = w_buf; c.w_off = (int)w_off; c.sign_off = -1;
+    c.w_buf = w_buf; c.w_off = (int)w_off; c.sign_off = -1; c.w16_row = w16_row;
     return c;
+}
+
+// registers the fp16 image of sum(srcs) (optionally transposed) and returns its first row in the fp16 weight tensor
+static int mat16(Plan& p, const std::vector<int64_t>& srcs, bool transpose) {
+    for (const auto& op : p.derive16_ops) {
+        if (op.transpose != (int)transpose || op.n_src != (int)srcs.size()) continue;
+        bool same = true;
+        for (size_t i = 0; i < srcs.size(); ++i) same = same && op.src_off[i] == (int)srcs[i];
+        if (same) return op.dst_row;
+    }
+    Derive16Op op{};
+    op.dst_row = p.n_mats16 * H; op.transpose = transpose; op.n_src = (int)srcs.size();
+    for (size_t i = 0; i < srcs.size(); ++i) op.src_off[i] = (int)srcs[i];
+    p.derive16_ops.push_back(op);
+    p.n_mats16++;
+    return op.dst_row;
 }
 
 static Tile empty_tile() {
@@ -158,6 +174,13 @@ std::string build_plan(const mshgnn_desc* d, Plan& p) {
     }
     if (p.signs.empty()) p.signs.push_back(1.f);
 
+    auto roots_of = [&](int l, int t) {
+        std::vector<int64_t> r;
+        for (int e = 0; e < p.n_etypes; ++e)
+            if (p.e_dst_t[e] == t) r.push_back(p.off_root_w[l * p.n_etypes + e]);
+        return r;
+    };
+
     // ---------------- forward contribution lists ----------------
     // contrib[d] = list of (src slot, edge type); the root term is implicit.
     struct Contrib { int src, e; };
@@ -214,20 +237,21 @@ std::string build_plan(const mshgnn_desc* d, Plan& p) {
             const int t = p.slot_type[dslot], n = p.slot_local[dslot];
             Tile T = empty_tile();
             for (auto& c : contrib[dslot])
-                T.chunks[T.n_chunks++] = slab_chunk(BUF_H0 + l, c.src, BUF_DERIVED, p.der_relT[l * p.n_etypes + c.e]);
-            T.chunks[T.n_chunks++] = slab_chunk(BUF_H0 + l, dslot, BUF_DERIVED, p.der_rootT[l * p.n_types + t]);
+                T.chunks[T.n_chunks++] = slab_chunk(BUF_H0 + l, c.src, BUF_DERIVED, p.der_relT[l * p.n_etypes + c.e],
+                                                    mat16(p, {p.off_rel_w[l * p.n_etypes + c.e]}, false));
+            T.chunks[T.n_chunks++] = slab_chunk(BUF_H0 + l, dslot, BUF_DERIVED, p.der_rootT[l * p.n_types + t], mat16(p, roots_of(l, t), false));
             T.bias_buf = BUF_DERIVED; T.bias_off = (int)p.der_bias[l * p.n_types + t];
             if (p.morph_sym && t == p.mlp_type) {
                 // conv -> c_base ; base_transform: Linear -> ReLU -> Linear ; + residual (hgnn_k4.py:L133-137,175-186)
                 T.relu = 0; T.out_buf = BUF_CT0 + l; T.out_slot = n;
                 conv.push_back(T);
                 Tile A = empty_tile();
-                A.chunks[A.n_chunks++] = slab_chunk(BUF_CT0 + l, n, BUF_DERIVED, p.der_mlpT[0]);
+                A.chunks[A.n_chunks++] = slab_chunk(BUF_CT0 + l, n, BUF_DERIVED, p.der_mlpT[0], mat16(p, {p.off_mlp_w[0]}, false));
                 A.bias_buf = BUF_PARAMS; A.bias_off = (int)p.off_mlp_b[0]; A.relu = 1;
                 A.out_buf = BUF_CT0 + l; A.out_slot = p.nm + n;
                 m1.push_back(A);
                 Tile Bt = empty_tile();
-                Bt.chunks[Bt.n_chunks++] = slab_chunk(BUF_CT0 + l, p.nm + n, BUF_DERIVED, p.der_mlpT[1]);
+                Bt.chunks[Bt.n_chunks++] = slab_chunk(BUF_CT0 + l, p.nm + n, BUF_DERIVED, p.der_mlpT[1], mat16(p, {p.off_mlp_w[1]}, false));
                 Bt.bias_buf = BUF_PARAMS; Bt.bias_off = (int)p.off_mlp_b[1]; Bt.relu = 0;
                 Bt.res_buf = BUF_H0 + l; Bt.res_slot = dslot;
                 Bt.out_buf = BUF_H0 + l + 1; Bt.out_slot = dslot;
@@ -260,12 +284,12 @@ std::string build_plan(const mshgnn_desc* d, Plan& p) {
                 const int s = p.slot_of(p.mlp_type, n);
                 if (!p.need[l + 1][s]) continue;
                 Tile A = empty_tile();   // dpre = (du * W2) (*) (t > 0)
-                A.chunks[A.n_chunks++] = slab_chunk(DHn, s, BUF_PARAMS, p.off_mlp_w[1]);
+                A.chunks[A.n_chunks++] = slab_chunk(DHn, s, BUF_PARAMS, p.off_mlp_w[1], mat16(p, {p.off_mlp_w[1]}, true));
                 A.posmask_buf = BUF_CT0 + l; A.posmask_slot = p.nm + n;
                 A.out_buf = BUF_DU; A.out_slot = n;
                 b1.push_back(A);
                 Tile Bt = empty_tile();  // dc_base = dpre * W1
-                Bt.chunks[Bt.n_chunks++] = slab_chunk(BUF_DU, n, BUF_PARAMS, p.off_mlp_w[0]);
+                Bt.chunks[Bt.n_chunks++] = slab_chunk(BUF_DU, n, BUF_PARAMS, p.off_mlp_w[0], mat16(p, {p.off_mlp_w[0]}, true));
                 Bt.out_buf = DCc; Bt.out_slot = s;
                 b2.push_back(Bt);
             }
@@ -275,9 +299,10 @@ std::string build_plan(const mshgnn_desc* d, Plan& p) {
             Tile T = empty_tile();
             for (auto& og : outgoing[s])
                 if (p.need[l + 1][og.src])   // og.src holds the destination slot here
-                    T.chunks[T.n_chunks++] = slab_chunk(DCc, og.src, BUF_PARAMS, p.off_rel_w[l * p.n_etypes + og.e]);
+                    T.chunks[T.n_chunks++] = slab_chunk(DCc, og.src, BUF_PARAMS, p.off_rel_w[l * p.n_etypes + og.e],
+                                                        mat16(p, {p.off_rel_w[l * p.n_etypes + og.e]}, true));
             if (p.need[l + 1][s]) {
-                T.chunks[T.n_chunks++] = slab_chunk(DCc, s, BUF_DERIVED, p.der_root[l * p.n_types + t]);
+                T.chunks[T.n_chunks++] = slab_chunk(DCc, s, BUF_DERIVED, p.der_root[l * p.n_types + t], mat16(p, roots_of(l, t), true));
                 if (p.morph_sym) { T.res_buf = DHn; T.res_slot = s; }
             }
             if (l == 0) {
@@ -383,7 +408,7 @@ std::string build_plan(const mshgnn_desc* d, Plan& p) {
 }
 
 WsLayout ws_layout(const Plan& p, int64_t B, int train, int mode) {
-    (void)mode;
+    const bool tc = mode != MSHGNN_MODE_FP32;
     WsLayout w{};
     w.Bp = round_up(B < 1 ? 1 : B, TILE_M);
     int ns = (int)((B + 511) / 512);
@@ -409,6 +434,25 @@ WsLayout ws_layout(const Plan& p, int64_t B, int train, int mode) {
         const int64_t a = take(slab), b = take(slab);
         for (int l = 0; l <= p.L; ++l) w.h[l] = (l & 1) ? b : a;
         if (p.morph_sym) { const int64_t c = take(ctb); for (int l = 0; l < p.L; ++l) w.ct[l] = c; }
+    }
+    for (int l = 0; l <= MAX_LAYERS; ++l) w.h16[l][0] = w.h16[l][1] = -1;
+    for (int l = 0; l < MAX_LAYERS; ++l) w.ct16[l][0] = w.ct16[l][1] = -1;
+    for (int i = 0; i < 2; ++i) { w.dh16[i][0] = w.dh16[i][1] = w.dc16[i][0] = w.dc16[i][1] = -1; w.du16[i] = -1; w.w16[i] = -1; }
+    if (tc) {
+        for (int i = 0; i < 2; ++i) w.w16[i] = take((int64_t)p.n_mats16 * H * H * 2);
+        if (train) {
+            for (int l = 0; l <= p.L; ++l) for (int i = 0; i < 2; ++i) w.h16[l][i] = take(slab / 2);
+            if (p.morph_sym)
+                for (int l = 0; l < p.L; ++l) for (int i = 0; i < 2; ++i) w.ct16[l][i] = take(ctb / 2);
+            for (int b = 0; b < 2; ++b) for (int i = 0; i < 2; ++i) { w.dh16[b][i] = take(slab / 2); w.dc16[b][i] = take(slab / 2); }
+            if (p.morph_sym) for (int i = 0; i < 2; ++i) w.du16[i] = take((int64_t)p.nm * w.Bp * H * 2);
+        } else {
+            int64_t a[2], b[2], c[2] = {-1, -1};
+            for (int i = 0; i < 2; ++i) { a[i] = take(slab / 2); b[i] = take(slab / 2); }
+            if (p.morph_sym) for (int i = 0; i < 2; ++i) c[i] = take(ctb / 2);
+            for (int l = 0; l <= p.L; ++l) for (int i = 0; i < 2; ++i) w.h16[l][i] = (l & 1) ? b[i] : a[i];
+            for (int l = 0; l < p.L; ++l) for (int i = 0; i < 2; ++i) w.ct16[l][i] = c[i];
+        }
     }
     w.loss_part = take(LOSS_BLOCKS * 8);
     w.total = o;

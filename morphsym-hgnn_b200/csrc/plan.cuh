@@ -50,6 +50,8 @@ struct Plan {
     std::vector<int64_t> der_rootT, der_root, der_bias;       // [l*n_types+t]  (-1 when type has no in-edges)
     int64_t der_mlpT[2] = {-1, -1};
     std::vector<DeriveOp> derive_ops;
+    std::vector<Derive16Op> derive16_ops;   // fp16 (hi, lo) weight images for the tensor-core kernels
+    int n_mats16 = 0;
 
     // ---- signs ----
     std::vector<float> signs;          // host copy of BUF_SIGNS
@@ -80,6 +82,7 @@ struct Plan {
     mutable RPair* d_rpairs = nullptr;
     mutable OutGroup* d_groups = nullptr;
     mutable DeriveOp* d_derive = nullptr;
+    mutable Derive16Op* d_derive16 = nullptr;
     mutable float* d_signs = nullptr;
 
     int slot_of(int type, int local) const { return type_base[type] + local; }
@@ -94,6 +97,8 @@ struct WsLayout {
     int64_t mask[MAX_LAYERS];
     int64_t dh[2], dc[2], du = 0;
     int64_t part_w = 0, part_b = 0, dec_part = 0, loss_part = 0;
+    // tensor-core modes: (hi, lo) fp16 images; index [0] = hi, [1] = lo; -1 when absent
+    int64_t h16[MAX_LAYERS + 1][2], ct16[MAX_LAYERS][2], dh16[2][2], dc16[2][2], du16[2], w16[2];
     int64_t total = 0;
 };
 

@@ -163,6 +163,18 @@ class NativeHGNN(nn.Module):
         self._expected_edges: Dict[tuple, torch.Tensor] = {}
         self._fwd_token = None
 
+    _MODES = {"fp32": N.MODE_FP32, "tc": N.MODE_TC, "tc1x": N.MODE_TC_1X}
+
+    def set_mode(self, mode) -> "NativeHGNN":
+        """Arithmetic mode of the native kernels: 'fp32' (SIMT fp32 FMA, the 1e-4 parity mode), 'tc' (tcgen05, split-fp16
+        operands = 3 MMAs per product, fp32 accumulate: fp32-class accuracy) or 'tc1x' (tcgen05, one fp16 MMA per
+        product: 1e-3 on predictions only, for inference)."""
+        code = self._MODES[mode] if isinstance(mode, str) else int(mode)
+        self.mode = code
+        for e in self._engines.values():
+            e.mode = code
+        return self
+
     def __getstate__(self):
         # native handles / device buffers are rebuilt lazily after copy or unpickle
         d = self.__dict__.copy()

@@ -106,6 +106,59 @@ def c2_tables(group: Optional[dict], with_feet: bool = True):
 
 
 # ----------------------------------------------------------------------------------------
+# ReLU tap: lets a test record every pre-activation and force the sign decision of chosen elements
+# ----------------------------------------------------------------------------------------
+class ReluTap:
+    """While installed (``with ReluTap() as tap``) every ReLU of the oracle goes through ``_relu``:
+    ``record=True`` keeps the pre-activation tensors (in call order, with gradients retained);
+    ``forced[i] = (flat_idx LongTensor, BoolTensor)`` overrides the (x > 0) decision of those elements of call i.
+    Used by the parity tests to compare gradients under the ReLU sign pattern an fp32 implementation actually
+    took where the fp64 pre-activation is numerically ambiguous (|x| below the implementation's forward error)."""
+
+    def __init__(self, record: bool = False, forced=None):
+        self.record = record
+        self.forced = forced or {}
+        self.pre: List[torch.Tensor] = []
+        self.counter = 0
+
+    def __enter__(self):
+        global _TAP
+        self._prev = _TAP
+        _TAP = self
+        return self
+
+    def __exit__(self, *a):
+        global _TAP
+        _TAP = self._prev
+
+
+_TAP: Optional[ReluTap] = None
+
+
+def _relu(x: torch.Tensor) -> torch.Tensor:
+    tap = _TAP
+    if tap is None:
+        return torch.relu(x)
+    i = tap.counter
+    tap.counter += 1
+    if tap.record:
+        if x.requires_grad:
+            x.retain_grad()
+        tap.pre.append(x)
+    mask = x > 0
+    if i in tap.forced:
+        idx, val = tap.forced[i]
+        mask = mask.clone()
+        mask.view(-1)[idx] = val
+    return x * mask.to(x.dtype)
+
+
+class _TapReLU(nn.Module):
+    def forward(self, x):
+        return _relu(x)
+
+
+# ----------------------------------------------------------------------------------------
 # building blocks
 # ----------------------------------------------------------------------------------------
 class _Lin(nn.Module):
@@ -221,7 +274,7 @@ class _HGNNBase(nn.Module):
         if self.morph_sym:
             # one MLP shared by every layer: hgnn_k4.py:L133-137
             self.base_transform = nn.Sequential(
-                _TorchLinear(hidden_channels, hidden_channels), nn.ReLU(),
+                _TorchLinear(hidden_channels, hidden_channels), _TapReLU(),
                 _TorchLinear(hidden_channels, hidden_channels))
         self.decoder = _Lin(hidden_channels, out_channels, bias=True)
 
@@ -243,15 +296,15 @@ class _HGNNBase(nn.Module):
 
     def embed(self, x_dict, edge_index_dict):
         x_dict = self.input_signs(dict(x_dict))   # never mutate the caller's dict
-        h = {k: torch.relu(v) for k, v in self.encoder(x_dict).items()}
+        h = {k: _relu(v) for k, v in self.encoder(x_dict).items()}
         for conv in self.convs:
             c = conv(h, edge_index_dict)
             if self.morph_sym:
                 # hgnn_k4.py:L175-186: base -> shared MLP (no ReLU around it), others -> ReLU, then residual
-                n = {k: (self.base_transform(v) if k == "base" else torch.relu(v)) for k, v in c.items()}
+                n = {k: (self.base_transform(v) if k == "base" else _relu(v)) for k, v in c.items()}
                 h = {k: (n[k] + h[k] if (k in h and h[k].shape == n[k].shape) else n[k]) for k in n}
             else:
-                h = {k: torch.relu(v) for k, v in c.items()}   # hgnn.py:L60-62
+                h = {k: _relu(v) for k, v in c.items()}   # hgnn.py:L60-62
         return h
 
     def forward(self, x_dict, edge_index_dict):

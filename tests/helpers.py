@@ -62,3 +62,85 @@ def oracle_fp32_floor(cfg, model, batch, ref_out, ref_grads):
     loss.backward()
     floor = {n: (rel_err(p.grad, ref_grads[n]) if p.grad is not None else 0.0) for n, p in m32.named_parameters()}
     return rel_err(out, ref_out), floor
+
+
+# ------------------------------------------------------------------------------------------------
+# ReLU-sign-aware gradient comparison
+# ------------------------------------------------------------------------------------------------
+def _flat(grads, names):
+    return torch.cat([grads[n].detach().double().cpu().reshape(-1) for n in names])
+
+
+def oracle_grads_with_forced(cfg, model, batch, forced):
+    x = {k: v.double() for k, v in batch.x_dict.items()}
+    model.zero_grad()
+    with O.ReluTap(forced=forced):
+        out = model(x, batch.edge_index_dict)
+        loss = oracle_loss(cfg, out, batch.y.double(), batch.batch_size)
+        loss.backward()
+    return {n: (p.grad.clone() if p.grad is not None else torch.zeros_like(p)) for n, p in model.named_parameters()}
+
+
+def relu_aware_gradient_check(cfg, model, batch, native_grads, fwd_rel_err, tol=TOL_FP32, max_candidates=48):
+    """Returns (ok, info).  The native gradient must equal, per tensor within ``tol`` (norm-wise), the oracle's
+    fp64 gradient for SOME ReLU sign pattern that differs from the oracle's own only at numerically ambiguous
+    pre-activations: |x| < 8 * fwd_rel_err * rms(x), i.e. inside the native path's measured forward error.
+
+    Why: ReLU makes d(loss)/d(params) discontinuous in the forward numerics.  An implementation whose forward
+    pass is accurate to 1e-6 may legitimately put a pre-activation of +-1e-7 on the other side of zero, and that
+    moves whole gradient tensors by 1e-4..1e-2 (plain PyTorch fp32 does the same against fp64).  Single flips act
+    (to first order) additively, so the set of flipped elements is found by projecting the residual on each
+    candidate's gradient delta and then VERIFIED with one exact oracle backward under the chosen pattern."""
+    names = [n for n, _ in model.named_parameters()]
+    x = {k: v.double() for k, v in batch.x_dict.items()}
+    model.zero_grad()
+    with O.ReluTap(record=True) as tap:
+        out = model(x, batch.edge_index_dict)
+        loss = oracle_loss(cfg, out, batch.y.double(), batch.batch_size)
+        loss.backward()
+    g0 = {n: (p.grad.clone() if p.grad is not None else torch.zeros_like(p)) for n, p in model.named_parameters()}
+
+    def worst(ga):
+        w = 0.0
+        for n in names:
+            nb = ga[n].norm().item()
+            if nb == 0.0:
+                if native_grads[n].abs().max().item() != 0.0:
+                    return float("inf")
+                continue
+            w = max(w, rel_err(native_grads[n], ga[n]))
+        return w
+
+    e0 = worst(g0)
+    if e0 <= tol:
+        return True, {"flips": 0, "err": e0}
+    # candidates: ambiguous pre-activations that carry gradient
+    cands = []
+    for i, pre in enumerate(tap.pre):
+        if pre.grad is None:
+            continue
+        v = pre.detach()
+        thr = 8.0 * max(fwd_rel_err, 1e-7) * v.pow(2).mean().sqrt().item()
+        # the upstream gradient of relu(x) is what matters: grad wrt x is zero where the mask is off, so use |x| only
+        idx = torch.nonzero(v.abs().reshape(-1) < thr).reshape(-1)
+        for j in idx.tolist():
+            cands.append((i, j, bool(v.reshape(-1)[j] > 0)))
+    if not cands or len(cands) > max_candidates:
+        return False, {"flips": None, "err": e0, "candidates": len(cands)}
+    r = _flat(native_grads, names) - _flat(g0, names)
+    chosen = []
+    for (i, j, cur) in cands:
+        gj = oracle_grads_with_forced(cfg, model, batch, {i: (torch.tensor([j]), torch.tensor([not cur]))})
+        d = _flat(gj, names) - _flat(g0, names)
+        dn = d.dot(d).item()
+        if dn > 0 and r.dot(d).item() / dn > 0.5:
+            chosen.append((i, j, cur))
+    if not chosen:
+        return False, {"flips": 0, "err": e0, "candidates": len(cands)}
+    forced = {}
+    for (i, j, cur) in chosen:
+        idx, val = forced.get(i, (torch.empty(0, dtype=torch.long), torch.empty(0, dtype=torch.bool)))
+        forced[i] = (torch.cat((idx, torch.tensor([j]))), torch.cat((val, torch.tensor([not cur]))))
+    g1 = oracle_grads_with_forced(cfg, model, batch, forced)
+    e1 = worst(g1)
+    return e1 <= tol, {"flips": len(chosen), "err": e1, "err_default_pattern": e0, "candidates": len(cands)}
