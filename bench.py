@@ -43,13 +43,13 @@ ALG = {
     "train_flop": 2 * (2 * _ENC_MAC + 3 * _LAY_MAC + 3 * _DEC_MAC),        # 50.36 MFLOP
     "in_bytes": 43200,                                                     # fp32 features per graph
     # per kernel kind (names from mshgnn_kernel_kind_name)
-    "encoder_fwd(k_rowgemm)": 2 * _ENC_MAC,
-    "conv_fwd(k_rowgemm)": 2 * (_LAY_MAC - 8 * 7 * 128 * 128),             # layer rows minus the base-MLP rows
-    "base_mlp_fwd(k_rowgemm)": 2 * (8 * 7 * 128 * 128),
-    "dx_bwd(k_rowgemm)": 2 * (_LAY_MAC - 8 * 7 * 128 * 128),
-    "base_mlp_bwd(k_rowgemm)": 2 * (8 * 7 * 128 * 128),
-    "dw_layers(k_reducegemm)": 2 * _LAY_MAC,
-    "dw_encoder(k_reducegemm)": 2 * _ENC_MAC,
+    "encoder_fwd": 2 * _ENC_MAC,
+    "conv_fwd": 2 * (_LAY_MAC - 8 * 7 * 128 * 128),             # layer rows minus the base-MLP rows
+    "base_mlp_fwd": 2 * (8 * 7 * 128 * 128),
+    "dx_bwd": 2 * (_LAY_MAC - 8 * 7 * 128 * 128),
+    "base_mlp_bwd": 2 * (8 * 7 * 128 * 128),
+    "dw_layers": 2 * _LAY_MAC,
+    "dw_encoder": 2 * _ENC_MAC,
 }
 
 

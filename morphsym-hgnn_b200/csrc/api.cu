@@ -42,8 +42,8 @@ int fail(int code, const char* fmt, ...) {
 enum Kind : int { K_DERIVE = 0, K_ENC_FWD, K_CONV_FWD, K_MLP_FWD, K_DEC_FWD, K_LOSS, K_DEC_BWD, K_MLP_BWD, K_DX_BWD,
                   K_DW_LAYER, K_DW_ENC, K_REDUCE, K_OPTIM, K_MEMSET, K_NKINDS };
 const char* const kKindNames[MSHGNN_NUM_KERNEL_KINDS] = {
-    "derive_weights", "encoder_fwd(k_rowgemm)", "conv_fwd(k_rowgemm)", "base_mlp_fwd(k_rowgemm)", "decoder_fwd", "loss",
-    "decoder_bwd", "base_mlp_bwd(k_rowgemm)", "dx_bwd(k_rowgemm)", "dw_layers(k_reducegemm)", "dw_encoder(k_reducegemm)",
+    "derive_weights", "encoder_fwd", "conv_fwd", "base_mlp_fwd", "decoder_fwd", "loss",
+    "decoder_bwd", "base_mlp_bwd", "dx_bwd", "dw_layers", "dw_encoder",
     "reduce_partials", "optimizer", "memset", "", ""};
 struct ProfRec { int kind; cudaEvent_t a, b; };
 std::mutex g_prof_mu;
@@ -161,14 +161,14 @@ int get_encode_fn(EncodeTiledFn* out) {
 }
 
 // [rows, 128] fp16 row-major tensor, box = 128 rows x 64 columns, 128-byte swizzle (the UMMA K-major SW128 layout)
-int make_map16(CUtensorMap* m, const void* base, int64_t rows) {
+int make_map16(CUtensorMap* m, const void* base, int64_t rows, int box_rows = 128) {
     EncodeTiledFn enc;
     int rc = get_encode_fn(&enc);
     if (rc) return rc;
-    if (!base || rows < 128) return fail(MSHGNN_ERR_ARG, "internal: bad fp16 tensor for a TMA map");
+    if (!base || rows < box_rows) return fail(MSHGNN_ERR_ARG, "internal: bad fp16 tensor for a TMA map");
     cuuint64_t dims[2] = {(cuuint64_t)H, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)H * 2};
-    cuuint32_t box[2] = {64, 128};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -205,6 +205,45 @@ int launch_tc_rowgemm(int kind, const Plan& p, const Launch& L, const BufTable& 
     ProfScope ps(kind, st);
     dim3 grid((unsigned)(Bp / TILE_M), (unsigned)L.count);
     k_tc_rowgemm<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(maps, p.d_tiles + L.begin, bt, bh, B, Bp, split);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+// first 256-byte row of every fp16 image relative to the workspace base (one TMA map then covers all of them)
+void fill_rows16(const Plan& p, const WsLayout& w, BufRows& br) {
+    for (int i = 0; i < MAX_BUFS; ++i) br.hi[i] = br.lo[i] = 0;
+    auto at = [&](int64_t off) -> int { return off < 0 ? 0 : (int)(off / 256); };
+    for (int b = 0; b < 2; ++b) {
+        br.hi[BUF_DH0 + b] = at(w.dh16[b][0]); br.lo[BUF_DH0 + b] = at(w.dh16[b][1]);
+        br.hi[BUF_DC0 + b] = at(w.dc16[b][0]); br.lo[BUF_DC0 + b] = at(w.dc16[b][1]);
+    }
+    br.hi[BUF_DU] = at(w.du16[0]); br.lo[BUF_DU] = at(w.du16[1]);
+    for (int l = 0; l <= p.L; ++l) { br.hi[BUF_H0 + l] = at(w.h16[l][0]); br.lo[BUF_H0 + l] = at(w.h16[l][1]); }
+    for (int l = 0; l < p.L; ++l) { br.hi[BUF_CT0 + l] = at(w.ct16[l][0]); br.lo[BUF_CT0 + l] = at(w.ct16[l][1]); }
+}
+
+int launch_tc_dw(int kind, const Plan& p, const Launch& L, const WsLayout& w, const BufRows& br, const void* ws, int64_t B, int split,
+                 float* part_w, float* part_b, cudaStream_t st) {
+    if (L.count == 0) return 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(k_tc_reducegemm, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM_BYTES));
+        attr_set = true;
+    }
+    for (int i = 0; i < L.count; ++i) {
+        const RTask& T = p.rtasks[L.begin + i];
+        if (T.n_pairs > DW_MAX_PAIRS) return fail(MSHGNN_ERR_ARG, "internal: weight-gradient task with more than %d pairs", DW_MAX_PAIRS);
+        for (int j = 0; j < T.n_pairs; ++j)
+            if (p.rpairs[T.pair_begin + j].a_kind != A_SLAB) return fail(MSHGNN_ERR_ARG, "internal: tensor-core weight-gradient task must read slabs");
+    }
+    CUtensorMap map;
+    int rc;
+    if (w.total / 256 > 0x7fffffffLL) return fail(MSHGNN_ERR_ARG, "workspace too large for one TMA map");
+    if ((rc = make_map16(&map, ws, w.total / 256, DW_KB))) return rc;
+    ProfScope ps(kind, st);
+    dim3 grid((unsigned)L.count, (unsigned)w.n_splits_tc);
+    k_tc_reducegemm<<<grid, TC_THREADS, DW_SMEM_BYTES, st>>>(map, p.d_rtasks, p.d_rpairs, L.begin, br, B, w.Bp, w.rows_per_tc, w.n_splits_tc,
+                                                             split, part_w, part_b);
     LAUNCH_CHECK();
     return 0;
 }
@@ -403,6 +442,8 @@ int mshgnn_backward(const mshgnn_plan* plan, int64_t B, const void* const* x, in
     const __half* w_lo = tc ? (const __half*)(ws + w.w16[1]) : nullptr;
     // tensor-core modes carry every backward quantity multiplied by a power of two G ~ #output rows so that the
     // fp16 (hi, lo) images of dL/dh stay in the normal range; the final reductions multiply by 1/G (exact).
+    BufRows br;
+    fill_rows16(p, w, br);
     float G = 1.f;
     if (tc) { int e = 0; std::frexp((double)(B * p.dec.n_dec), &e); G = (float)std::ldexp(1.0, e - 1); }
 
@@ -438,7 +479,7 @@ int mshgnn_backward(const mshgnn_plan* plan, int64_t B, const void* const* x, in
         if (tc) {
             if ((rc = launch_tc_rowgemm(K_MLP_BWD, p, p.bwd_m1[l], bt, bh, w_hi, w_lo, B, w.Bp, split, st))) return rc;
             if ((rc = launch_tc_rowgemm(K_MLP_BWD, p, p.bwd_m2[l], bt, bh, w_hi, w_lo, B, w.Bp, split, st))) return rc;
-            if ((rc = launch_dw(K_DW_LAYER, p.dw_layer[l]))) return rc;
+            if ((rc = launch_tc_dw(K_DW_LAYER, p, p.dw_layer[l], w, br, ws, B, split, part_w, part_b, st))) return rc;
             if ((rc = launch_tc_rowgemm(K_DX_BWD, p, p.bwd_dx[l], bt, bh, w_hi, w_lo, B, w.Bp, split, st))) return rc;
         } else {
             if ((rc = launch_rowgemm(K_MLP_BWD, p, p.bwd_m1[l], bt, B, w.Bp, 0, st))) return rc;
@@ -448,10 +489,18 @@ int mshgnn_backward(const mshgnn_plan* plan, int64_t B, const void* const* x, in
         }
     }
     if ((rc = launch_dw(K_DW_ENC, p.dw_enc))) return rc;
-    if (!p.groups.empty()) {
-        dim3 grid((unsigned)p.groups.size(), 8);
+    // layer-stack groups were produced with the split count of the kernel that ran them, encoder groups with the SIMT one
+    const int ngl = p.n_groups_layers, nge = (int)p.groups.size() - ngl;
+    if (ngl > 0) {
+        dim3 grid((unsigned)ngl, 8);
         ProfScope ps(K_REDUCE, st);
-        k_reduce_partials<<<grid, 256, 0, st>>>(p.d_groups, part_w, part_b, w.n_splits, grads, 1.f / G);
+        k_reduce_partials<<<grid, 256, 0, st>>>(p.d_groups, part_w, part_b, tc ? w.n_splits_tc : w.n_splits, grads, 1.f / G);
+        LAUNCH_CHECK();
+    }
+    if (nge > 0) {
+        dim3 grid((unsigned)nge, 8);
+        ProfScope ps(K_REDUCE, st);
+        k_reduce_partials<<<grid, 256, 0, st>>>(p.d_groups + ngl, part_w, part_b, w.n_splits, grads, 1.f / G);
         LAUNCH_CHECK();
     }
     return 0;

@@ -191,7 +191,14 @@ k_rowgemm(const Tile* __restrict__ tiles, const BufTable bt, const int64_t B, co
                     *mp = word;
                 }
             }
-            if (!live) continue;
+            if (!live) {
+                if (write16) {   // rows [B, Bp) of the fp16 images stay zero (read in whole 64-row blocks by k_tc_reducegemm)
+                    const float z[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (t.out_buf >= 0) split_store4(bh.hi[t.out_buf], bh.lo[t.out_buf], ((int64_t)t.out_slot * Bp + row) * H + col, z);
+                    if (t.out2_buf >= 0) split_store4(bh.hi[t.out2_buf], bh.lo[t.out2_buf], ((int64_t)t.out2_slot * Bp + row) * H + col, z);
+                }
+                continue;
+            }
             if (t.posmask_buf >= 0) {
                 const float4 q = *reinterpret_cast<const float4*>(
                     (const float*)bt.p[t.posmask_buf] + ((int64_t)t.posmask_slot * Bp + row) * H + col);
@@ -489,6 +496,15 @@ k_decoder_bwd(const DecoderDesc dd, const float* __restrict__ hslab, const float
             }
             *reinterpret_cast<float4*>(dc + off) = d;
             if (dc_hi) { const float vv[4] = {d.x, d.y, d.z, d.w}; split_store4(dc_hi, dc_lo, off, vv); }
+        }
+    }
+    if (dh_hi || dc_hi) {   // rows [B, Bp) of the decoded slots' fp16 images stay zero
+        const int64_t pad = Bp - B;
+        const float z[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int64_t r = warp; r < pad * dd.n_dec; r += stride) {
+            const int64_t off = ((int64_t)dd.slots[r / pad] * Bp + B + r % pad) * H + lane * 4;
+            if (dh_hi) split_store4(dh_hi, dh_lo, off, z);
+            if (dc_hi) split_store4(dc_hi, dc_lo, off, z);
         }
     }
 #pragma unroll

@@ -222,8 +222,25 @@ k_tc_rowgemm(const __grid_constant__ TcMaps maps, const Tile* __restrict__ tiles
             uint32_t raw[32], raw1[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + cc * 32, raw);
             if (split) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + 128 + cc * 32, raw1);
-            if (!live) continue;
             const int col = cc * 32;
+            if (!live) {
+                // rows [B, Bp) of every fp16 image are kept at zero: the weight-gradient kernel reduces over whole
+                // 64-row blocks (k_tc_reducegemm) and must not see stale data there
+                if (row < Bp) {
+                    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+                    if (t.out_buf >= 0) {
+                        const int64_t off = ((int64_t)t.out_slot * Bp + row) * H + col;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) { *reinterpret_cast<uint4*>(bh.hi[t.out_buf] + off + j * 8) = z; *reinterpret_cast<uint4*>(bh.lo[t.out_buf] + off + j * 8) = z; }
+                    }
+                    if (t.out2_buf >= 0) {
+                        const int64_t off = ((int64_t)t.out2_slot * Bp + row) * H + col;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) { *reinterpret_cast<uint4*>(bh.hi[t.out2_buf] + off + j * 8) = z; *reinterpret_cast<uint4*>(bh.lo[t.out2_buf] + off + j * 8) = z; }
+                    }
+                }
+                continue;
+            }
             float v[32];
             unsigned mask = 0;
 #pragma unroll
@@ -289,6 +306,182 @@ k_tc_rowgemm(const __grid_constant__ TcMaps maps, const Tile* __restrict__ tiles
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TC_TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// reduce-over-rows GEMM on tcgen05 (weight gradients):  dW[128 out, 128 in] = sum_pairs dC[rows,128]^T * A[rows,128]
+// ------------------------------------------------------------------------------------------
+//  The reduction dimension is the graph-row dimension, so both MMA operands are "MN-major": the fp16 images are
+//  [row][feature] and a TMA box of 64 features x 64 rows (SWIZZLE_128B) is exactly the canonical MN-major SW128 atom
+//  sequence (8 rows x 128 B per atom, SBO = 1024 B between 8-row groups, LBO = 8192 B between the two 64-feature
+//  halves).  No transposed copy of any activation is ever made.
+//  Bias gradients (column sums of dC) ride on the same operand: one extra N=16 MMA against an all-ones B tile.
+//  Accumulators (TMEM columns): D0 [0,128) hi*hi, D1 [128,256) cross terms (x 2^11), D2 [256,272) colsum hi,
+//  D3 [288,304) colsum lo (x 2^11).  One CTA = one task (<= 4 pairs) x one row split; fp32 partials go to part_w /
+//  part_b and are summed in double by k_reduce_partials (deterministic, no atomics).
+struct BufRows {                 // first 256-byte row of each fp16 image, relative to the workspace base
+    int hi[MAX_BUFS];
+    int lo[MAX_BUFS];
+};
+
+constexpr int DW_STAGES = 3;
+constexpr int DW_KB = 64;                              // graph rows (MMA K) per pipeline stage
+constexpr int DW_IMG_BYTES = DW_KB * H * 2;            // 64 rows x 128 fp16 = two 64x64 boxes
+constexpr int DW_STAGE_BYTES = 4 * DW_IMG_BYTES;       // dC_hi, dC_lo, A_hi, A_lo
+constexpr int DW_ONES_BYTES = 2048;
+constexpr int DW_SMEM_BYTES = DW_STAGES * DW_STAGE_BYTES + DW_ONES_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr uint32_t DW_TMEM_COLS = 512;
+constexpr int DW_MAX_PAIRS = 4;
+
+// MN-major, 128B-swizzled operand of 128 (MN) x 16 (K) fp16: LBO = 8192 B (next 64 MN elements), SBO = 1024 B (next 8 K rows)
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t saddr) {
+    const uint32_t lo = ((saddr & 0x3FFFFu) >> 4) | ((uint32_t)(DW_IMG_BYTES / 2 >> 4) << 16);
+    const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    return ((uint64_t)hi << 32) | lo;
+}
+// kind::f16, fp16 x fp16 -> fp32, A and B MN-major, M = 128, N = 128
+constexpr uint32_t DW_IDESC = (1u << 4) | (1u << 15) | (1u << 16) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+// column sums: A MN-major (dC), B K-major (all ones), M = 128, N = 16
+constexpr uint32_t DW_IDESC_CS = (1u << 4) | (1u << 15) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_tc_reducegemm(const __grid_constant__ CUtensorMap map, const RTask* __restrict__ tasks, const RPair* __restrict__ pairs,
+                const int task0, const BufRows br, const int64_t B, const int64_t Bp, const int rows_per, const int n_splits,
+                const int split, float* __restrict__ part_w, float* __restrict__ part_b) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ RTask t;
+    __shared__ RPair prs[DW_MAX_PAIRS];
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* ones = smem + DW_STAGES * DW_STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ones + DW_ONES_BYTES);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + DW_STAGES), accum_bar = smem_u32(bars + 2 * DW_STAGES);
+    const uint32_t smem_base = smem_u32(smem);
+
+    const int task = task0 + blockIdx.x;
+    if (tid < (int)(sizeof(RTask) / 4)) reinterpret_cast<int*>(&t)[tid] = reinterpret_cast<const int*>(tasks + task)[tid];
+    for (int i = tid; i < DW_ONES_BYTES / 4; i += TC_THREADS) reinterpret_cast<uint32_t*>(ones)[i] = 0x3C003C00u;   // fp16 1.0 pairs
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // the ones tile is read by the MMA (async proxy)
+    if (tid == 0) {
+        for (int s = 0; s < DW_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), DW_TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    {
+        const int np = t.n_pairs < DW_MAX_PAIRS ? t.n_pairs : DW_MAX_PAIRS;
+        const int* src = reinterpret_cast<const int*>(pairs + t.pair_begin);
+        int* dst = reinterpret_cast<int*>(prs);
+        for (int i = tid; i < np * (int)(sizeof(RPair) / 4); i += TC_THREADS) dst[i] = src[i];
+    }
+    __syncthreads();
+    const uint32_t tmem_base = tmem_base_s;
+
+    const int sp = blockIdx.y;
+    const int64_t r_begin = (int64_t)sp * rows_per;
+    const int64_t r_end = (r_begin + rows_per < B) ? (r_begin + rows_per) : B;
+    const int n_kb = r_end > r_begin ? (int)((r_end - r_begin + DW_KB - 1) / DW_KB) : 0;
+    const int n_pairs = t.n_pairs < DW_MAX_PAIRS ? t.n_pairs : DW_MAX_PAIRS;
+    const int n_steps = n_kb * n_pairs;
+    const int want_cs = t.want_colsum;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint32_t tx_bytes = split ? 4 * DW_IMG_BYTES : 2 * DW_IMG_BYTES;
+            for (int i = 0; i < n_steps; ++i) {
+                const int s = i % DW_STAGES;
+                mbar_wait(empty0 + 8 * s, ((i / DW_STAGES) & 1) ^ 1);
+                const RPair& pr = prs[i / n_kb];
+                const int r0 = (int)(r_begin + (int64_t)(i % n_kb) * DW_KB);
+                const int d_off = (int)((int64_t)pr.d_slot * Bp) + r0, a_off = (int)((int64_t)pr.a_slot * Bp) + r0;
+                const uint32_t st = smem_base + s * DW_STAGE_BYTES;
+                const uint32_t fb = full0 + 8 * s;
+                mbar_expect_tx(fb, tx_bytes);
+                tma_load_2d(st, &map, fb, 0, br.hi[pr.d_buf] + d_off);
+                tma_load_2d(st + DW_IMG_BYTES / 2, &map, fb, 64, br.hi[pr.d_buf] + d_off);
+                tma_load_2d(st + 2 * DW_IMG_BYTES, &map, fb, 0, br.hi[pr.a_buf] + a_off);
+                tma_load_2d(st + 2 * DW_IMG_BYTES + DW_IMG_BYTES / 2, &map, fb, 64, br.hi[pr.a_buf] + a_off);
+                if (split) {
+                    tma_load_2d(st + DW_IMG_BYTES, &map, fb, 0, br.lo[pr.d_buf] + d_off);
+                    tma_load_2d(st + DW_IMG_BYTES + DW_IMG_BYTES / 2, &map, fb, 64, br.lo[pr.d_buf] + d_off);
+                    tma_load_2d(st + 3 * DW_IMG_BYTES, &map, fb, 0, br.lo[pr.a_buf] + a_off);
+                    tma_load_2d(st + 3 * DW_IMG_BYTES + DW_IMG_BYTES / 2, &map, fb, 64, br.lo[pr.a_buf] + a_off);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint64_t ones_desc = smem_desc_sw128(smem_u32(ones));
+            for (int i = 0; i < n_steps; ++i) {
+                const int s = i % DW_STAGES;
+                mbar_wait(full0 + 8 * s, (i / DW_STAGES) & 1);
+                tc_fence_after();
+                const uint32_t st = smem_base + s * DW_STAGE_BYTES;
+                const uint64_t d_hi = smem_desc_mn_sw128(st), d_lo = smem_desc_mn_sw128(st + DW_IMG_BYTES);
+                const uint64_t a_hi = smem_desc_mn_sw128(st + 2 * DW_IMG_BYTES), a_lo = smem_desc_mn_sw128(st + 3 * DW_IMG_BYTES);
+#pragma unroll
+                for (int ks = 0; ks < DW_KB / 16; ++ks) {
+                    const uint64_t adv = (uint64_t)(ks * (2048 >> 4));          // 16 rows = two 8-row groups of 1024 B
+                    const uint32_t acc = (i | ks) ? 1u : 0u;
+                    umma_f16(tmem_base, d_hi + adv, a_hi + adv, DW_IDESC, acc);                       // D0 += dC_hi^T A_hi
+                    if (split) {
+                        umma_f16(tmem_base + 128, d_lo + adv, a_hi + adv, DW_IDESC, acc);             // D1 += dC_lo^T A_hi
+                        umma_f16(tmem_base + 128, d_hi + adv, a_lo + adv, DW_IDESC, 1u);              // D1 += dC_hi^T A_lo
+                    }
+                    if (want_cs) {
+                        umma_f16(tmem_base + 256, d_hi + adv, ones_desc, DW_IDESC_CS, acc);           // D2 += dC_hi^T 1
+                        if (split) umma_f16(tmem_base + 288, d_lo + adv, ones_desc, DW_IDESC_CS, acc); // D3 += dC_lo^T 1
+                    }
+                }
+                umma_commit(empty0 + 8 * s);
+            }
+            umma_commit(accum_bar);
+        }
+        __syncwarp();
+    } else {
+        // ---------------- epilogue: one thread per output feature (TMEM lane) ----------------
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+        const int q = warp & 3;
+        const int o = q * 32 + lane;
+        const int64_t slot = (int64_t)task * n_splits + sp;
+        float* pw = part_w + slot * (H * H) + (int64_t)o * H;
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+            uint32_t raw[32], raw1[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + cc * 32, raw);
+            if (split) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + 128 + cc * 32, raw1);
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                float x = __uint_as_float(raw[j]);
+                if (split) x = fmaf(__uint_as_float(raw1[j]), TC_LO_UNSCALE, x);
+                v[j] = n_steps ? x : 0.f;
+            }
+            float4* dst = reinterpret_cast<float4*>(pw + cc * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        if (want_cs) {
+            uint32_t raw[32], raw1[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + 256, raw);
+            float x = __uint_as_float(raw[0]);
+            if (split) { tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + 288, raw1); x = fmaf(__uint_as_float(raw1[0]), TC_LO_UNSCALE, x); }
+            part_b[slot * H + o] = n_steps ? x : 0.f;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, DW_TMEM_COLS);
     }
 }
 

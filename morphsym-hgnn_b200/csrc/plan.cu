@@ -384,6 +384,7 @@ std::string build_plan(const mshgnn_desc* d, Plan& p) {
             OutGroup gb = gw; gb.kind = 1; gb.outs[0] = (int)p.off_mlp_b[i];
             p.groups.push_back(gw); p.groups.push_back(gb);
         }
+    p.n_groups_layers = (int)p.groups.size();
     // ---- encoder weight gradients: dW_enc[t] = sum_slots dpre0[s]^T (x[s] * sign[s]) ----
     p.dw_enc.begin = (int)p.rtasks.size();
     for (int t = 0; t < p.n_types; ++t) {
@@ -413,6 +414,12 @@ WsLayout ws_layout(const Plan& p, int64_t B, int train, int mode) {
     w.Bp = round_up(B < 1 ? 1 : B, TILE_M);
     int ns = (int)((B + 511) / 512);
     w.n_splits = ns < 1 ? 1 : (ns > 64 ? 64 : ns);
+    {   // tcgen05 reduce-GEMM: ~2048 rows per split (fp32 accumulation in TMEM, splits summed in double), no empty split
+        int64_t target = (B + 2047) / 2048;
+        target = target < 1 ? 1 : (target > 64 ? 64 : target);
+        w.rows_per_tc = (int)round_up((B + target - 1) / target, 64);
+        w.n_splits_tc = (int)((B + w.rows_per_tc - 1) / w.rows_per_tc);
+    }
     int64_t o = 0;
     auto take = [&](int64_t bytes) { int64_t at = o; o += round_up(bytes, 256); return at; };
     const int64_t slab = (int64_t)p.S * w.Bp * H * 4;
@@ -427,8 +434,9 @@ WsLayout ws_layout(const Plan& p, int64_t B, int train, int mode) {
             for (int l = 0; l < p.L; ++l) { w.ct[l] = take(ctb); w.mask[l] = take((int64_t)p.S * w.Bp * 16); }
         w.dh[0] = take(slab); w.dh[1] = take(slab); w.dc[0] = take(slab); w.dc[1] = take(slab);
         if (p.morph_sym) w.du = take((int64_t)p.nm * w.Bp * H * 4);
-        w.part_w = take((int64_t)p.rtasks.size() * w.n_splits * H * H * 4);
-        w.part_b = take((int64_t)p.rtasks.size() * w.n_splits * H * 4);
+        const int ns_max = w.n_splits > w.n_splits_tc ? w.n_splits : w.n_splits_tc;
+        w.part_w = take((int64_t)p.rtasks.size() * ns_max * H * H * 4);
+        w.part_b = take((int64_t)p.rtasks.size() * ns_max * H * 4);
         w.dec_part = take((int64_t)DEC_BLOCKS * (DEC_MAXC * H + DEC_MAXC) * 4);
     } else {
         const int64_t a = take(slab), b = take(slab);

@@ -71,6 +71,7 @@ struct Plan {
     std::vector<Launch> dw_layer;                                // per layer (task ranges)
     Launch dw_enc;
     std::vector<OutGroup> groups;
+    int n_groups_layers = 0;           // groups [0, n_groups_layers) belong to the layer stack, the rest to the encoder
     DecoderDesc dec;
 
     // ---- device copies (lazy) ----
@@ -90,7 +91,8 @@ struct Plan {
 
 struct WsLayout {
     int64_t Bp = 0;
-    int n_splits = 1;
+    int n_splits = 1;                  // row splits of the SIMT reduce-GEMM (<= 512 rows each)
+    int n_splits_tc = 1, rows_per_tc = 64;   // row splits of the tcgen05 reduce-GEMM (multiples of 64 rows)
     int64_t derived = 0;
     int64_t h[MAX_LAYERS + 1];
     int64_t ct[MAX_LAYERS];
