@@ -101,6 +101,8 @@ int ensure_uploaded(const Plan& p) {
     if ((rc = upload(p.derive_ops, &p.d_derive))) return rc;
     if ((rc = upload(p.derive16_ops, &p.d_derive16))) return rc;
     if ((rc = upload(p.signs, &p.d_signs))) return rc;
+    if ((rc = upload(p.enc_units, &p.d_enc_units))) return rc;
+    if ((rc = upload(p.enc_groups, &p.d_enc_groups))) return rc;
     p.device = dev;
     p.uploaded = true;
     return 0;
@@ -114,6 +116,7 @@ void fill_bufs(const Plan& p, const WsLayout& w, char* ws, BufTable& bt) {
     bt.p[BUF_DH0] = at(w.dh[0]); bt.p[BUF_DH1] = at(w.dh[1]);
     bt.p[BUF_DC0] = at(w.dc[0]); bt.p[BUF_DC1] = at(w.dc[1]);
     bt.p[BUF_DU] = at(w.du);
+    bt.p[BUF_MASKE] = at(w.maske);
     for (int l = 0; l <= p.L; ++l) bt.p[BUF_H0 + l] = at(w.h[l]);
     for (int l = 0; l < p.L; ++l) { bt.p[BUF_CT0 + l] = at(w.ct[l]); bt.p[BUF_MASK0 + l] = at(w.mask[l]); }
 }
@@ -173,6 +176,49 @@ int make_map16(CUtensorMap* m, const void* base, int64_t rows, int box_rows = 12
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(MSHGNN_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return 0;
+}
+
+// [rows, cols] fp16 row-major tensor, box = 128 rows x 64 columns, 128-byte swizzle
+int make_map16_2d(CUtensorMap* m, const void* base, int64_t rows, int64_t cols) {
+    EncodeTiledFn enc;
+    int rc = get_encode_fn(&enc);
+    if (rc) return rc;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    cuuint32_t box[2] = {64, 128};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(MSHGNN_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return 0;
+}
+
+int launch_tc_encoder(const Plan& p, const Launch& L, const WsLayout& w, const BufTable& bt, const BufTable16& bh, char* ws,
+                      const float* params, int64_t B, int xf64, int split, cudaStream_t st) {
+    if (L.count == 0) return 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(k_tc_encoder, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+        attr_set = true;
+    }
+    __half* e_hi = (__half*)(ws + w.wenc16[0]);
+    __half* e_lo = (__half*)(ws + w.wenc16[1]);
+    {
+        ProfScope ps(K_DERIVE, st);
+        for (int t = 0; t < p.n_types; ++t) {
+            k_derive_enc16<<<32, 256, 0, st>>>(params, p.off_enc_w[t], p.in_w[t], p.enc_kmax, t * H, e_hi, e_lo);
+            LAUNCH_CHECK();
+        }
+    }
+    EncMaps maps;
+    int rc;
+    if ((rc = make_map16_2d(&maps.w_hi, e_hi, (int64_t)p.n_types * H, p.enc_kmax))) return rc;
+    if ((rc = make_map16_2d(&maps.w_lo, e_lo, (int64_t)p.n_types * H, p.enc_kmax))) return rc;
+    ProfScope ps(K_ENC_FWD, st);
+    dim3 grid((unsigned)(w.Bp / TILE_M), (unsigned)L.count);
+    k_tc_encoder<<<grid, ENC_THREADS, TC_SMEM_BYTES, st>>>(maps, p.d_tiles + L.begin, bt, bh, B, w.Bp, xf64, split);
+    LAUNCH_CHECK();
     return 0;
 }
 
@@ -277,7 +323,7 @@ void mshgnn_plan_destroy(mshgnn_plan* plan) {
     Plan& p = plan->p;
     if (p.uploaded) {
         cudaFree(p.d_tiles); cudaFree(p.d_rtasks); cudaFree(p.d_rpairs);
-        cudaFree(p.d_groups); cudaFree(p.d_derive); cudaFree(p.d_derive16); cudaFree(p.d_signs);
+        cudaFree(p.d_groups); cudaFree(p.d_derive); cudaFree(p.d_derive16); cudaFree(p.d_signs); cudaFree(p.d_enc_units); cudaFree(p.d_enc_groups);
     }
     delete plan;
 }
@@ -348,10 +394,10 @@ int mshgnn_forward(const mshgnn_plan* plan, int64_t B, const void* const* x, int
         LAUNCH_CHECK();
     }
     if (mode == MSHGNN_MODE_FP32) {
-        if ((rc = launch_rowgemm(K_ENC_FWD, p, p.enc_launch, bt, B, w.Bp, xf64, st))) return rc;
+        if ((rc = launch_rowgemm(K_ENC_FWD, p, train ? p.enc_train : p.enc_launch, bt, B, w.Bp, xf64, st))) return rc;
         for (int l = 0; l < p.L; ++l) {
             if ((rc = launch_rowgemm(K_CONV_FWD, p, train ? p.conv_train[l] : p.conv_infer[l], bt, B, w.Bp, 0, st))) return rc;
-            if ((rc = launch_rowgemm(K_MLP_FWD, p, p.mlp1[l], bt, B, w.Bp, 0, st))) return rc;
+            if ((rc = launch_rowgemm(K_MLP_FWD, p, (train ? p.mlp1_train[l] : p.mlp1[l]), bt, B, w.Bp, 0, st))) return rc;
             if ((rc = launch_rowgemm(K_MLP_FWD, p, p.mlp2[l], bt, B, w.Bp, 0, st))) return rc;
         }
     } else {
@@ -368,10 +414,10 @@ int mshgnn_forward(const mshgnn_plan* plan, int64_t B, const void* const* x, int
             k_derive16<<<grid, 256, 0, st>>>(p.d_derive16, params, w_hi, w_lo);
             LAUNCH_CHECK();
         }
-        if ((rc = launch_rowgemm(K_ENC_FWD, p, p.enc_launch, bt, B, w.Bp, xf64, st, &bh))) return rc;
+        if ((rc = launch_tc_encoder(p, train ? p.enc_train : p.enc_launch, w, bt, bh, (char*)workspace, params, B, xf64, split, st))) return rc;
         for (int l = 0; l < p.L; ++l) {
             if ((rc = launch_tc_rowgemm(K_CONV_FWD, p, train ? p.conv_train[l] : p.conv_infer[l], bt, bh, w_hi, w_lo, B, w.Bp, split, st))) return rc;
-            if ((rc = launch_tc_rowgemm(K_MLP_FWD, p, p.mlp1[l], bt, bh, w_hi, w_lo, B, w.Bp, split, st))) return rc;
+            if ((rc = launch_tc_rowgemm(K_MLP_FWD, p, train ? p.mlp1_train[l] : p.mlp1[l], bt, bh, w_hi, w_lo, B, w.Bp, split, st))) return rc;
             if ((rc = launch_tc_rowgemm(K_MLP_FWD, p, p.mlp2[l], bt, bh, w_hi, w_lo, B, w.Bp, split, st))) return rc;
         }
     }
@@ -456,7 +502,7 @@ int mshgnn_backward(const mshgnn_plan* plan, int64_t B, const void* const* x, in
             dh = (float*)bt.p[BUF_DH0 + (L & 1)];
             if (p.dec_type != p.mlp_type) { dc = (float*)bt.p[BUF_DC0 + ((L - 1) & 1)]; mk = MK_BITS; mbuf = bt.p[BUF_MASK0 + L - 1]; }
         } else {
-            dc = (float*)bt.p[BUF_DC0 + ((L - 1) & 1)]; mk = MK_POS; mbuf = bt.p[BUF_H0 + L];
+            dc = (float*)bt.p[BUF_DC0 + ((L - 1) & 1)]; mk = MK_BITS; mbuf = bt.p[BUF_MASK0 + L - 1];
         }
         ProfScope ps(K_DEC_BWD, st);
         const int dhb = BUF_DH0 + (L & 1), dcb = BUF_DC0 + ((L - 1) & 1);
@@ -488,7 +534,32 @@ int mshgnn_backward(const mshgnn_plan* plan, int64_t B, const void* const* x, in
             if ((rc = launch_rowgemm(K_DX_BWD, p, p.bwd_dx[l], bt, B, w.Bp, 0, st))) return rc;
         }
     }
-    if ((rc = launch_dw(K_DW_ENC, p.dw_enc))) return rc;
+    if (tc) {
+        if (!p.enc_units.empty()) {
+            static bool attr_set = false;
+            if (!attr_set) {
+                CUDA_TRY(cudaFuncSetAttribute(k_tc_encoder_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, EDW_SMEM_BYTES));
+                attr_set = true;
+            }
+            CUtensorMap map;
+            if ((rc = make_map16(&map, ws, w.total / 256, DW_KB))) return rc;
+            float* pe_w = (float*)(ws + w.part_enc_w);
+            float* pe_b = (float*)(ws + w.part_enc_b);
+            {
+                ProfScope ps(K_DW_ENC, st);
+                dim3 grid((unsigned)p.enc_units.size(), (unsigned)w.n_splits_enc);
+                k_tc_encoder_dw<<<grid, ENC_THREADS, EDW_SMEM_BYTES, st>>>(map, p.d_enc_units, bt, br, B, w.Bp, w.rows_per_enc, w.n_splits_enc, xf64,
+                                                                           split, pe_w, pe_b);
+                LAUNCH_CHECK();
+            }
+            {
+                ProfScope ps(K_REDUCE, st);
+                dim3 grid((unsigned)p.enc_groups.size(), 8);
+                k_reduce_enc<<<grid, 256, 0, st>>>(p.d_enc_groups, pe_w, pe_b, w.n_splits_enc, grads, 1.f / G);
+                LAUNCH_CHECK();
+            }
+        }
+    } else if ((rc = launch_dw(K_DW_ENC, p.dw_enc))) return rc;
     // layer-stack groups were produced with the split count of the kernel that ran them, encoder groups with the SIMT one
     const int ngl = p.n_groups_layers, nge = (int)p.groups.size() - ngl;
     if (ngl > 0) {
@@ -497,7 +568,7 @@ int mshgnn_backward(const mshgnn_plan* plan, int64_t B, const void* const* x, in
         k_reduce_partials<<<grid, 256, 0, st>>>(p.d_groups, part_w, part_b, tc ? w.n_splits_tc : w.n_splits, grads, 1.f / G);
         LAUNCH_CHECK();
     }
-    if (nge > 0) {
+    if (nge > 0 && !tc) {
         dim3 grid((unsigned)nge, 8);
         ProfScope ps(K_REDUCE, st);
         k_reduce_partials<<<grid, 256, 0, st>>>(p.d_groups + ngl, part_w, part_b, w.n_splits, grads, 1.f / G);

@@ -21,7 +21,7 @@ constexpr int TILE_M = 128;
 constexpr int DEC_MAXC = 8;     // max decoder width
 
 enum AKind : int { A_SLAB = 0, A_EXT = 1 };
-enum MaskKind : int { MK_NONE = 0, MK_BITS = 1, MK_POS = 2 };
+enum MaskKind : int { MK_NONE = 0, MK_BITS = 1 };
 
 // base pointers resolved per call (buffer id -> device pointer)
 struct BufTable {
@@ -54,12 +54,12 @@ struct Tile {
     int out_buf, out_slot;            // primary fp32 slab output (-1: none)
     int bias_buf, bias_off;           // bias [128] (-1: none)
     int relu;                         // relu after bias
-    int posmask_buf, posmask_slot;    // multiply by (slab > 0) after relu (-1: none)
+    int posmask_buf, posmask_slot;    // multiply by a stored ReLU bitmask after relu (-1: none)
     int res_buf, res_slot;            // residual add (-1: none)
-    int mask_out_buf;                 // store bitmask of (pre-activation > 0) at out_slot (-1: none)
+    int mask_out_buf;                 // store bitmask of (pre-activation > 0) at mask_out_slot (-1: none)
     int out2_buf, out2_slot;          // secondary output = result (*) mask (-1: none)
     int out2_mask_kind, out2_mask_buf, out2_mask_slot;
-    int pad;
+    int mask_out_slot;
     Chunk chunks[MAX_CHUNKS];
 };
 
@@ -104,6 +104,27 @@ struct Derive16Op {
     int transpose;        // dst[n][k] = src[k][n]
     int n_src;
     int src_off[4];       // float offsets in params, summed
+    int pad;
+};
+
+// One unit of the tensor-core encoder weight gradient: dW_enc[t][:, k0 : k0 + 64*nkb] += sum over <= 4 slots of type t
+// and one row split of dpre[slot]^T (x[slot] * sign[slot]).
+struct EncDwUnit {
+    int x_buf, lda, K;             // caller's x tensor of the node type, graph-row stride (elements), in-width
+    int k0, nkb;                   // first in-column (multiple of 64), number of 64-column blocks (1..3)
+    int n_slots;                   // 1..4
+    int d_slot[4];                 // slab slot of dpre (BUF_DC1 images)
+    int a_off[4];                  // element offset of the slot inside a graph's row block (local node * in_width)
+    int sign_off[4];               // BUF_SIGNS offset of the [K] +-1 vector or -1
+    int want_colsum;               // also reduce the bias gradient (only the k0 == 0 units)
+    int pad;
+};
+
+// Units [first, first + count) share (type, k0): the reduce sums their partials into the flat gradient buffer.
+struct EncDwGroup {
+    int first, count;
+    int K, k0, width;              // in-width of the type, first column, valid columns (<= 192)
+    int w_off, b_off;              // flat gradient offsets of encoder weight / bias (b_off = -1: no bias in this group)
     int pad;
 };
 

@@ -187,7 +187,7 @@ k_rowgemm(const Tile* __restrict__ tiles, const BufTable bt, const int64_t B, co
                 word |= __shfl_xor_sync(0xffffffffu, word, 2);
                 word |= __shfl_xor_sync(0xffffffffu, word, 4);
                 if (live && (tx & 7) == 0) {
-                    unsigned* mp = (unsigned*)bt.p[t.mask_out_buf] + ((int64_t)t.out_slot * Bp + row) * 4 + hh * 2 + (tx >> 3);
+                    unsigned* mp = (unsigned*)bt.p[t.mask_out_buf] + ((int64_t)t.mask_out_slot * Bp + row) * 4 + hh * 2 + (tx >> 3);
                     *mp = word;
                 }
             }
@@ -200,10 +200,11 @@ k_rowgemm(const Tile* __restrict__ tiles, const BufTable bt, const int64_t B, co
                 continue;
             }
             if (t.posmask_buf >= 0) {
-                const float4 q = *reinterpret_cast<const float4*>(
-                    (const float*)bt.p[t.posmask_buf] + ((int64_t)t.posmask_slot * Bp + row) * H + col);
-                v[0] = q.x > 0.f ? v[0] : 0.f; v[1] = q.y > 0.f ? v[1] : 0.f;
-                v[2] = q.z > 0.f ? v[2] : 0.f; v[3] = q.w > 0.f ? v[3] : 0.f;
+                const unsigned w = *((const unsigned*)bt.p[t.posmask_buf] +
+                                     ((int64_t)t.posmask_slot * Bp + row) * 4 + hh * 2 + (tx >> 3));
+                const unsigned nb = (w >> lane_shift) & 0xFu;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] = ((nb >> j) & 1u) ? v[j] : 0.f;
             }
             if (t.res_buf >= 0) {
                 const float4 q = *reinterpret_cast<const float4*>(
@@ -222,11 +223,6 @@ k_rowgemm(const Tile* __restrict__ tiles, const BufTable bt, const int64_t B, co
                     const unsigned nb = (w >> lane_shift) & 0xFu;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) v[j] = ((nb >> j) & 1u) ? v[j] : 0.f;
-                } else if (t.out2_mask_kind == MK_POS) {
-                    const float4 q = *reinterpret_cast<const float4*>(
-                        (const float*)bt.p[t.out2_mask_buf] + ((int64_t)t.out2_mask_slot * Bp + row) * H + col);
-                    v[0] = q.x > 0.f ? v[0] : 0.f; v[1] = q.y > 0.f ? v[1] : 0.f;
-                    v[2] = q.z > 0.f ? v[2] : 0.f; v[3] = q.w > 0.f ? v[3] : 0.f;
                 }
                 const int64_t off2 = ((int64_t)t.out2_slot * Bp + row) * H + col;
                 *reinterpret_cast<float4*>((float*)bt.p[t.out2_buf] + off2) = make_float4(v[0], v[1], v[2], v[3]);
@@ -489,10 +485,6 @@ k_decoder_bwd(const DecoderDesc dd, const float* __restrict__ hslab, const float
                 const unsigned nb = (wd >> ((lane & 7) * 4)) & 0xFu;
                 d.x = (nb & 1u) ? d.x : 0.f; d.y = (nb & 2u) ? d.y : 0.f;
                 d.z = (nb & 4u) ? d.z : 0.f; d.w = (nb & 8u) ? d.w : 0.f;
-            } else if (mask_kind == MK_POS) {
-                const float4 q = *reinterpret_cast<const float4*>((const float*)mask_buf + off);
-                d.x = q.x > 0.f ? d.x : 0.f; d.y = q.y > 0.f ? d.y : 0.f;
-                d.z = q.z > 0.f ? d.z : 0.f; d.w = q.w > 0.f ? d.w : 0.f;
             }
             *reinterpret_cast<float4*>(dc + off) = d;
             if (dc_hi) { const float vv[4] = {d.x, d.y, d.z, d.w}; split_store4(dc_hi, dc_lo, off, vv); }

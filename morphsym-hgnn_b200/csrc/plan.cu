@@ -41,7 +41,7 @@ static Tile empty_tile() {
     Tile t{};
     t.n_chunks = 0;
     t.out_buf = -1; t.out_slot = 0; t.bias_buf = -1; t.bias_off = 0; t.relu = 0;
-    t.posmask_buf = -1; t.posmask_slot = 0; t.res_buf = -1; t.res_slot = 0; t.mask_out_buf = -1;
+    t.posmask_buf = -1; t.posmask_slot = 0; t.res_buf = -1; t.res_slot = 0; t.mask_out_buf = -1; t.mask_out_slot = 0;
     t.out2_buf = -1; t.out2_slot = 0; t.out2_mask_kind = MK_NONE; t.out2_mask_buf = -1; t.out2_mask_slot = 0;
     return t;
 }
@@ -223,12 +223,15 @@ std::string build_plan(const mshgnn_desc* d, Plan& p) {
             Chunk c{};
             c.a_kind = A_EXT; c.a_buf = BUF_X0 + t; c.a_slot = 0; c.K = p.in_w[t]; c.lda = p.nodes[t] * p.in_w[t];
             c.a_off = n * p.in_w[t]; c.w_buf = BUF_DERIVED; c.w_off = (int)p.der_encT[t]; c.sign_off = p.sign_off_slot[s];
+            c.w16_row = t * H;   // tensor-core encoder: first row of this type's [128][enc_kmax] fp16 weight image
             T.chunks[T.n_chunks++] = c;
             T.bias_buf = BUF_PARAMS; T.bias_off = (int)p.off_enc_b[t]; T.relu = 1;
             T.out_buf = BUF_H0; T.out_slot = s;
             v.push_back(T);
         }
         p.enc_launch = push_launch(v);
+        for (auto& T : v) { T.mask_out_buf = BUF_MASKE; T.mask_out_slot = T.out_slot; }
+        p.enc_train = push_launch(v);
     }
     for (int l = 0; l < p.L; ++l) {
         std::vector<Tile> conv, m1, m2;
@@ -264,11 +267,12 @@ std::string build_plan(const mshgnn_desc* d, Plan& p) {
         }
         // inference copy (no ReLU bitmask), training copy (bitmask for MS joint/foot rows)
         p.conv_infer.push_back(push_launch(conv));
-        if (p.morph_sym)
-            for (auto& T : conv)
-                if (T.relu) T.mask_out_buf = BUF_MASK0 + l;
+        for (auto& T : conv)
+            if (T.relu) { T.mask_out_buf = BUF_MASK0 + l; T.mask_out_slot = T.out_slot; }
         p.conv_train.push_back(push_launch(conv));
         p.mlp1.push_back(push_launch(m1));
+        for (auto& T : m1) { T.mask_out_buf = BUF_MASK0 + l; T.mask_out_slot = p.S + (T.out_slot - p.nm); }
+        p.mlp1_train.push_back(push_launch(m1));
         p.mlp2.push_back(push_launch(m2));
     }
 
@@ -285,7 +289,7 @@ std::string build_plan(const mshgnn_desc* d, Plan& p) {
                 if (!p.need[l + 1][s]) continue;
                 Tile A = empty_tile();   // dpre = (du * W2) (*) (t > 0)
                 A.chunks[A.n_chunks++] = slab_chunk(DHn, s, BUF_PARAMS, p.off_mlp_w[1], mat16(p, {p.off_mlp_w[1]}, true));
-                A.posmask_buf = BUF_CT0 + l; A.posmask_slot = p.nm + n;
+                A.posmask_buf = BUF_MASK0 + l; A.posmask_slot = p.S + n;
                 A.out_buf = BUF_DU; A.out_slot = n;
                 b1.push_back(A);
                 Tile Bt = empty_tile();  // dc_base = dpre * W1
@@ -306,14 +310,14 @@ std::string build_plan(const mshgnn_desc* d, Plan& p) {
                 if (p.morph_sym) { T.res_buf = DHn; T.res_slot = s; }
             }
             if (l == 0) {
-                T.out2_buf = DCp; T.out2_slot = s; T.out2_mask_kind = MK_POS; T.out2_mask_buf = BUF_H0; T.out2_mask_slot = s;
+                T.out2_buf = DCp; T.out2_slot = s; T.out2_mask_kind = MK_BITS; T.out2_mask_buf = BUF_MASKE; T.out2_mask_slot = s;
             } else if (p.morph_sym) {
                 T.out_buf = DHo; T.out_slot = s;
                 if (t != p.mlp_type) {
                     T.out2_buf = DCp; T.out2_slot = s; T.out2_mask_kind = MK_BITS; T.out2_mask_buf = BUF_MASK0 + l - 1; T.out2_mask_slot = s;
                 }
             } else {
-                T.out2_buf = DCp; T.out2_slot = s; T.out2_mask_kind = MK_POS; T.out2_mask_buf = BUF_H0 + l; T.out2_mask_slot = s;
+                T.out2_buf = DCp; T.out2_slot = s; T.out2_mask_kind = MK_BITS; T.out2_mask_buf = BUF_MASK0 + l - 1; T.out2_mask_slot = s;
             }
             dx.push_back(T);
         }
@@ -405,6 +409,33 @@ std::string build_plan(const mshgnn_desc* d, Plan& p) {
         }
     }
     p.dw_enc.count = (int)p.rtasks.size() - p.dw_enc.begin;
+    // ---- tensor-core encoder weight-gradient units: (type, 192-column range, group of <= 4 slots) ----
+    p.enc_kmax = 64;
+    for (int t = 0; t < p.n_types; ++t) if (round_up(p.in_w[t], 64) > p.enc_kmax) p.enc_kmax = (int)round_up(p.in_w[t], 64);
+    for (int t = 0; t < p.n_types; ++t) {
+        std::vector<int> slots;
+        for (int n = 0; n < p.nodes[t]; ++n) if (p.need[0][p.slot_of(t, n)]) slots.push_back(n);
+        if (slots.empty()) continue;
+        for (int k0 = 0; k0 < p.in_w[t]; k0 += 192) {
+            EncDwGroup g{};
+            g.first = (int)p.enc_units.size(); g.K = p.in_w[t]; g.k0 = k0;
+            g.width = p.in_w[t] - k0 < 192 ? p.in_w[t] - k0 : 192;
+            g.w_off = (int)p.off_enc_w[t]; g.b_off = k0 == 0 ? (int)p.off_enc_b[t] : -1;
+            for (size_t b = 0; b < slots.size(); b += 4) {
+                EncDwUnit u{};
+                u.x_buf = BUF_X0 + t; u.lda = p.nodes[t] * p.in_w[t]; u.K = p.in_w[t]; u.k0 = k0; u.nkb = (g.width + 63) / 64;
+                u.want_colsum = k0 == 0;
+                for (size_t i = b; i < slots.size() && i < b + 4; ++i) {
+                    const int n = slots[i], s = p.slot_of(t, n);
+                    u.d_slot[u.n_slots] = s; u.a_off[u.n_slots] = n * p.in_w[t]; u.sign_off[u.n_slots] = p.sign_off_slot[s];
+                    u.n_slots++;
+                }
+                p.enc_units.push_back(u);
+            }
+            g.count = (int)p.enc_units.size() - g.first;
+            p.enc_groups.push_back(g);
+        }
+    }
     return "";
 }
 
@@ -431,7 +462,9 @@ WsLayout ws_layout(const Plan& p, int64_t B, int train, int mode) {
     if (train) {
         for (int l = 0; l <= p.L; ++l) w.h[l] = take(slab);
         if (p.morph_sym)
-            for (int l = 0; l < p.L; ++l) { w.ct[l] = take(ctb); w.mask[l] = take((int64_t)p.S * w.Bp * 16); }
+            for (int l = 0; l < p.L; ++l) w.ct[l] = take(ctb);
+        for (int l = 0; l < p.L; ++l) w.mask[l] = take((int64_t)(p.S + p.nm) * w.Bp * 16);
+        w.maske = take((int64_t)p.S * w.Bp * 16);
         w.dh[0] = take(slab); w.dh[1] = take(slab); w.dc[0] = take(slab); w.dc[1] = take(slab);
         if (p.morph_sym) w.du = take((int64_t)p.nm * w.Bp * H * 4);
         const int ns_max = w.n_splits > w.n_splits_tc ? w.n_splits : w.n_splits_tc;
@@ -460,6 +493,15 @@ WsLayout ws_layout(const Plan& p, int64_t B, int train, int mode) {
             if (p.morph_sym) for (int i = 0; i < 2; ++i) c[i] = take(ctb / 2);
             for (int l = 0; l <= p.L; ++l) for (int i = 0; i < 2; ++i) w.h16[l][i] = (l & 1) ? b[i] : a[i];
             for (int l = 0; l < p.L; ++l) for (int i = 0; i < 2; ++i) w.ct16[l][i] = c[i];
+        }
+    }
+    if (tc) {
+        for (int i = 0; i < 2; ++i) w.wenc16[i] = take((int64_t)p.n_types * H * p.enc_kmax * 2);
+        if (train) {
+            w.rows_per_enc = 512;
+            w.n_splits_enc = (int)((B + w.rows_per_enc - 1) / w.rows_per_enc);
+            w.part_enc_w = take((int64_t)p.enc_units.size() * w.n_splits_enc * H * 192 * 4);
+            w.part_enc_b = take((int64_t)p.enc_units.size() * w.n_splits_enc * H * 4);
         }
     }
     w.loss_part = take(LOSS_BLOCKS * 8);

@@ -15,9 +15,11 @@ enum : int {
     BUF_PARAMS = 0, BUF_DERIVED = 1, BUF_SIGNS = 2, BUF_GRADS = 3,
     BUF_X0 = 4,                       // +type
     BUF_DH0 = 8, BUF_DH1 = 9, BUF_DC0 = 10, BUF_DC1 = 11, BUF_DU = 12,
+    BUF_MASKE = 13,                   // ReLU bitmask of the encoder output
+
     BUF_H0 = 16,                      // +layer (0..L)
     BUF_CT0 = 32,                     // +layer
-    BUF_MASK0 = 48                    // +layer
+    BUF_MASK0 = 48                    // +layer: ReLU bitmasks, slots [0,S) conv outputs, [S,S+nm) base-MLP hidden
 };
 constexpr int MAX_LAYERS = 15;
 
@@ -63,14 +65,18 @@ struct Plan {
 
     // ---- compiled tables ----
     std::vector<Tile> tiles;
-    Launch enc_launch;
-    std::vector<Launch> conv_train, conv_infer, mlp1, mlp2;      // per layer
+    Launch enc_launch, enc_train;
+    std::vector<Launch> conv_train, conv_infer, mlp1, mlp1_train, mlp2;      // per layer
     std::vector<Launch> bwd_m1, bwd_m2, bwd_dx;                  // per layer
     std::vector<RTask> rtasks;
     std::vector<RPair> rpairs;
     std::vector<Launch> dw_layer;                                // per layer (task ranges)
     Launch dw_enc;
     std::vector<OutGroup> groups;
+    // tensor-core encoder: fp16 weight image [n_types*128][enc_kmax] and weight-gradient units
+    int enc_kmax = 64;
+    std::vector<EncDwUnit> enc_units;
+    std::vector<EncDwGroup> enc_groups;
     int n_groups_layers = 0;           // groups [0, n_groups_layers) belong to the layer stack, the rest to the encoder
     DecoderDesc dec;
 
@@ -85,6 +91,8 @@ struct Plan {
     mutable DeriveOp* d_derive = nullptr;
     mutable Derive16Op* d_derive16 = nullptr;
     mutable float* d_signs = nullptr;
+    mutable EncDwUnit* d_enc_units = nullptr;
+    mutable EncDwGroup* d_enc_groups = nullptr;
 
     int slot_of(int type, int local) const { return type_base[type] + local; }
 };
@@ -97,8 +105,12 @@ struct WsLayout {
     int64_t h[MAX_LAYERS + 1];
     int64_t ct[MAX_LAYERS];
     int64_t mask[MAX_LAYERS];
+    int64_t maske = -1;
     int64_t dh[2], dc[2], du = 0;
     int64_t part_w = 0, part_b = 0, dec_part = 0, loss_part = 0;
+    int n_splits_enc = 1, rows_per_enc = 512;          // row splits of the tensor-core encoder weight gradient
+    int64_t part_enc_w = -1, part_enc_b = -1;          // [unit][split][128][192] fp32 / [unit][split][128]
+    int64_t wenc16[2] = {-1, -1};                      // encoder weight images [n_types*128][enc_kmax] fp16 (hi, lo)
     // tensor-core modes: (hi, lo) fp16 images; index [0] = hi, [1] = lo; -1 when absent
     int64_t h16[MAX_LAYERS + 1][2], ct16[MAX_LAYERS][2], dh16[2][2], dc16[2][2], du16[2], w16[2];
     int64_t total = 0;
