@@ -163,43 +163,43 @@ int get_encode_fn(EncodeTiledFn* out) {
     return 0;
 }
 
-// [rows, 128] fp16 row-major tensor, box = 128 rows x 64 columns, 128-byte swizzle (the UMMA K-major SW128 layout)
-int make_map16(CUtensorMap* m, const void* base, int64_t rows, int box_rows = 128) {
+// [rows, cols] fp16 row-major tensor viewed through a (box_cols x box_rows) box with the given swizzle
+int make_map_2d(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int box_cols, int box_rows, CUtensorMapSwizzle sw) {
     EncodeTiledFn enc;
     int rc = get_encode_fn(&enc);
     if (rc) return rc;
-    if (!base || rows < box_rows) return fail(MSHGNN_ERR_ARG, "internal: bad fp16 tensor for a TMA map");
-    cuuint64_t dims[2] = {(cuuint64_t)H, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)H * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(MSHGNN_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-    return 0;
-}
-
-// [rows, cols] fp16 row-major tensor, box = 128 rows x 64 columns, 128-byte swizzle
-int make_map16_2d(CUtensorMap* m, const void* base, int64_t rows, int64_t cols) {
-    EncodeTiledFn enc;
-    int rc = get_encode_fn(&enc);
-    if (rc) return rc;
+    if (!base || rows < 1) return fail(MSHGNN_ERR_ARG, "internal: bad fp16 tensor for a TMA map");
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
-    cuuint32_t box[2] = {64, 128};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(MSHGNN_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return 0;
 }
 
-int launch_tc_encoder(const Plan& p, const Launch& L, const WsLayout& w, const BufTable& bt, const BufTable16& bh, char* ws,
+// The whole workspace as one [total/256 rows][128 fp16] tensor: every (hi, lo) image of every buffer (and the 128x128
+// weight images) is a row range of it, so three maps serve every tensor-core launch of a call.
+struct WsMaps {
+    TcMaps tc;            // .k: 32 x 128 SWIZZLE_64B (operand K blocks), .o: 64 x 128 SWIZZLE_128B (epilogue tiles)
+    CUtensorMap dw;       // 64 x 64 SWIZZLE_128B (MN-major operands of the weight-gradient kernels)
+};
+int make_ws_maps(WsMaps* m, const void* ws, const WsLayout& w) {
+    if (w.total / 256 > 0x7fffffffLL) return fail(MSHGNN_ERR_ARG, "workspace too large for one TMA map");
+    int rc;
+    if ((rc = make_map_2d(&m->tc.k, ws, w.total / 256, H, TC_KB, 128, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    if ((rc = make_map_2d(&m->tc.o, ws, w.total / 256, H, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    if ((rc = make_map_2d(&m->dw, ws, w.total / 256, H, 64, DW_KB, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    return 0;
+}
+
+int launch_tc_encoder(const Plan& p, const Launch& L, const WsLayout& w, const BufTable& bt, const BufRows& br, const WsMaps& wm, char* ws,
                       const float* params, int64_t B, int xf64, int split, cudaStream_t st) {
     if (L.count == 0) return 0;
     static bool attr_set = false;
     if (!attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute(k_tc_encoder, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(k_tc_encoder, cudaFuncAttributeMaxDynamicSharedMemorySize, ENC_SMEM_BYTES));
         attr_set = true;
     }
     __half* e_hi = (__half*)(ws + w.wenc16[0]);
@@ -213,44 +213,31 @@ int launch_tc_encoder(const Plan& p, const Launch& L, const WsLayout& w, const B
     }
     EncMaps maps;
     int rc;
-    if ((rc = make_map16_2d(&maps.w_hi, e_hi, (int64_t)p.n_types * H, p.enc_kmax))) return rc;
-    if ((rc = make_map16_2d(&maps.w_lo, e_lo, (int64_t)p.n_types * H, p.enc_kmax))) return rc;
+    if ((rc = make_map_2d(&maps.w_hi, e_hi, (int64_t)p.n_types * H, p.enc_kmax, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    if ((rc = make_map_2d(&maps.w_lo, e_lo, (int64_t)p.n_types * H, p.enc_kmax, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    maps.o = wm.tc.o;
     ProfScope ps(K_ENC_FWD, st);
     dim3 grid((unsigned)(w.Bp / TILE_M), (unsigned)L.count);
-    k_tc_encoder<<<grid, ENC_THREADS, TC_SMEM_BYTES, st>>>(maps, p.d_tiles + L.begin, bt, bh, B, w.Bp, xf64, split);
+    k_tc_encoder<<<grid, ENC_THREADS, ENC_SMEM_BYTES, st>>>(maps, p.d_tiles + L.begin, bt, br, B, w.Bp, xf64, split);
     LAUNCH_CHECK();
     return 0;
 }
 
-int buf_rows(const Plan& p, int buf, int64_t Bp) {
-    if (buf >= BUF_CT0 && buf < BUF_CT0 + MAX_LAYERS) return (int)(2 * p.nm * Bp);
-    if (buf == BUF_DU) return (int)(p.nm * Bp);
-    return (int)(p.S * Bp);
-}
-
-int launch_tc_rowgemm(int kind, const Plan& p, const Launch& L, const BufTable& bt, const BufTable16& bh, const __half* w_hi,
-                      const __half* w_lo, int64_t B, int64_t Bp, int split, cudaStream_t st) {
+int launch_tc_rowgemm(int kind, const Plan& p, const Launch& L, const BufTable& bt, const BufRows& br, const WsMaps& wm,
+                      int64_t B, int64_t Bp, int split, cudaStream_t st) {
     if (L.count == 0) return 0;
     static bool attr_set = false;
     if (!attr_set) {
         CUDA_TRY(cudaFuncSetAttribute(k_tc_rowgemm, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
         attr_set = true;
     }
-    const int a_buf = p.tiles[L.begin].chunks[0].a_buf;
     for (int i = 0; i < L.count; ++i)
         for (int c = 0; c < p.tiles[L.begin + i].n_chunks; ++c)
-            if (p.tiles[L.begin + i].chunks[c].a_buf != a_buf || p.tiles[L.begin + i].chunks[c].a_kind != A_SLAB)
-                return fail(MSHGNN_ERR_ARG, "internal: a tensor-core launch must read one slab buffer");
-    TcMaps maps;
-    int rc;
-    const int64_t rows = buf_rows(p, a_buf, Bp);
-    if ((rc = make_map16(&maps.a_hi, bh.hi[a_buf], rows))) return rc;
-    if ((rc = make_map16(&maps.a_lo, bh.lo[a_buf], rows))) return rc;
-    if ((rc = make_map16(&maps.w_hi, w_hi, (int64_t)p.n_mats16 * H))) return rc;
-    if ((rc = make_map16(&maps.w_lo, w_lo, (int64_t)p.n_mats16 * H))) return rc;
+            if (p.tiles[L.begin + i].chunks[c].a_kind != A_SLAB)
+                return fail(MSHGNN_ERR_ARG, "internal: a tensor-core row-GEMM launch must read slab buffers");
     ProfScope ps(kind, st);
-    dim3 grid((unsigned)(Bp / TILE_M), (unsigned)L.count);
-    k_tc_rowgemm<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(maps, p.d_tiles + L.begin, bt, bh, B, Bp, split);
+    dim3 grid((unsigned)L.count, (unsigned)(Bp / TILE_M));
+    k_tc_rowgemm<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(wm.tc, p.d_tiles + L.begin, bt, br, B, Bp, split);
     LAUNCH_CHECK();
     return 0;
 }
@@ -266,9 +253,10 @@ void fill_rows16(const Plan& p, const WsLayout& w, BufRows& br) {
     br.hi[BUF_DU] = at(w.du16[0]); br.lo[BUF_DU] = at(w.du16[1]);
     for (int l = 0; l <= p.L; ++l) { br.hi[BUF_H0 + l] = at(w.h16[l][0]); br.lo[BUF_H0 + l] = at(w.h16[l][1]); }
     for (int l = 0; l < p.L; ++l) { br.hi[BUF_CT0 + l] = at(w.ct16[l][0]); br.lo[BUF_CT0 + l] = at(w.ct16[l][1]); }
+    br.w_hi = at(w.w16[0]); br.w_lo = at(w.w16[1]);
 }
 
-int launch_tc_dw(int kind, const Plan& p, const Launch& L, const WsLayout& w, const BufRows& br, const void* ws, int64_t B, int split,
+int launch_tc_dw(int kind, const Plan& p, const Launch& L, const WsLayout& w, const BufRows& br, const WsMaps& wm, int64_t B, int split,
                  float* part_w, float* part_b, cudaStream_t st) {
     if (L.count == 0) return 0;
     static bool attr_set = false;
@@ -282,13 +270,9 @@ int launch_tc_dw(int kind, const Plan& p, const Launch& L, const WsLayout& w, co
         for (int j = 0; j < T.n_pairs; ++j)
             if (p.rpairs[T.pair_begin + j].a_kind != A_SLAB) return fail(MSHGNN_ERR_ARG, "internal: tensor-core weight-gradient task must read slabs");
     }
-    CUtensorMap map;
-    int rc;
-    if (w.total / 256 > 0x7fffffffLL) return fail(MSHGNN_ERR_ARG, "workspace too large for one TMA map");
-    if ((rc = make_map16(&map, ws, w.total / 256, DW_KB))) return rc;
     ProfScope ps(kind, st);
     dim3 grid((unsigned)L.count, (unsigned)w.n_splits_tc);
-    k_tc_reducegemm<<<grid, TC_THREADS, DW_SMEM_BYTES, st>>>(map, p.d_rtasks, p.d_rpairs, L.begin, br, B, w.Bp, w.rows_per_tc, w.n_splits_tc,
+    k_tc_reducegemm<<<grid, TC_THREADS, DW_SMEM_BYTES, st>>>(wm.dw, p.d_rtasks, p.d_rpairs, L.begin, br, B, w.Bp, w.rows_per_tc, w.n_splits_tc,
                                                              split, part_w, part_b);
     LAUNCH_CHECK();
     return 0;
@@ -401,10 +385,11 @@ int mshgnn_forward(const mshgnn_plan* plan, int64_t B, const void* const* x, int
             if ((rc = launch_rowgemm(K_MLP_FWD, p, p.mlp2[l], bt, B, w.Bp, 0, st))) return rc;
         }
     } else {
-        // tensor-core path: fp16 (hi, lo) weight images, encoder on the SIMT kernel (it reads the caller's fp32/fp64 rows
-        // and folds the symmetry signs into the load) writing fp32 + (hi, lo) slabs, layers on tcgen05
-        BufTable16 bh;
-        fill_bufs16(p, w, (char*)workspace, bh);
+        // tensor-core path: every activation lives as a (hi, lo) fp16 image pair only; TMA in, TMA out
+        BufRows br;
+        fill_rows16(p, w, br);
+        WsMaps wm;
+        if ((rc = make_ws_maps(&wm, workspace, w))) return rc;
         __half* w_hi = (__half*)((char*)workspace + w.w16[0]);
         __half* w_lo = (__half*)((char*)workspace + w.w16[1]);
         const int split = mode == MSHGNN_MODE_TC;
@@ -414,11 +399,11 @@ int mshgnn_forward(const mshgnn_plan* plan, int64_t B, const void* const* x, int
             k_derive16<<<grid, 256, 0, st>>>(p.d_derive16, params, w_hi, w_lo);
             LAUNCH_CHECK();
         }
-        if ((rc = launch_tc_encoder(p, train ? p.enc_train : p.enc_launch, w, bt, bh, (char*)workspace, params, B, xf64, split, st))) return rc;
+        if ((rc = launch_tc_encoder(p, train ? p.enc_train : p.enc_launch, w, bt, br, wm, (char*)workspace, params, B, xf64, split, st))) return rc;
         for (int l = 0; l < p.L; ++l) {
-            if ((rc = launch_tc_rowgemm(K_CONV_FWD, p, train ? p.conv_train[l] : p.conv_infer[l], bt, bh, w_hi, w_lo, B, w.Bp, split, st))) return rc;
-            if ((rc = launch_tc_rowgemm(K_MLP_FWD, p, train ? p.mlp1_train[l] : p.mlp1[l], bt, bh, w_hi, w_lo, B, w.Bp, split, st))) return rc;
-            if ((rc = launch_tc_rowgemm(K_MLP_FWD, p, p.mlp2[l], bt, bh, w_hi, w_lo, B, w.Bp, split, st))) return rc;
+            if ((rc = launch_tc_rowgemm(K_CONV_FWD, p, train ? p.conv_train[l] : p.conv_infer[l], bt, br, wm, B, w.Bp, split, st))) return rc;
+            if ((rc = launch_tc_rowgemm(K_MLP_FWD, p, train ? p.mlp1_train[l] : p.mlp1[l], bt, br, wm, B, w.Bp, split, st))) return rc;
+            if ((rc = launch_tc_rowgemm(K_MLP_FWD, p, p.mlp2[l], bt, br, wm, B, w.Bp, split, st))) return rc;
         }
     }
     {
@@ -426,7 +411,11 @@ int mshgnn_forward(const mshgnn_plan* plan, int64_t B, const void* const* x, int
         int blocks = (int)((rows + 7) / 8);
         if (blocks > 148 * 8) blocks = 148 * 8;
         ProfScope ps(K_DEC_FWD, st);
-        k_decoder_fwd<<<blocks, 256, 0, st>>>(p.dec, (const float*)bt.p[BUF_H0 + p.L], params, p.d_signs, out, B, w.Bp);
+        const bool tcm = mode != MSHGNN_MODE_FP32;
+        const char* wsb = (const char*)workspace;
+        k_decoder_fwd<<<blocks, 256, 0, st>>>(p.dec, tcm ? nullptr : (const float*)bt.p[BUF_H0 + p.L],
+                                              tcm ? (const __half*)(wsb + w.h16[p.L][0]) : nullptr, tcm ? (const __half*)(wsb + w.h16[p.L][1]) : nullptr,
+                                              params, p.d_signs, out, B, w.Bp);
         LAUNCH_CHECK();
     }
     return 0;
@@ -484,8 +473,8 @@ int mshgnn_backward(const mshgnn_plan* plan, int64_t B, const void* const* x, in
     const int split = mode == MSHGNN_MODE_TC;
     BufTable16 bh;
     fill_bufs16(p, w, ws, bh);
-    const __half* w_hi = tc ? (const __half*)(ws + w.w16[0]) : nullptr;
-    const __half* w_lo = tc ? (const __half*)(ws + w.w16[1]) : nullptr;
+    WsMaps wm;
+    if (tc && (rc = make_ws_maps(&wm, workspace, w))) return rc;
     // tensor-core modes carry every backward quantity multiplied by a power of two G ~ #output rows so that the
     // fp16 (hi, lo) images of dL/dh stay in the normal range; the final reductions multiply by 1/G (exact).
     BufRows br;
@@ -506,9 +495,11 @@ int mshgnn_backward(const mshgnn_plan* plan, int64_t B, const void* const* x, in
         }
         ProfScope ps(K_DEC_BWD, st);
         const int dhb = BUF_DH0 + (L & 1), dcb = BUF_DC0 + ((L - 1) & 1);
-        k_decoder_bwd<<<DEC_BLOCKS, 256, 0, st>>>(p.dec, (const float*)bt.p[BUF_H0 + L], params, p.d_signs, dout, dh, dc, mk, mbuf,
-                                                  dec_part, B, w.Bp, G, (tc && dh) ? bh.hi[dhb] : nullptr, (tc && dh) ? bh.lo[dhb] : nullptr,
-                                                  (tc && dc) ? bh.hi[dcb] : nullptr, (tc && dc) ? bh.lo[dcb] : nullptr);
+        const bool want_dh = p.morph_sym, want_dc = !p.morph_sym || p.dec_type != p.mlp_type;
+        k_decoder_bwd<<<DEC_BLOCKS, 256, 0, st>>>(p.dec, tc ? nullptr : (const float*)bt.p[BUF_H0 + L], tc ? bh.hi[BUF_H0 + L] : nullptr,
+                                                  tc ? bh.lo[BUF_H0 + L] : nullptr, params, p.d_signs, dout, tc ? nullptr : dh, tc ? nullptr : dc, mk, mbuf,
+                                                  dec_part, B, w.Bp, G, (tc && want_dh) ? bh.hi[dhb] : nullptr, (tc && want_dh) ? bh.lo[dhb] : nullptr,
+                                                  (tc && want_dc) ? bh.hi[dcb] : nullptr, (tc && want_dc) ? bh.lo[dcb] : nullptr);
         LAUNCH_CHECK();
         k_decoder_bwd_reduce<<<4, 256, 0, st>>>(p.dec, dec_part, DEC_BLOCKS, grads, 1.f / G);
         LAUNCH_CHECK();
@@ -523,10 +514,10 @@ int mshgnn_backward(const mshgnn_plan* plan, int64_t B, const void* const* x, in
     };
     for (int l = p.L - 1; l >= 0; --l) {
         if (tc) {
-            if ((rc = launch_tc_rowgemm(K_MLP_BWD, p, p.bwd_m1[l], bt, bh, w_hi, w_lo, B, w.Bp, split, st))) return rc;
-            if ((rc = launch_tc_rowgemm(K_MLP_BWD, p, p.bwd_m2[l], bt, bh, w_hi, w_lo, B, w.Bp, split, st))) return rc;
-            if ((rc = launch_tc_dw(K_DW_LAYER, p, p.dw_layer[l], w, br, ws, B, split, part_w, part_b, st))) return rc;
-            if ((rc = launch_tc_rowgemm(K_DX_BWD, p, p.bwd_dx[l], bt, bh, w_hi, w_lo, B, w.Bp, split, st))) return rc;
+            if ((rc = launch_tc_rowgemm(K_MLP_BWD, p, p.bwd_m1[l], bt, br, wm, B, w.Bp, split, st))) return rc;
+            if ((rc = launch_tc_rowgemm(K_MLP_BWD, p, p.bwd_m2[l], bt, br, wm, B, w.Bp, split, st))) return rc;
+            if ((rc = launch_tc_dw(K_DW_LAYER, p, p.dw_layer[l], w, br, wm, B, split, part_w, part_b, st))) return rc;
+            if ((rc = launch_tc_rowgemm(K_DX_BWD, p, p.bwd_dx[l], bt, br, wm, B, w.Bp, split, st))) return rc;
         } else {
             if ((rc = launch_rowgemm(K_MLP_BWD, p, p.bwd_m1[l], bt, B, w.Bp, 0, st))) return rc;
             if ((rc = launch_rowgemm(K_MLP_BWD, p, p.bwd_m2[l], bt, B, w.Bp, 0, st))) return rc;
@@ -541,14 +532,12 @@ int mshgnn_backward(const mshgnn_plan* plan, int64_t B, const void* const* x, in
                 CUDA_TRY(cudaFuncSetAttribute(k_tc_encoder_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, EDW_SMEM_BYTES));
                 attr_set = true;
             }
-            CUtensorMap map;
-            if ((rc = make_map16(&map, ws, w.total / 256, DW_KB))) return rc;
             float* pe_w = (float*)(ws + w.part_enc_w);
             float* pe_b = (float*)(ws + w.part_enc_b);
             {
                 ProfScope ps(K_DW_ENC, st);
                 dim3 grid((unsigned)p.enc_units.size(), (unsigned)w.n_splits_enc);
-                k_tc_encoder_dw<<<grid, ENC_THREADS, EDW_SMEM_BYTES, st>>>(map, p.d_enc_units, bt, br, B, w.Bp, w.rows_per_enc, w.n_splits_enc, xf64,
+                k_tc_encoder_dw<<<grid, ENC_THREADS, EDW_SMEM_BYTES, st>>>(wm.dw, p.d_enc_units, bt, br, B, w.Bp, w.rows_per_enc, w.n_splits_enc, xf64,
                                                                            split, pe_w, pe_b);
                 LAUNCH_CHECK();
             }

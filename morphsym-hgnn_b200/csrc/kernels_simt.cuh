@@ -32,6 +32,16 @@ __device__ __forceinline__ void split_store4(__half* hi, __half* lo, int64_t off
     *reinterpret_cast<uint2*>(lo + off) = *reinterpret_cast<uint2*>(l);
 }
 
+// 4 consecutive activations from the fp32 slab, or (tensor-core modes: no fp32 slab) rebuilt from the (hi, lo) images
+__device__ __forceinline__ float4 load_h4(const float* slab, const __half* hi, const __half* lo, int64_t off) {
+    if (slab) return *reinterpret_cast<const float4*>(slab + off);
+    const uint2 a = *reinterpret_cast<const uint2*>(hi + off), b = *reinterpret_cast<const uint2*>(lo + off);
+    const float2 a0 = __half22float2(*reinterpret_cast<const __half2*>(&a.x)), a1 = __half22float2(*reinterpret_cast<const __half2*>(&a.y));
+    const float2 b0 = __half22float2(*reinterpret_cast<const __half2*>(&b.x)), b1 = __half22float2(*reinterpret_cast<const __half2*>(&b.y));
+    const float u = 1.f / 2048.f;
+    return make_float4(fmaf(b0.x, u, a0.x), fmaf(b0.y, u, a0.y), fmaf(b1.x, u, a1.x), fmaf(b1.y, u, a1.y));
+}
+
 // ------------------------------------------------------------------------------------------
 // row-GEMM
 // ------------------------------------------------------------------------------------------
@@ -405,8 +415,8 @@ k_derive(const DeriveOp* __restrict__ ops, const float* __restrict__ params, flo
 // decoder: out[g*n_dec + j, c] = (h[slot_j][g] . Wdec[c] + b[c]) * sign[j*C + c]
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_decoder_fwd(const DecoderDesc dd, const float* __restrict__ hslab, const float* __restrict__ params,
-              const float* __restrict__ signs, float* __restrict__ out, const int64_t B, const int64_t Bp) {
+k_decoder_fwd(const DecoderDesc dd, const float* __restrict__ hslab, const __half* __restrict__ h_hi, const __half* __restrict__ h_lo,
+              const float* __restrict__ params, const float* __restrict__ signs, float* __restrict__ out, const int64_t B, const int64_t Bp) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int64_t n_rows = B * dd.n_dec;
@@ -419,7 +429,7 @@ k_decoder_fwd(const DecoderDesc dd, const float* __restrict__ hslab, const float
     for (int64_t row = warp; row < n_rows; row += stride) {
         const int64_t g = row / dd.n_dec;
         const int j = (int)(row % dd.n_dec);
-        const float4 h = *reinterpret_cast<const float4*>(hslab + ((int64_t)dd.slots[j] * Bp + g) * H + lane * 4);
+        const float4 h = load_h4(hslab, h_hi, h_lo, ((int64_t)dd.slots[j] * Bp + g) * H + lane * 4);
 #pragma unroll
         for (int c = 0; c < DEC_MAXC; ++c) {
             if (c >= dd.C) break;
@@ -438,7 +448,8 @@ k_decoder_fwd(const DecoderDesc dd, const float* __restrict__ hslab, const float
 // backward: dH[slot_j][g][:] = sum_c dout'[c] Wdec[c][:]   (written to dh_buf, masked copy to dc_buf)
 //           partial dWdec / db per block -> part[(block*(C*H + C))]
 __global__ void __launch_bounds__(256)
-k_decoder_bwd(const DecoderDesc dd, const float* __restrict__ hslab, const float* __restrict__ params,
+k_decoder_bwd(const DecoderDesc dd, const float* __restrict__ hslab, const __half* __restrict__ h_hi, const __half* __restrict__ h_lo,
+              const float* __restrict__ params,
               const float* __restrict__ signs, const float* __restrict__ dout,
               float* __restrict__ dh, float* __restrict__ dc, const int mask_kind, const void* __restrict__ mask_buf,
               float* __restrict__ part, const int64_t B, const int64_t Bp, const float gscale,
@@ -462,7 +473,7 @@ k_decoder_bwd(const DecoderDesc dd, const float* __restrict__ hslab, const float
         const int64_t g = row / dd.n_dec;
         const int j = (int)(row % dd.n_dec);
         const int64_t off = ((int64_t)dd.slots[j] * Bp + g) * H + lane * 4;
-        const float4 h = *reinterpret_cast<const float4*>(hslab + off);
+        const float4 h = load_h4(hslab, h_hi, h_lo, off);
         float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int c = 0; c < DEC_MAXC; ++c) {
@@ -475,18 +486,16 @@ k_decoder_bwd(const DecoderDesc dd, const float* __restrict__ hslab, const float
             gw[c].z = fmaf(dv, h.z, gw[c].z); gw[c].w = fmaf(dv, h.w, gw[c].w);
             gb[c] += dv;
         }
-        if (dh) {
-            *reinterpret_cast<float4*>(dh + off) = d;
-            if (dh_hi) { const float vv[4] = {d.x, d.y, d.z, d.w}; split_store4(dh_hi, dh_lo, off, vv); }
-        }
-        if (dc) {
+        if (dh) *reinterpret_cast<float4*>(dh + off) = d;
+        if (dh_hi) { const float vv[4] = {d.x, d.y, d.z, d.w}; split_store4(dh_hi, dh_lo, off, vv); }
+        if (dc || dc_hi) {
             if (mask_kind == MK_BITS) {
                 const unsigned wd = *((const unsigned*)mask_buf + ((int64_t)dd.slots[j] * Bp + g) * 4 + (lane >> 3));
                 const unsigned nb = (wd >> ((lane & 7) * 4)) & 0xFu;
                 d.x = (nb & 1u) ? d.x : 0.f; d.y = (nb & 2u) ? d.y : 0.f;
                 d.z = (nb & 4u) ? d.z : 0.f; d.w = (nb & 8u) ? d.w : 0.f;
             }
-            *reinterpret_cast<float4*>(dc + off) = d;
+            if (dc) *reinterpret_cast<float4*>(dc + off) = d;
             if (dc_hi) { const float vv[4] = {d.x, d.y, d.z, d.w}; split_store4(dc_hi, dc_lo, off, vv); }
         }
     }

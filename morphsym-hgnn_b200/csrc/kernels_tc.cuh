@@ -22,9 +22,10 @@
 namespace mshgnn {
 
 constexpr int TC_STAGES = 3;
-constexpr int TC_TILE_BYTES = 128 * 128;           // 128 rows x 64 fp16 (one 128B-swizzled K block)
-constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;  // A_hi, A_lo, W_hi, W_lo
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int TC_KB = 32;                          // K columns per pipeline stage of the row-GEMM (one 64B-swizzled block)
+constexpr int TC_TILE_BYTES = 128 * TC_KB * 2;     // 128 rows x 32 fp16 = 8 KB
+constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;  // A_hi, A_lo, W_hi, W_lo = 32 KB
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;   // 2 CTAs per SM
 constexpr int TC_THREADS = 192;
 constexpr float TC_W_SCALE = 256.f;                // weights are stored as fp16 pairs of (w * 2^8)
 constexpr float TC_W_UNSCALE = 1.f / 256.f;
@@ -35,10 +36,6 @@ constexpr float TC_W_UNSCALE = 1.f / 256.f;
 constexpr float TC_LO_SCALE = 2048.f;
 constexpr float TC_LO_UNSCALE = 1.f / 2048.f;
 constexpr uint32_t TC_TMEM_COLS = 256;
-
-struct alignas(64) TcMaps {
-    CUtensorMap a_hi, a_lo, w_hi, w_lo;
-};
 
 // ------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -111,111 +108,198 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
     const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
     return ((uint64_t)hi << 32) | lo;
 }
+// K-major, 64B-swizzled operand (32 fp16 of K per row): 8-row groups 512 B apart, layout type 4 (SWIZZLE_64B).
+__device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t saddr) {
+    const uint32_t lo = ((saddr & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t hi = (512u >> 4) | (1u << 14) | (4u << 29);
+    return ((uint64_t)hi << 32) | lo;
+}
 // kind::f16, A = B = fp16, D = fp32, both K-major, M = 128, N = 128
 constexpr uint32_t TC_IDESC = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 
-__device__ __forceinline__ void split_store(__half* hi, __half* lo, int64_t off, const float (&v)[32]) {
-    // 32 consecutive columns of one row -> 4 x 16-byte stores per image
+// first 256-byte row of each fp16 image, relative to the workspace base: one TMA map over the whole workspace
+// ([total/256 rows][128 fp16]) then reaches every activation / gradient / weight image.
+struct BufRows {
+    int hi[MAX_BUFS];
+    int lo[MAX_BUFS];
+    int w_hi, w_lo;              // 128x128 weight images (row = w16_row of the chunk)
+};
+
+struct alignas(64) TcMaps {
+    CUtensorMap k;               // box 32 columns x 128 rows, SWIZZLE_64B : MMA operand K blocks (activations and weights)
+    CUtensorMap o;               // box 64 columns x 128 rows, SWIZZLE_128B: epilogue tiles (residual in, results out)
+};
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
+                 "r"(src), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// 8 consecutive values -> 16 bytes of the hi image and 16 bytes of the lo image
+__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
+    uint32_t h[4], l[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        __half2 h[4], l[4];
+    for (int j = 0; j < 4; ++j) {
+        const float a = v[2 * j], b = v[2 * j + 1];
+        const __half ha = __float2half_rn(a), hb = __float2half_rn(b);
+        const __half2 hh = __halves2half2(ha, hb);
+        const __half2 ll = __halves2half2(__float2half_rn((a - __half2float(ha)) * TC_LO_SCALE), __float2half_rn((b - __half2float(hb)) * TC_LO_SCALE));
+        h[j] = *reinterpret_cast<const uint32_t*>(&hh);
+        l[j] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+__device__ __forceinline__ void join8_add(float* v, const uint4 hi, const uint4 lo) {
+    const uint32_t h[4] = {hi.x, hi.y, hi.z, hi.w}, l[4] = {lo.x, lo.y, lo.z, lo.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float a = v[q * 8 + 2 * j], b = v[q * 8 + 2 * j + 1];
-            const __half ha = __float2half_rn(a), hb = __float2half_rn(b);
-            h[j] = __halves2half2(ha, hb);
-            l[j] = __halves2half2(__float2half_rn((a - __half2float(ha)) * TC_LO_SCALE), __float2half_rn((b - __half2float(hb)) * TC_LO_SCALE));
-        }
-        *reinterpret_cast<uint4*>(hi + off + q * 8) = *reinterpret_cast<uint4*>(h);
-        *reinterpret_cast<uint4*>(lo + off + q * 8) = *reinterpret_cast<uint4*>(l);
+    for (int j = 0; j < 4; ++j) {
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&h[j]));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&l[j]));
+        v[2 * j] += fmaf(b.x, TC_LO_UNSCALE, a.x);
+        v[2 * j + 1] += fmaf(b.y, TC_LO_UNSCALE, a.y);
     }
 }
 
-// Epilogue shared by the row-GEMM and the encoder: one thread per graph row reads the fp32 accumulators from TMEM
-// (D0 + D1 * 2^-11), applies bias / ReLU / stored-mask / residual and writes the fp32 slab plus its (hi, lo) images.
-__device__ __forceinline__ void tc_epilogue_rows(const Tile& t, const BufTable& bt, const BufTable16& bh, const uint32_t tmem_base,
-                                                 const int row0, const int64_t B, const int64_t Bp, const int split, const int warp, const int lane) {
-    const int q = warp & 3;                       // TMEM lane quarter this warp may access
-    const int64_t row = row0 + q * 32 + lane;
+// Epilogue shared by the row-GEMM and the encoder.  The four epilogue warps own one TMEM lane quarter each (one thread
+// per graph row): accumulators (D0 + D1 * 2^-11) -> bias / ReLU / stored mask / residual -> (hi, lo) fp16 pairs written
+// into 128B-swizzled staging tiles in shared memory -> TMA stores.  The residual tile arrives the same way (TMA load into
+// the staging tiles, combined in place), so no thread ever touches a global activation row directly: every HBM/L2
+// transaction of the activation stream is a full-line bulk transfer.  Staging re-uses the (drained) operand pipeline.
+struct EpiSmem {
+    uint32_t stg;        // 64 KB: [column half][hi | lo] tiles of 128 rows x 64 fp16 (16 KB each)  - primary output / residual
+    uint32_t stg2;       // 32 KB: [hi | lo] tiles of one column half                                  - masked second output
+    uint32_t res_bar;    // mbarrier: residual tiles landed
+    uint32_t accum_bar;  // mbarrier: accumulator complete, operand pipeline drained
+};
+
+__device__ __forceinline__ void tc_epilogue(const Tile& t, const BufTable& bt, const BufRows& br, const CUtensorMap* map_o,
+                                            const uint32_t tmem_base, const int row0, const int64_t B, const int64_t Bp,
+                                            const int split, const int q /*TMEM lane quarter*/, const int lane, const bool leader,
+                                            const EpiSmem es) {
+    const int rl = q * 32 + lane;                  // row inside the tile
+    const int64_t row = (int64_t)row0 + rl;
     const bool live = row < B;
+    const uint32_t rsw = (uint32_t)(rl & 7);
+    const uint32_t rbase = (uint32_t)rl * 128u;
+    uint4 pm = make_uint4(~0u, ~0u, ~0u, ~0u), m2 = make_uint4(~0u, ~0u, ~0u, ~0u);
+    if (live && t.posmask_buf >= 0) pm = __ldg(reinterpret_cast<const uint4*>(bt.p[t.posmask_buf]) + (int64_t)t.posmask_slot * Bp + row);
+    if (live && t.out2_buf >= 0 && t.out2_mask_kind == MK_BITS)
+        m2 = __ldg(reinterpret_cast<const uint4*>(bt.p[t.out2_mask_buf]) + (int64_t)t.out2_mask_slot * Bp + row);
+    const uint32_t pmw[4] = {pm.x, pm.y, pm.z, pm.w}, m2w[4] = {m2.x, m2.y, m2.z, m2.w};
+    uint32_t mw[4] = {0u, 0u, 0u, 0u};
+
+    mbar_wait(es.accum_bar, 0);
+    tc_fence_after();
+    if (t.res_buf >= 0) {
+        if (leader) {
+            const int r_hi = br.hi[t.res_buf] + (int)((int64_t)t.res_slot * Bp) + row0, r_lo = br.lo[t.res_buf] + (int)((int64_t)t.res_slot * Bp) + row0;
+            mbar_expect_tx(es.res_bar, 4 * 16384);
+            tma_load_2d(es.stg, map_o, es.res_bar, 0, r_hi);
+            tma_load_2d(es.stg + 16384, map_o, es.res_bar, 0, r_lo);
+            tma_load_2d(es.stg + 32768, map_o, es.res_bar, 64, r_hi);
+            tma_load_2d(es.stg + 49152, map_o, es.res_bar, 64, r_lo);
+        }
+        mbar_wait(es.res_bar, 0);
+    }
 #pragma unroll 1
-    for (int cc = 0; cc < 4; ++cc) {
-        uint32_t raw[32], raw1[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + cc * 32, raw);
-        if (split) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + 128 + cc * 32, raw1);
-        const int col = cc * 32;
-        if (!live) {
-            // rows [B, Bp) of every fp16 image are kept at zero: the weight-gradient kernel reduces over whole
-            // 64-row blocks (k_tc_reducegemm) and must not see stale data there
-            if (row < Bp) {
-                const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (int half = 0; half < 2; ++half) {
+        if (half == 1 && t.out2_buf >= 0) {      // the second-output staging tile is re-used: its first store must have been read
+            if (leader) tma_store_wait_read();
+            epi_bar_sync();
+        }
+#pragma unroll 1
+        for (int c2 = 0; c2 < 2; ++c2) {
+            const int cc = half * 2 + c2;
+            uint32_t raw[32], raw1[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + cc * 32, raw);
+            if (split) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + 128 + cc * 32, raw1);
+            float v[32];
+            unsigned mask = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                float x = __uint_as_float(raw[j]);
+                if (split) x = fmaf(__uint_as_float(raw1[j]), TC_LO_UNSCALE, x);
+                x *= TC_W_UNSCALE;
+                if (t.bias_buf >= 0) x += __ldg((const float*)bt.p[t.bias_buf] + t.bias_off + cc * 32 + j);
+                if (x > 0.f) mask |= 1u << j;
+                if (t.relu) x = fmaxf(x, 0.f);
+                v[j] = ((pmw[cc] >> j) & 1u) ? x : 0.f;
+            }
+            mw[cc] = mask;
+            const uint32_t tile = es.stg + (uint32_t)half * 32768u + rbase;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const uint32_t a = tile + ((((uint32_t)(c2 * 4 + g)) ^ rsw) << 4);
+                if (t.res_buf >= 0) join8_add(v + g * 8, lds128(a), lds128(a + 16384));
                 if (t.out_buf >= 0) {
-                    const int64_t off = ((int64_t)t.out_slot * Bp + row) * H + col;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) { *reinterpret_cast<uint4*>(bh.hi[t.out_buf] + off + j * 8) = z; *reinterpret_cast<uint4*>(bh.lo[t.out_buf] + off + j * 8) = z; }
-                }
-                if (t.out2_buf >= 0) {
-                    const int64_t off = ((int64_t)t.out2_slot * Bp + row) * H + col;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) { *reinterpret_cast<uint4*>(bh.hi[t.out2_buf] + off + j * 8) = z; *reinterpret_cast<uint4*>(bh.lo[t.out2_buf] + off + j * 8) = z; }
+                    uint4 hi, lo;
+                    split8(v + g * 8, hi, lo);
+                    if (!live) { hi = make_uint4(0u, 0u, 0u, 0u); lo = hi; }     // rows [B, Bp) of every image stay zero
+                    sts128(a, hi);
+                    sts128(a + 16384, lo);
                 }
             }
-            continue;
-        }
-        float v[32];
-        unsigned mask = 0;
+            if (t.out2_buf >= 0) {
+                const uint32_t tile2 = es.stg2 + rbase;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(raw[j]);
-            if (split) x = fmaf(__uint_as_float(raw1[j]), TC_LO_UNSCALE, x);
-            x *= TC_W_UNSCALE;
-            if (t.bias_buf >= 0) x += __ldg((const float*)bt.p[t.bias_buf] + t.bias_off + col + j);
-            if (x > 0.f) mask |= 1u << j;
-            if (t.relu) x = fmaxf(x, 0.f);
-            v[j] = x;
-        }
-        if (t.mask_out_buf >= 0)
-            *((unsigned*)bt.p[t.mask_out_buf] + ((int64_t)t.mask_out_slot * Bp + row) * 4 + cc) = mask;
-        if (t.posmask_buf >= 0) {
-            const unsigned w = *((const unsigned*)bt.p[t.posmask_buf] + ((int64_t)t.posmask_slot * Bp + row) * 4 + cc);
+                for (int g = 0; g < 4; ++g) {
+                    float u[8];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = ((w >> j) & 1u) ? v[j] : 0.f;
-        }
-        if (t.res_buf >= 0) {
-            const float4* p = reinterpret_cast<const float4*>((const float*)bt.p[t.res_buf] + ((int64_t)t.res_slot * Bp + row) * H + col);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float4 m = p[j];
-                v[4 * j] += m.x; v[4 * j + 1] += m.y; v[4 * j + 2] += m.z; v[4 * j + 3] += m.w;
+                    for (int e = 0; e < 8; ++e) u[e] = ((m2w[cc] >> (g * 8 + e)) & 1u) ? v[g * 8 + e] : 0.f;
+                    uint4 hi, lo;
+                    split8(u, hi, lo);
+                    if (!live) { hi = make_uint4(0u, 0u, 0u, 0u); lo = hi; }
+                    const uint32_t a = tile2 + ((((uint32_t)(c2 * 4 + g)) ^ rsw) << 4);
+                    sts128(a, hi);
+                    sts128(a + 16384, lo);
+                }
             }
         }
-        if (t.out_buf >= 0) {
-            const int64_t off = ((int64_t)t.out_slot * Bp + row) * H + col;
-            float4* o = reinterpret_cast<float4*>((float*)bt.p[t.out_buf] + off);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            split_store(bh.hi[t.out_buf], bh.lo[t.out_buf], off, v);
-        }
-        if (t.out2_buf >= 0) {
-            if (t.out2_mask_kind == MK_BITS) {
-                const unsigned w = *((const unsigned*)bt.p[t.out2_mask_buf] + ((int64_t)t.out2_mask_slot * Bp + row) * 4 + cc);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = ((w >> j) & 1u) ? v[j] : 0.f;
+        fence_proxy_async_smem();
+        epi_bar_sync();
+        if (leader) {
+            if (t.out_buf >= 0) {
+                const int o = (int)((int64_t)t.out_slot * Bp) + row0;
+                tma_store_2d(map_o, es.stg + (uint32_t)half * 32768u, half * 64, br.hi[t.out_buf] + o);
+                tma_store_2d(map_o, es.stg + (uint32_t)half * 32768u + 16384u, half * 64, br.lo[t.out_buf] + o);
             }
-            const int64_t off = ((int64_t)t.out2_slot * Bp + row) * H + col;
-            float4* o = reinterpret_cast<float4*>((float*)bt.p[t.out2_buf] + off);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            split_store(bh.hi[t.out2_buf], bh.lo[t.out2_buf], off, v);
+            if (t.out2_buf >= 0) {
+                const int o = (int)((int64_t)t.out2_slot * Bp) + row0;
+                tma_store_2d(map_o, es.stg2, half * 64, br.hi[t.out2_buf] + o);
+                tma_store_2d(map_o, es.stg2 + 16384u, half * 64, br.lo[t.out2_buf] + o);
+            }
+            tma_store_commit();
         }
     }
+    if (live && t.mask_out_buf >= 0)
+        *(reinterpret_cast<uint4*>(bt.p[t.mask_out_buf]) + (int64_t)t.mask_out_slot * Bp + row) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+    if (leader) tma_store_wait_all();
 }
 
 // ------------------------------------------------------------------------------------------
 // row-GEMM on tcgen05
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TC_THREADS, 1)
-k_tc_rowgemm(const __grid_constant__ TcMaps maps, const Tile* __restrict__ tiles, const BufTable bt, const BufTable16 bh,
+//  Two CTAs share an SM (96 KB of operand pipeline and 256 TMEM columns each): while one CTA drains its accumulator
+//  through the epilogue the other one keeps the tensor pipe and the L2->SMEM stream busy.
+//  grid = (tiles of the launch, row tiles): CTAs that run together read the same 128 graphs, so every source slot
+//  tile is fetched from HBM once and re-read from L2 by the other destination slots that gather it.
+__global__ void __launch_bounds__(TC_THREADS, 2)
+k_tc_rowgemm(const __grid_constant__ TcMaps maps, const Tile* __restrict__ tiles, const BufTable bt, const BufRows br,
              const int64_t B, const int64_t Bp, const int split) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ Tile t;
@@ -225,17 +309,19 @@ k_tc_rowgemm(const __grid_constant__ TcMaps maps, const Tile* __restrict__ tiles
     const int warp = tid >> 5, lane = tid & 31;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
-    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + TC_STAGES), accum_bar = smem_u32(bars + 2 * TC_STAGES);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + TC_STAGES), accum_bar = smem_u32(bars + 2 * TC_STAGES),
+                   res_bar = smem_u32(bars + 2 * TC_STAGES + 1);
     const uint32_t smem_base = smem_u32(smem);
 
     {
-        const int* src = reinterpret_cast<const int*>(tiles + blockIdx.y);
+        const int* src = reinterpret_cast<const int*>(tiles + blockIdx.x);
         int* dst = reinterpret_cast<int*>(&t);
         for (int i = tid; i < (int)(sizeof(Tile) / 4); i += TC_THREADS) dst[i] = src[i];
     }
     if (tid == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
         mbar_init(accum_bar, 1);
+        mbar_init(res_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), TC_TMEM_COLS);
@@ -244,8 +330,8 @@ k_tc_rowgemm(const __grid_constant__ TcMaps maps, const Tile* __restrict__ tiles
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
 
-    const int row0 = blockIdx.x * TILE_M;
-    const int n_steps = t.n_chunks * 2;   // two 64-wide K blocks per 128-wide chunk
+    const int row0 = blockIdx.y * TILE_M;
+    const int n_steps = t.n_chunks * (H / TC_KB);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -253,17 +339,17 @@ k_tc_rowgemm(const __grid_constant__ TcMaps maps, const Tile* __restrict__ tiles
             for (int i = 0; i < n_steps; ++i) {
                 const int s = i % TC_STAGES;
                 mbar_wait(empty0 + 8 * s, ((i / TC_STAGES) & 1) ^ 1);
-                const Chunk& ch = t.chunks[i >> 1];
-                const int kcol = (i & 1) * 64;
-                const int arow = (int)((int64_t)ch.a_slot * Bp + row0);
+                const Chunk& ch = t.chunks[i / (H / TC_KB)];
+                const int kcol = (i % (H / TC_KB)) * TC_KB;
+                const int arow = (int)((int64_t)ch.a_slot * Bp) + row0;
                 const uint32_t st = smem_base + s * TC_STAGE_BYTES;
                 const uint32_t fb = full0 + 8 * s;
                 mbar_expect_tx(fb, tx_bytes);
-                tma_load_2d(st, &maps.a_hi, fb, kcol, arow);
-                tma_load_2d(st + 2 * TC_TILE_BYTES, &maps.w_hi, fb, kcol, ch.w16_row);
+                tma_load_2d(st, &maps.k, fb, kcol, br.hi[ch.a_buf] + arow);
+                tma_load_2d(st + 2 * TC_TILE_BYTES, &maps.k, fb, kcol, br.w_hi + ch.w16_row);
                 if (split) {
-                    tma_load_2d(st + TC_TILE_BYTES, &maps.a_lo, fb, kcol, arow);
-                    tma_load_2d(st + 3 * TC_TILE_BYTES, &maps.w_lo, fb, kcol, ch.w16_row);
+                    tma_load_2d(st + TC_TILE_BYTES, &maps.k, fb, kcol, br.lo[ch.a_buf] + arow);
+                    tma_load_2d(st + 3 * TC_TILE_BYTES, &maps.k, fb, kcol, br.w_lo + ch.w16_row);
                 }
             }
         }
@@ -274,10 +360,10 @@ k_tc_rowgemm(const __grid_constant__ TcMaps maps, const Tile* __restrict__ tiles
                 mbar_wait(full0 + 8 * s, (i / TC_STAGES) & 1);
                 tc_fence_after();
                 const uint32_t st = smem_base + s * TC_STAGE_BYTES;
-                const uint64_t a_hi = smem_desc_sw128(st), a_lo = smem_desc_sw128(st + TC_TILE_BYTES);
-                const uint64_t w_hi = smem_desc_sw128(st + 2 * TC_TILE_BYTES), w_lo = smem_desc_sw128(st + 3 * TC_TILE_BYTES);
+                const uint64_t a_hi = smem_desc_sw64(st), a_lo = smem_desc_sw64(st + TC_TILE_BYTES);
+                const uint64_t w_hi = smem_desc_sw64(st + 2 * TC_TILE_BYTES), w_lo = smem_desc_sw64(st + 3 * TC_TILE_BYTES);
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
+                for (int ks = 0; ks < TC_KB / 16; ++ks) {
                     const uint64_t adv = (uint64_t)(ks * 2);      // +32 bytes (16 fp16) along K inside the swizzle atom
                     umma_f16(tmem_base, a_hi + adv, w_hi + adv, TC_IDESC, (i | ks) ? 1u : 0u);             // D0 += hi * hi
                     if (split) {
@@ -287,14 +373,13 @@ k_tc_rowgemm(const __grid_constant__ TcMaps maps, const Tile* __restrict__ tiles
                 }
                 umma_commit(empty0 + 8 * s);          // frees the stage once these MMAs have read it
             }
-            umma_commit(accum_bar);                   // accumulator complete
+            umma_commit(accum_bar);                   // accumulator complete, every stage drained
         }
         __syncwarp();
     } else {
-        // ---------------- epilogue: one thread per graph row ----------------
-        mbar_wait(accum_bar, 0);
-        tc_fence_after();
-        tc_epilogue_rows(t, bt, bh, tmem_base, row0, B, Bp, split, warp, lane);
+        EpiSmem es;
+        es.stg = smem_base; es.stg2 = smem_base + 65536u; es.res_bar = res_bar; es.accum_bar = accum_bar;
+        tc_epilogue(t, bt, br, &maps.o, tmem_base, row0, B, Bp, split, warp & 3, lane, tid == 64, es);
     }
     tc_fence_before();
     __syncthreads();
@@ -316,10 +401,6 @@ k_tc_rowgemm(const __grid_constant__ TcMaps maps, const Tile* __restrict__ tiles
 //  D3 [288,304) colsum lo (x 2^11).  One CTA = one task (<= 4 pairs) x one row split; fp32 partials go to part_w /
 //  part_b and are summed in double by k_reduce_partials (deterministic, no atomics).
 constexpr int BUF_DC1_ID = 11;     // plan.cuh BUF_DC1: dpre of the encoder lives there after the layer-0 dX launch
-struct BufRows {                 // first 256-byte row of each fp16 image, relative to the workspace base
-    int hi[MAX_BUFS];
-    int lo[MAX_BUFS];
-};
 
 constexpr int DW_STAGES = 3;
 constexpr int DW_KB = 64;                              // graph rows (MMA K) per pipeline stage
@@ -485,21 +566,26 @@ k_tc_reducegemm(const __grid_constant__ CUtensorMap map, const RTask* __restrict
 // encoder on tcgen05:  h0[slot] = relu((x[slot] * sign[slot]) W_enc[type]^T + b)          (hgnn_k4.py:L159-160, L198-237)
 // ------------------------------------------------------------------------------------------
 //  The caller's fp32 (or fp64) feature rows are the only HBM stream of the whole model.  Eight loader warps read them
-//  with 128-bit coalesced loads, fold the +-1 symmetry signs in, split every value into the (hi, lo) fp16 pair and write
-//  it straight into the 128B-swizzled K-major UMMA operand layout in shared memory; the weight tiles come by TMA from
-//  the padded fp16 weight image [n_types*128][enc_kmax].  Two loader groups alternate K blocks so that two blocks of
-//  loads are in flight per SM.  warp roles: 0 = TMA (weights), 1 = MMA issuer, 2..9 = loaders, 2..5 = epilogue.
+//  with 128-bit coalesced loads (all loads of a K block are issued before the first one is consumed, and the next block
+//  of the group is already in flight while the current one is converted), fold the +-1 symmetry signs in, split every
+//  value into the (hi, lo) fp16 pair and write it straight into the 128B-swizzled K-major UMMA operand layout in shared
+//  memory; the weight tiles come by TMA from the padded fp16 weight image [n_types*128][enc_kmax].  Two loader groups
+//  alternate K blocks.  warp roles: 0 = TMA (weights), 1 = MMA issuer, 2..9 = loaders, 2..5 = epilogue.
 constexpr int ENC_THREADS = 320;
 constexpr int ENC_LOADER_WARPS = 4;               // per group
+constexpr int ENC_STAGES = 3;
+constexpr int ENC_TILE_BYTES = 128 * 128;         // 128 rows x 64 fp16 (one 128B-swizzled K block)
+constexpr int ENC_STAGE_BYTES = 4 * ENC_TILE_BYTES;   // A_hi, A_lo, W_hi, W_lo = 64 KB
+constexpr int ENC_SMEM_BYTES = ENC_STAGES * ENC_STAGE_BYTES + 1024 + 256;
 
 struct alignas(64) EncMaps {
-    CUtensorMap w_hi, w_lo;
+    CUtensorMap w_hi, w_lo;      // encoder weight images, box 64 x 128, SWIZZLE_128B
+    CUtensorMap o;               // workspace images, box 64 x 128, SWIZZLE_128B (epilogue stores)
 };
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // 4 consecutive values of one row -> 8 bytes in the hi tile and 8 bytes in the lo tile
 __device__ __forceinline__ void split_to_smem(uint32_t hi_addr, uint32_t lo_addr, const float4 v) {
@@ -511,47 +597,95 @@ __device__ __forceinline__ void split_to_smem(uint32_t hi_addr, uint32_t lo_addr
     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(lo_addr), "r"(*reinterpret_cast<const uint32_t*>(&c)), "r"(*reinterpret_cast<const uint32_t*>(&d)) : "memory");
 }
 
-// 4 consecutive feature values x[row][k .. k+3] (zero outside [0, K) / beyond the batch), times their signs
-__device__ __forceinline__ float4 load_x4(const void* xb, const int x_f64, const int64_t idx, const int k, const int K, const bool row_ok,
-                                          const float4 sg) {
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (row_ok && k < K) {
-        if (!x_f64) {
-            const float* pf = (const float*)xb + idx;
-            if (k + 3 < K && ((reinterpret_cast<uintptr_t>(pf) & 15) == 0)) {
-                v = __ldg(reinterpret_cast<const float4*>(pf));
-            } else {
-                v.x = __ldg(pf);
-                if (k + 1 < K) v.y = __ldg(pf + 1);
-                if (k + 2 < K) v.z = __ldg(pf + 2);
-                if (k + 3 < K) v.w = __ldg(pf + 3);
-            }
-        } else {
-            const double* pd = (const double*)xb + idx;
-            v.x = (float)__ldg(pd);
-            if (k + 1 < K) v.y = (float)__ldg(pd + 1);
-            if (k + 2 < K) v.z = (float)__ldg(pd + 2);
-            if (k + 3 < K) v.w = (float)__ldg(pd + 3);
-        }
-        v.x *= sg.x; v.y *= sg.y; v.z *= sg.z; v.w *= sg.w;
-    }
-    return v;
+// How the rows of one node of one type are addressed inside the caller's x tensor [B * nodes, K] (row-major).
+struct XRows {
+    const void* base;
+    int64_t lda;          // elements between the same node of consecutive graphs
+    int a_off;            // element offset of the node inside a graph's block
+    int K;
+    int f64;
+    int vec;              // widest aligned vector: fp32 4 / 2 / 1 elements, fp64 2 / 1 elements
+};
+__device__ __forceinline__ XRows make_xrows(const void* base, int f64, int64_t lda, int a_off, int K) {
+    XRows x;
+    x.base = base; x.lda = lda; x.a_off = a_off; x.K = K; x.f64 = f64;
+    const uintptr_t p = reinterpret_cast<uintptr_t>(base);
+    const bool even = ((lda | a_off | K) & 1) == 0, quad = ((lda | a_off | K) & 3) == 0;
+    if (f64) x.vec = (even && (p & 15) == 0) ? 2 : 1;
+    else x.vec = (quad && (p & 15) == 0) ? 4 : ((even && (p & 7) == 0) ? 2 : 1);
+    return x;
 }
 
-__device__ __forceinline__ float4 load_sign4(const float* signs, const int sign_off, const int k, const int K) {
-    float4 sg = make_float4(1.f, 1.f, 1.f, 1.f);
-    if (sign_off >= 0 && k < K) {
-        const float* sp = signs + sign_off + k;
-        sg.x = __ldg(sp);
-        if (k + 1 < K) sg.y = __ldg(sp + 1);
-        if (k + 2 < K) sg.z = __ldg(sp + 2);
-        if (k + 3 < K) sg.w = __ldg(sp + 3);
+// v[it] = x[row_first + 8*it][k .. k+3] * sign, zero outside [0, K) and for rows >= row_limit.  Every load is issued
+// unconditionally on a clamped (always valid) address before any value is consumed, so all N loads are in flight together.
+template <int N>
+__device__ __forceinline__ void load_x_block(float4 (&v)[N], const XRows& x, const float* __restrict__ signs, const int sign_off,
+                                             const int64_t row_first, const int64_t row_limit, const int64_t row_last, const int k) {
+    const int K = x.K;
+    const bool kin = k < K;
+    const int kc = kin ? k : 0;
+    const int c1 = min(kc + 1, K - 1), c2 = min(kc + 2, K - 1), c3 = min(kc + 3, K - 1);
+    if (!x.f64) {
+        const float* b = (const float*)x.base + x.a_off;
+        if (x.vec == 4) {
+#pragma unroll
+            for (int it = 0; it < N; ++it) {
+                const int64_t r = min(row_first + it * 8, row_last);
+                v[it] = __ldg(reinterpret_cast<const float4*>(b + r * x.lda + kc));
+            }
+        } else if (x.vec == 2) {
+            const int kd = min(kc + 2, K - 2);
+#pragma unroll
+            for (int it = 0; it < N; ++it) {
+                const int64_t r = min(row_first + it * 8, row_last);
+                const float2 p = __ldg(reinterpret_cast<const float2*>(b + r * x.lda + kc));
+                const float2 q = __ldg(reinterpret_cast<const float2*>(b + r * x.lda + kd));
+                v[it] = make_float4(p.x, p.y, q.x, q.y);
+            }
+        } else {
+#pragma unroll
+            for (int it = 0; it < N; ++it) {
+                const float* pr = b + min(row_first + it * 8, row_last) * x.lda;
+                v[it] = make_float4(__ldg(pr + kc), __ldg(pr + c1), __ldg(pr + c2), __ldg(pr + c3));
+            }
+        }
+    } else {
+        const double* b = (const double*)x.base + x.a_off;
+        if (x.vec == 2) {
+            const int kd = min(kc + 2, K - 2);
+#pragma unroll
+            for (int it = 0; it < N; ++it) {
+                const int64_t r = min(row_first + it * 8, row_last);
+                const double2 p = __ldg(reinterpret_cast<const double2*>(b + r * x.lda + kc));
+                const double2 q = __ldg(reinterpret_cast<const double2*>(b + r * x.lda + kd));
+                v[it] = make_float4((float)p.x, (float)p.y, (float)q.x, (float)q.y);
+            }
+        } else {
+#pragma unroll
+            for (int it = 0; it < N; ++it) {
+                const double* pr = b + min(row_first + it * 8, row_last) * x.lda;
+                v[it] = make_float4((float)__ldg(pr + kc), (float)__ldg(pr + c1), (float)__ldg(pr + c2), (float)__ldg(pr + c3));
+            }
+        }
     }
-    return sg;
+    float4 sg = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (sign_off >= 0) {
+        const float* sp = signs + sign_off;
+        sg = make_float4(__ldg(sp + kc), __ldg(sp + c1), __ldg(sp + c2), __ldg(sp + c3));
+    }
+    const bool e0 = kin, e1 = k + 1 < K, e2 = k + 2 < K, e3 = k + 3 < K;
+#pragma unroll
+    for (int it = 0; it < N; ++it) {
+        const bool rok = row_first + it * 8 < row_limit;
+        v[it].x = (rok && e0) ? v[it].x * sg.x : 0.f;
+        v[it].y = (rok && e1) ? v[it].y * sg.y : 0.f;
+        v[it].z = (rok && e2) ? v[it].z * sg.z : 0.f;
+        v[it].w = (rok && e3) ? v[it].w * sg.w : 0.f;
+    }
 }
 
 __global__ void __launch_bounds__(ENC_THREADS, 1)
-k_tc_encoder(const __grid_constant__ EncMaps maps, const Tile* __restrict__ tiles, const BufTable bt, const BufTable16 bh,
+k_tc_encoder(const __grid_constant__ EncMaps maps, const Tile* __restrict__ tiles, const BufTable bt, const BufRows br,
              const int64_t B, const int64_t Bp, const int x_f64, const int split) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ Tile t;
@@ -560,8 +694,9 @@ k_tc_encoder(const __grid_constant__ EncMaps maps, const Tile* __restrict__ tile
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
-    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + TC_STAGES), accum_bar = smem_u32(bars + 2 * TC_STAGES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ENC_STAGES * ENC_STAGE_BYTES);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + ENC_STAGES), accum_bar = smem_u32(bars + 2 * ENC_STAGES),
+                   res_bar = smem_u32(bars + 2 * ENC_STAGES + 1);
     const uint32_t smem_base = smem_u32(smem);
     {
         const int* src = reinterpret_cast<const int*>(tiles + blockIdx.y);
@@ -569,8 +704,9 @@ k_tc_encoder(const __grid_constant__ EncMaps maps, const Tile* __restrict__ tile
         for (int i = tid; i < (int)(sizeof(Tile) / 4); i += ENC_THREADS) dst[i] = src[i];
     }
     if (tid == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full0 + 8 * s, 1 + ENC_LOADER_WARPS); mbar_init(empty0 + 8 * s, 1); }
+        for (int s = 0; s < ENC_STAGES; ++s) { mbar_init(full0 + 8 * s, 1 + ENC_LOADER_WARPS); mbar_init(empty0 + 8 * s, 1); }
         mbar_init(accum_bar, 1);
+        mbar_init(res_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), TC_TMEM_COLS);
@@ -585,27 +721,27 @@ k_tc_encoder(const __grid_constant__ EncMaps maps, const Tile* __restrict__ tile
 
     if (warp == 0) {
         if (lane == 0) {
-            const uint32_t tx_bytes = split ? 2 * TC_TILE_BYTES : TC_TILE_BYTES;
+            const uint32_t tx_bytes = split ? 2 * ENC_TILE_BYTES : ENC_TILE_BYTES;
             const int wrow = t.chunks[0].w16_row;
             for (int i = 0; i < n_kb; ++i) {
-                const int s = i % TC_STAGES;
-                mbar_wait(empty0 + 8 * s, ((i / TC_STAGES) & 1) ^ 1);
-                const uint32_t st = smem_base + s * TC_STAGE_BYTES;
+                const int s = i % ENC_STAGES;
+                mbar_wait(empty0 + 8 * s, ((i / ENC_STAGES) & 1) ^ 1);
+                const uint32_t st = smem_base + s * ENC_STAGE_BYTES;
                 const uint32_t fb = full0 + 8 * s;
                 mbar_expect_tx(fb, tx_bytes);
-                tma_load_2d(st + 2 * TC_TILE_BYTES, &maps.w_hi, fb, i * 64, wrow);
-                if (split) tma_load_2d(st + 3 * TC_TILE_BYTES, &maps.w_lo, fb, i * 64, wrow);
+                tma_load_2d(st + 2 * ENC_TILE_BYTES, &maps.w_hi, fb, i * 64, wrow);
+                if (split) tma_load_2d(st + 3 * ENC_TILE_BYTES, &maps.w_lo, fb, i * 64, wrow);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             for (int i = 0; i < n_kb; ++i) {
-                const int s = i % TC_STAGES;
-                mbar_wait(full0 + 8 * s, (i / TC_STAGES) & 1);
+                const int s = i % ENC_STAGES;
+                mbar_wait(full0 + 8 * s, (i / ENC_STAGES) & 1);
                 tc_fence_after();
-                const uint32_t st = smem_base + s * TC_STAGE_BYTES;
-                const uint64_t a_hi = smem_desc_sw128(st), a_lo = smem_desc_sw128(st + TC_TILE_BYTES);
-                const uint64_t w_hi = smem_desc_sw128(st + 2 * TC_TILE_BYTES), w_lo = smem_desc_sw128(st + 3 * TC_TILE_BYTES);
+                const uint32_t st = smem_base + s * ENC_STAGE_BYTES;
+                const uint64_t a_hi = smem_desc_sw128(st), a_lo = smem_desc_sw128(st + ENC_TILE_BYTES);
+                const uint64_t w_hi = smem_desc_sw128(st + 2 * ENC_TILE_BYTES), w_lo = smem_desc_sw128(st + 3 * ENC_TILE_BYTES);
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
                     const uint64_t adv = (uint64_t)(ks * 2);
@@ -625,37 +761,39 @@ k_tc_encoder(const __grid_constant__ EncMaps maps, const Tile* __restrict__ tile
         const int g = (warp - 2) / ENC_LOADER_WARPS;
         const int gt = tid - 64 - g * (ENC_LOADER_WARPS * 32);
         const Chunk& ch = t.chunks[0];
-        const void* xb = bt.p[ch.a_buf];
+        const XRows xr = make_xrows(bt.p[ch.a_buf], x_f64, ch.lda, ch.a_off, K);
         const float* signs = (const float*)bt.p[2];
         const int kq = gt & 15;                                   // which 4-column group of the 64-column block
         const int rsub = gt >> 4;                                 // 0..7
-        for (int kb = g; kb < n_kb; kb += 2) {
-            const int s = kb % TC_STAGES;
-            const int k = kb * 64 + kq * 4;
-            const float4 sg = load_sign4(signs, ch.sign_off, k, K);
-            float4 v[16];
-#pragma unroll
-            for (int it = 0; it < 16; ++it) {
-                const int64_t row = row0 + it * 8 + rsub;
-                v[it] = load_x4(xb, x_f64, row * (int64_t)ch.lda + ch.a_off + k, k, K, row < B, sg);
-            }
-            mbar_wait(empty0 + 8 * s, ((kb / TC_STAGES) & 1) ^ 1);
-            const uint32_t st = smem_base + s * TC_STAGE_BYTES;
+        const int64_t row_first = (int64_t)row0 + rsub;
+        float4 cur[16], nxt[16];
+        int kb = g;
+        if (kb < n_kb) load_x_block<16>(cur, xr, signs, ch.sign_off, row_first, B, B - 1, kb * 64 + kq * 4);
+        for (; kb < n_kb; kb += 2) {
+            const bool more = kb + 2 < n_kb;
+            if (more) load_x_block<16>(nxt, xr, signs, ch.sign_off, row_first, B, B - 1, (kb + 2) * 64 + kq * 4);
+            const int s = kb % ENC_STAGES;
+            mbar_wait(empty0 + 8 * s, ((kb / ENC_STAGES) & 1) ^ 1);
+            const uint32_t st = smem_base + s * ENC_STAGE_BYTES;
 #pragma unroll
             for (int it = 0; it < 16; ++it) {
                 const int r = it * 8 + rsub;
                 const uint32_t off = (uint32_t)(r * 128 + ((((kq >> 1) ^ (r & 7))) << 4) + ((kq & 1) << 3));
-                split_to_smem(st + off, st + TC_TILE_BYTES + off, v[it]);
+                split_to_smem(st + off, st + ENC_TILE_BYTES + off, cur[it]);
             }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(full0 + 8 * s);
+            if (more) {
+#pragma unroll
+                for (int it = 0; it < 16; ++it) cur[it] = nxt[it];
+            }
         }
         if (warp < 6) {
             // ---------------- epilogue (warps 2..5 = TMEM lane quarters 2, 3, 0, 1) ----------------
-            mbar_wait(accum_bar, 0);
-            tc_fence_after();
-            tc_epilogue_rows(t, bt, bh, tmem_base, row0, B, Bp, split, warp, lane);
+            EpiSmem es;
+            es.stg = smem_base; es.stg2 = smem_base + 65536u; es.res_bar = res_bar; es.accum_bar = accum_bar;
+            tc_epilogue(t, bt, br, &maps.o, tmem_base, row0, B, Bp, split, warp & 3, lane, tid == 64, es);
         }
     }
     tc_fence_before();
@@ -770,33 +908,29 @@ k_tc_encoder_dw(const __grid_constant__ CUtensorMap map, const EncDwUnit* __rest
         // ---------------- loaders: group g takes the steps i = g (mod 2) ----------------
         const int g = (warp - 2) / ENC_LOADER_WARPS;
         const int gt = tid - 64 - g * (ENC_LOADER_WARPS * 32);
-        const void* xb = bt.p[u.x_buf];
         const float* signs = (const float*)bt.p[2];
         const int kq = gt & 15, rsub = gt >> 4;
-        const int K = u.K;
         for (int i = g; i < n_steps; i += 2) {
             const int s = i % EDW_STAGES;
             const int j = i / n_rb;
-            const int64_t r0 = r_begin + (int64_t)(i % n_rb) * DW_KB;
+            const XRows xr = make_xrows(bt.p[u.x_buf], x_f64, u.lda, u.a_off[j], u.K);
+            const int64_t r0 = r_begin + (int64_t)(i % n_rb) * DW_KB + rsub;
             const uint32_t st = smem_base + s * EDW_STAGE_BYTES + 2 * EDW_DC_BYTES;
-            bool waited = false;
-            for (int jb = 0; jb < nkb; ++jb) {
-                const int k = u.k0 + jb * 64 + kq * 4;
-                const float4 sg = load_sign4(signs, u.sign_off[j], k, K);
-                float4 v[8];
+            float4 v[3][8];
 #pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    const int64_t row = r0 + it * 8 + rsub;
-                    v[it] = load_x4(xb, x_f64, row * (int64_t)u.lda + u.a_off[j] + k, k, K, row < r_end, sg);
-                }
-                if (!waited) { mbar_wait(empty0 + 8 * s, ((i / EDW_STAGES) & 1) ^ 1); waited = true; }
+            for (int jb = 0; jb < 3; ++jb)
+                if (jb < nkb) load_x_block<8>(v[jb], xr, signs, u.sign_off[j], r0, r_end, B - 1, u.k0 + jb * 64 + kq * 4);
+            mbar_wait(empty0 + 8 * s, ((i / EDW_STAGES) & 1) ^ 1);
 #pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    const int r = it * 8 + rsub;
-                    const uint32_t off = (uint32_t)(jb * 8192 + r * 128 + ((((kq >> 1) ^ (r & 7))) << 4) + ((kq & 1) << 3));
-                    split_to_smem(st + off, st + EDW_X_BYTES + off, v[it]);
+            for (int jb = 0; jb < 3; ++jb)
+                if (jb < nkb) {
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int r = it * 8 + rsub;
+                        const uint32_t off = (uint32_t)(jb * 8192 + r * 128 + ((((kq >> 1) ^ (r & 7))) << 4) + ((kq & 1) << 3));
+                        split_to_smem(st + off, st + EDW_X_BYTES + off, v[jb][it]);
+                    }
                 }
-            }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(full0 + 8 * s);

@@ -459,19 +459,24 @@ WsLayout ws_layout(const Plan& p, int64_t B, int train, int mode) {
     for (int l = 0; l <= MAX_LAYERS; ++l) w.h[l] = -1;
     for (int l = 0; l < MAX_LAYERS; ++l) { w.ct[l] = -1; w.mask[l] = -1; }
     w.dh[0] = w.dh[1] = w.dc[0] = w.dc[1] = w.du = w.part_w = w.part_b = w.dec_part = -1;
+    // fp32 slabs exist in MODE_FP32 only: the tensor-core modes keep every activation / gradient as (hi, lo) fp16 images
     if (train) {
-        for (int l = 0; l <= p.L; ++l) w.h[l] = take(slab);
-        if (p.morph_sym)
-            for (int l = 0; l < p.L; ++l) w.ct[l] = take(ctb);
+        if (!tc) {
+            for (int l = 0; l <= p.L; ++l) w.h[l] = take(slab);
+            if (p.morph_sym)
+                for (int l = 0; l < p.L; ++l) w.ct[l] = take(ctb);
+        }
         for (int l = 0; l < p.L; ++l) w.mask[l] = take((int64_t)(p.S + p.nm) * w.Bp * 16);
         w.maske = take((int64_t)p.S * w.Bp * 16);
-        w.dh[0] = take(slab); w.dh[1] = take(slab); w.dc[0] = take(slab); w.dc[1] = take(slab);
-        if (p.morph_sym) w.du = take((int64_t)p.nm * w.Bp * H * 4);
+        if (!tc) {
+            w.dh[0] = take(slab); w.dh[1] = take(slab); w.dc[0] = take(slab); w.dc[1] = take(slab);
+            if (p.morph_sym) w.du = take((int64_t)p.nm * w.Bp * H * 4);
+        }
         const int ns_max = w.n_splits > w.n_splits_tc ? w.n_splits : w.n_splits_tc;
         w.part_w = take((int64_t)p.rtasks.size() * ns_max * H * H * 4);
         w.part_b = take((int64_t)p.rtasks.size() * ns_max * H * 4);
         w.dec_part = take((int64_t)DEC_BLOCKS * (DEC_MAXC * H + DEC_MAXC) * 4);
-    } else {
+    } else if (!tc) {
         const int64_t a = take(slab), b = take(slab);
         for (int l = 0; l <= p.L; ++l) w.h[l] = (l & 1) ? b : a;
         if (p.morph_sym) { const int64_t c = take(ctb); for (int l = 0; l < p.L; ++l) w.ct[l] = c; }
