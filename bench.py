@@ -313,7 +313,8 @@ def main():
         roofline = {"kernel": dom["kernel"], "bound": "tensor", "achieved": dom["achieved_tflops"], "peak": pk["tflops"],
                     "unit": "TFLOP/s", "frac": dom["frac_tensor_peak"], "traffic": None, "peak_source": pk["src"] + " (bf16 dense, sustained)",
                     "launches_per_step": dom["launches_per_step"], "ms_per_launch": dom["ms_per_step"] / max(dom["launches_per_step"], 1),
-                    "note": "fp32 SIMT FMA kernel measured against the dense bf16 tensor peak; algorithmic FLOPs per SURVEY 8d"}
+                    "note": "algorithmic FLOPs per SURVEY 8d (one MAC per product; the fp32-class mode issues 3 fp16 MMAs per product, "
+                            "so tensor-pipe occupancy is ~3x this fraction)"}
 
     # ---------------- CPU baseline (oracle on host cores), bounded sample ----------------
     cpu = None
@@ -332,7 +333,7 @@ def main():
         "ms_per_step": train_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "tc": "f16x2-split (f32 accumulate)", "tc1x": "f16 (f32 accumulate)"}[args.mode],
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world, "hidden": 128, "layers": 8,
-                   "parallelism": f"dp{world}", "mode": {"fp32": "fp32 SIMT FMA", "tc": "tcgen05 split-fp16 x3 (fp32-class accuracy) + SIMT dW/encoder", "tc1x": "tcgen05 fp16 x1"}[args.mode], "l2": "inputs (708 MB/step/GPU) exceed the 126 MB L2; no flush needed"},
+                   "parallelism": f"dp{world}", "mode": {"fp32": "fp32 SIMT FMA", "tc": "tcgen05 split-fp16 x3 (fp32-class accuracy): encoder, layers, dX, dW all on tensor cores", "tc1x": "tcgen05 fp16 x1"}[args.mode], "l2": "inputs (708 MB/step/GPU) exceed the 126 MB L2; no flush needed"},
         "inference": {"value": total_graphs / (infer_ms * 1e-3), "unit": "graphs/s", "ms_per_step": infer_ms / K},
         "e2e": None if e2e_ms is None else {"value": total_graphs / (e2e_ms * 1e-3), "unit": "graphs/s", "ms_per_step": e2e_ms / K,
                                             "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,

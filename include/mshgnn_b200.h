@@ -155,6 +155,14 @@ int mshgnn_profile_read(double* ms_out, int64_t* launches_out, int32_t n);
 const char* mshgnn_kernel_kind_name(int32_t kind);
 
 /* number of kernels launched by this library since process start (for gpu_launches accounting) */
+/* Introspection for the parity tests: where a training-mode forward left the ReLU sign pattern it took.
+ * layer = -1: encoder output; layer = l (0..L-1): slots [0, S) = ReLU of the HeteroConv output of node slot s
+ * (hgnn_k4.py:L175-186), slots [S, S + n_mlp) = hidden ReLU of base_transform (hgnn_k4.py:L133-137) of MLP-type node n.
+ * Layout at workspace + *byte_off: uint32 [n_slots][*rows_padded][4]; bit (c % 32) of word (c / 32) <=> pre-activation
+ * of hidden channel c > 0.  Slots whose value cannot reach the output are never written. */
+int mshgnn_relu_mask_offset(const mshgnn_plan* plan, int64_t B, int32_t mode, int32_t layer,
+                            int64_t* byte_off, int64_t* n_slots, int64_t* rows_padded);
+
 int64_t mshgnn_launch_count(void);
 const char* mshgnn_last_error(void);
 const char* mshgnn_version(void);

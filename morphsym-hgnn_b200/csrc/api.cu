@@ -618,6 +618,18 @@ const char* mshgnn_kernel_kind_name(int32_t kind) {
     return (kind >= 0 && kind < MSHGNN_NUM_KERNEL_KINDS) ? kKindNames[kind] : "";
 }
 
+int mshgnn_relu_mask_offset(const mshgnn_plan* plan, int64_t B, int32_t mode, int32_t layer, int64_t* byte_off, int64_t* n_slots,
+                            int64_t* rows_padded) {
+    if (!plan || !byte_off || !n_slots || !rows_padded || B < 1) return fail(MSHGNN_ERR_ARG, "bad argument");
+    const Plan& p = plan->p;
+    if (layer < -1 || layer >= p.L) return fail(MSHGNN_ERR_ARG, "layer out of range");
+    const WsLayout w = ws_layout(p, B, 1, mode);
+    *byte_off = layer < 0 ? w.maske : w.mask[layer];
+    *n_slots = layer < 0 ? p.S : p.S + p.nm;
+    *rows_padded = w.Bp;
+    return 0;
+}
+
 int64_t mshgnn_launch_count(void) { return g_launches.load(); }
 const char* mshgnn_last_error(void) { return g_err; }
 const char* mshgnn_version(void) { return "mshgnn_b200 0.1 (sm_100a)"; }

@@ -28,6 +28,7 @@ EXPORTS = (
     "mshgnn_workspace_bytes", "mshgnn_out_rows", "mshgnn_forward", "mshgnn_loss", "mshgnn_backward",
     "mshgnn_adam_step", "mshgnn_sgd_step", "mshgnn_plan_describe", "mshgnn_launch_count",
     "mshgnn_last_error", "mshgnn_version", "mshgnn_profile_enable", "mshgnn_profile_read", "mshgnn_kernel_kind_name",
+    "mshgnn_relu_mask_offset",
 )
 
 
@@ -94,6 +95,8 @@ def lib() -> C.CDLL:
     L.mshgnn_profile_enable.argtypes = [i32]; L.mshgnn_profile_enable.restype = C.c_int
     L.mshgnn_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(i64), i32]; L.mshgnn_profile_read.restype = C.c_int
     L.mshgnn_kernel_kind_name.argtypes = [i32]; L.mshgnn_kernel_kind_name.restype = C.c_char_p
+    L.mshgnn_relu_mask_offset.argtypes = [vp, i64, i32, i32, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
+    L.mshgnn_relu_mask_offset.restype = C.c_int
     _lib = L
     return L
 
@@ -185,6 +188,12 @@ class NativePlan:
 
     def out_rows(self, B: int) -> int:
         return int(lib().mshgnn_out_rows(self.handle, B))
+
+    def relu_mask_offset(self, B: int, mode: int, layer: int):
+        """(byte offset in the training workspace, slots, padded rows) of the stored ReLU sign pattern (layer -1 = encoder)."""
+        off, ns, bp = C.c_int64(), C.c_int64(), C.c_int64()
+        check(lib().mshgnn_relu_mask_offset(self.handle, B, mode, layer, C.byref(off), C.byref(ns), C.byref(bp)), "mshgnn_relu_mask_offset")
+        return off.value, ns.value, bp.value
 
     def describe(self) -> dict:
         import json

@@ -119,6 +119,8 @@ class ReluTap:
         self.record = record
         self.forced = forced or {}
         self.pre: List[torch.Tensor] = []
+        self.tags: List[tuple] = []      # ("enc", type) | ("conv", layer, type) | ("mlp", layer, type), one per recorded call
+        self.ctx = None                  # tag of the next call made from inside an nn.Module (base_transform's ReLU)
         self.counter = 0
 
     def __enter__(self):
@@ -135,7 +137,7 @@ class ReluTap:
 _TAP: Optional[ReluTap] = None
 
 
-def _relu(x: torch.Tensor) -> torch.Tensor:
+def _relu(x: torch.Tensor, tag=None) -> torch.Tensor:
     tap = _TAP
     if tap is None:
         return torch.relu(x)
@@ -145,6 +147,7 @@ def _relu(x: torch.Tensor) -> torch.Tensor:
         if x.requires_grad:
             x.retain_grad()
         tap.pre.append(x)
+        tap.tags.append(tag if tag is not None else tap.ctx)
     mask = x > 0
     if i in tap.forced:
         idx, val = tap.forced[i]
@@ -296,15 +299,17 @@ class _HGNNBase(nn.Module):
 
     def embed(self, x_dict, edge_index_dict):
         x_dict = self.input_signs(dict(x_dict))   # never mutate the caller's dict
-        h = {k: _relu(v) for k, v in self.encoder(x_dict).items()}
-        for conv in self.convs:
+        h = {k: _relu(v, ("enc", k)) for k, v in self.encoder(x_dict).items()}
+        for l, conv in enumerate(self.convs):
             c = conv(h, edge_index_dict)
             if self.morph_sym:
                 # hgnn_k4.py:L175-186: base -> shared MLP (no ReLU around it), others -> ReLU, then residual
-                n = {k: (self.base_transform(v) if k == "base" else _relu(v)) for k, v in c.items()}
+                if _TAP is not None:
+                    _TAP.ctx = ("mlp", l, "base")
+                n = {k: (self.base_transform(v) if k == "base" else _relu(v, ("conv", l, k))) for k, v in c.items()}
                 h = {k: (n[k] + h[k] if (k in h and h[k].shape == n[k].shape) else n[k]) for k in n}
             else:
-                h = {k: _relu(v) for k, v in c.items()}   # hgnn.py:L60-62
+                h = {k: _relu(v, ("conv", l, k)) for k, v in c.items()}   # hgnn.py:L60-62
         return h
 
     def forward(self, x_dict, edge_index_dict):

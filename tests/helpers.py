@@ -65,12 +65,8 @@ def oracle_fp32_floor(cfg, model, batch, ref_out, ref_grads):
 
 
 # ------------------------------------------------------------------------------------------------
-# ReLU-sign-aware gradient comparison
+# oracle backward under a forced ReLU sign pattern
 # ------------------------------------------------------------------------------------------------
-def _flat(grads, names):
-    return torch.cat([grads[n].detach().double().cpu().reshape(-1) for n in names])
-
-
 def oracle_grads_with_forced(cfg, model, batch, forced):
     x = {k: v.double() for k, v in batch.x_dict.items()}
     model.zero_grad()
@@ -81,80 +77,89 @@ def oracle_grads_with_forced(cfg, model, batch, forced):
     return {n: (p.grad.clone() if p.grad is not None else torch.zeros_like(p)) for n, p in model.named_parameters()}
 
 
-def relu_aware_gradient_check(cfg, model, batch, native_grads, fwd_rel_err, tol=TOL_FP32, max_candidates=400):
-    """Returns (ok, info).  The native gradient must equal, per tensor within ``tol`` (norm-wise), the oracle's
-    fp64 gradient for SOME ReLU sign pattern that differs from the oracle's own only at numerically ambiguous
-    pre-activations: |x| < 16 * fwd_rel_err * rms(x), i.e. inside the native path's measured forward error.
+# ------------------------------------------------------------------------------------------------
+# Gradient comparison under the ReLU sign pattern the native forward actually took
+# ------------------------------------------------------------------------------------------------
+def native_relu_pattern(model, B):
+    """{oracle tap tag: BoolTensor [B * nodes_of_type, 128]} read back from the native training workspace
+    (mshgnn_relu_mask_offset), plus the plan's liveness table.  Rows are re-ordered to the oracle's graph-major layout."""
+    from ms_hgnn import _native as N
+    eng = next(iter(model._engines.values()))
+    spec, plan = eng.spec, eng.plan
+    types, npg = spec["node_types"], spec["nodes_per_graph"]
+    base = [sum(npg[:i]) for i in range(len(types))]
+    S = sum(npg)
+    need = plan.describe()["need"]                       # need[l][slot], l = 0..L
+    torch.cuda.synchronize()
+    ws = eng._ws
+    shifts = torch.arange(32, device=ws.device, dtype=torch.int64)
 
-    Why: ReLU makes d(loss)/d(params) discontinuous in the forward numerics.  An implementation whose forward
-    pass is accurate to 1e-6 may legitimately put a pre-activation of +-1e-7 on the other side of zero, and that
-    moves whole gradient tensors by 1e-4..1e-2 (plain PyTorch fp32 does the same against fp64).  Single flips act
-    (to first order) additively, so the set of flipped elements is found by projecting the residual on each
-    candidate's gradient delta and then VERIFIED with one exact oracle backward under the chosen pattern."""
+    def read(layer):
+        off, ns, bp = plan.relu_mask_offset(B, eng.mode, layer)
+        words = ws[off:off + ns * bp * 16].view(torch.int32).view(ns, bp, 4)[:, :B].to(torch.int64) & 0xFFFFFFFF
+        return ((words.unsqueeze(-1) >> shifts) & 1).bool().reshape(ns, B, 128).cpu()          # [slot][graph][channel]
+
+    def rows_of(bits, first_slot, n):                    # -> [B * n, 128], row = graph * n + local node
+        return bits[first_slot:first_slot + n].permute(1, 0, 2).reshape(B * n, 128)
+
+    def live_of(l, first_slot, n):                       # [B * n] bool
+        return torch.tensor([bool(need[l][first_slot + j]) for j in range(n)]).repeat(B)
+
+    out = {}
+    enc = read(-1)
+    for t, name in enumerate(types):
+        out[("enc", name)] = (rows_of(enc, base[t], npg[t]), live_of(0, base[t], npg[t]))
+    mlp_t = spec["mlp_type"]
+    for l in range(spec["num_layers"]):
+        bits = read(l)
+        for t, name in enumerate(types):
+            if spec["morph_sym"] and t == mlp_t:
+                out[("mlp", l, name)] = (rows_of(bits, S, npg[t]), live_of(l + 1, base[t], npg[t]))
+            else:
+                out[("conv", l, name)] = (rows_of(bits, base[t], npg[t]), live_of(l + 1, base[t], npg[t]))
+    return out
+
+
+def gradient_check_under_native_pattern(cfg, model, batch, native_model, native_grads, fwd_rel_err, tol=TOL_FP32):
+    """Returns (ok, info).  ReLU makes d(loss)/d(params) discontinuous in the forward numerics: an implementation whose
+    forward is accurate to 1e-6 may put a pre-activation of +-1e-7 on the other side of zero, which moves whole gradient
+    tensors by 1e-4..1e-2 (plain PyTorch fp32 does the same against fp64).  So the native gradient is compared, strictly
+    (``tol`` per tensor, norm-wise), with the oracle's fp64 gradient under the sign pattern the native forward took, after
+    checking that this pattern differs from the oracle's own ONLY at numerically ambiguous pre-activations:
+    |x| < 16 * max(forward error, 1e-7) * rms(x)."""
     names = [n for n, _ in model.named_parameters()]
+    B = batch.batch_size
+    pattern = native_relu_pattern(native_model, B)
     x = {k: v.double() for k, v in batch.x_dict.items()}
-    model.zero_grad()
-    with O.ReluTap(record=True) as tap:
-        out = model(x, batch.edge_index_dict)
-        loss = oracle_loss(cfg, out, batch.y.double(), batch.batch_size)
-        loss.backward()
-    g0 = {n: (p.grad.clone() if p.grad is not None else torch.zeros_like(p)) for n, p in model.named_parameters()}
-
-    def worst(ga):
-        w = 0.0
-        for n in names:
-            nb = ga[n].norm().item()
-            if nb == 0.0:
-                if native_grads[n].abs().max().item() != 0.0:
-                    return float("inf")
-                continue
-            w = max(w, rel_err(native_grads[n], ga[n]))
-        return w
-
-    e0 = worst(g0)
-    if e0 <= tol:
-        return True, {"flips": 0, "err": e0}
-    # candidates: ambiguous pre-activations that carry gradient
-    cands = []
-    for i, pre in enumerate(tap.pre):
-        if pre.grad is None:
-            continue
+    with torch.no_grad(), O.ReluTap(record=True) as tap:
+        model(x, batch.edge_index_dict)
+    forced, flips, worst_ratio = {}, 0, 0.0
+    for i, (pre, tag) in enumerate(zip(tap.pre, tap.tags)):
+        if tag not in pattern:
+            return False, {"error": f"no native pattern for oracle ReLU {tag}"}
+        bits, live = pattern[tag]
         v = pre.detach()
-        thr = 16.0 * max(fwd_rel_err, 1e-7) * v.pow(2).mean().sqrt().item()
-        # the upstream gradient of relu(x) is what matters: grad wrt x is zero where the mask is off, so use |x| only
-        idx = torch.nonzero(v.abs().reshape(-1) < thr).reshape(-1)
-        for j in idx.tolist():
-            cands.append((i, j, bool(v.reshape(-1)[j] > 0)))
-    if not cands or len(cands) > max_candidates:
-        return False, {"flips": None, "err": e0, "candidates": len(cands)}
-    def merge(chosen):
-        forced = {}
-        for (i, j, cur) in chosen:
-            idx, val = forced.get(i, (torch.empty(0, dtype=torch.long), torch.empty(0, dtype=torch.bool)))
-            forced[i] = (torch.cat((idx, torch.tensor([j]))), torch.cat((val, torch.tensor([not cur]))))
-        return forced
-
-    # Greedy rounds: project the residual on every remaining candidate's gradient delta (taken around the pattern chosen
-    # so far, so interactions between flips on one path are seen in the next round), keep those that explain it,
-    # and VERIFY with an exact oracle backward under the chosen pattern.
-    chosen, g_cur, e_cur = [], g0, e0
-    for _ in range(4):
-        r = _flat(native_grads, names) - _flat(g_cur, names)
-        base = _flat(g_cur, names)
-        picked = []
-        for c in cands:
-            if c in chosen:
-                continue
-            gj = oracle_grads_with_forced(cfg, model, batch, merge(chosen + [c]))
-            d = _flat(gj, names) - base
-            dn = d.dot(d).item()
-            if dn > 0 and r.dot(d).item() / dn > 0.5:
-                picked.append(c)
-        if not picked:
-            break
-        chosen += picked
-        g_cur = oracle_grads_with_forced(cfg, model, batch, merge(chosen))
-        e_cur = worst(g_cur)
-        if e_cur <= tol:
-            break
-    return e_cur <= tol, {"flips": len(chosen), "err": e_cur, "err_default_pattern": e0, "candidates": len(cands)}
+        if tuple(bits.shape) != tuple(v.shape):
+            return False, {"error": f"shape mismatch at {tag}: {tuple(bits.shape)} vs {tuple(v.shape)}"}
+        diff = ((v > 0) != bits) & live[:, None]
+        if diff.any():
+            thr = 16.0 * max(fwd_rel_err, 1e-7) * v.pow(2).mean().sqrt().item()
+            ratio = (v.abs()[diff].max().item() / thr) if thr > 0 else float("inf")
+            worst_ratio = max(worst_ratio, ratio)
+            idx = torch.nonzero(diff.reshape(-1)).reshape(-1)
+            forced[i] = (idx, bits.reshape(-1)[idx])
+            flips += int(idx.numel())
+    if worst_ratio > 1.0:
+        return False, {"error": "native ReLU pattern differs from the oracle at a NON-ambiguous pre-activation",
+                       "worst |x| / threshold": worst_ratio, "flips": flips}
+    g = oracle_grads_with_forced(cfg, model, batch, forced)
+    worst, worst_name = 0.0, None
+    for n in names:
+        if g[n].norm().item() == 0.0:
+            if native_grads[n].abs().max().item() != 0.0:
+                return False, {"error": f"{n}: oracle gradient is exactly zero, native is not"}
+            continue
+        e = rel_err(native_grads[n], g[n])
+        if e > worst:
+            worst, worst_name = e, n
+    return worst <= tol, {"flips": flips, "err": worst, "tensor": worst_name, "worst |x| / threshold": worst_ratio}
