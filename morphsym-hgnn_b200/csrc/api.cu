@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -223,12 +224,27 @@ int launch_tc_encoder(const Plan& p, const Launch& L, const WsLayout& w, const B
     return 0;
 }
 
+int sm_count(int* out) {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        CUDA_TRY(cudaGetDevice(&dev));
+        CUDA_TRY(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    }
+    *out = n;
+    return 0;
+}
+
 int launch_tc_rowgemm(int kind, const Plan& p, const Launch& L, const BufTable& bt, const BufRows& br, const WsMaps& wm,
                       int64_t B, int64_t Bp, int split, cudaStream_t st) {
     if (L.count == 0) return 0;
     static bool attr_set = false;
+    static bool use_v2 = false;       // MSHGNN_ROWGEMM=tile selects the one-tile-per-CTA kernel (A/B measurements)
     if (!attr_set) {
         CUDA_TRY(cudaFuncSetAttribute(k_tc_rowgemm, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(k_tc_rowgemm_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, PK_SMEM_BYTES));
+        const char* e = getenv("MSHGNN_ROWGEMM");
+        use_v2 = e && !strcmp(e, "tile");
         attr_set = true;
     }
     for (int i = 0; i < L.count; ++i)
@@ -236,8 +252,17 @@ int launch_tc_rowgemm(int kind, const Plan& p, const Launch& L, const BufTable& 
             if (p.tiles[L.begin + i].chunks[c].a_kind != A_SLAB)
                 return fail(MSHGNN_ERR_ARG, "internal: a tensor-core row-GEMM launch must read slab buffers");
     ProfScope ps(kind, st);
-    dim3 grid((unsigned)L.count, (unsigned)(Bp / TILE_M));
-    k_tc_rowgemm<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(wm.tc, p.d_tiles + L.begin, bt, br, B, Bp, split);
+    if (use_v2 || L.count > PK_MAX_TILES) {
+        dim3 grid((unsigned)L.count, (unsigned)(Bp / TILE_M));
+        k_tc_rowgemm<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(wm.tc, p.d_tiles + L.begin, bt, br, B, Bp, split);
+    } else {
+        int n_sm = 0, rc;
+        if ((rc = sm_count(&n_sm))) return rc;
+        const int64_t n_items = (int64_t)L.count * (Bp / TILE_M);
+        if (n_items > 0x7fffffffLL) return fail(MSHGNN_ERR_ARG, "batch too large for one row-GEMM launch");
+        const unsigned grid = (unsigned)(n_items < n_sm ? n_items : n_sm);
+        k_tc_rowgemm_persistent<<<grid, PK_THREADS, PK_SMEM_BYTES, st>>>(wm.tc, p.d_tiles + L.begin, L.count, (int)n_items, bt, br, B, Bp, split);
+    }
     LAUNCH_CHECK();
     return 0;
 }

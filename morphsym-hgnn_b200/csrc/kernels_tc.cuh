@@ -48,6 +48,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n"
@@ -99,8 +102,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
           "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, 128B-swizzled shared-memory operand: 8-row groups 1024 B apart (SBO), descriptor version 1.
 __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
@@ -149,15 +152,15 @@ __device__ __forceinline__ void sts128(uint32_t addr, const uint4 v) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-// 8 consecutive values -> 16 bytes of the hi image and 16 bytes of the lo image
+// 8 consecutive values -> 16 bytes of the hi image and 16 bytes of the lo image (packed conversions)
 __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
     uint32_t h[4], l[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const float a = v[2 * j], b = v[2 * j + 1];
-        const __half ha = __float2half_rn(a), hb = __float2half_rn(b);
-        const __half2 hh = __halves2half2(ha, hb);
-        const __half2 ll = __halves2half2(__float2half_rn((a - __half2float(ha)) * TC_LO_SCALE), __float2half_rn((b - __half2float(hb)) * TC_LO_SCALE));
+        const __half2 hh = __floats2half2_rn(a, b);
+        const float2 g = __half22float2(hh);
+        const __half2 ll = __floats2half2_rn((a - g.x) * TC_LO_SCALE, (b - g.y) * TC_LO_SCALE);
         h[j] = *reinterpret_cast<const uint32_t*>(&hh);
         l[j] = *reinterpret_cast<const uint32_t*>(&ll);
     }
@@ -175,120 +178,183 @@ __device__ __forceinline__ void join8_add(float* v, const uint4 hi, const uint4 
     }
 }
 
-// Epilogue shared by the row-GEMM and the encoder.  The four epilogue warps own one TMEM lane quarter each (one thread
-// per graph row): accumulators (D0 + D1 * 2^-11) -> bias / ReLU / stored mask / residual -> (hi, lo) fp16 pairs written
-// into 128B-swizzled staging tiles in shared memory -> TMA stores.  The residual tile arrives the same way (TMA load into
-// the staging tiles, combined in place), so no thread ever touches a global activation row directly: every HBM/L2
-// transaction of the activation stream is a full-line bulk transfer.  Staging re-uses the (drained) operand pipeline.
+// Epilogue shared by the row-GEMM kernels and the encoder.  Epilogue warps own one TMEM lane quarter each (one thread per
+// graph row); a GROUP of four warps covers the 128 rows.  With two groups each takes one 64-column half of the tile, with
+// one group it walks both halves.  accumulators (D0 + D1 * 2^-11) -> bias / ReLU / stored mask / residual -> (hi, lo) fp16
+// pairs written into 128B-swizzled staging tiles in shared memory -> TMA stores.  The residual tile arrives the same way
+// (TMA load into the staging tiles, combined in place), so no thread ever touches a global activation row directly: every
+// HBM/L2 transaction of the activation stream is a full-line bulk transfer.  A masked second output (dc = dh (*) ReLU mask)
+// is produced by clearing the masked-off fp16 lanes of the staged tile in place after the first store has been read.
 struct EpiSmem {
-    uint32_t stg;        // 64 KB: [column half][hi | lo] tiles of 128 rows x 64 fp16 (16 KB each)  - primary output / residual
-    uint32_t stg2;       // 32 KB: [hi | lo] tiles of one column half                                  - masked second output
-    uint32_t res_bar;    // mbarrier: residual tiles landed
-    uint32_t accum_bar;  // mbarrier: accumulator complete, operand pipeline drained
+    uint32_t stg;        // 64 KB: [column half][hi | lo] tiles of 128 rows x 64 fp16 (16 KB each)
+    uint32_t bias;       // 512 B: bias of the current tile
+    uint32_t res_bar;    // mbarriers (one per group, 8 bytes apart): residual tiles landed
+    uint32_t accum_bar;  // mbarrier: accumulator complete (non-persistent kernels: operand pipeline drained, too)
+    uint32_t free_bar;   // persistent kernel: mbarrier every epilogue thread arrives on once the accumulator is drained (0: none)
+    uint32_t acc_parity, res_parity;
+    int persistent;      // staging is dedicated memory: the residual is fetched before the accumulator is waited for
+    int n_groups;        // 1 or 2
 };
+
+__device__ __forceinline__ void group_bar_sync(const int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory"); }
+
+// clears the fp16 lanes of a 16-byte chunk whose mask bit is off (bits of `m`, lowest = first lane)
+__device__ __forceinline__ uint4 mask8(const uint4 v, const uint32_t m) {
+    uint4 r;
+    r.x = v.x & (((m & 1u) ? 0xFFFFu : 0u) | ((m & 2u) ? 0xFFFF0000u : 0u));
+    r.y = v.y & (((m & 4u) ? 0xFFFFu : 0u) | ((m & 8u) ? 0xFFFF0000u : 0u));
+    r.z = v.z & (((m & 16u) ? 0xFFFFu : 0u) | ((m & 32u) ? 0xFFFF0000u : 0u));
+    r.w = v.w & (((m & 64u) ? 0xFFFFu : 0u) | ((m & 128u) ? 0xFFFF0000u : 0u));
+    return r;
+}
 
 __device__ __forceinline__ void tc_epilogue(const Tile& t, const BufTable& bt, const BufRows& br, const CUtensorMap* map_o,
                                             const uint32_t tmem_base, const int row0, const int64_t B, const int64_t Bp,
-                                            const int split, const int q /*TMEM lane quarter*/, const int lane, const bool leader,
-                                            const EpiSmem es) {
+                                            const int split, const int warp /*CTA warp index, epilogue warps start at 2*/,
+                                            const int lane, const EpiSmem es) {
+    const int q = warp & 3;                        // TMEM lane quarter this warp may access (hardware rule: warp index mod 4)
+    const int grp = es.n_groups == 2 ? ((warp - 2) >> 2) : 0;
+    const int h0 = es.n_groups == 2 ? grp : 0, h1 = es.n_groups == 2 ? grp + 1 : 2;    // column halves of this group
+    const bool leader = ((warp - 2) & 3) == 0 && lane == 0;                                // one per group
     const int rl = q * 32 + lane;                  // row inside the tile
     const int64_t row = (int64_t)row0 + rl;
     const bool live = row < B;
     const uint32_t rsw = (uint32_t)(rl & 7);
     const uint32_t rbase = (uint32_t)rl * 128u;
+    const uint32_t res_bar = es.res_bar + 8u * grp;
+    const bool has_out = t.out_buf >= 0, has_out2 = t.out2_buf >= 0, has_res = t.res_buf >= 0;
+    const bool want_mask = t.relu || t.mask_out_buf >= 0;
+
+    auto fetch_residual = [&]() {
+        const int r_hi = br.hi[t.res_buf] + (int)((int64_t)t.res_slot * Bp) + row0, r_lo = br.lo[t.res_buf] + (int)((int64_t)t.res_slot * Bp) + row0;
+        mbar_expect_tx(res_bar, (uint32_t)(h1 - h0) * 2u * 16384u);
+        for (int half = h0; half < h1; ++half) {
+            tma_load_2d(es.stg + half * 32768, map_o, res_bar, half * 64, r_hi);
+            tma_load_2d(es.stg + half * 32768 + 16384, map_o, res_bar, half * 64, r_lo);
+        }
+    };
+    if (es.persistent) {
+        // the staging tiles still feed the previous item's TMA stores: wait until those have been read, then (residual
+        // tiles) fetch early so that their latency hides behind the MMAs of this item
+        if (leader) {
+            tma_store_wait_read();
+            if (has_res) fetch_residual();
+        }
+    }
+    // bias of this group's columns -> shared memory (read back as broadcasts)
+    if (rl < 64 * (h1 - h0)) {
+        const int c = h0 * 64 + rl;
+        const float bv = t.bias_buf >= 0 ? __ldg((const float*)bt.p[t.bias_buf] + t.bias_off + c) : 0.f;
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(es.bias + 4u * c), "f"(bv) : "memory");
+    }
     uint4 pm = make_uint4(~0u, ~0u, ~0u, ~0u), m2 = make_uint4(~0u, ~0u, ~0u, ~0u);
     if (live && t.posmask_buf >= 0) pm = __ldg(reinterpret_cast<const uint4*>(bt.p[t.posmask_buf]) + (int64_t)t.posmask_slot * Bp + row);
-    if (live && t.out2_buf >= 0 && t.out2_mask_kind == MK_BITS)
+    if (live && has_out2 && t.out2_mask_kind == MK_BITS)
         m2 = __ldg(reinterpret_cast<const uint4*>(bt.p[t.out2_mask_buf]) + (int64_t)t.out2_mask_slot * Bp + row);
     const uint32_t pmw[4] = {pm.x, pm.y, pm.z, pm.w}, m2w[4] = {m2.x, m2.y, m2.z, m2.w};
     uint32_t mw[4] = {0u, 0u, 0u, 0u};
+    group_bar_sync(grp);
 
-    mbar_wait(es.accum_bar, 0);
+    mbar_wait(es.accum_bar, es.acc_parity);
     tc_fence_after();
-    if (t.res_buf >= 0) {
-        if (leader) {
-            const int r_hi = br.hi[t.res_buf] + (int)((int64_t)t.res_slot * Bp) + row0, r_lo = br.lo[t.res_buf] + (int)((int64_t)t.res_slot * Bp) + row0;
-            mbar_expect_tx(es.res_bar, 4 * 16384);
-            tma_load_2d(es.stg, map_o, es.res_bar, 0, r_hi);
-            tma_load_2d(es.stg + 16384, map_o, es.res_bar, 0, r_lo);
-            tma_load_2d(es.stg + 32768, map_o, es.res_bar, 64, r_hi);
-            tma_load_2d(es.stg + 49152, map_o, es.res_bar, 64, r_lo);
-        }
-        mbar_wait(es.res_bar, 0);
+    if (has_res) {
+        if (leader && !es.persistent) fetch_residual();
+        mbar_wait(res_bar, es.res_parity);
     }
 #pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
-        if (half == 1 && t.out2_buf >= 0) {      // the second-output staging tile is re-used: its first store must have been read
-            if (leader) tma_store_wait_read();
-            epi_bar_sync();
-        }
+    for (int half = h0; half < h1; ++half) {
 #pragma unroll 1
         for (int c2 = 0; c2 < 2; ++c2) {
             const int cc = half * 2 + c2;
             uint32_t raw[32], raw1[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + cc * 32, raw);
             if (split) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + 128 + cc * 32, raw1);
+            tmem_ld_wait();
+            if (cc == 2 * h1 - 1 && es.free_bar) {       // last read of this accumulator by this thread: hand it back
+                tc_fence_before();
+                mbar_arrive(es.free_bar);
+            }
             float v[32];
             unsigned mask = 0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                float x = __uint_as_float(raw[j]);
-                if (split) x = fmaf(__uint_as_float(raw1[j]), TC_LO_UNSCALE, x);
-                x *= TC_W_UNSCALE;
-                if (t.bias_buf >= 0) x += __ldg((const float*)bt.p[t.bias_buf] + t.bias_off + cc * 32 + j);
-                if (x > 0.f) mask |= 1u << j;
-                if (t.relu) x = fmaxf(x, 0.f);
-                v[j] = ((pmw[cc] >> j) & 1u) ? x : 0.f;
+            for (int j4 = 0; j4 < 8; ++j4) {
+                float4 b4;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(es.bias + 4u * (cc * 32 + j4 * 4)));
+                const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int j = j4 * 4 + e;
+                    float x = __uint_as_float(raw[j]);
+                    if (split) x = fmaf(__uint_as_float(raw1[j]), TC_LO_UNSCALE, x);
+                    x = fmaf(x, TC_W_UNSCALE, bb[e]);
+                    if (want_mask && x > 0.f) mask |= 1u << j;
+                    if (t.relu) x = fmaxf(x, 0.f);
+                    v[j] = x;
+                }
             }
             mw[cc] = mask;
+            if (t.posmask_buf >= 0) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = ((pmw[cc] >> j) & 1u) ? v[j] : 0.f;
+            }
             const uint32_t tile = es.stg + (uint32_t)half * 32768u + rbase;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
                 const uint32_t a = tile + ((((uint32_t)(c2 * 4 + g)) ^ rsw) << 4);
-                if (t.res_buf >= 0) join8_add(v + g * 8, lds128(a), lds128(a + 16384));
-                if (t.out_buf >= 0) {
+                if (has_res) join8_add(v + g * 8, lds128(a), lds128(a + 16384));
+                if (has_out || has_out2) {
                     uint4 hi, lo;
                     split8(v + g * 8, hi, lo);
+                    if (!has_out) { hi = mask8(hi, m2w[cc] >> (g * 8)); lo = mask8(lo, m2w[cc] >> (g * 8)); }
                     if (!live) { hi = make_uint4(0u, 0u, 0u, 0u); lo = hi; }     // rows [B, Bp) of every image stay zero
-                    sts128(a, hi);
-                    sts128(a + 16384, lo);
-                }
-            }
-            if (t.out2_buf >= 0) {
-                const uint32_t tile2 = es.stg2 + rbase;
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    float u[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) u[e] = ((m2w[cc] >> (g * 8 + e)) & 1u) ? v[g * 8 + e] : 0.f;
-                    uint4 hi, lo;
-                    split8(u, hi, lo);
-                    if (!live) { hi = make_uint4(0u, 0u, 0u, 0u); lo = hi; }
-                    const uint32_t a = tile2 + ((((uint32_t)(c2 * 4 + g)) ^ rsw) << 4);
                     sts128(a, hi);
                     sts128(a + 16384, lo);
                 }
             }
         }
         fence_proxy_async_smem();
-        epi_bar_sync();
+        group_bar_sync(grp);
         if (leader) {
-            if (t.out_buf >= 0) {
-                const int o = (int)((int64_t)t.out_slot * Bp) + row0;
-                tma_store_2d(map_o, es.stg + (uint32_t)half * 32768u, half * 64, br.hi[t.out_buf] + o);
-                tma_store_2d(map_o, es.stg + (uint32_t)half * 32768u + 16384u, half * 64, br.lo[t.out_buf] + o);
+            const int ob = has_out ? t.out_buf : t.out2_buf, os = has_out ? t.out_slot : t.out2_slot;
+            if (ob >= 0) {
+                const int o = (int)((int64_t)os * Bp) + row0;
+                tma_store_2d(map_o, es.stg + (uint32_t)half * 32768u, half * 64, br.hi[ob] + o);
+                tma_store_2d(map_o, es.stg + (uint32_t)half * 32768u + 16384u, half * 64, br.lo[ob] + o);
+                tma_store_commit();
             }
-            if (t.out2_buf >= 0) {
-                const int o = (int)((int64_t)t.out2_slot * Bp) + row0;
-                tma_store_2d(map_o, es.stg2, half * 64, br.hi[t.out2_buf] + o);
-                tma_store_2d(map_o, es.stg2 + 16384u, half * 64, br.lo[t.out2_buf] + o);
+        }
+    }
+    if (has_out && has_out2) {
+        // second output = first output with the masked-off lanes cleared, made in place once the first store has read the tile
+        if (leader) tma_store_wait_read();
+        group_bar_sync(grp);
+        for (int half = h0; half < h1; ++half) {
+            const uint32_t tile = es.stg + (uint32_t)half * 32768u + rbase;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const uint32_t a = tile + ((((uint32_t)c) ^ rsw) << 4);
+                const uint32_t m = m2w[half * 2 + (c >> 2)] >> ((c & 3) * 8);
+                sts128(a, mask8(lds128(a), m));
+                sts128(a + 16384, mask8(lds128(a + 16384), m));
+            }
+        }
+        fence_proxy_async_smem();
+        group_bar_sync(grp);
+        if (leader) {
+            const int o = (int)((int64_t)t.out2_slot * Bp) + row0;
+            for (int half = h0; half < h1; ++half) {
+                tma_store_2d(map_o, es.stg + (uint32_t)half * 32768u, half * 64, br.hi[t.out2_buf] + o);
+                tma_store_2d(map_o, es.stg + (uint32_t)half * 32768u + 16384u, half * 64, br.lo[t.out2_buf] + o);
             }
             tma_store_commit();
         }
     }
-    if (live && t.mask_out_buf >= 0)
-        *(reinterpret_cast<uint4*>(bt.p[t.mask_out_buf]) + (int64_t)t.mask_out_slot * Bp + row) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
-    if (leader) tma_store_wait_all();
+    if (live && t.mask_out_buf >= 0) {
+        uint32_t* mp = reinterpret_cast<uint32_t*>(bt.p[t.mask_out_buf]) + ((int64_t)t.mask_out_slot * Bp + row) * 4;
+        if (h1 - h0 == 2) *reinterpret_cast<uint4*>(mp) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+        else *reinterpret_cast<uint2*>(mp + 2 * h0) = make_uint2(mw[2 * h0], mw[2 * h0 + 1]);
+    }
+    if (leader && !es.persistent) tma_store_wait_all();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -303,6 +369,7 @@ k_tc_rowgemm(const __grid_constant__ TcMaps maps, const Tile* __restrict__ tiles
              const int64_t B, const int64_t Bp, const int split) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ Tile t;
+    __shared__ __align__(16) float bias_s[H];
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x;
@@ -322,6 +389,7 @@ k_tc_rowgemm(const __grid_constant__ TcMaps maps, const Tile* __restrict__ tiles
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
         mbar_init(accum_bar, 1);
         mbar_init(res_bar, 1);
+        mbar_init(res_bar + 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), TC_TMEM_COLS);
@@ -378,14 +446,143 @@ k_tc_rowgemm(const __grid_constant__ TcMaps maps, const Tile* __restrict__ tiles
         __syncwarp();
     } else {
         EpiSmem es;
-        es.stg = smem_base; es.stg2 = smem_base + 65536u; es.res_bar = res_bar; es.accum_bar = accum_bar;
-        tc_epilogue(t, bt, br, &maps.o, tmem_base, row0, B, Bp, split, warp & 3, lane, tid == 64, es);
+        es.stg = smem_base; es.bias = smem_u32(bias_s); es.res_bar = res_bar; es.accum_bar = accum_bar;
+        es.free_bar = 0; es.acc_parity = 0; es.res_parity = 0; es.persistent = 0; es.n_groups = 1;
+        tc_epilogue(t, bt, br, &maps.o, tmem_base, row0, B, Bp, split, warp, lane, es);
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TC_TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// persistent row-GEMM: one CTA per SM walks the (row tile, output tile) items of a launch
+// ------------------------------------------------------------------------------------------
+//  Three roles run decoupled, linked by mbarriers only: warp 0 streams operand K blocks by TMA (3-stage ring that keeps
+//  running across items), warp 1 issues the MMAs into one of TWO accumulator sets in TMEM (2 x 256 columns), warps 2..5
+//  drain the other set through the epilogue (dedicated staging tiles, residual prefetched).  So the tensor pipe never
+//  waits for an epilogue, and tile prologues (barrier init, TMEM allocation, descriptor fetch) are paid once per SM.
+//  Item i = blockIdx.x + k * gridDim.x  ->  row tile i / n_tiles, output tile i % n_tiles: CTAs that run together work
+//  on the same few row tiles, so gathered source tiles are re-read from L2, not HBM.
+constexpr int PK_MAX_TILES = 32;
+constexpr int PK_STAGES = 4;
+constexpr int PK_THREADS = 320;                                           // TMA warp, MMA warp, 8 epilogue warps
+constexpr int PK_PIPE_BYTES = PK_STAGES * TC_STAGE_BYTES;                 // 128 KB operand ring
+constexpr int PK_SMEM_BYTES = PK_PIPE_BYTES + 65536 + 1024 /*align*/ + 256 /*barriers*/;
+constexpr uint32_t PK_TMEM_COLS = 512;
+
+__global__ void __launch_bounds__(PK_THREADS, 1)
+k_tc_rowgemm_persistent(const __grid_constant__ TcMaps maps, const Tile* __restrict__ tiles, const int n_tiles, const int n_items,
+                        const BufTable bt, const BufRows br, const int64_t B, const int64_t Bp, const int split) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ Tile ts[PK_MAX_TILES];
+    __shared__ __align__(16) float bias_s[H];
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PK_PIPE_BYTES + 65536);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + PK_STAGES), acc_full0 = smem_u32(bars + 2 * PK_STAGES),
+                   acc_free0 = smem_u32(bars + 2 * PK_STAGES + 2), res_bar = smem_u32(bars + 2 * PK_STAGES + 4);
+    const uint32_t smem_base = smem_u32(smem);
+
+    {
+        const int* src = reinterpret_cast<const int*>(tiles);
+        int* dst = reinterpret_cast<int*>(ts);
+        for (int i = tid; i < n_tiles * (int)(sizeof(Tile) / 4); i += PK_THREADS) dst[i] = src[i];
+    }
+    if (tid == 0) {
+        for (int s = 0; s < PK_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(acc_full0 + 8 * a, 1); mbar_init(acc_free0 + 8 * a, 256); mbar_init(res_bar + 8 * a, 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), PK_TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    constexpr int SPC = H / TC_KB;                 // pipeline steps per chunk
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint32_t tx_bytes = split ? 4 * TC_TILE_BYTES : 2 * TC_TILE_BYTES;
+            uint32_t g = 0;                        // pipeline step counter, runs across items
+            for (int i = blockIdx.x; i < n_items; i += gridDim.x) {
+                const Tile& t = ts[i % n_tiles];
+                const int row0 = (i / n_tiles) * TILE_M;
+                const int n_steps = t.n_chunks * SPC;
+                for (int j = 0; j < n_steps; ++j, ++g) {
+                    const uint32_t s = g % PK_STAGES;
+                    mbar_wait(empty0 + 8 * s, ((g / PK_STAGES) & 1) ^ 1);
+                    const Chunk& ch = t.chunks[j / SPC];
+                    const int kcol = (j % SPC) * TC_KB;
+                    const int arow = (int)((int64_t)ch.a_slot * Bp) + row0;
+                    const uint32_t st = smem_base + s * TC_STAGE_BYTES;
+                    const uint32_t fb = full0 + 8 * s;
+                    mbar_expect_tx(fb, tx_bytes);
+                    tma_load_2d(st, &maps.k, fb, kcol, br.hi[ch.a_buf] + arow);
+                    tma_load_2d(st + 2 * TC_TILE_BYTES, &maps.k, fb, kcol, br.w_hi + ch.w16_row);
+                    if (split) {
+                        tma_load_2d(st + TC_TILE_BYTES, &maps.k, fb, kcol, br.lo[ch.a_buf] + arow);
+                        tma_load_2d(st + 3 * TC_TILE_BYTES, &maps.k, fb, kcol, br.w_lo + ch.w16_row);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            uint32_t g = 0, k = 0;
+            for (int i = blockIdx.x; i < n_items; i += gridDim.x, ++k) {
+                const int n_steps = ts[i % n_tiles].n_chunks * SPC;
+                const uint32_t a = k & 1;
+                mbar_wait(acc_free0 + 8 * a, ((k >> 1) & 1) ^ 1);      // the epilogue has drained this accumulator set
+                tc_fence_after();
+                const uint32_t d0 = tmem_base + a * 256, d1 = d0 + 128;
+                for (int j = 0; j < n_steps; ++j, ++g) {
+                    const uint32_t s = g % PK_STAGES;
+                    mbar_wait(full0 + 8 * s, (g / PK_STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t st = smem_base + s * TC_STAGE_BYTES;
+                    const uint64_t a_hi = smem_desc_sw64(st), a_lo = smem_desc_sw64(st + TC_TILE_BYTES);
+                    const uint64_t w_hi = smem_desc_sw64(st + 2 * TC_TILE_BYTES), w_lo = smem_desc_sw64(st + 3 * TC_TILE_BYTES);
+#pragma unroll
+                    for (int ks = 0; ks < TC_KB / 16; ++ks) {
+                        const uint64_t adv = (uint64_t)(ks * 2);
+                        umma_f16(d0, a_hi + adv, w_hi + adv, TC_IDESC, (j | ks) ? 1u : 0u);
+                        if (split) {
+                            umma_f16(d1, a_lo + adv, w_hi + adv, TC_IDESC, (j | ks) ? 1u : 0u);
+                            umma_f16(d1, a_hi + adv, w_lo + adv, TC_IDESC, 1u);
+                        }
+                    }
+                    umma_commit(empty0 + 8 * s);
+                }
+                umma_commit(acc_full0 + 8 * a);
+            }
+        }
+        __syncwarp();
+    } else {
+        EpiSmem es;
+        es.stg = smem_base + PK_PIPE_BYTES; es.bias = smem_u32(bias_s); es.res_bar = res_bar; es.persistent = 1; es.n_groups = 2;
+        uint32_t k = 0, n_res = 0;
+        for (int i = blockIdx.x; i < n_items; i += gridDim.x, ++k) {
+            const Tile& t = ts[i % n_tiles];
+            const uint32_t a = k & 1;
+            es.accum_bar = acc_full0 + 8 * a; es.free_bar = acc_free0 + 8 * a;
+            es.acc_parity = (k >> 1) & 1; es.res_parity = n_res & 1;
+            if (t.res_buf >= 0) ++n_res;
+            tc_epilogue(t, bt, br, &maps.o, tmem_base + a * 256, (i / n_tiles) * TILE_M, B, Bp, split, warp, lane, es);
+        }
+        if (((warp - 2) & 3) == 0 && lane == 0) tma_store_wait_all();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, PK_TMEM_COLS);
     }
 }
 
@@ -535,6 +732,7 @@ k_tc_reducegemm(const __grid_constant__ CUtensorMap map, const RTask* __restrict
             uint32_t raw[32], raw1[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + cc * 32, raw);
             if (split) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + 128 + cc * 32, raw1);
+            tmem_ld_wait();
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -549,8 +747,10 @@ k_tc_reducegemm(const __grid_constant__ CUtensorMap map, const RTask* __restrict
         if (want_cs) {
             uint32_t raw[32], raw1[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + 256, raw);
+            if (split) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + 288, raw1);
+            tmem_ld_wait();
             float x = __uint_as_float(raw[0]);
-            if (split) { tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + 288, raw1); x = fmaf(__uint_as_float(raw1[0]), TC_LO_UNSCALE, x); }
+            if (split) x = fmaf(__uint_as_float(raw1[0]), TC_LO_UNSCALE, x);
             part_b[slot * H + o] = n_steps ? x : 0.f;
         }
     }
@@ -583,18 +783,17 @@ struct alignas(64) EncMaps {
     CUtensorMap o;               // workspace images, box 64 x 128, SWIZZLE_128B (epilogue stores)
 };
 
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
 
-// 4 consecutive values of one row -> 8 bytes in the hi tile and 8 bytes in the lo tile
-__device__ __forceinline__ void split_to_smem(uint32_t hi_addr, uint32_t lo_addr, const float4 v) {
-    const __half h0 = __float2half_rn(v.x), h1 = __float2half_rn(v.y), h2 = __float2half_rn(v.z), h3 = __float2half_rn(v.w);
-    const __half2 a = __halves2half2(h0, h1), b = __halves2half2(h2, h3);
-    const __half2 c = __halves2half2(__float2half_rn((v.x - __half2float(h0)) * TC_LO_SCALE), __float2half_rn((v.y - __half2float(h1)) * TC_LO_SCALE));
-    const __half2 d = __halves2half2(__float2half_rn((v.z - __half2float(h2)) * TC_LO_SCALE), __float2half_rn((v.w - __half2float(h3)) * TC_LO_SCALE));
-    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(hi_addr), "r"(*reinterpret_cast<const uint32_t*>(&a)), "r"(*reinterpret_cast<const uint32_t*>(&b)) : "memory");
-    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(lo_addr), "r"(*reinterpret_cast<const uint32_t*>(&c)), "r"(*reinterpret_cast<const uint32_t*>(&d)) : "memory");
+// 4 consecutive values of one row, times their column factors f (+-1 sign, 0 outside [0, K)) -> 8 bytes in the hi tile
+// and 8 bytes in the lo tile.  hi = fp16(v f), lo = fp16((v f - hi) * 2^11) with packed conversions: 18 ALU ops per 4 values.
+__device__ __forceinline__ void split_to_smem(uint32_t hi_addr, uint32_t lo_addr, const float4 v, const float4 f) {
+    const float ax = v.x * f.x, ay = v.y * f.y, az = v.z * f.z, aw = v.w * f.w;
+    const __half2 h01 = __floats2half2_rn(ax, ay), h23 = __floats2half2_rn(az, aw);
+    const float2 g01 = __half22float2(h01), g23 = __half22float2(h23);
+    const __half2 l01 = __floats2half2_rn((ax - g01.x) * TC_LO_SCALE, (ay - g01.y) * TC_LO_SCALE);
+    const __half2 l23 = __floats2half2_rn((az - g23.x) * TC_LO_SCALE, (aw - g23.y) * TC_LO_SCALE);
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(hi_addr), "r"(*reinterpret_cast<const uint32_t*>(&h01)), "r"(*reinterpret_cast<const uint32_t*>(&h23)) : "memory");
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(lo_addr), "r"(*reinterpret_cast<const uint32_t*>(&l01)), "r"(*reinterpret_cast<const uint32_t*>(&l23)) : "memory");
 }
 
 // How the rows of one node of one type are addressed inside the caller's x tensor [B * nodes, K] (row-major).
@@ -616,14 +815,26 @@ __device__ __forceinline__ XRows make_xrows(const void* base, int f64, int64_t l
     return x;
 }
 
-// v[it] = x[row_first + 8*it][k .. k+3] * sign, zero outside [0, K) and for rows >= row_limit.  Every load is issued
-// unconditionally on a clamped (always valid) address before any value is consumed, so all N loads are in flight together.
+// Column factors of the 4 values a thread handles in a K block: the +-1 symmetry sign, 0 outside [0, K).
+__device__ __forceinline__ float4 x_factors(const float* __restrict__ signs, const int sign_off, const int k, const int K) {
+    float4 f;
+    f.x = k < K ? 1.f : 0.f; f.y = k + 1 < K ? 1.f : 0.f; f.z = k + 2 < K ? 1.f : 0.f; f.w = k + 3 < K ? 1.f : 0.f;
+    if (sign_off >= 0) {
+        const float* sp = signs + sign_off;
+        const int kc = k < K ? k : 0;
+        f.x *= __ldg(sp + kc); f.y *= __ldg(sp + min(kc + 1, K - 1)); f.z *= __ldg(sp + min(kc + 2, K - 1)); f.w *= __ldg(sp + min(kc + 3, K - 1));
+    }
+    return f;
+}
+
+// v[it] = x[min(row_first + 8*it, row_last)][k .. k+3] (columns clamped into [0, K)).  Every load is issued unconditionally
+// on a clamped (always valid) address, so all N loads are in flight together; columns outside [0, K) are zeroed later by
+// their factor, rows beyond the batch alias the last row and only ever meet zero partners (dead accumulator rows in
+// the forward pass, zero dC rows in the weight gradient).
 template <int N>
-__device__ __forceinline__ void load_x_block(float4 (&v)[N], const XRows& x, const float* __restrict__ signs, const int sign_off,
-                                             const int64_t row_first, const int64_t row_limit, const int64_t row_last, const int k) {
+__device__ __forceinline__ void load_x_block(float4 (&v)[N], const XRows& x, const int64_t row_first, const int64_t row_last, const int k) {
     const int K = x.K;
-    const bool kin = k < K;
-    const int kc = kin ? k : 0;
+    const int kc = k < K ? k : 0;
     const int c1 = min(kc + 1, K - 1), c2 = min(kc + 2, K - 1), c3 = min(kc + 3, K - 1);
     if (!x.f64) {
         const float* b = (const float*)x.base + x.a_off;
@@ -668,27 +879,16 @@ __device__ __forceinline__ void load_x_block(float4 (&v)[N], const XRows& x, con
             }
         }
     }
-    float4 sg = make_float4(1.f, 1.f, 1.f, 1.f);
-    if (sign_off >= 0) {
-        const float* sp = signs + sign_off;
-        sg = make_float4(__ldg(sp + kc), __ldg(sp + c1), __ldg(sp + c2), __ldg(sp + c3));
-    }
-    const bool e0 = kin, e1 = k + 1 < K, e2 = k + 2 < K, e3 = k + 3 < K;
-#pragma unroll
-    for (int it = 0; it < N; ++it) {
-        const bool rok = row_first + it * 8 < row_limit;
-        v[it].x = (rok && e0) ? v[it].x * sg.x : 0.f;
-        v[it].y = (rok && e1) ? v[it].y * sg.y : 0.f;
-        v[it].z = (rok && e2) ? v[it].z * sg.z : 0.f;
-        v[it].w = (rok && e3) ? v[it].w * sg.w : 0.f;
-    }
 }
+
+__device__ __forceinline__ int kb_count(const int g, const int n_kb) { return n_kb > g ? (n_kb - g + 1) / 2 : 0; }   // K blocks g, g+2, ...
 
 __global__ void __launch_bounds__(ENC_THREADS, 1)
 k_tc_encoder(const __grid_constant__ EncMaps maps, const Tile* __restrict__ tiles, const BufTable bt, const BufRows br,
              const int64_t B, const int64_t Bp, const int x_f64, const int split) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ Tile t;
+    __shared__ __align__(16) float bias_s[H];
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x;
@@ -707,6 +907,7 @@ k_tc_encoder(const __grid_constant__ EncMaps maps, const Tile* __restrict__ tile
         for (int s = 0; s < ENC_STAGES; ++s) { mbar_init(full0 + 8 * s, 1 + ENC_LOADER_WARPS); mbar_init(empty0 + 8 * s, 1); }
         mbar_init(accum_bar, 1);
         mbar_init(res_bar, 1);
+        mbar_init(res_bar + 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), TC_TMEM_COLS);
@@ -766,34 +967,45 @@ k_tc_encoder(const __grid_constant__ EncMaps maps, const Tile* __restrict__ tile
         const int kq = gt & 15;                                   // which 4-column group of the 64-column block
         const int rsub = gt >> 4;                                 // 0..7
         const int64_t row_first = (int64_t)row0 + rsub;
-        float4 cur[16], nxt[16];
-        int kb = g;
-        if (kb < n_kb) load_x_block<16>(cur, xr, signs, ch.sign_off, row_first, B, B - 1, kb * 64 + kq * 4);
-        for (; kb < n_kb; kb += 2) {
-            const bool more = kb + 2 < n_kb;
-            if (more) load_x_block<16>(nxt, xr, signs, ch.sign_off, row_first, B, B - 1, (kb + 2) * 64 + kq * 4);
+        // Work units of 64 rows x 64 columns (half a K block); three register sets rotate so that the loads of units
+        // n + 1 and n + 2 are in flight while unit n is converted and written to shared memory.
+        const int n_units = kb_count(g, n_kb) * 2;
+        float4 va[8], vb[8], vc[8];
+        auto load = [&](float4 (&v)[8], const int n) {
+            if (n < n_units) load_x_block<8>(v, xr, row_first + (n & 1) * 64, B - 1, (g + 2 * (n >> 1)) * 64 + kq * 4);
+        };
+        auto convert = [&](const float4 (&v)[8], const int n) {
+            if (n >= n_units) return;
+            const int kb = g + 2 * (n >> 1), half = n & 1;
+            const float4 f = x_factors(signs, ch.sign_off, kb * 64 + kq * 4, K);
             const int s = kb % ENC_STAGES;
-            mbar_wait(empty0 + 8 * s, ((kb / ENC_STAGES) & 1) ^ 1);
+            if (!half) mbar_wait(empty0 + 8 * s, ((kb / ENC_STAGES) & 1) ^ 1);
             const uint32_t st = smem_base + s * ENC_STAGE_BYTES;
 #pragma unroll
-            for (int it = 0; it < 16; ++it) {
-                const int r = it * 8 + rsub;
+            for (int it = 0; it < 8; ++it) {
+                const int r = half * 64 + it * 8 + rsub;
                 const uint32_t off = (uint32_t)(r * 128 + ((((kq >> 1) ^ (r & 7))) << 4) + ((kq & 1) << 3));
-                split_to_smem(st + off, st + ENC_TILE_BYTES + off, cur[it]);
+                split_to_smem(st + off, st + ENC_TILE_BYTES + off, v[it], f);
             }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(full0 + 8 * s);
-            if (more) {
-#pragma unroll
-                for (int it = 0; it < 16; ++it) cur[it] = nxt[it];
+            if (half) {
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full0 + 8 * s);
             }
+        };
+        load(va, 0);
+        load(vb, 1);
+        for (int n = 0; n < n_units; n += 3) {
+            load(vc, n + 2); convert(va, n);
+            load(va, n + 3); convert(vb, n + 1);
+            load(vb, n + 4); convert(vc, n + 2);
         }
-        if (warp < 6) {
-            // ---------------- epilogue (warps 2..5 = TMEM lane quarters 2, 3, 0, 1) ----------------
+        {
+            // ---------------- epilogue: warps 2..5 take columns 0..63, warps 6..9 columns 64..127 ----------------
             EpiSmem es;
-            es.stg = smem_base; es.stg2 = smem_base + 65536u; es.res_bar = res_bar; es.accum_bar = accum_bar;
-            tc_epilogue(t, bt, br, &maps.o, tmem_base, row0, B, Bp, split, warp & 3, lane, tid == 64, es);
+            es.stg = smem_base; es.bias = smem_u32(bias_s); es.res_bar = res_bar; es.accum_bar = accum_bar;
+            es.free_bar = 0; es.acc_parity = 0; es.res_parity = 0; es.persistent = 0; es.n_groups = 2;
+            tc_epilogue(t, bt, br, &maps.o, tmem_base, row0, B, Bp, split, warp, lane, es);
         }
     }
     tc_fence_before();
@@ -919,16 +1131,17 @@ k_tc_encoder_dw(const __grid_constant__ CUtensorMap map, const EncDwUnit* __rest
             float4 v[3][8];
 #pragma unroll
             for (int jb = 0; jb < 3; ++jb)
-                if (jb < nkb) load_x_block<8>(v[jb], xr, signs, u.sign_off[j], r0, r_end, B - 1, u.k0 + jb * 64 + kq * 4);
+                if (jb < nkb) load_x_block<8>(v[jb], xr, r0, B - 1, u.k0 + jb * 64 + kq * 4);
             mbar_wait(empty0 + 8 * s, ((i / EDW_STAGES) & 1) ^ 1);
 #pragma unroll
             for (int jb = 0; jb < 3; ++jb)
                 if (jb < nkb) {
+                    const float4 f = x_factors(signs, u.sign_off[j], u.k0 + jb * 64 + kq * 4, u.K);
 #pragma unroll
                     for (int it = 0; it < 8; ++it) {
                         const int r = it * 8 + rsub;
                         const uint32_t off = (uint32_t)(jb * 8192 + r * 128 + ((((kq >> 1) ^ (r & 7))) << 4) + ((kq & 1) << 3));
-                        split_to_smem(st + off, st + EDW_X_BYTES + off, v[jb][it]);
+                        split_to_smem(st + off, st + EDW_X_BYTES + off, v[jb][it], f);
                     }
                 }
             fence_proxy_async_smem();
@@ -947,6 +1160,7 @@ k_tc_encoder_dw(const __grid_constant__ CUtensorMap map, const EncDwUnit* __rest
                 uint32_t raw[32], raw1[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + cc * 32, raw);
                 if (split) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + EDW_NMAX + cc * 32, raw1);
+                tmem_ld_wait();
                 float4* dst = reinterpret_cast<float4*>(pw + cc * 32);
 #pragma unroll
                 for (int jj = 0; jj < 8; ++jj) {
@@ -963,8 +1177,10 @@ k_tc_encoder_dw(const __grid_constant__ CUtensorMap map, const EncDwUnit* __rest
             if (want_cs) {
                 uint32_t raw[32], raw1[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + 384, raw);
+                if (split) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + 416, raw1);
+                tmem_ld_wait();
                 float x = __uint_as_float(raw[0]);
-                if (split) { tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + 416, raw1); x = fmaf(__uint_as_float(raw1[0]), TC_LO_UNSCALE, x); }
+                if (split) x = fmaf(__uint_as_float(raw1[0]), TC_LO_UNSCALE, x);
                 part_b[slot * H + o] = n_steps ? x : 0.f;
             }
         }
