@@ -26,7 +26,7 @@ __device__ __forceinline__ void split_store4(__half* hi, __half* lo, int64_t off
     for (int j = 0; j < 2; ++j) {
         const __half ha = __float2half_rn(v[2 * j]), hb = __float2half_rn(v[2 * j + 1]);
         h[j] = __halves2half2(ha, hb);
-        l[j] = __halves2half2(__float2half_rn((v[2 * j] - __half2float(ha)) * 2048.f), __float2half_rn((v[2 * j + 1] - __half2float(hb)) * 2048.f));
+        l[j] = __halves2half2(__float2half_rn((v[2 * j] - __half2float(ha)) * LO_SCALE), __float2half_rn((v[2 * j + 1] - __half2float(hb)) * LO_SCALE));
     }
     *reinterpret_cast<uint2*>(hi + off) = *reinterpret_cast<uint2*>(h);
     *reinterpret_cast<uint2*>(lo + off) = *reinterpret_cast<uint2*>(l);
@@ -38,7 +38,7 @@ __device__ __forceinline__ float4 load_h4(const float* slab, const __half* hi, c
     const uint2 a = *reinterpret_cast<const uint2*>(hi + off), b = *reinterpret_cast<const uint2*>(lo + off);
     const float2 a0 = __half22float2(*reinterpret_cast<const __half2*>(&a.x)), a1 = __half22float2(*reinterpret_cast<const __half2*>(&a.y));
     const float2 b0 = __half22float2(*reinterpret_cast<const __half2*>(&b.x)), b1 = __half22float2(*reinterpret_cast<const __half2*>(&b.y));
-    const float u = 1.f / 2048.f;
+    const float u = 1.f / LO_SCALE;
     return make_float4(fmaf(b0.x, u, a0.x), fmaf(b0.y, u, a0.y), fmaf(b1.x, u, a1.x), fmaf(b1.y, u, a1.y));
 }
 

@@ -29,13 +29,14 @@ constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ 
 constexpr int TC_THREADS = 192;
 constexpr float TC_W_SCALE = 256.f;                // weights are stored as fp16 pairs of (w * 2^8)
 constexpr float TC_W_UNSCALE = 1.f / 256.f;
-// The low halves are stored multiplied by 2^11: lo = fp16((v - hi) * 2048), which is always a NORMAL fp16 when hi
-// is (|lo*2048| <= |v|), so the pair keeps ~22 significant bits over fp16's whole normal range instead of hitting the
-// 2^-24 subnormal floor for |v| < 0.25.  The cross terms therefore accumulate in a second TMEM accumulator (D1) and the
-// epilogue combines D0 + D1 * 2^-11.
-constexpr float TC_LO_SCALE = 2048.f;
-constexpr float TC_LO_UNSCALE = 1.f / 2048.f;
-constexpr uint32_t TC_TMEM_COLS = 256;
+// The low halves are stored unscaled: lo = fp16(v - hi).  |lo| <= 2^-11 |v|, so lo is a normal fp16 (pair error 2^-22 |v|)
+// for |v| >= 2^-3 and a subnormal one below that (pair error <= 2^-25 absolute).  Every slab the kernels carry is O(1) by
+// construction (z-scored inputs, ReLU features, gradients pre-multiplied by G ~ #output rows), so the absolute floor sits
+// seven decades under the tensor norms - and the three products hi*hi + lo*hi + hi*lo share ONE fp32 accumulator in
+// TMEM (128 columns per 128x128 tile), which is what lets a CTA keep two row tiles x two accumulator sets resident.
+constexpr float TC_LO_SCALE = LO_SCALE;
+constexpr float TC_LO_UNSCALE = 1.f / LO_SCALE;
+constexpr uint32_t TC_TMEM_COLS = 128;
 
 // ------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -266,9 +267,8 @@ __device__ __forceinline__ void tc_epilogue(const Tile& t, const BufTable& bt, c
 #pragma unroll 1
         for (int c2 = 0; c2 < 2; ++c2) {
             const int cc = half * 2 + c2;
-            uint32_t raw[32], raw1[32];
+            uint32_t raw[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + cc * 32, raw);
-            if (split) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + 128 + cc * 32, raw1);
             tmem_ld_wait();
             if (cc == 2 * h1 - 1 && es.free_bar) {       // last read of this accumulator by this thread: hand it back
                 tc_fence_before();
@@ -284,9 +284,7 @@ __device__ __forceinline__ void tc_epilogue(const Tile& t, const BufTable& bt, c
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const int j = j4 * 4 + e;
-                    float x = __uint_as_float(raw[j]);
-                    if (split) x = fmaf(__uint_as_float(raw1[j]), TC_LO_UNSCALE, x);
-                    x = fmaf(x, TC_W_UNSCALE, bb[e]);
+                    float x = fmaf(__uint_as_float(raw[j]), TC_W_UNSCALE, bb[e]);
                     if (want_mask && x > 0.f) mask |= 1u << j;
                     if (t.relu) x = fmaxf(x, 0.f);
                     v[j] = x;
@@ -435,8 +433,8 @@ k_tc_rowgemm(const __grid_constant__ TcMaps maps, const Tile* __restrict__ tiles
                     const uint64_t adv = (uint64_t)(ks * 2);      // +32 bytes (16 fp16) along K inside the swizzle atom
                     umma_f16(tmem_base, a_hi + adv, w_hi + adv, TC_IDESC, (i | ks) ? 1u : 0u);             // D0 += hi * hi
                     if (split) {
-                        umma_f16(tmem_base + 128, a_lo + adv, w_hi + adv, TC_IDESC, (i | ks) ? 1u : 0u);   // D1 += lo * hi
-                        umma_f16(tmem_base + 128, a_hi + adv, w_lo + adv, TC_IDESC, 1u);                   // D1 += hi * lo
+                        umma_f16(tmem_base, a_lo + adv, w_hi + adv, TC_IDESC, 1u);                         // D0 += lo * hi
+                        umma_f16(tmem_base, a_hi + adv, w_lo + adv, TC_IDESC, 1u);                         // D0 += hi * lo
                     }
                 }
                 umma_commit(empty0 + 8 * s);          // frees the stage once these MMAs have read it
@@ -472,7 +470,7 @@ constexpr int PK_STAGES = 4;
 constexpr int PK_THREADS = 320;                                           // TMA warp, MMA warp, 8 epilogue warps
 constexpr int PK_PIPE_BYTES = PK_STAGES * TC_STAGE_BYTES;                 // 128 KB operand ring
 constexpr int PK_SMEM_BYTES = PK_PIPE_BYTES + 65536 + 1024 /*align*/ + 256 /*barriers*/;
-constexpr uint32_t PK_TMEM_COLS = 512;
+constexpr uint32_t PK_TMEM_COLS = 256;
 
 __global__ void __launch_bounds__(PK_THREADS, 1)
 k_tc_rowgemm_persistent(const __grid_constant__ TcMaps maps, const Tile* __restrict__ tiles, const int n_tiles, const int n_items,
@@ -541,7 +539,7 @@ k_tc_rowgemm_persistent(const __grid_constant__ TcMaps maps, const Tile* __restr
                 const uint32_t a = k & 1;
                 mbar_wait(acc_free0 + 8 * a, ((k >> 1) & 1) ^ 1);      // the epilogue has drained this accumulator set
                 tc_fence_after();
-                const uint32_t d0 = tmem_base + a * 256, d1 = d0 + 128;
+                const uint32_t d0 = tmem_base + a * 128;
                 for (int j = 0; j < n_steps; ++j, ++g) {
                     const uint32_t s = g % PK_STAGES;
                     mbar_wait(full0 + 8 * s, (g / PK_STAGES) & 1);
@@ -554,8 +552,8 @@ k_tc_rowgemm_persistent(const __grid_constant__ TcMaps maps, const Tile* __restr
                         const uint64_t adv = (uint64_t)(ks * 2);
                         umma_f16(d0, a_hi + adv, w_hi + adv, TC_IDESC, (j | ks) ? 1u : 0u);
                         if (split) {
-                            umma_f16(d1, a_lo + adv, w_hi + adv, TC_IDESC, (j | ks) ? 1u : 0u);
-                            umma_f16(d1, a_hi + adv, w_lo + adv, TC_IDESC, 1u);
+                            umma_f16(d0, a_lo + adv, w_hi + adv, TC_IDESC, 1u);
+                            umma_f16(d0, a_hi + adv, w_lo + adv, TC_IDESC, 1u);
                         }
                     }
                     umma_commit(empty0 + 8 * s);
@@ -574,7 +572,7 @@ k_tc_rowgemm_persistent(const __grid_constant__ TcMaps maps, const Tile* __restr
             es.accum_bar = acc_full0 + 8 * a; es.free_bar = acc_free0 + 8 * a;
             es.acc_parity = (k >> 1) & 1; es.res_parity = n_res & 1;
             if (t.res_buf >= 0) ++n_res;
-            tc_epilogue(t, bt, br, &maps.o, tmem_base + a * 256, (i / n_tiles) * TILE_M, B, Bp, split, warp, lane, es);
+            tc_epilogue(t, bt, br, &maps.o, tmem_base + a * 128, (i / n_tiles) * TILE_M, B, Bp, split, warp, lane, es);
         }
         if (((warp - 2) & 3) == 0 && lane == 0) tma_store_wait_all();
     }
@@ -605,7 +603,7 @@ constexpr int DW_IMG_BYTES = DW_KB * H * 2;            // 64 rows x 128 fp16 = t
 constexpr int DW_STAGE_BYTES = 4 * DW_IMG_BYTES;       // dC_hi, dC_lo, A_hi, A_lo
 constexpr int DW_ONES_BYTES = 2048;
 constexpr int DW_SMEM_BYTES = DW_STAGES * DW_STAGE_BYTES + DW_ONES_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr uint32_t DW_TMEM_COLS = 512;
+constexpr uint32_t DW_TMEM_COLS = 256;
 constexpr int DW_MAX_PAIRS = 4;
 
 // MN-major, 128B-swizzled operand of 128 (MN) x 16 (K) fp16: LBO = 8192 B (next 64 MN elements), SBO = 1024 B (next 8 K rows)
@@ -706,12 +704,12 @@ k_tc_reducegemm(const __grid_constant__ CUtensorMap map, const RTask* __restrict
                     const uint32_t acc = (i | ks) ? 1u : 0u;
                     umma_f16(tmem_base, d_hi + adv, a_hi + adv, DW_IDESC, acc);                       // D0 += dC_hi^T A_hi
                     if (split) {
-                        umma_f16(tmem_base + 128, d_lo + adv, a_hi + adv, DW_IDESC, acc);             // D1 += dC_lo^T A_hi
-                        umma_f16(tmem_base + 128, d_hi + adv, a_lo + adv, DW_IDESC, 1u);              // D1 += dC_hi^T A_lo
+                        umma_f16(tmem_base, d_lo + adv, a_hi + adv, DW_IDESC, 1u);                    // D0 += dC_lo^T A_hi
+                        umma_f16(tmem_base, d_hi + adv, a_lo + adv, DW_IDESC, 1u);                    // D0 += dC_hi^T A_lo
                     }
                     if (want_cs) {
-                        umma_f16(tmem_base + 256, d_hi + adv, ones_desc, DW_IDESC_CS, acc);           // D2 += dC_hi^T 1
-                        if (split) umma_f16(tmem_base + 288, d_lo + adv, ones_desc, DW_IDESC_CS, acc); // D3 += dC_lo^T 1
+                        umma_f16(tmem_base + 128, d_hi + adv, ones_desc, DW_IDESC_CS, acc);           // D2 += dC_hi^T 1
+                        if (split) umma_f16(tmem_base + 128, d_lo + adv, ones_desc, DW_IDESC_CS, 1u); // D2 += dC_lo^T 1
                     }
                 }
                 umma_commit(empty0 + 8 * s);
@@ -729,29 +727,21 @@ k_tc_reducegemm(const __grid_constant__ CUtensorMap map, const RTask* __restrict
         float* pw = part_w + slot * (H * H) + (int64_t)o * H;
 #pragma unroll 1
         for (int cc = 0; cc < 4; ++cc) {
-            uint32_t raw[32], raw1[32];
+            uint32_t raw[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + cc * 32, raw);
-            if (split) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + 128 + cc * 32, raw1);
             tmem_ld_wait();
             float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                float x = __uint_as_float(raw[j]);
-                if (split) x = fmaf(__uint_as_float(raw1[j]), TC_LO_UNSCALE, x);
-                v[j] = n_steps ? x : 0.f;
-            }
+            for (int j = 0; j < 32; ++j) v[j] = n_steps ? __uint_as_float(raw[j]) : 0.f;
             float4* dst = reinterpret_cast<float4*>(pw + cc * 32);
 #pragma unroll
             for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
         if (want_cs) {
-            uint32_t raw[32], raw1[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + 256, raw);
-            if (split) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + 288, raw1);
+            uint32_t raw[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + 128, raw);
             tmem_ld_wait();
-            float x = __uint_as_float(raw[0]);
-            if (split) x = fmaf(__uint_as_float(raw1[0]), TC_LO_UNSCALE, x);
-            part_b[slot * H + o] = n_steps ? x : 0.f;
+            part_b[slot * H + o] = n_steps ? __uint_as_float(raw[0]) : 0.f;
         }
     }
     tc_fence_before();
@@ -948,8 +938,8 @@ k_tc_encoder(const __grid_constant__ EncMaps maps, const Tile* __restrict__ tile
                     const uint64_t adv = (uint64_t)(ks * 2);
                     umma_f16(tmem_base, a_hi + adv, w_hi + adv, TC_IDESC, (i | ks) ? 1u : 0u);
                     if (split) {
-                        umma_f16(tmem_base + 128, a_lo + adv, w_hi + adv, TC_IDESC, (i | ks) ? 1u : 0u);
-                        umma_f16(tmem_base + 128, a_hi + adv, w_lo + adv, TC_IDESC, 1u);
+                        umma_f16(tmem_base, a_lo + adv, w_hi + adv, TC_IDESC, 1u);
+                        umma_f16(tmem_base, a_hi + adv, w_lo + adv, TC_IDESC, 1u);
                     }
                 }
                 umma_commit(empty0 + 8 * s);
@@ -1103,12 +1093,12 @@ k_tc_encoder_dw(const __grid_constant__ CUtensorMap map, const EncDwUnit* __rest
                     const uint32_t acc = (i | ks) ? 1u : 0u;
                     umma_f16(tmem_base, d_hi + adv, x_hi + adv, idesc, acc);
                     if (split) {
-                        umma_f16(tmem_base + EDW_NMAX, d_lo + adv, x_hi + adv, idesc, acc);
-                        umma_f16(tmem_base + EDW_NMAX, d_hi + adv, x_lo + adv, idesc, 1u);
+                        umma_f16(tmem_base, d_lo + adv, x_hi + adv, idesc, 1u);
+                        umma_f16(tmem_base, d_hi + adv, x_lo + adv, idesc, 1u);
                     }
                     if (want_cs) {
-                        umma_f16(tmem_base + 384, d_hi + adv, ones_desc, DW_IDESC_CS, acc);
-                        if (split) umma_f16(tmem_base + 416, d_lo + adv, ones_desc, DW_IDESC_CS, acc);
+                        umma_f16(tmem_base + EDW_NMAX, d_hi + adv, ones_desc, DW_IDESC_CS, acc);
+                        if (split) umma_f16(tmem_base + EDW_NMAX, d_lo + adv, ones_desc, DW_IDESC_CS, 1u);
                     }
                 }
                 umma_commit(empty0 + 8 * s);
@@ -1157,9 +1147,8 @@ k_tc_encoder_dw(const __grid_constant__ CUtensorMap map, const EncDwUnit* __rest
             const int64_t slot = (int64_t)blockIdx.x * n_splits + sp;
             float* pw = part_w + slot * (H * EDW_NMAX) + (int64_t)o * EDW_NMAX;
             for (int cc = 0; cc < nkb * 2; ++cc) {
-                uint32_t raw[32], raw1[32];
+                uint32_t raw[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + cc * 32, raw);
-                if (split) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + EDW_NMAX + cc * 32, raw1);
                 tmem_ld_wait();
                 float4* dst = reinterpret_cast<float4*>(pw + cc * 32);
 #pragma unroll
@@ -1167,21 +1156,16 @@ k_tc_encoder_dw(const __grid_constant__ CUtensorMap map, const EncDwUnit* __rest
                     float x[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        float y = __uint_as_float(raw[4 * jj + e]);
-                        if (split) y = fmaf(__uint_as_float(raw1[4 * jj + e]), TC_LO_UNSCALE, y);
-                        x[e] = n_steps ? y : 0.f;
+                        x[e] = n_steps ? __uint_as_float(raw[4 * jj + e]) : 0.f;
                     }
                     dst[jj] = make_float4(x[0], x[1], x[2], x[3]);
                 }
             }
             if (want_cs) {
-                uint32_t raw[32], raw1[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + 384, raw);
-                if (split) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + 416, raw1);
+                uint32_t raw[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + EDW_NMAX, raw);
                 tmem_ld_wait();
-                float x = __uint_as_float(raw[0]);
-                if (split) x = fmaf(__uint_as_float(raw1[0]), TC_LO_UNSCALE, x);
-                part_b[slot * H + o] = n_steps ? x : 0.f;
+                part_b[slot * H + o] = n_steps ? __uint_as_float(raw[0]) : 0.f;
             }
         }
     }
