@@ -140,6 +140,42 @@ int mshgnn_adam_step(float* params, const float* grads, float* exp_avg, float* e
 /* plain SGD: p -= lr * g */
 int mshgnn_sgd_step(float* params, const float* grads, int64_t n, float lr, void* stream);
 
+/* ---- device-side window builder ---------------------------------------------
+ * Replaces, batched on the GPU, the reference's per-sample dataset path
+ *   LinTzuYaunDataset.load_data_at_dataset_seq        datasets_py/LinTzuYaunDataset.py:L66-88
+ *   LinTzuYaunDataset_Morph.load_data_sorted_k4/_c2   datasets_py/LinTzuYaunDataset_Morph.py:L156-347
+ *   ..._Morph.get_helper_heterogeneous_gnn(_c2)       datasets_py/LinTzuYaunDataset_Morph.py:L555-697
+ *   FlexibleDataset.get_helper_heterogeneous_gnn      datasets_py/flexibleDataset.py:L537-607
+ * plus torch_geometric's collate of the node features and labels.
+ * seq: device [n_rows, seq_cols] row-major, every raw channel array side by side in dataset column order.
+ * Graph g is the window of rows [starts[g], starts[g] + history_length).  A node row of type t is
+ * blocks_per_node[t] blocks of block_len[t] values; block (t, node, k) - index first(t) + node*blocks + k
+ * in block_col / block_sign - holds column block_col[.] of the window over time (the reference's
+ * flatten('F')), z-scored per window when normalize != 0 (mean, Bessel std, NaN -> 0:
+ * flexibleDataset.py:L388-396), times block_sign[.] (+-1: the datasets' apply_symmetry,
+ * LinTzuYaunDataset_Morph.py:L349-408, commutes with the z-score).  block_col < 0 with block_len 1 is
+ * the constant feature of a type without variables (value block_sign, 1 in the reference).
+ * Labels: y[g, i] = label_seq[starts[g] + history_length - 1, label_col[i]] * label_sign[i].
+ * starts is a DEVICE pointer; entries are clamped into [0, n_rows - history_length]. */
+typedef struct mshgnn_window_desc {
+    int32_t history_length;
+    int32_t seq_cols;
+    int32_t label_cols;
+    int32_t n_node_types;
+    int32_t nodes_per_graph[MSHGNN_MAX_NODE_TYPES];
+    int32_t blocks_per_node[MSHGNN_MAX_NODE_TYPES];
+    int32_t block_len[MSHGNN_MAX_NODE_TYPES];      /* history_length, or 1 for the constant feature */
+    int32_t normalize;
+    int32_t n_labels;
+    const int32_t* block_col;                      /* host, [sum_t nodes*blocks] */
+    const int32_t* block_sign;                     /* host, same shape; NULL = ones */
+    const int32_t* label_col;                      /* host, [n_labels] */
+    const int32_t* label_sign;                     /* host, [n_labels]; NULL = ones */
+} mshgnn_window_desc;
+
+int mshgnn_build_windows(const mshgnn_window_desc* desc, const void* seq, const void* label_seq, int32_t seq_dtype,
+                         int64_t n_rows, const int64_t* starts, int64_t B, float* const* x, float* y, void* stream);
+
 /* JSON summary of the compiled tables (slots, liveness, gather lists); returns the bytes needed
  * (including the terminating NUL).  Host-only: usable without a GPU. */
 int64_t mshgnn_plan_describe(const mshgnn_plan* plan, char* buf, int64_t cap);

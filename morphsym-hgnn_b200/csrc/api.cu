@@ -1,4 +1,5 @@
 // C ABI of libmshgnn_b200.so (see include/mshgnn_b200.h): launch sequencing of the hot path.
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
@@ -12,6 +13,7 @@
 #include "kernels_simt.cuh"
 #include "kernels_tc.cuh"
 #include "plan.cuh"
+#include "windows.cuh"
 
 using namespace mshgnn;
 
@@ -41,11 +43,11 @@ int fail(int code, const char* fmt, ...) {
 
 // ---- per-kernel event profiling ----
 enum Kind : int { K_DERIVE = 0, K_ENC_FWD, K_CONV_FWD, K_MLP_FWD, K_DEC_FWD, K_LOSS, K_DEC_BWD, K_MLP_BWD, K_DX_BWD,
-                  K_DW_LAYER, K_DW_ENC, K_REDUCE, K_OPTIM, K_MEMSET, K_NKINDS };
+                  K_DW_LAYER, K_DW_ENC, K_REDUCE, K_OPTIM, K_MEMSET, K_WINDOWS, K_NKINDS };
 const char* const kKindNames[MSHGNN_NUM_KERNEL_KINDS] = {
     "derive_weights", "encoder_fwd", "conv_fwd", "base_mlp_fwd", "decoder_fwd", "loss",
     "decoder_bwd", "base_mlp_bwd", "dx_bwd", "dw_layers", "dw_encoder",
-    "reduce_partials", "optimizer", "memset", "", ""};
+    "reduce_partials", "optimizer", "memset", "window_builder", ""};
 struct ProfRec { int kind; cudaEvent_t a, b; };
 std::mutex g_prof_mu;
 bool g_prof_on = false;
@@ -526,7 +528,7 @@ int mshgnn_backward(const mshgnn_plan* plan, int64_t B, const void* const* x, in
                                                   dec_part, B, w.Bp, G, (tc && want_dh) ? bh.hi[dhb] : nullptr, (tc && want_dh) ? bh.lo[dhb] : nullptr,
                                                   (tc && want_dc) ? bh.hi[dcb] : nullptr, (tc && want_dc) ? bh.lo[dcb] : nullptr);
         LAUNCH_CHECK();
-        k_decoder_bwd_reduce<<<4, 256, 0, st>>>(p.dec, dec_part, DEC_BLOCKS, grads, 1.f / G);
+        k_decoder_bwd_reduce<<<p.dec.C * H + p.dec.C, 256, 0, st>>>(p.dec, dec_part, DEC_BLOCKS, grads, 1.f / G);
         LAUNCH_CHECK();
     }
     auto launch_dw = [&](int kind, const Launch& L) -> int {
@@ -568,7 +570,7 @@ int mshgnn_backward(const mshgnn_plan* plan, int64_t B, const void* const* x, in
             }
             {
                 ProfScope ps(K_REDUCE, st);
-                dim3 grid((unsigned)p.enc_groups.size(), 8);
+                dim3 grid((unsigned)p.enc_groups.size(), 48);
                 k_reduce_enc<<<grid, 256, 0, st>>>(p.d_enc_groups, pe_w, pe_b, w.n_splits_enc, grads, 1.f / G);
                 LAUNCH_CHECK();
             }
@@ -577,13 +579,13 @@ int mshgnn_backward(const mshgnn_plan* plan, int64_t B, const void* const* x, in
     // layer-stack groups were produced with the split count of the kernel that ran them, encoder groups with the SIMT one
     const int ngl = p.n_groups_layers, nge = (int)p.groups.size() - ngl;
     if (ngl > 0) {
-        dim3 grid((unsigned)ngl, 8);
+        dim3 grid((unsigned)ngl, 32);
         ProfScope ps(K_REDUCE, st);
         k_reduce_partials<<<grid, 256, 0, st>>>(p.d_groups, part_w, part_b, tc ? w.n_splits_tc : w.n_splits, grads, 1.f / G);
         LAUNCH_CHECK();
     }
     if (nge > 0 && !tc) {
-        dim3 grid((unsigned)nge, 8);
+        dim3 grid((unsigned)nge, 32);
         ProfScope ps(K_REDUCE, st);
         k_reduce_partials<<<grid, 256, 0, st>>>(p.d_groups + ngl, part_w, part_b, w.n_splits, grads, 1.f / G);
         LAUNCH_CHECK();
@@ -610,6 +612,69 @@ int mshgnn_sgd_step(float* params, const float* grads, int64_t n, float lr, void
     if (blocks > 148 * 8) blocks = 148 * 8;
     ProfScope ps(K_OPTIM, (cudaStream_t)stream);
     k_sgd<<<blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, n, lr);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+int mshgnn_build_windows(const mshgnn_window_desc* d, const void* seq, const void* label_seq, int32_t seq_dtype, int64_t n_rows,
+                         const int64_t* starts, int64_t B, float* const* x, float* y, void* stream) {
+    if (!d || !seq || !starts || !x || B < 1) return fail(MSHGNN_ERR_ARG, "bad argument");
+    if (seq_dtype != MSHGNN_F32 && seq_dtype != MSHGNN_F64) return fail(MSHGNN_ERR_ARG, "seq_dtype must be F32 or F64");
+    const int T = d->history_length, C = d->seq_cols;
+    if (T < 1 || (d->normalize && T < 2)) return fail(MSHGNN_ERR_ARG, "history_length %d unsupported (normalisation needs >= 2 rows)", T);
+    if (C < 1 || C > WIN_MAX_COLS) return fail(MSHGNN_ERR_ARG, "seq_cols %d outside [1, %d]", C, WIN_MAX_COLS);
+    if (n_rows < T) return fail(MSHGNN_ERR_ARG, "sequence has %lld rows, fewer than history_length %d", (long long)n_rows, T);
+    if (d->n_node_types < 1 || d->n_node_types > 4) return fail(MSHGNN_ERR_ARG, "n_node_types out of range");
+    if (d->n_labels < 0 || d->n_labels > WIN_MAX_LABELS) return fail(MSHGNN_ERR_ARG, "n_labels out of range");
+    if (y && d->n_labels > 0 && (!label_seq || d->label_cols < 1 || !d->label_col)) return fail(MSHGNN_ERR_ARG, "labels requested without a label sequence");
+    WindowTable tb;
+    memset(&tb, 0, sizeof tb);
+    tb.T = T; tb.C = C; tb.CL = d->label_cols; tb.n_types = d->n_node_types; tb.normalize = d->normalize != 0;
+    tb.n_labels = y ? d->n_labels : 0;
+    WindowPtrs out;
+    memset(&out, 0, sizeof out);
+    int nb = 0;
+    for (int t = 0; t < d->n_node_types; ++t) {
+        const int nodes = d->nodes_per_graph[t], blocks = d->blocks_per_node[t], len = d->block_len[t];
+        if (nodes < 0 || blocks < 0 || (nodes * blocks > 0 && len != T && len != 1)) return fail(MSHGNN_ERR_ARG, "type %d: bad block shape", t);
+        if (nodes * blocks > 0 && !x[t]) return fail(MSHGNN_ERR_ARG, "type %d: null output", t);
+        tb.nodes[t] = nodes; tb.blocks[t] = blocks > 0 ? blocks : 1; tb.blen[t] = len; tb.first_block[t] = nb;
+        out.x[t] = x[t];
+        if (nb + nodes * blocks > WIN_MAX_BLOCKS) return fail(MSHGNN_ERR_ARG, "more than %d feature blocks per graph", WIN_MAX_BLOCKS);
+        for (int i = 0; i < nodes * blocks; ++i) {
+            const int c = d->block_col[nb + i], sg = d->block_sign ? d->block_sign[nb + i] : 1;
+            if (c >= C) return fail(MSHGNN_ERR_ARG, "block %d reads column %d of a %d-column sequence", nb + i, c, C);
+            if (c >= 0 && len != T) return fail(MSHGNN_ERR_ARG, "type %d: a constant-length block cannot read a column", t);
+            if (sg < -127 || sg > 127) return fail(MSHGNN_ERR_ARG, "block factor out of range");
+            tb.col[nb + i] = (int16_t)(c < 0 ? -1 : c); tb.sign[nb + i] = (int8_t)sg;
+            if (c >= 0) tb.col_used[c] = 1;
+        }
+        nb += nodes * blocks;
+    }
+    tb.n_blocks = nb;
+    for (int i = 0; i < tb.n_labels; ++i) {
+        const int c = d->label_col[i];
+        if (c < 0 || c >= d->label_cols) return fail(MSHGNN_ERR_ARG, "label column out of range");
+        tb.label_col[i] = (int16_t)c; tb.label_sign[i] = (int8_t)(d->label_sign ? d->label_sign[i] : 1);
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int Tp = T | 1;
+    const size_t esz = seq_dtype == MSHGNN_F64 ? 8 : 4;
+    const size_t smem = (size_t)C * Tp * (esz + 4);
+    if (smem > 200 * 1024) return fail(MSHGNN_ERR_ARG, "window of %d x %d does not fit in shared memory", T, C);
+    int dev = 0, sms = 148;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / (smem + 1024)));
+    const int grid = (int)std::min<int64_t>(B, (int64_t)sms * per_sm);
+    ProfScope ps(K_WINDOWS, st);
+    if (seq_dtype == MSHGNN_F64) {
+        CUDA_TRY(cudaFuncSetAttribute(k_build_windows<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_build_windows<double><<<grid, WIN_THREADS, smem, st>>>(tb, (const double*)seq, (const double*)label_seq, n_rows, starts, B, out, y);
+    } else {
+        CUDA_TRY(cudaFuncSetAttribute(k_build_windows<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_build_windows<float><<<grid, WIN_THREADS, smem, st>>>(tb, (const float*)seq, (const float*)label_seq, n_rows, starts, B, out, y);
+    }
     LAUNCH_CHECK();
     return 0;
 }

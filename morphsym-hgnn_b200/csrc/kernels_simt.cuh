@@ -375,7 +375,15 @@ k_reduce_partials(const OutGroup* __restrict__ groups, const float* __restrict__
             double sd = 0.0;
             for (int ti = 0; ti < g.n_tasks; ++ti) {
                 const float* p = part_w + (int64_t)g.tasks[ti] * n_splits * (H * H) + e;
-                for (int sp = 0; sp < n_splits; ++sp) sd += (double)p[(int64_t)sp * (H * H)];
+                int sp = 0;
+                for (; sp + 8 <= n_splits; sp += 8) {      // 8 independent loads in flight, summed in the fixed order
+                    float v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = __ldg(p + (int64_t)(sp + j) * (H * H));
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) sd += (double)v[j];
+                }
+                for (; sp < n_splits; ++sp) sd += (double)__ldg(p + (int64_t)sp * (H * H));
             }
             const float s = (float)(sd * (double)g.scale * (double)rscale);
             for (int oi = 0; oi < g.n_outs; ++oi) grads[(int64_t)g.outs[oi] + (int64_t)o * g.K + g.k0 + i] = s;
@@ -534,12 +542,21 @@ k_decoder_bwd(const DecoderDesc dd, const float* __restrict__ hslab, const __hal
 __global__ void __launch_bounds__(256)
 k_decoder_bwd_reduce(const DecoderDesc dd, const float* __restrict__ part, const int n_blocks, float* __restrict__ grads,
                      const float scale) {
-    for (int e = blockIdx.x * 256 + threadIdx.x; e < dd.C * H + dd.C; e += gridDim.x * 256) {
-        const int src = (e < dd.C * H) ? e : (DEC_MAXC * H + (e - dd.C * H));
-        float s = 0.f;
-        for (int b = 0; b < n_blocks; ++b) s += part[(int64_t)b * (DEC_MAXC * H + DEC_MAXC) + src];
-        s *= scale;
-        if (e < dd.C * H) grads[dd.w_off + e] = s; else grads[dd.b_off + (e - dd.C * H)] = s;
+    // one CTA per output element: thread t sums the partials of blocks t, t + 256, ... (fixed order), then a fixed tree
+    __shared__ float sh[256];
+    const int e = blockIdx.x;
+    const int src = (e < dd.C * H) ? e : (DEC_MAXC * H + (e - dd.C * H));
+    float s = 0.f;
+    for (int b = threadIdx.x; b < n_blocks; b += 256) s += __ldg(part + (int64_t)b * (DEC_MAXC * H + DEC_MAXC) + src);
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const float r = sh[0] * scale;
+        if (e < dd.C * H) grads[dd.w_off + e] = r; else grads[dd.b_off + (e - dd.C * H)] = r;
     }
 }
 

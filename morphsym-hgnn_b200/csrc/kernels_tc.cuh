@@ -1187,7 +1187,16 @@ k_reduce_enc(const EncDwGroup* __restrict__ groups, const float* __restrict__ pa
         const int o = e / g.width, i = e % g.width;
         double sd = 0.0;
         const float* p = part_w + (int64_t)g.first * n_splits * (H * EDW_NMAX) + (int64_t)o * EDW_NMAX + i;
-        for (int us = 0; us < g.count * n_splits; ++us) sd += (double)p[(int64_t)us * (H * EDW_NMAX)];
+        const int n_part = g.count * n_splits;
+        int us = 0;
+        for (; us + 8 <= n_part; us += 8) {          // 8 independent loads in flight, summed in the fixed order
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __ldg(p + (int64_t)(us + j) * (H * EDW_NMAX));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sd += (double)v[j];
+        }
+        for (; us < n_part; ++us) sd += (double)__ldg(p + (int64_t)us * (H * EDW_NMAX));
         grads[(int64_t)g.w_off + (int64_t)o * g.K + g.k0 + i] = (float)(sd * (double)rscale);
     }
     if (g.b_off >= 0 && blockIdx.y == 0)

@@ -28,7 +28,7 @@ EXPORTS = (
     "mshgnn_workspace_bytes", "mshgnn_out_rows", "mshgnn_forward", "mshgnn_loss", "mshgnn_backward",
     "mshgnn_adam_step", "mshgnn_sgd_step", "mshgnn_plan_describe", "mshgnn_launch_count",
     "mshgnn_last_error", "mshgnn_version", "mshgnn_profile_enable", "mshgnn_profile_read", "mshgnn_kernel_kind_name",
-    "mshgnn_relu_mask_offset",
+    "mshgnn_relu_mask_offset", "mshgnn_build_windows",
 )
 
 
@@ -52,6 +52,18 @@ class Desc(C.Structure):
         ("out_channels", C.c_int32),
         ("in_sign", C.POINTER(C.c_float) * MAX_NODE_TYPES),
         ("out_sign", C.POINTER(C.c_float)),
+    ]
+
+
+class WindowDesc(C.Structure):
+    """mshgnn_window_desc (include/mshgnn_b200.h)."""
+    _fields_ = [
+        ("history_length", C.c_int32), ("seq_cols", C.c_int32), ("label_cols", C.c_int32), ("n_node_types", C.c_int32),
+        ("nodes_per_graph", C.c_int32 * MAX_NODE_TYPES), ("blocks_per_node", C.c_int32 * MAX_NODE_TYPES),
+        ("block_len", C.c_int32 * MAX_NODE_TYPES),
+        ("normalize", C.c_int32), ("n_labels", C.c_int32),
+        ("block_col", C.POINTER(C.c_int32)), ("block_sign", C.POINTER(C.c_int32)),
+        ("label_col", C.POINTER(C.c_int32)), ("label_sign", C.POINTER(C.c_int32)),
     ]
 
 
@@ -97,6 +109,8 @@ def lib() -> C.CDLL:
     L.mshgnn_kernel_kind_name.argtypes = [i32]; L.mshgnn_kernel_kind_name.restype = C.c_char_p
     L.mshgnn_relu_mask_offset.argtypes = [vp, i64, i32, i32, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
     L.mshgnn_relu_mask_offset.restype = C.c_int
+    L.mshgnn_build_windows.argtypes = [C.POINTER(WindowDesc), vp, vp, i32, i64, vp, i64, C.POINTER(vp), vp, vp]
+    L.mshgnn_build_windows.restype = C.c_int
     _lib = L
     return L
 

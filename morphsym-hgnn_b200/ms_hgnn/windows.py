@@ -1,0 +1,192 @@
+"""Device-side dataset: sliding windows of a raw sequence -> collated HeteroData node features, on the GPU.
+
+The reference materialises every 150-row window on the host, per sample, in fp64
+(``LinTzuYaunDataset.load_data_at_dataset_seq`` LinTzuYaunDataset.py:L66-88, ``load_data_sorted_k4/_c2``
+LinTzuYaunDataset_Morph.py:L156-347, ``get_helper_heterogeneous_gnn(_c2)`` L555-697, ``FlexibleDataset.get``
+flexibleDataset.py:L444-470) and the DataLoader collates them: 43.2 KB of features per graph cross the host link
+although consecutive windows share 149 of their 150 rows.  Here the raw sequence (216 B per time step for the Mini
+Cheetah data) is uploaded once; a batch is a tensor of window start rows, and ``mshgnn_build_windows`` writes the
+collated ``x_dict`` / ``y`` straight into device memory.  The column order (URDF sort), the base tiling
+and the optional dataset-level group action (``apply_symmetry`` L349-408) are compiled once into a
+column / sign table; the kernel reads no index tensor besides the start rows.
+
+There is no CPU path: ``DeviceSequence`` requires a CUDA device and raises otherwise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _native as N
+from . import morphology as M
+from .synthetic import HeteroBatch
+
+# raw channel arrays of data.mat in the order they are packed side by side (LinTzuYaunDataset.py:L79-85; tau_est is
+# loaded by the reference but returned as None, so it never reaches the model)
+MINI_CHEETAH_CHANNELS = (("imu_acc", 3), ("imu_omega", 3), ("q", 12), ("qd", 12), ("p", 12), ("v", 12))
+# LinTzuYaunDataset.get_urdf_name_to_dataset_array_index (L34-60) composed with the URDF node order RL, FL, RR, FR
+# (flexibleDataset.py:L131-142)
+MINI_CHEETAH_JOINT_ORDER = (9, 10, 11, 3, 4, 5, 6, 7, 8, 0, 1, 2)
+MINI_CHEETAH_FOOT_ORDER = (3, 1, 2, 0)
+
+_MODEL_TYPES = {"heterogeneous_gnn": ("mi_quadruped", 1), "heterogeneous_gnn_k4": ("k4_mini_cheetah", 4),
+                "heterogeneous_gnn_c2": ("c2_mini_cheetah", 2)}
+
+
+def _compose(perm: Sequence[Sequence[int]], coef: Sequence[Sequence[float]], op: Optional[str], n: int, morphsym: bool):
+    """(source index, factor) of every output column j of ``apply_symmetry``: out[:, j] = in[:, src[j]] * f[j]."""
+    if op is None:
+        return list(range(n)), [1] * n
+    one = [1] * n
+    gs = [int(v) for v in coef[0]] if morphsym else one
+    gt = [int(v) for v in coef[1]] if morphsym else one
+    if op == "gs":
+        return [int(perm[0][j]) for j in range(n)], gs
+    if op == "gt":
+        return [int(perm[1][j]) for j in range(n)], gt
+    if op == "gr":      # data[:, P0][:, P1] * (gs * gt)
+        return [int(perm[0][int(perm[1][j])]) for j in range(n)], [gs[j] * gt[j] for j in range(n)]
+    raise ValueError(f"symmetry_operator must be 'gs', 'gt', 'gr' or None, not {op!r}")
+
+
+class WindowSpec:
+    """Compiled column / sign tables of one (dataset, model_type, symmetry) combination."""
+
+    def __init__(self, model_type: str, history_length: int, normalize: bool = True, symmetry_operator: Optional[str] = None,
+                 symmetry_mode: Optional[str] = None, group_operator_path: Optional[str] = None):
+        if model_type not in _MODEL_TYPES:
+            raise ValueError(f"model_type {model_type!r} has no heterogeneous graph layout")
+        # same argument checks as LinTzuYaunDataset_Morph.__init__ (L40-46)
+        if symmetry_operator is not None and ((symmetry_mode != "MorphSym" and symmetry_mode != "Euclidean") or group_operator_path is None):
+            raise ValueError("symmetry_mode must be 'MorphSym' or 'Euclidean' when symmetry_operator is not None.")
+        if symmetry_operator is not None and model_type == "heterogeneous_gnn":
+            raise ValueError("the dataset-level group action exists only for the k4 / c2 graph layouts")
+        if normalize and history_length < 2:
+            raise ValueError("normalize=True needs history_length >= 2")
+        tpl_name, nb = _MODEL_TYPES[model_type]
+        self.template = M.TEMPLATES[tpl_name]
+        self.model_type, self.T, self.normalize = model_type, int(history_length), bool(normalize)
+        off, o = {}, 0
+        for name, w in MINI_CHEETAH_CHANNELS:
+            off[name] = o
+            o += w
+        self.seq_cols = o
+        group = M.load_group(group_operator_path) if symmetry_operator is not None else None
+        ms = symmetry_mode == "MorphSym"
+        op = symmetry_operator
+        g = group or {}
+        # base: np.tile(raw, (1, nb)) then apply_symmetry('base'); tiled column m reads raw column m % 3
+        bsrc, blin = _compose(g.get("permutation_Q_bs"), g.get("reflection_Q_bs_lin"), op, 3 * nb, ms)
+        _, bang = _compose(g.get("permutation_Q_bs"), g.get("reflection_Q_bs_ang"), op, 3 * nb, ms)
+        jsrc, jf = _compose(g.get("permutation_Q_js"), g.get("reflection_Q_js"), op, 12, ms)
+        fsrc, ff = _compose(g.get("permutation_Q_fs"), g.get("reflection_Q_fs"), op, 12, ms)
+        lsrc, lf = _compose(g.get("permutation_Q_ls"), g.get("reflection_Q_ls"), op, 4, ms)
+        col: List[int] = []
+        sign: List[int] = []
+        for i in range(nb):                                 # base node i: [lin_acc xyz | ang_vel xyz], each flatten('F')
+            for name, f in (("imu_acc", blin), ("imu_omega", bang)):
+                for a in range(3):
+                    col.append(off[name] + bsrc[3 * i + a] % 3)
+                    sign.append(f[3 * i + a])
+        for i in range(12):                                 # joint node i: [q | qd]
+            for name in ("q", "qd"):
+                col.append(off[name] + MINI_CHEETAH_JOINT_ORDER[jsrc[i]])
+                sign.append(jf[i])
+        for i in range(4):                                  # foot node i: [p xyz | v xyz]
+            for name in ("p", "v"):
+                for a in range(3):
+                    m = fsrc[3 * i + a]                     # column of the URDF-sorted foot array
+                    col.append(off[name] + 3 * MINI_CHEETAH_FOOT_ORDER[m // 3] + m % 3)
+                    sign.append(ff[3 * i + a])
+        self.nodes = [nb, 12, 4]
+        self.blocks = [6, 2, 6]
+        self.block_len = [self.T] * 3
+        self.block_col, self.block_sign = col, sign
+        self.label_col = [MINI_CHEETAH_FOOT_ORDER[lsrc[i]] for i in range(4)]
+        self.label_sign = list(lf)
+        self.label_cols = 4
+
+    @property
+    def widths(self) -> Dict[str, int]:
+        return {t: self.blocks[k] * self.block_len[k] for k, t in enumerate(self.template.node_types)}
+
+    def pack(self, mat: Dict[str, np.ndarray], dtype=np.float32):
+        """data.mat arrays -> (seq [n_rows, 54], labels [n_rows, 4]) in the packed column order."""
+        n = int(np.asarray(mat["contacts"]).shape[0])
+        seq = np.concatenate([np.asarray(mat[name]).reshape(n, w) for name, w in MINI_CHEETAH_CHANNELS], axis=1).astype(dtype)
+        return np.ascontiguousarray(seq), np.ascontiguousarray(np.asarray(mat["contacts"]).reshape(n, 4).astype(dtype))
+
+
+class DeviceSequence:
+    """One dataset sequence resident on the GPU; ``batch(idx)`` is ``Batch.from_data_list([dataset[i] for i in idx])``.
+
+    ``len()`` and index semantics follow ``FlexibleDataset`` (flexibleDataset.py:L90: ``length = entries - history_length + 1``;
+    entry ``i`` is the window of rows ``[i, i + history_length)`` labelled by its last row)."""
+
+    def __init__(self, mat: Dict[str, np.ndarray], spec: WindowSpec, device, dtype=torch.float32):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("DeviceSequence builds windows with the native CUDA library: no CPU path")
+        if dtype not in (torch.float32, torch.float64):
+            raise ValueError("dtype must be float32 or float64")
+        self.spec, self.device, self.dtype = spec, device, dtype
+        seq, lab = spec.pack(mat, np.float64 if dtype == torch.float64 else np.float32)
+        self.n_rows = seq.shape[0]
+        if self.n_rows < spec.T:
+            raise ValueError("Dataset has too few entries for the provided 'history_length'.")
+        self.seq = torch.from_numpy(seq).to(device)
+        self.labels = torch.from_numpy(lab).to(device)
+        self._edges: Dict[int, dict] = {}
+        s = spec
+        n = len(s.block_col)
+        self._keep = [(C.c_int32 * n)(*s.block_col), (C.c_int32 * n)(*s.block_sign), (C.c_int32 * 4)(*s.label_col), (C.c_int32 * 4)(*s.label_sign)]
+        d = N.WindowDesc()
+        d.history_length, d.seq_cols, d.label_cols, d.n_node_types = s.T, s.seq_cols, s.label_cols, 3
+        for t in range(3):
+            d.nodes_per_graph[t], d.blocks_per_node[t], d.block_len[t] = s.nodes[t], s.blocks[t], s.block_len[t]
+        d.normalize, d.n_labels = int(s.normalize), 4
+        d.block_col = C.cast(self._keep[0], C.POINTER(C.c_int32)); d.block_sign = C.cast(self._keep[1], C.POINTER(C.c_int32))
+        d.label_col = C.cast(self._keep[2], C.POINTER(C.c_int32)); d.label_sign = C.cast(self._keep[3], C.POINTER(C.c_int32))
+        self._desc = d
+
+    def __len__(self) -> int:
+        return self.n_rows - self.spec.T + 1
+
+    def get_data_metadata(self):
+        return self.spec.template.metadata
+
+    def edge_index_dict(self, B: int):
+        if B not in self._edges:
+            self._edges[B] = self.spec.template.edge_index_dict(B, self.device)
+        return self._edges[B]
+
+    def batch(self, idx: torch.Tensor, out: Optional[HeteroBatch] = None) -> HeteroBatch:
+        """Collated batch of the dataset entries ``idx`` (int64; host or device).  ``out``: a batch of the same size
+        returned earlier, whose tensors are overwritten instead of allocating new ones."""
+        idx = torch.as_tensor(idx, dtype=torch.int64)
+        if idx.ndim != 1 or idx.numel() < 1:
+            raise ValueError("idx must be a non-empty 1-D index tensor")
+        if idx.device.type != "cuda":
+            if int(idx.min()) < 0 or int(idx.max()) >= len(self):
+                raise IndexError("dataset index out of range")
+            idx = idx.to(self.device, non_blocking=True)
+        B = idx.numel()
+        s = self.spec
+        names = s.template.node_types
+        if out is None:
+            x = {t: torch.empty(B * s.nodes[k], s.blocks[k] * s.block_len[k], dtype=torch.float32, device=self.device) for k, t in enumerate(names)}
+            y = torch.empty(B * 4, dtype=torch.float32, device=self.device)
+            out = HeteroBatch(x, self.edge_index_dict(B), y, B)
+        elif out.batch_size != B:
+            raise ValueError("out has a different batch size")
+        xs = out.x_dict
+        ptrs = (C.c_void_p * 4)(*[xs[t].data_ptr() for t in names], None)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            N.check(N.lib().mshgnn_build_windows(C.byref(self._desc), self.seq.data_ptr(), self.labels.data_ptr(),
+                                                 N.F64 if self.dtype == torch.float64 else N.F32, self.n_rows, idx.data_ptr(), B,
+                                                 ptrs, out.y.data_ptr(), stream), "mshgnn_build_windows")
+        return out

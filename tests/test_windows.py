@@ -1,0 +1,182 @@
+"""Window builder: compiled column tables and the CUDA kernel vs the numpy restatement of the
+reference's dataset path (oracle/window_oracle.py).
+
+CPU tests: the z-score pin on the reference's golden matrices, and the compiled tables interpreted in numpy (a test-only
+interpreter of the table semantics stated in include/mshgnn_b200.h) against the oracle.  GPU tests: the kernel through
+``DeviceSequence`` (ctypes -> C ABI) against the oracle; tolerance 1e-6 absolute on z-scored features for fp64 sequences
+(the kernel's statistics are fp64, its outputs fp32), labels exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+import window_oracle as WO
+from ms_hgnn import morphology as M
+from ms_hgnn.windows import DeviceSequence, WindowSpec
+
+T = 150
+CASES = [("heterogeneous_gnn_k4", None), ("heterogeneous_gnn_k4", "gs"), ("heterogeneous_gnn_k4", "gt"), ("heterogeneous_gnn_k4", "gr"),
+         ("heterogeneous_gnn_c2", None), ("heterogeneous_gnn_c2", "gs"), ("heterogeneous_gnn", None)]
+
+
+def _kw(model_type, op, mode="MorphSym"):
+    if op is None:
+        return {}, {}
+    name = "mini_cheetah-k4" if model_type.endswith("k4") else "mini_cheetah-c2"
+    path = M.cfg_path(name)
+    return (dict(symmetry_operator=op, symmetry_mode=mode, group_operator_path=path),
+            dict(symmetry_operator=op, symmetry_mode=mode, group=M.load_group(path)))
+
+
+def interpret_table(spec: WindowSpec, seq: np.ndarray, lab: np.ndarray, starts):
+    """Test-only numpy reading of the table contract (mshgnn_window_desc): what the kernel must produce."""
+    xs = [[] for _ in spec.nodes]
+    ys = []
+    for s in starts:
+        w = seq[s:s + spec.T].astype(np.float64)
+        z = WO.zscore(w) if spec.normalize else w
+        b = 0
+        for t, (n, k) in enumerate(zip(spec.nodes, spec.blocks)):
+            rows = np.empty((n, k * spec.T))
+            for i in range(n):
+                for j in range(k):
+                    rows[i, j * spec.T:(j + 1) * spec.T] = np.asarray(z)[:, spec.block_col[b]] * spec.block_sign[b]
+                    b += 1
+            xs[t].append(rows)
+        ys.append(lab[s + spec.T - 1, spec.label_col] * np.asarray(spec.label_sign))
+    return [np.concatenate(v) for v in xs], np.concatenate(ys)
+
+
+def test_zscore_pinned_by_reference_golden_matrices():
+    """tests/testDatasets.py:L513-539 holds z-scored [6, n] matrices (history 6); re-normalising them must be the identity
+    iff the standard deviation uses Bessel's correction (flexibleDataset.py:L396)."""
+    des_la = np.array([[-0.5362300252378239, -1.6632797193920590, -1.5898042183134058],
+                       [0.0423700008727095, -0.2257869376580193, -0.3294529164335535],
+                       [0.0423700008727095, -0.2257869376580193, -0.3294529164335535],
+                       [-0.0272254120334773, 0.0614106314680039, 0.3784460702629509],
+                       [-1.2761523397622021, 1.1253516629229292, 1.3613238439024378],
+                       [1.7548677752880986, 0.9280913003171616, 0.5089401370151242]])
+    des_av = np.array([[0.3922097071448895, -1.9912456309175439, -1.6041605549730955],
+                       [-0.9026040953610488, 0.1920045172187222, -0.2748544676177472],
+                       [-0.9026040953610488, 0.1920045172187222, -0.2748544676177472],
+                       [-0.7582570552051391, 0.7857144431190286, 0.0388281714139248],
+                       [0.7083651482760132, 0.3541357390230436, 0.9208249386706086],
+                       [1.4628903905063348, 0.4673864143380300, 1.1942163801239956]])
+    for des in (des_la, des_av):
+        np.testing.assert_allclose(np.asarray(WO.zscore(des)), des, atol=1e-12)
+        biased = (des - des.mean(0)) / des.std(0)          # n instead of n - 1: must NOT reproduce the pins
+        assert np.abs(biased - des).max() > 1e-2
+    const = np.full((6, 2), 3.25)
+    assert np.all(np.asarray(WO.zscore(const)) == 0.0)     # 0/0 -> NaN -> 0
+
+
+@pytest.mark.parametrize("model_type,op", CASES)
+def test_compiled_tables_match_reference_restatement(model_type, op):
+    mat = WO.synthetic_mat(400, seed=3)
+    skw, okw = _kw(model_type, op)
+    spec = WindowSpec(model_type, T, True, **skw)
+    seq, lab = spec.pack(mat, np.float64)
+    starts = [0, 1, 17, 250]
+    xs, y = interpret_table(spec, seq, lab, starts)
+    xo, yo = WO.batch(mat, starts, model_type, T, normalize=True, **okw)
+    for t, name in enumerate(("base", "joint", "foot")):
+        assert xs[t].shape == tuple(xo[name].shape)
+        np.testing.assert_allclose(xs[t], xo[name].numpy(), atol=1e-12, rtol=0)
+    np.testing.assert_array_equal(y, yo.numpy())
+
+
+def test_euclidean_mode_and_unnormalised_tables():
+    mat = WO.synthetic_mat(300, seed=5)
+    skw, okw = _kw("heterogeneous_gnn_k4", "gr", "Euclidean")
+    spec = WindowSpec("heterogeneous_gnn_k4", 10, False, **skw)
+    seq, lab = spec.pack(mat, np.float64)
+    xs, y = interpret_table(spec, seq, lab, [5, 100])
+    xo, yo = WO.batch(mat, [5, 100], "heterogeneous_gnn_k4", 10, normalize=False, **okw)
+    for t, name in enumerate(("base", "joint", "foot")):
+        np.testing.assert_array_equal(xs[t], xo[name].numpy())
+    np.testing.assert_array_equal(y, yo.numpy())
+
+
+def test_argument_errors_mirror_the_reference():
+    with pytest.raises(ValueError):
+        WindowSpec("heterogeneous_gnn_k4", T, True, symmetry_operator="gs")                      # no mode / path
+    with pytest.raises(ValueError):
+        WindowSpec("dynamics", T)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        DeviceSequence(WO.synthetic_mat(200), WindowSpec("heterogeneous_gnn_k4", T), "cpu")
+
+
+# ------------------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("model_type,op", CASES)
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_kernel_matches_oracle(model_type, op, dtype):
+    mat = WO.synthetic_mat(600, seed=11, dtype=np.float64 if dtype == torch.float64 else np.float32)
+    skw, okw = _kw(model_type, op)
+    spec = WindowSpec(model_type, T, True, **skw)
+    ds = DeviceSequence(mat, spec, "cuda:0", dtype)
+    assert len(ds) == 600 - T + 1
+    g = torch.Generator().manual_seed(1)
+    idx = torch.cat((torch.tensor([0, len(ds) - 1, 7, 7]), torch.randint(0, len(ds), (61,), generator=g)))
+    b = ds.batch(idx)
+    xo, yo = WO.batch(mat, idx.tolist(), model_type, T, normalize=True, **okw)
+    # fp64 sequence: fp64 statistics, fp32 rounding of the result only.  fp32 sequence: the oracle sees the same fp32
+    # samples (promoted exactly to fp64), so the same bound holds.
+    for name in ("base", "joint", "foot"):
+        got = b.x_dict[name].cpu().double()
+        assert got.shape == xo[name].shape
+        assert (got - xo[name]).abs().max().item() <= 1e-6
+    assert torch.equal(b.y.cpu().double(), yo)
+    ei = b.edge_index_dict
+    for et, v in spec.template.edge_index_dict(idx.numel()).items():
+        assert torch.equal(ei[et].cpu(), v)                      # bit-exact batching
+
+
+@pytest.mark.gpu
+def test_kernel_unnormalised_short_history_and_reuse():
+    mat = WO.synthetic_mat(64, seed=2)
+    spec = WindowSpec("heterogeneous_gnn_c2", 5, False)
+    ds = DeviceSequence(mat, spec, "cuda:0", torch.float64)
+    idx = torch.arange(len(ds))
+    b = ds.batch(idx)
+    xo, yo = WO.batch(mat, idx.tolist(), "heterogeneous_gnn_c2", 5, normalize=False)
+    for name in ("base", "joint", "foot"):
+        assert torch.equal(b.x_dict[name].cpu(), xo[name].float())
+    b2 = ds.batch(idx.flip(0).cuda(), out=b)                      # device indices, buffers reused
+    assert b2 is b
+    assert torch.equal(b.y.cpu().double(), yo.reshape(-1, 4).flip(0).reshape(-1))
+    with pytest.raises(IndexError):
+        ds.batch(torch.tensor([len(ds)]))
+
+
+@pytest.mark.gpu
+def test_windowed_batch_feeds_the_model_like_a_host_batch():
+    """Full-size property (16384 graphs): a batch built on the device equals the host-collated one bit for bit after the
+    same fp32 rounding, so the native forward gives identical logits for both."""
+    from ms_hgnn.synthetic import CONFIGS, HeteroBatch, build_model
+    mat = WO.synthetic_mat(16384 + T - 1, seed=4, dtype=np.float32)
+    spec = WindowSpec("heterogeneous_gnn_k4", T, True)
+    ds = DeviceSequence(mat, spec, "cuda:0", torch.float32)
+    idx = torch.randperm(len(ds), generator=torch.Generator().manual_seed(9))
+    b = ds.batch(idx)
+    assert b.batch_size == 16384
+    # z-scored blocks: mean 0, Bessel std 1 (or all-zero for the constant column) for EVERY block of every graph
+    for name, k in (("base", 6), ("joint", 2), ("foot", 6)):
+        v = b.x_dict[name].view(-1, k, T).double()
+        assert v.mean(-1).abs().max().item() < 1e-5
+        sd = v.std(-1)
+        assert ((sd - 1).abs() < 1e-5).logical_or(sd == 0).all()
+    # spot-check 32 graphs against the oracle and run the model on both
+    sel = torch.arange(0, 16384, 512)
+    xo, yo = WO.batch(mat, idx[sel].tolist(), "heterogeneous_gnn_k4", T, normalize=True)
+    for name, n in (("base", 4), ("joint", 12), ("foot", 4)):
+        rows = (sel[:, None] * n + torch.arange(n)[None]).reshape(-1)
+        assert (b.x_dict[name][rows.cuda()].cpu().double() - xo[name]).abs().max().item() <= 1e-6
+    cfg = CONFIGS["mini_cheetah-k4-contact"]
+    nm = build_model(cfg, layers=8, seed=3).to("cuda:0")
+    with torch.no_grad():
+        y_dev = nm(b.x_dict, b.edge_index_dict)
+        host = HeteroBatch({k: v.cpu() for k, v in b.x_dict.items()}, {k: v.cpu() for k, v in b.edge_index_dict.items()}, b.y.cpu(), 16384)
+        hb = host.to("cuda:0")
+        y_host = nm(hb.x_dict, hb.edge_index_dict)
+    assert torch.equal(y_dev, y_host)
