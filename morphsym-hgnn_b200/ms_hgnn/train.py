@@ -11,6 +11,7 @@ flat fp32 gradient buffer (8.6 MB for the K4 model) is summed with a single all-
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -23,7 +24,7 @@ def allreduce_flat_(grads: torch.Tensor, world: int, group=None) -> torch.Tensor
 
     Each rank's loss gradient is pre-scaled by 1/world (``loss_scale``), so the sum equals the gradient of the
     mean loss over the global batch when the shards have equal size; no post-divide is needed."""
-    if world > 1:
+    if world > 1 and not os.environ.get("MSHGNN_DEBUG_SKIP_ALLREDUCE"):     # debug switch: isolates the collective's cost
         torch.distributed.all_reduce(grads, op=torch.distributed.ReduceOp.SUM, group=group)
     return grads
 

@@ -73,7 +73,7 @@ class WindowSpec:
         for name, w in MINI_CHEETAH_CHANNELS:
             off[name] = o
             o += w
-        self.seq_cols = o
+        self.seq_cols = (o + 3) // 4 * 4        # rows padded to a 16-byte multiple: one bulk async copy per window
         group = M.load_group(group_operator_path) if symmetry_operator is not None else None
         ms = symmetry_mode == "MorphSym"
         op = symmetry_operator
@@ -114,9 +114,11 @@ class WindowSpec:
         return {t: self.blocks[k] * self.block_len[k] for k, t in enumerate(self.template.node_types)}
 
     def pack(self, mat: Dict[str, np.ndarray], dtype=np.float32):
-        """data.mat arrays -> (seq [n_rows, 54], labels [n_rows, 4]) in the packed column order."""
+        """data.mat arrays -> (seq [n_rows, 56] (54 channels + zero padding), labels [n_rows, 4]) in the packed column order."""
         n = int(np.asarray(mat["contacts"]).shape[0])
         seq = np.concatenate([np.asarray(mat[name]).reshape(n, w) for name, w in MINI_CHEETAH_CHANNELS], axis=1).astype(dtype)
+        if seq.shape[1] < self.seq_cols:
+            seq = np.concatenate([seq, np.zeros((n, self.seq_cols - seq.shape[1]), dtype=dtype)], axis=1)
         return np.ascontiguousarray(seq), np.ascontiguousarray(np.asarray(mat["contacts"]).reshape(n, 4).astype(dtype))
 
 

@@ -133,6 +133,22 @@ def test_kernel_matches_oracle(model_type, op, dtype):
 
 
 @pytest.mark.gpu
+def test_kernel_unpadded_rows_take_the_element_load_path():
+    """54-column rows are not 16-byte multiples: the kernel falls back from the bulk async copy to element loads."""
+    mat = WO.synthetic_mat(500, seed=13)
+    spec = WindowSpec("heterogeneous_gnn_k4", T, True)
+    spec.seq_cols = 54
+    ds = DeviceSequence(mat, spec, "cuda:0", torch.float64)
+    assert ds.seq.shape[1] == 54
+    idx = torch.arange(0, len(ds), 3)
+    b = ds.batch(idx)
+    xo, yo = WO.batch(mat, idx.tolist(), "heterogeneous_gnn_k4", T, normalize=True)
+    for name in ("base", "joint", "foot"):
+        assert (b.x_dict[name].cpu().double() - xo[name]).abs().max().item() <= 1e-6
+    assert torch.equal(b.y.cpu().double(), yo)
+
+
+@pytest.mark.gpu
 def test_kernel_unnormalised_short_history_and_reuse():
     mat = WO.synthetic_mat(64, seed=2)
     spec = WindowSpec("heterogeneous_gnn_c2", 5, False)
