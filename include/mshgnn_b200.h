@@ -176,6 +176,20 @@ typedef struct mshgnn_window_desc {
 int mshgnn_build_windows(const mshgnn_window_desc* desc, const void* seq, const void* label_seq, int32_t seq_dtype,
                          int64_t n_rows, const int64_t* starts, int64_t B, float* const* x, float* y, void* stream);
 
+/* ---- fused step metrics -------------------------------------------------------
+ * Everything Base_Lightning.calculate_losses_step derives from (y_pred, y) besides the loss gradient
+ * (gnnLightning.py:L124-151, L285-348; customMetrics.py:L6-54), without a host sync:
+ *   MSHGNN_LOSS_CE2: n = graphs, out [n*feet, 2] logits, labels [n, feet] in {0,1}
+ *     slots 0 CE sum, 1 rows, 2 graphs whose 16-class argmax is right, 3 graphs, 4+4*leg+{0,1,2,3} = tp fp fn tn,
+ *     20 CE mean (fp32-rounded), 21 16-class accuracy, 22..25 binary F1 of leg 0..3 (NaN -> 0)
+ *   MSHGNN_LOSS_MSE: n = elements; slots 0 sum sq. err, 1 sum abs. err, 2 n, 20 MSE, 21 RMSE, 22 L1
+ * batch[MSHGNN_METRIC_SLOTS] receives this call's values; slots 0..19 are also ADDED to epoch[] when it is not NULL
+ * (torchmetrics' dist_reduce_fx="sum" states).  scratch: MSHGNN_METRIC_SCRATCH doubles of device memory. */
+#define MSHGNN_METRIC_SLOTS   32
+#define MSHGNN_METRIC_SCRATCH (296 * 32)
+int mshgnn_step_metrics(int32_t loss_kind, int64_t n, int32_t feet, const float* out, const void* labels, int32_t label_dtype,
+                        double* batch, double* epoch, double* scratch, void* stream);
+
 /* JSON summary of the compiled tables (slots, liveness, gather lists); returns the bytes needed
  * (including the terminating NUL).  Host-only: usable without a GPU. */
 int64_t mshgnn_plan_describe(const mshgnn_plan* plan, char* buf, int64_t cap);

@@ -14,6 +14,7 @@
 #include "kernels_tc.cuh"
 #include "plan.cuh"
 #include "windows.cuh"
+#include "metrics.cuh"
 
 using namespace mshgnn;
 
@@ -43,11 +44,11 @@ int fail(int code, const char* fmt, ...) {
 
 // ---- per-kernel event profiling ----
 enum Kind : int { K_DERIVE = 0, K_ENC_FWD, K_CONV_FWD, K_MLP_FWD, K_DEC_FWD, K_LOSS, K_DEC_BWD, K_MLP_BWD, K_DX_BWD,
-                  K_DW_LAYER, K_DW_ENC, K_REDUCE, K_OPTIM, K_MEMSET, K_WINDOWS, K_NKINDS };
+                  K_DW_LAYER, K_DW_ENC, K_REDUCE, K_OPTIM, K_MEMSET, K_WINDOWS, K_METRICS, K_NKINDS };
 const char* const kKindNames[MSHGNN_NUM_KERNEL_KINDS] = {
     "derive_weights", "encoder_fwd", "conv_fwd", "base_mlp_fwd", "decoder_fwd", "loss",
     "decoder_bwd", "base_mlp_bwd", "dx_bwd", "dw_layers", "dw_encoder",
-    "reduce_partials", "optimizer", "memset", "window_builder", ""};
+    "reduce_partials", "optimizer", "memset", "window_builder", "step_metrics"};
 struct ProfRec { int kind; cudaEvent_t a, b; };
 std::mutex g_prof_mu;
 bool g_prof_on = false;
@@ -678,6 +679,23 @@ int mshgnn_build_windows(const mshgnn_window_desc* d, const void* seq, const voi
         CUDA_TRY(cudaFuncSetAttribute(k_build_windows<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_build_windows<float><<<grid, WIN_THREADS, smem, st>>>(tb, (const float*)seq, (const float*)label_seq, n_rows, starts, B, out, y, bulk);
     }
+    LAUNCH_CHECK();
+    return 0;
+}
+
+int mshgnn_step_metrics(int32_t loss_kind, int64_t n, int32_t feet, const float* out, const void* labels, int32_t label_dtype,
+                        double* batch, double* epoch, double* scratch, void* stream) {
+    if (!out || !labels || !batch || !scratch || n < 1) return fail(MSHGNN_ERR_ARG, "bad argument");
+    if (loss_kind != MSHGNN_LOSS_MSE && loss_kind != MSHGNN_LOSS_CE2) return fail(MSHGNN_ERR_ARG, "bad loss_kind");
+    if (loss_kind == MSHGNN_LOSS_CE2 && (feet < 1 || feet > 4)) return fail(MSHGNN_ERR_ARG, "classification metrics need 1..4 rows per graph");
+    if (label_dtype < 0 || label_dtype > 2) return fail(MSHGNN_ERR_ARG, "bad label_dtype");
+    cudaStream_t st = (cudaStream_t)stream;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > MET_BLOCKS) blocks = MET_BLOCKS;
+    ProfScope ps(K_METRICS, st);
+    k_metrics_partial<<<blocks, 256, 0, st>>>(loss_kind, feet, out, labels, label_dtype, n, scratch);
+    LAUNCH_CHECK();
+    k_metrics_final<<<1, 32, 0, st>>>(loss_kind, scratch, blocks, batch, epoch);
     LAUNCH_CHECK();
     return 0;
 }

@@ -355,6 +355,148 @@ __device__ __forceinline__ void tc_epilogue(const Tile& t, const BufTable& bt, c
     if (leader && !es.persistent) tma_store_wait_all();
 }
 
+// Epilogue of the persistent kernel: ONE group of four warps (one TMEM lane quarter each) drains a whole 128 x 128
+// accumulator through its private 32 KB staging pair (hi | lo tiles of 128 rows x 64 fp16), one column half after the
+// other.  The two groups of a CTA work on ALTERNATE items (group g always owns accumulator set g), so the latency chain
+// of one item - residual tiles in by TMA, accumulator read-back, TMA stores that must have read the staging before it is
+// reused - overlaps the arithmetic of the other group instead of stalling all eight warps at once (ncu: with both groups
+// on the same item the epilogue warps, not the MMA or the operand stream, paced the kernel).
+__device__ __forceinline__ void tc_epilogue_alt(const Tile& t, const BufTable& bt, const BufRows& br, const CUtensorMap* map_o,
+                                                const uint32_t tmem_acc, const int row0, const int64_t B, const int64_t Bp,
+                                                const int split, const int warp, const int lane, const int grp, const EpiSmem es,
+                                                uint32_t& res_count) {
+    const int q = warp & 3;                        // TMEM lane quarter this warp may access (hardware rule: warp index mod 4)
+    const bool leader = ((warp - 2) & 3) == 0 && lane == 0;
+    const int rl = q * 32 + lane;                  // row inside the tile
+    const int64_t row = (int64_t)row0 + rl;
+    const bool live = row < B;
+    const uint32_t rsw = (uint32_t)(rl & 7);
+    const uint32_t tile = es.stg + (uint32_t)rl * 128u;
+    const bool has_out = t.out_buf >= 0, has_out2 = t.out2_buf >= 0, has_res = t.res_buf >= 0;
+    const bool want_mask = t.relu || t.mask_out_buf >= 0;
+
+    auto fetch_residual = [&](const int half) {
+        const int r_hi = br.hi[t.res_buf] + (int)((int64_t)t.res_slot * Bp) + row0, r_lo = br.lo[t.res_buf] + (int)((int64_t)t.res_slot * Bp) + row0;
+        mbar_expect_tx(es.res_bar, 2u * 16384u);
+        tma_load_2d(es.stg, map_o, es.res_bar, half * 64, r_hi);
+        tma_load_2d(es.stg + 16384, map_o, es.res_bar, half * 64, r_lo);
+    };
+    // the staging tiles may still feed this group's previous TMA stores: wait until those have been read, then fetch the
+    // residual of the first column half early so that its latency hides behind the MMAs of this item
+    if (leader) {
+        tma_store_wait_read();
+        if (has_res) fetch_residual(0);
+    }
+    {
+        const float bv = t.bias_buf >= 0 ? __ldg((const float*)bt.p[t.bias_buf] + t.bias_off + rl) : 0.f;
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(es.bias + 4u * rl), "f"(bv) : "memory");
+    }
+    uint4 pm = make_uint4(~0u, ~0u, ~0u, ~0u), m2 = make_uint4(~0u, ~0u, ~0u, ~0u);
+    if (live && t.posmask_buf >= 0) pm = __ldg(reinterpret_cast<const uint4*>(bt.p[t.posmask_buf]) + (int64_t)t.posmask_slot * Bp + row);
+    if (live && has_out2 && t.out2_mask_kind == MK_BITS)
+        m2 = __ldg(reinterpret_cast<const uint4*>(bt.p[t.out2_mask_buf]) + (int64_t)t.out2_mask_slot * Bp + row);
+    const uint32_t pmw[4] = {pm.x, pm.y, pm.z, pm.w}, m2w[4] = {m2.x, m2.y, m2.z, m2.w};
+    uint32_t mw[4] = {0u, 0u, 0u, 0u};
+    group_bar_sync(grp);
+
+    mbar_wait(es.accum_bar, es.acc_parity);
+    tc_fence_after();
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+        if (half == 1) {
+            if (leader) {
+                tma_store_wait_read();
+                if (has_res) fetch_residual(1);
+            }
+            group_bar_sync(grp);
+        }
+        if (has_res) {
+            mbar_wait(es.res_bar, res_count & 1u);
+            ++res_count;
+        }
+#pragma unroll 1
+        for (int c2 = 0; c2 < 2; ++c2) {
+            const int cc = half * 2 + c2;
+            uint32_t raw[32];
+            tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + cc * 32, raw);
+            tmem_ld_wait();
+            if (cc == 3) {                         // last read of this accumulator by this thread: hand it back
+                tc_fence_before();
+                mbar_arrive(es.free_bar);
+            }
+            float v[32];
+            unsigned mask = 0;
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+                float4 b4;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(es.bias + 4u * (cc * 32 + j4 * 4)));
+                const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int j = j4 * 4 + e;
+                    float x = fmaf(__uint_as_float(raw[j]), TC_W_UNSCALE, bb[e]);
+                    if (want_mask && x > 0.f) mask |= 1u << j;
+                    if (t.relu) x = fmaxf(x, 0.f);
+                    v[j] = x;
+                }
+            }
+            mw[cc] = mask;
+            if (t.posmask_buf >= 0) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = ((pmw[cc] >> j) & 1u) ? v[j] : 0.f;
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const uint32_t a = tile + ((((uint32_t)(c2 * 4 + g)) ^ rsw) << 4);
+                if (has_res) join8_add(v + g * 8, lds128(a), lds128(a + 16384));
+                if (has_out || has_out2) {
+                    uint4 hi, lo;
+                    split8(v + g * 8, hi, lo);
+                    if (!has_out) { hi = mask8(hi, m2w[cc] >> (g * 8)); lo = mask8(lo, m2w[cc] >> (g * 8)); }
+                    if (!live) { hi = make_uint4(0u, 0u, 0u, 0u); lo = hi; }     // rows [B, Bp) of every image stay zero
+                    sts128(a, hi);
+                    sts128(a + 16384, lo);
+                }
+            }
+        }
+        fence_proxy_async_smem();
+        group_bar_sync(grp);
+        if (leader) {
+            const int ob = has_out ? t.out_buf : t.out2_buf, os = has_out ? t.out_slot : t.out2_slot;
+            if (ob >= 0) {
+                const int o = (int)((int64_t)os * Bp) + row0;
+                tma_store_2d(map_o, es.stg, half * 64, br.hi[ob] + o);
+                tma_store_2d(map_o, es.stg + 16384u, half * 64, br.lo[ob] + o);
+                tma_store_commit();
+            }
+        }
+        if (has_out && has_out2) {
+            // second output = first output with the masked-off lanes cleared, made in place once the first store has read the tile
+            if (leader) tma_store_wait_read();
+            group_bar_sync(grp);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const uint32_t a = tile + ((((uint32_t)c) ^ rsw) << 4);
+                const uint32_t m = m2w[half * 2 + (c >> 2)] >> ((c & 3) * 8);
+                sts128(a, mask8(lds128(a), m));
+                sts128(a + 16384, mask8(lds128(a + 16384), m));
+            }
+            fence_proxy_async_smem();
+            group_bar_sync(grp);
+            if (leader) {
+                const int o = (int)((int64_t)t.out2_slot * Bp) + row0;
+                tma_store_2d(map_o, es.stg, half * 64, br.hi[t.out2_buf] + o);
+                tma_store_2d(map_o, es.stg + 16384u, half * 64, br.lo[t.out2_buf] + o);
+                tma_store_commit();
+            }
+        }
+    }
+    if (live && t.mask_out_buf >= 0) {
+        uint32_t* mp = reinterpret_cast<uint32_t*>(bt.p[t.mask_out_buf]) + ((int64_t)t.mask_out_slot * Bp + row) * 4;
+        *reinterpret_cast<uint4*>(mp) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // row-GEMM on tcgen05
 // ------------------------------------------------------------------------------------------
@@ -477,7 +619,7 @@ k_tc_rowgemm_persistent(const __grid_constant__ TcMaps maps, const Tile* __restr
                         const BufTable bt, const BufRows br, const int64_t B, const int64_t Bp, const int split) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ Tile ts[PK_MAX_TILES];
-    __shared__ __align__(16) float bias_s[H];
+    __shared__ __align__(16) float bias_s[2][H];          // one per epilogue group
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x;
@@ -495,7 +637,8 @@ k_tc_rowgemm_persistent(const __grid_constant__ TcMaps maps, const Tile* __restr
     }
     if (tid == 0) {
         for (int s = 0; s < PK_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(acc_full0 + 8 * a, 1); mbar_init(acc_free0 + 8 * a, 256); mbar_init(res_bar + 8 * a, 1); }
+        // acc_free: the 128 threads of the epilogue group that owns the accumulator set arrive once per item
+        for (int a = 0; a < 2; ++a) { mbar_init(acc_full0 + 8 * a, 1); mbar_init(acc_free0 + 8 * a, 128); mbar_init(res_bar + 8 * a, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), PK_TMEM_COLS);
@@ -563,16 +706,17 @@ k_tc_rowgemm_persistent(const __grid_constant__ TcMaps maps, const Tile* __restr
         }
         __syncwarp();
     } else {
+        // group g (warps 2 + 4g .. 5 + 4g) drains accumulator set g: the items k = g (mod 2) of this CTA
+        const int grp = (warp - 2) >> 2;
         EpiSmem es;
-        es.stg = smem_base + PK_PIPE_BYTES; es.bias = smem_u32(bias_s); es.res_bar = res_bar; es.persistent = 1; es.n_groups = 2;
+        es.stg = smem_base + PK_PIPE_BYTES + grp * 32768; es.bias = smem_u32(bias_s[grp]); es.res_bar = res_bar + 8 * grp;
+        es.persistent = 1; es.n_groups = 2;
+        es.accum_bar = acc_full0 + 8 * grp; es.free_bar = acc_free0 + 8 * grp; es.res_parity = 0;
         uint32_t k = 0, n_res = 0;
         for (int i = blockIdx.x; i < n_items; i += gridDim.x, ++k) {
-            const Tile& t = ts[i % n_tiles];
-            const uint32_t a = k & 1;
-            es.accum_bar = acc_full0 + 8 * a; es.free_bar = acc_free0 + 8 * a;
-            es.acc_parity = (k >> 1) & 1; es.res_parity = n_res & 1;
-            if (t.res_buf >= 0) ++n_res;
-            tc_epilogue(t, bt, br, &maps.o, tmem_base + a * 128, (i / n_tiles) * TILE_M, B, Bp, split, warp, lane, es);
+            if ((int)(k & 1u) != grp) continue;
+            es.acc_parity = (k >> 1) & 1;
+            tc_epilogue_alt(ts[i % n_tiles], bt, br, &maps.o, tmem_base + grp * 128, (i / n_tiles) * TILE_M, B, Bp, split, warp, lane, grp, es, n_res);
         }
         if (((warp - 2) & 3) == 0 && lane == 0) tma_store_wait_all();
     }

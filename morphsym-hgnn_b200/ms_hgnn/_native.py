@@ -28,7 +28,7 @@ EXPORTS = (
     "mshgnn_workspace_bytes", "mshgnn_out_rows", "mshgnn_forward", "mshgnn_loss", "mshgnn_backward",
     "mshgnn_adam_step", "mshgnn_sgd_step", "mshgnn_plan_describe", "mshgnn_launch_count",
     "mshgnn_last_error", "mshgnn_version", "mshgnn_profile_enable", "mshgnn_profile_read", "mshgnn_kernel_kind_name",
-    "mshgnn_relu_mask_offset", "mshgnn_build_windows",
+    "mshgnn_relu_mask_offset", "mshgnn_build_windows", "mshgnn_step_metrics",
 )
 
 
@@ -111,6 +111,7 @@ def lib() -> C.CDLL:
     L.mshgnn_relu_mask_offset.restype = C.c_int
     L.mshgnn_build_windows.argtypes = [C.POINTER(WindowDesc), vp, vp, i32, i64, vp, i64, C.POINTER(vp), vp, vp]
     L.mshgnn_build_windows.restype = C.c_int
+    L.mshgnn_step_metrics.argtypes = [i32, i64, i32, vp, vp, i32, vp, vp, vp, vp]; L.mshgnn_step_metrics.restype = C.c_int
     _lib = L
     return L
 
@@ -230,6 +231,14 @@ class NativePlan:
         arr = (C.c_void_p * len(x_ptrs))(*x_ptrs)
         check(lib().mshgnn_backward(self.handle, B, arr, x_dtype, params_ptr, dout_ptr, grads_ptr, ws_ptr, ws_bytes, mode, stream),
               "mshgnn_backward")
+
+
+METRIC_SLOTS, METRIC_SCRATCH = 32, 296 * 32
+
+
+def step_metrics(kind, n, feet, out_ptr, labels_ptr, label_dtype, batch_ptr, epoch_ptr, scratch_ptr, stream):
+    check(lib().mshgnn_step_metrics(kind, n, feet, out_ptr, labels_ptr, label_dtype, batch_ptr, epoch_ptr, scratch_ptr, stream),
+          "mshgnn_step_metrics")
 
 
 def adam_step(params_ptr, grads_ptr, m_ptr, v_ptr, n, step, lr, b1, b2, eps, wd, stream):

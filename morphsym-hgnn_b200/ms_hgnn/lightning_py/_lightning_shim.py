@@ -51,6 +51,9 @@ except Exception:
                 x, ei, y = eb
                 B = x["base"].shape[0] if "base" in x else 1
                 hp["dummy_batch"] = HeteroBatch(x, ei, y, B)
+            elif isinstance(hp.get("dummy_batch"), dict) and "x" in hp["dummy_batch"]:      # train_model's own checkpoints
+                d = hp["dummy_batch"]
+                hp["dummy_batch"] = HeteroBatch(d["x"], d["edge_index"], d["y"], d["batch_size"])
             hp.update(overrides)
             names = [p for p in inspect.signature(cls.__init__).parameters if p != "self"]
             obj = cls(**{k: v for k, v in hp.items() if k in names})

@@ -10,10 +10,54 @@ import torch
 from torch import nn
 
 
+class FusedStepMetrics:
+    """Device-side accumulators of ``mshgnn_step_metrics`` (include/mshgnn_b200.h): one native call per step produces this
+    batch's values (``batch``) and adds the counts to the epoch states (``epoch``), replacing ~80 small torch launches of
+    the op-by-op path below (and the reference's host-side sklearn / python loop, gnnLightning.py:L285-348)."""
+
+    def __init__(self):
+        self.batch = self.epoch = self.scratch = None
+        self.dirty = False
+
+    def update(self, kind: int, out2d: torch.Tensor, labels: torch.Tensor, n: int, feet: int) -> torch.Tensor:
+        from .. import _native as N
+        dev = out2d.device
+        if self.batch is None or self.batch.device != dev:
+            self.batch = torch.zeros(N.METRIC_SLOTS, dtype=torch.float64, device=dev)
+            self.epoch = torch.zeros(N.METRIC_SLOTS, dtype=torch.float64, device=dev)
+            self.scratch = torch.empty(N.METRIC_SCRATCH, dtype=torch.float64, device=dev)
+        if out2d.dtype != torch.float32 or not out2d.is_contiguous():
+            out2d = out2d.float().contiguous()
+        labels = labels.reshape(-1).contiguous()
+        code = {torch.float32: N.F32, torch.float64: N.F64, torch.int64: N.I64}.get(labels.dtype)
+        if code is None:
+            labels, code = labels.double(), N.F64
+        with torch.cuda.device(dev):
+            N.step_metrics(kind, n, feet, out2d.data_ptr(), labels.data_ptr(), code, self.batch.data_ptr(), self.epoch.data_ptr(),
+                           self.scratch.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+        self.dirty = True
+        return self.batch
+
+    def reset(self):
+        if self.epoch is not None:
+            self.epoch.zero_()
+        self.dirty = False
+
+
 class _Metric(nn.Module):
     def __init__(self):
         super().__init__()
         self._state = {}
+        self._fused = None
+        self._fused_fn = None
+
+    def bind(self, fused: FusedStepMetrics, fn):
+        """Epoch value comes from the fused accumulators (``fn(epoch) -> tensor``) whenever the fused kernel fed this epoch."""
+        self._fused, self._fused_fn = fused, fn
+        return self
+
+    def _from_fused(self):
+        return self._fused is not None and self._fused.dirty and not self._state
 
     def _acc(self, name, value):
         v = value.detach().double()
@@ -21,6 +65,8 @@ class _Metric(nn.Module):
 
     def reset(self):
         self._state = {}
+        if self._fused is not None:
+            self._fused.reset()
 
     def forward(self, preds, target):
         batch = self.update(preds, target)
@@ -40,6 +86,8 @@ class MeanSquaredError(_Metric):
         return mse if self.squared else torch.sqrt(mse)
 
     def compute(self):
+        if self._from_fused():
+            return self._fused_fn(self._fused.epoch)
         mse = self._state["sse"] / self._state["n"]
         return mse if self.squared else torch.sqrt(mse)
 
@@ -51,6 +99,8 @@ class MeanAbsoluteError(_Metric):
         return d.mean()
 
     def compute(self):
+        if self._from_fused():
+            return self._fused_fn(self._fused.epoch)
         return self._state["sae"] / self._state["n"]
 
 
@@ -70,6 +120,8 @@ class CrossEntropyLossMetric(_Metric):
         self._acc("n", torch.tensor(float(n_rows), device=batch_mean.device))
 
     def compute(self):
+        if self._from_fused():
+            return self._fused_fn(self._fused.epoch)
         return self._state["sum"].float() / self._state["n"]
 
 
@@ -80,6 +132,8 @@ class MulticlassAccuracy(_Metric):
         return ok.double() / preds.numel()
 
     def compute(self):
+        if self._from_fused():
+            return self._fused_fn(self._fused.epoch)
         return self._state["ok"] / self._state["n"]
 
 
@@ -100,6 +154,8 @@ class BinaryF1Score(_Metric):
         return torch.nan_to_num(2 * (precision * recall) / (precision + recall))
 
     def compute(self):
+        if self._from_fused():
+            return self._fused_fn(self._fused.epoch)
         return self._f1(self._state["tp"], self._state["fp"], self._state["fn"])
 
 

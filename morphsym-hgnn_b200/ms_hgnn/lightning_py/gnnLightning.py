@@ -19,7 +19,7 @@ from torch import nn, optim
 from .. import _native as N
 from ..modules import native_loss
 from ._lightning_shim import LightningModule
-from .customMetrics import (BinaryF1Score, CrossEntropyLossMetric, MeanAbsoluteError, MeanSquaredError,
+from .customMetrics import (BinaryF1Score, CrossEntropyLossMetric, FusedStepMetrics, MeanAbsoluteError, MeanSquaredError,
                             MulticlassAccuracy)
 from .hgnn import GRF_HGNN
 from .hgnn_c2 import GRF_HGNN_C2
@@ -47,6 +47,18 @@ class Base_Lightning(LightningModule):
         self.metric_f1_leg3 = BinaryF1Score()
         self.mse_loss = self.rmse_loss = self.l1_loss = self.ce_loss = self.acc = None
         self.f1_leg0 = self.f1_leg1 = self.f1_leg2 = self.f1_leg3 = None
+        # CUDA batches: one fused native call per step feeds every metric (mshgnn_step_metrics)
+        self._fused = FusedStepMetrics()
+        f1 = BinaryF1Score._f1
+        if regression:
+            self.metric_mse.bind(self._fused, lambda e: e[0] / e[2])
+            self.metric_rmse.bind(self._fused, lambda e: torch.sqrt(e[0] / e[2]))
+            self.metric_l1.bind(self._fused, lambda e: e[1] / e[2])
+        else:
+            self.metric_ce.bind(self._fused, lambda e: e[0].float() / e[1])
+            self.metric_acc.bind(self._fused, lambda e: e[2] / e[3])
+            for leg, m in enumerate((self.metric_f1_leg0, self.metric_f1_leg1, self.metric_f1_leg2, self.metric_f1_leg3)):
+                m.bind(self._fused, lambda e, k=leg: f1(e[4 + 4 * k], e[5 + 4 * k], e[6 + 4 * k]))
 
     # ---- logging ----
     def log_losses(self, step_name: str, on_step: bool):
@@ -64,7 +76,19 @@ class Base_Lightning(LightningModule):
 
     # ---- loss heads ----
     def calculate_losses_step(self, y: torch.Tensor, y_pred: torch.Tensor):
-        if self.regression:
+        if self.regression and y_pred.is_cuda:
+            self.mse_loss = native_loss(self.model, y_pred, y, N.LOSS_MSE)
+            with torch.no_grad():
+                b = self._fused.update(N.LOSS_MSE, y_pred.detach().reshape(-1), y, y_pred.numel(), 1)
+                self.rmse_loss, self.l1_loss = b[21], b[22]
+        elif not self.regression and y_pred.is_cuda and y_pred.shape[1] == 8:
+            # gradient-carrying CE from the fused loss head; accuracy / F1 / epoch states from ONE fused metrics call
+            self.ce_loss = native_loss(self.model, y_pred, y, N.LOSS_CE2)
+            with torch.no_grad():
+                b = self._fused.update(N.LOSS_CE2, y_pred.detach().reshape(-1, 2), y, y_pred.shape[0], 4)
+                self.acc = b[21]
+                self.f1_leg0, self.f1_leg1, self.f1_leg2, self.f1_leg3 = b[22], b[23], b[24], b[25]
+        elif self.regression:
             # native fused MSE (gradient-carrying) + metric accumulation
             self.mse_loss = native_loss(self.model, y_pred, y, N.LOSS_MSE)
             with torch.no_grad():
@@ -305,3 +329,7 @@ class HGNN_C2_Lightning_Reg(Base_Lightning):
         return self._loss()
 
     test_step = validation_step
+
+
+# train_model / evaluate_model live next to the modules in the reference (gnnLightning.py:L913-1421)
+from .trainer import WindowSubset, evaluate_model, train_model  # noqa: E402,F401

@@ -160,6 +160,9 @@ class DeviceSequence:
     def get_data_metadata(self):
         return self.spec.template.metadata
 
+    def get_data_format(self) -> str:
+        return self.spec.model_type
+
     def edge_index_dict(self, B: int):
         if B not in self._edges:
             self._edges[B] = self.spec.template.edge_index_dict(B, self.device)

@@ -6,6 +6,7 @@ import torch
 
 import mshgnn_oracle as O
 from helpers import TOL_FP32, oracle_loss, oracle_model, rel_err
+from ms_hgnn import _native as N
 from ms_hgnn import morphology as M
 from ms_hgnn.lightning_py.gnnLightning import (Heterogeneous_GNN_Lightning, HGNN_C2_Lightning_Reg, HGNN_K4_Lightning)
 from ms_hgnn.lightning_py.gnnLightning_com import COM_HGNN_SYM_Lightning
@@ -135,3 +136,101 @@ def test_metrics_match_reference_literals_on_device():
     p16, y16 = Base_Lightning.classification_conversion_16_class(None, torch.tensor([[0.9, 0.3, 0.8, 0.55]], dtype=torch.float64),
                                                                  torch.tensor([[1, 0, 1, 1]]))
     assert y16.tolist() == [[11]] and abs(p16[0, 11].item() - 0.2772) < 1e-12 and abs(p16[0, 0].item() - 0.0063) < 1e-12
+
+
+def test_fused_step_metrics_equal_the_op_by_op_metrics():
+    """mshgnn_step_metrics (one call per step) vs the torch op-by-op restatement of gnnLightning.py:L131-151 / customMetrics.py
+    on random logits: batch values, epoch accumulation over three steps, reset.  Counts exact, CE within 1e-6 relative."""
+    from ms_hgnn.lightning_py import customMetrics as CM
+    from ms_hgnn.lightning_py.gnnLightning import Base_Lightning
+    g = torch.Generator().manual_seed(5)
+    fused = CM.FusedStepMetrics()
+    ce, acc, f1s = CM.CrossEntropyLossMetric(), CM.MulticlassAccuracy(), [CM.BinaryF1Score() for _ in range(4)]
+    helper = Base_Lightning.__new__(Base_Lightning)
+    for step, B in enumerate((4096, 777, 16384)):
+        y_pred = (torch.randn(B, 8, generator=g) * 2).to(DEV)
+        y = (torch.rand(B, 4, generator=g) > 0.4).double().to(DEV)
+        if step == 1:
+            y_pred[:5, 0] = y_pred[:5, 1]                     # exact per-foot ties: argmax must pick class 0 on both paths
+        b = fused.update(N.LOSS_CE2, y_pred.reshape(-1, 2), y, B, 4).clone()
+        _, prob, p1 = Base_Lightning.classification_calculate_useful_values(helper, y_pred.double(), B)
+        p16, y16 = Base_Lightning.classification_conversion_16_class(helper, p1, y)
+        a = acc(torch.argmax(p16, dim=1), y16.squeeze(1))
+        p2 = torch.argmax(prob, dim=1).reshape(B, 4)
+        f = [f1s[k](p2[:, k], y[:, k]) for k in range(4)]
+        c = ce(y_pred.double().reshape(-1, 2), y.reshape(-1).long())
+        assert b[2].item() == round(a.item() * B) and abs(b[21].item() - a.item()) < 1e-14     # count exact, ratio to 1 ulp
+        for k in range(4):
+            assert abs(b[22 + k].item() - f[k].item()) < 1e-12
+        assert abs(b[20].item() - c.item()) <= 1e-6 * abs(c.item())
+    e = fused.epoch
+    assert e[3].item() == 4096 + 777 + 16384 and e[1].item() == 4 * e[3].item()
+    assert abs(e[2].item() / e[3].item() - acc.compute().item()) < 1e-14
+    for k in range(4):
+        assert abs(CM.BinaryF1Score._f1(e[4 + 4 * k], e[5 + 4 * k], e[6 + 4 * k]).item() - f1s[k].compute().item()) < 1e-12
+        assert (e[4 + 4 * k:8 + 4 * k].sum().item()) == e[3].item()              # tp + fp + fn + tn = graphs
+    assert abs((e[0].float() / e[1]).item() - ce.compute().item()) <= 1e-6 * abs(ce.compute().item())
+    fused.reset()
+    assert fused.epoch.abs().sum().item() == 0.0
+    # regression head
+    p = torch.randn(5000, generator=g).to(DEV); t = torch.randn(5000, generator=g, dtype=torch.float64).to(DEV)
+    b = fused.update(N.LOSS_MSE, p, t, 5000, 1)
+    d = p.double() - t
+    assert abs(b[20].item() - (d * d).mean().item()) < 1e-12 and abs(b[21].item() - (d * d).mean().sqrt().item()) < 1e-12
+    assert abs(b[22].item() - d.abs().mean().item()) < 1e-12
+
+
+def test_train_model_and_evaluate_model_rehost(tmp_path, monkeypatch):
+    """train_model / evaluate_model (gnnLightning.py:L913-1421) on a device-resident sequence: checkpoint naming and pruning
+    policy, resume, and evaluate_model's return tuple recomputed op by op from the checkpoint's own predictions."""
+    import numpy as np
+    import window_oracle as WO
+    from ms_hgnn.lightning_py.gnnLightning import WindowSubset, evaluate_model, train_model
+    from ms_hgnn.windows import DeviceSequence, WindowSpec
+    monkeypatch.chdir(tmp_path)
+    mat = WO.synthetic_mat(1500, seed=21, dtype=np.float32)
+    # learnable labels: contact of leg k = sign of a joint velocity channel
+    mat["contacts"] = (mat["qd"][:, [2, 5, 8, 11]] > 0).astype(np.float32)
+    ds = DeviceSequence(mat, WindowSpec("heterogeneous_gnn_k4", 150, True), DEV, torch.float32)
+    n = len(ds)
+    tr, va, te = WindowSubset(ds, torch.arange(0, 900)), WindowSubset(ds, torch.arange(900, 1100)), WindowSubset(ds, torch.arange(1100, n))
+    kw = dict(normalize=True, disable_logger=True, batch_size=128, num_layers=2, optimizer="adam", lr=1e-3, hidden_size=128,
+              regression=False, seed=3, symmetry_mode="MorphSym", group_operator_path=M.cfg_path("mini_cheetah-k4"))
+    path = train_model(tr, va, te, epochs=9, **kw)
+    ckpts = sorted(os.listdir(path))
+    names = [c for c in ckpts if c.endswith(".ckpt")]
+    assert "metrics.jsonl" in ckpts and 3 <= len(names) <= 9
+    import re
+    pat = re.compile(r"^epoch=(\d+)-val_CE_loss=\d+\.\d{5}-val_F1_Score_Leg_Avg=\d+\.\d{5}\.ckpt$")
+    epochs_kept = sorted(int(pat.match(c).group(1)) for c in names)
+    assert epochs_kept[-3:] == [6, 7, 8]                                   # the three latest epochs are always kept
+    import json
+    rows = [json.loads(l) for l in open(os.path.join(path, "metrics.jsonl"))]
+    val = [r["val_CE_loss"] for r in rows if "val_CE_loss" in r]
+    assert len(val) == 9 and all(v == v and v < 1e3 for v in val)
+    best7 = sorted(range(9), key=lambda e: val[e])[:7]
+    assert set(epochs_kept) == set(best7) | {6, 7, 8}
+    last = os.path.join(path, [c for c in names if c.startswith("epoch=8-")][0])
+    ck = torch.load(last, weights_only=False)
+    assert ck["epoch"] == 8 and ck["global_step"] == 9 * 8 and all(k.startswith("model.") for k in ck["state_dict"])
+    assert 0 < len(ck["optimizer_states"][0]["state"]) <= len(ck["state_dict"])
+    # resume: two more epochs continue the step count and the Adam moments
+    path2 = train_model(tr, va, te, epochs=11, ckpt_path=last, **kw)
+    rows2 = [json.loads(l) for l in open(os.path.join(path2, "metrics.jsonl")) if "epoch" in l]
+    assert [r["epoch"] for r in rows2 if "val_CE_loss" in r] == [9, 10] and rows2[-1]["global_step"] == 11 * 8
+    # evaluate_model
+    pred, lab, acc, f0, f1, f2, f3, favg = evaluate_model(last, te, symmetry_mode="MorphSym", group_operator_path=M.cfg_path("mini_cheetah-k4"),
+                                                          batch_size=100, task_type="classification")
+    assert pred.shape == lab.shape == (len(te),)
+    assert abs(acc.item() - (pred == lab).double().mean().item()) < 1e-12
+    bits = lambda v, k: (v >> (3 - k)) & 1
+    for k, f in enumerate((f0, f1, f2, f3)):
+        p, t = bits(pred, k).bool(), bits(lab, k).bool()
+        tp, fp, fn = (p & t).sum().double(), (p & ~t).sum().double(), (~p & t).sum().double()
+        ref = torch.nan_to_num(2 * (tp / (tp + fp)) * (tp / (tp + fn)) / (tp / (tp + fp) + tp / (tp + fn)))
+        assert abs(f.item() - ref.item()) < 1e-12
+    assert abs(favg.item() - (f0 + f1 + f2 + f3).item() / 4) < 1e-12
+    # the optimiser made progress on the data it saw: accuracy on the training windows far above the 1/16 chance level
+    acc_tr = evaluate_model(last, tr, symmetry_mode="MorphSym", group_operator_path=M.cfg_path("mini_cheetah-k4"), batch_size=300,
+                            task_type="classification")[2]
+    assert acc_tr.item() > 0.5
