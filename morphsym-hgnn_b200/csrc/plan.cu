@@ -6,6 +6,7 @@
 // weight) contributions, which layers/slots are live (the decoder only reads one node type,
 // so last-layer branches into the others are dead), and the transposed pattern
 // for the backward pass.
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <sstream>
@@ -445,8 +446,12 @@ WsLayout ws_layout(const Plan& p, int64_t B, int train, int mode) {
     w.Bp = round_up(B < 1 ? 1 : B, TILE_M);
     int ns = (int)((B + 511) / 512);
     w.n_splits = ns < 1 ? 1 : (ns > 64 ? 64 : ns);
-    {   // tcgen05 reduce-GEMM: ~2048 rows per split (fp32 accumulation in TMEM, splits summed in double), no empty split
-        int64_t target = (B + 2047) / 2048;
+    {   // tcgen05 reduce-GEMM: ~1024 rows per split (MSHGNN_DW_ROWS overrides for A/B runs) (fp32 accumulation in TMEM, splits summed in double), no empty split.
+        // Row range per CTA decides the L2 reuse: the CTAs resident together (148) cover 148 / n_tasks splits, and every
+        // dC / A slot tile of those rows is read by ~3 pairs at different times.  With 2048-row splits that working set was
+        // 336 MB (> 126 MB L2) and ncu counted 607 MB of DRAM reads per launch for 300 MB of operands.
+        static const int64_t dw_rows = [] { const char* e = getenv("MSHGNN_DW_ROWS"); const int64_t v = e ? atoll(e) : 1024; return v < 64 ? 64 : v; }();
+        int64_t target = (B + dw_rows - 1) / dw_rows;
         target = target < 1 ? 1 : (target > 64 ? 64 : target);
         w.rows_per_tc = (int)round_up((B + target - 1) / target, 64);
         w.n_splits_tc = (int)((B + w.rows_per_tc - 1) / w.rows_per_tc);
