@@ -53,6 +53,12 @@ ALG = {
 }
 
 
+def recorded_traffic():
+    """DRAM bytes from the committed ncu captures (profiles/): per launch of the dominant kernels and per train step."""
+    p = os.path.join(ROOT, "profiles", "r1_tc_v5_dominant_traffic.json")
+    return json.load(open(p)) if os.path.exists(p) else {}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -351,9 +357,18 @@ def main():
     per_kind.sort(key=lambda e: -e["ms_per_step"])
     dom = next((e for e in per_kind if "achieved_tflops" in e), None)
     roofline = None
+    traffic = recorded_traffic()
     if dom:
+        t_dom = traffic.get(dom["kernel"], {}).get("dram_bytes_per_launch") if B == PER_GPU_BATCH and args.mode == "tc" else None
+        ms_launch = dom["ms_per_step"] / max(dom["launches_per_step"], 1)
         roofline = {"kernel": dom["kernel"], "bound": "tensor", "achieved": dom["achieved_tflops"], "peak": pk["tflops"],
-                    "unit": "TFLOP/s", "frac": dom["frac_tensor_peak"], "traffic": None, "peak_source": pk["src"] + " (bf16 dense, sustained)",
+                    "unit": "TFLOP/s", "frac": dom["frac_tensor_peak"], "traffic": t_dom,
+                    "traffic_view": None if not t_dom else {
+                        "dram_gbs": t_dom / (ms_launch * 1e-3) / 1e9, "frac_hbm_peak": t_dom / (ms_launch * 1e-3) / 1e9 / pk["hbm_gbs"],
+                        "note": "the layer kernels stream every activation slab (fp16 hi/lo pair = 4 B/element, 168 MB per layer > L2) through "
+                                "HBM once per launch; their ncu DRAM bytes / measured launch time sits much closer to the HBM roof than their "
+                                "algorithmic FLOPs sit to the tensor roof (SURVEY 8d counts zero mandatory bytes for a fused stack)"},
+                    "peak_source": pk["src"] + " (bf16 dense, sustained)",
                     "launches_per_step": dom["launches_per_step"], "ms_per_launch": dom["ms_per_step"] / max(dom["launches_per_step"], 1),
                     "note": "algorithmic FLOPs per SURVEY 8d (one MAC per product; the fp32-class mode issues 3 fp16 MMAs per product, "
                             "so tensor-pipe occupancy is ~3x this fraction)"}
@@ -393,6 +408,10 @@ def main():
                         "train_tflops": ALG["train_flop"] * B * world / (train_ms / K * 1e-3) / 1e12,
                         "infer_tflops": ALG["fwd_flop"] * B * world / (infer_ms / K * 1e-3) / 1e12},
         "cpu_baseline": cpu,
+        "hbm_step": None if not (traffic.get("step") and B == PER_GPU_BATCH and args.mode == "tc") else {
+            "dram_bytes_per_step": traffic["step"]["dram_bytes"], "achieved_gbs": traffic["step"]["dram_bytes"] / (train_ms / K * 1e-3) / 1e9,
+            "peak_gbs": pk["hbm_gbs"], "frac": traffic["step"]["dram_bytes"] / (train_ms / K * 1e-3) / 1e9 / pk["hbm_gbs"],
+            "source": "profiles/r1_tc_v5_step_traffic.json (ncu DRAM counters of one step) / this run's step time"},
         "profiled_ms_per_step": prof_ms / K,
     }
     print(json.dumps(line), flush=True)

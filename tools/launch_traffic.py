@@ -16,14 +16,23 @@ for r in data:
         continue
     key = (r[0], r[kn].split("(")[0])
     per.setdefault(key, {})[r[mn]] = float(r[mv].replace(",", "")) * scale[r[mu]]
-# the capture window may cover a bit more than one step: keep exactly one period starting at the first encoder forward
+# the capture window covers a bit more than one step: keep exactly one period, from one optimizer launch to the next
 ids = list(per)
-starts = [i for i, k in enumerate(ids) if k[1].endswith("k_tc_encoder")]
-lo, hi = (starts[0], starts[1]) if len(starts) > 1 else (0, len(ids))
+ends = [i for i, k in enumerate(ids) if k[1].endswith("k_adam") or k[1].endswith("k_sgd")]
+lo, hi = (ends[0] + 1, ends[1] + 1) if len(ends) > 1 else (0, len(ids))
 agg = collections.OrderedDict()
+# the persistent row-GEMM serves four launch kinds; inside one step they come in a fixed order (api.cu): forward
+# [conv, base MLP] x L, backward [base MLP, dX] x L
+n_pk = sum(1 for k in ids[lo:hi] if k[1].endswith("k_tc_rowgemm_persistent"))
+pk_seen = 0
 for k in ids[lo:hi]:
     m = per[k]
-    a = agg.setdefault(k[1], {"launches": 0, "us": 0.0, "dram_read_bytes": 0.0, "dram_write_bytes": 0.0})
+    name = k[1]
+    if name.endswith("k_tc_rowgemm_persistent") and n_pk % 4 == 0:
+        fwd = pk_seen < n_pk // 2
+        name += ":" + (("conv_fwd", "base_mlp_fwd")[pk_seen % 2] if fwd else ("base_mlp_bwd", "dx_bwd")[pk_seen % 2])
+        pk_seen += 1
+    a = agg.setdefault(name, {"launches": 0, "us": 0.0, "dram_read_bytes": 0.0, "dram_write_bytes": 0.0})
     a["launches"] += 1; a["us"] += m.get("gpu__time_duration.sum", 0.0)
     a["dram_read_bytes"] += m.get("dram__bytes_read.sum", 0.0); a["dram_write_bytes"] += m.get("dram__bytes_write.sum", 0.0)
 tot = {"launches": 0, "us": 0.0, "dram_read_bytes": 0.0, "dram_write_bytes": 0.0}

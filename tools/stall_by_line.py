@@ -14,9 +14,9 @@ rep, kname = sys.argv[1], sys.argv[2]
 which = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-so = os.path.join(ROOT, "morphsym-hgnn_b200", "lib", "libmshgnn_b200.so")
+so = sys.argv[5] if len(sys.argv) > 5 else os.path.join(ROOT, "morphsym-hgnn_b200", "lib", "libmshgnn_b200.so")
 with tempfile.TemporaryDirectory() as td:
-    subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=td, capture_output=True)
+    subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=td, capture_output=True)
     cub = [f for f in os.listdir(td) if f.startswith("api.") and f.endswith(".cubin")][0]
     dis = subprocess.run(["nvdisasm", "-g", os.path.join(td, cub)], capture_output=True, text=True).stdout
 lines = dis.split("\n")
