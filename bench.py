@@ -75,7 +75,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                        "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -239,7 +239,6 @@ def main():
     n0 = N.launch_count()
     train_ms = timed(lambda: trainer.train_step(resident), K)
     launches = N.launch_count() - n0
-    clocks = sampler.stop() if sampler else {}
 
     # ---------------- per-kernel times (same steps, events around every launch) ----------------
     N.profile_enable(True)
@@ -251,6 +250,7 @@ def main():
     for _ in range(W):
         trainer.infer(resident)
     infer_ms = timed(lambda: trainer.infer(resident), K)
+    clocks = sampler.stop() if sampler else {}          # sampled across the three device-resident timed regions above
 
     # ---------------- end to end: pinned host buffers -> H2D -> train step -> D2H loss ----------------
     e2e_ms = None

@@ -452,6 +452,11 @@ WsLayout ws_layout(const Plan& p, int64_t B, int train, int mode) {
         // 336 MB (> 126 MB L2) and ncu counted 607 MB of DRAM reads per launch for 300 MB of operands.
         static const int64_t dw_rows = [] { const char* e = getenv("MSHGNN_DW_ROWS"); const int64_t v = e ? atoll(e) : 1024; return v < 64 ? 64 : v; }();
         int64_t target = (B + dw_rows - 1) / dw_rows;
+        // small batches: still give every SM a CTA (tasks x splits >= ~148), down to 64-row splits
+        int tasks = 1;
+        for (size_t l = 0; l < p.dw_layer.size(); ++l) tasks = p.dw_layer[l].count > tasks ? p.dw_layer[l].count : tasks;
+        const int64_t fill = (148 + tasks - 1) / tasks, most = (B + 63) / 64;
+        if (target < fill) target = fill < most ? fill : most;
         target = target < 1 ? 1 : (target > 64 ? 64 : target);
         w.rows_per_tc = (int)round_up((B + target - 1) / target, 64);
         w.n_splits_tc = (int)((B + w.rows_per_tc - 1) / w.rows_per_tc);
