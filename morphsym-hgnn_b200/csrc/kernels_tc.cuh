@@ -497,6 +497,125 @@ __device__ __forceinline__ void tc_epilogue_alt(const Tile& t, const BufTable& b
     }
 }
 
+// Epilogue of the persistent kernel, 16 warps: FOUR groups of four warps; group g drains the 32-column quarter g of the
+// accumulator (one tcgen05.ld.32x32b.x32 per thread) through a private 16 KB staging pair (hi | lo tiles of 128 rows x
+// 32 fp16, 64 B rows, SWIZZLE_64B - the same box shape as the operand K blocks, so the operand tensor map serves the
+// residual loads and the image stores).  Ablation runs showed the 8-warp epilogue alone - no loads, no MMAs -
+// taking 63-70 % of the kernel time at ~22 instructions per element with two warps per scheduler; four warps per scheduler
+// hide each other's dependent-issue and shared-memory latency.
+__device__ __forceinline__ void tc_epilogue_q(const Tile& t, const BufTable& bt, const BufRows& br, const CUtensorMap* map_k,
+                                              const uint32_t tmem_acc, const int row0, const int64_t B, const int64_t Bp,
+                                              const int warp, const int lane, const int grp, const EpiSmem es, uint32_t& res_count) {
+    const int q = warp & 3;                        // TMEM lane quarter this warp may access (hardware rule: warp index mod 4)
+    const bool leader = q == 2 && lane == 0;       // first warp of the group (warps 2 + 4g .. 5 + 4g): warp index = 2 mod 4
+    const int rl = q * 32 + lane;                  // row inside the tile
+    const int64_t row = (int64_t)row0 + rl;
+    const bool live = row < B;
+    const uint32_t rsw = (uint32_t)((rl >> 1) & 3);     // SWIZZLE_64B: 16-byte chunk index ^= address bits [7, 9)
+    const uint32_t tile = es.stg + (uint32_t)rl * 64u;
+    const bool has_out = t.out_buf >= 0, has_out2 = t.out2_buf >= 0, has_res = t.res_buf >= 0;
+    const bool want_mask = t.relu || t.mask_out_buf >= 0;
+    const int col0 = grp * 32;
+
+    if (leader) {
+        // the staging tiles may still feed this group's previous TMA stores
+        tma_store_wait_read();
+        if (has_res) {
+            const int r_hi = br.hi[t.res_buf] + (int)((int64_t)t.res_slot * Bp) + row0, r_lo = br.lo[t.res_buf] + (int)((int64_t)t.res_slot * Bp) + row0;
+            mbar_expect_tx(es.res_bar, 2u * 8192u);
+            tma_load_2d(es.stg, map_k, es.res_bar, col0, r_hi);
+            tma_load_2d(es.stg + 8192, map_k, es.res_bar, col0, r_lo);
+        }
+    }
+    if (rl < 32) {
+        const float bv = t.bias_buf >= 0 ? __ldg((const float*)bt.p[t.bias_buf] + t.bias_off + col0 + rl) : 0.f;
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(es.bias + 4u * rl), "f"(bv) : "memory");
+    }
+    uint32_t pm = ~0u, m2 = ~0u;
+    if (live && t.posmask_buf >= 0) pm = __ldg(reinterpret_cast<const uint32_t*>(bt.p[t.posmask_buf]) + ((int64_t)t.posmask_slot * Bp + row) * 4 + grp);
+    if (live && has_out2 && t.out2_mask_kind == MK_BITS)
+        m2 = __ldg(reinterpret_cast<const uint32_t*>(bt.p[t.out2_mask_buf]) + ((int64_t)t.out2_mask_slot * Bp + row) * 4 + grp);
+    group_bar_sync(grp);
+
+    mbar_wait(es.accum_bar, es.acc_parity);
+    tc_fence_after();
+    uint32_t raw[32];
+    tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + col0, raw);
+    tmem_ld_wait();
+    tc_fence_before();
+    mbar_arrive(es.free_bar);                      // this thread's part of the accumulator is in registers
+    if (has_res) {
+        mbar_wait(es.res_bar, res_count & 1u);
+        ++res_count;
+    }
+    float v[32];
+    unsigned mask = 0;
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+        float4 b4;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(es.bias + 16u * j4));
+        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int j = j4 * 4 + e;
+            float x = fmaf(__uint_as_float(raw[j]), TC_W_UNSCALE, bb[e]);
+            if (want_mask && x > 0.f) mask |= 1u << j;
+            if (t.relu) x = fmaxf(x, 0.f);
+            v[j] = x;
+        }
+    }
+    if (t.posmask_buf >= 0) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = ((pm >> j) & 1u) ? v[j] : 0.f;
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const uint32_t a = tile + ((((uint32_t)g) ^ rsw) << 4);
+        if (has_res) join8_add(v + g * 8, lds128(a), lds128(a + 8192));
+        if (has_out || has_out2) {
+            uint4 hi, lo;
+            split8(v + g * 8, hi, lo);
+            if (!has_out) { hi = mask8(hi, m2 >> (g * 8)); lo = mask8(lo, m2 >> (g * 8)); }
+            if (!live) { hi = make_uint4(0u, 0u, 0u, 0u); lo = hi; }     // rows [B, Bp) of every image stay zero
+            sts128(a, hi);
+            sts128(a + 8192, lo);
+        }
+    }
+    fence_proxy_async_smem();
+    group_bar_sync(grp);
+    if (leader) {
+        const int ob = has_out ? t.out_buf : t.out2_buf, os = has_out ? t.out_slot : t.out2_slot;
+        if (ob >= 0) {
+            const int o = (int)((int64_t)os * Bp) + row0;
+            tma_store_2d(map_k, es.stg, col0, br.hi[ob] + o);
+            tma_store_2d(map_k, es.stg + 8192u, col0, br.lo[ob] + o);
+            tma_store_commit();
+        }
+    }
+    if (has_out && has_out2) {
+        // second output = first output with the masked-off lanes cleared, made in place once the first store has read the tile
+        if (leader) tma_store_wait_read();
+        group_bar_sync(grp);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const uint32_t a = tile + ((((uint32_t)c) ^ rsw) << 4);
+            const uint32_t m = m2 >> (c * 8);
+            sts128(a, mask8(lds128(a), m));
+            sts128(a + 8192, mask8(lds128(a + 8192), m));
+        }
+        fence_proxy_async_smem();
+        group_bar_sync(grp);
+        if (leader) {
+            const int o = (int)((int64_t)t.out2_slot * Bp) + row0;
+            tma_store_2d(map_k, es.stg, col0, br.hi[t.out2_buf] + o);
+            tma_store_2d(map_k, es.stg + 8192u, col0, br.lo[t.out2_buf] + o);
+            tma_store_commit();
+        }
+    }
+    if (live && t.mask_out_buf >= 0)
+        *(reinterpret_cast<uint32_t*>(bt.p[t.mask_out_buf]) + ((int64_t)t.mask_out_slot * Bp + row) * 4 + grp) = mask;
+}
+
 // ------------------------------------------------------------------------------------------
 // row-GEMM on tcgen05
 // ------------------------------------------------------------------------------------------
@@ -609,7 +728,7 @@ k_tc_rowgemm(const __grid_constant__ TcMaps maps, const Tile* __restrict__ tiles
 //  on the same few row tiles, so gathered source tiles are re-read from L2, not HBM.
 constexpr int PK_MAX_TILES = 32;
 constexpr int PK_STAGES = 4;
-constexpr int PK_THREADS = 320;                                           // TMA warp, MMA warp, 8 epilogue warps
+constexpr int PK_THREADS = 576;                                           // TMA warp, MMA warp, 16 epilogue warps
 constexpr int PK_PIPE_BYTES = PK_STAGES * TC_STAGE_BYTES;                 // 128 KB operand ring
 constexpr int PK_SMEM_BYTES = PK_PIPE_BYTES + 65536 + 1024 /*align*/ + 256 /*barriers*/;
 constexpr uint32_t PK_TMEM_COLS = 256;
@@ -619,7 +738,7 @@ k_tc_rowgemm_persistent(const __grid_constant__ TcMaps maps, const Tile* __restr
                         const BufTable bt, const BufRows br, const int64_t B, const int64_t Bp, const int split) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ Tile ts[PK_MAX_TILES];
-    __shared__ __align__(16) float bias_s[2][H];          // one per epilogue group
+    __shared__ __align__(16) float bias_s[4][32];         // one quarter per epilogue group
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x;
@@ -627,7 +746,7 @@ k_tc_rowgemm_persistent(const __grid_constant__ TcMaps maps, const Tile* __restr
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PK_PIPE_BYTES + 65536);
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + PK_STAGES), acc_full0 = smem_u32(bars + 2 * PK_STAGES),
-                   acc_free0 = smem_u32(bars + 2 * PK_STAGES + 2), res_bar = smem_u32(bars + 2 * PK_STAGES + 4);
+                   acc_free0 = smem_u32(bars + 2 * PK_STAGES + 2), res_bar = smem_u32(bars + 2 * PK_STAGES + 4);   // 4 residual barriers
     const uint32_t smem_base = smem_u32(smem);
 
     {
@@ -637,8 +756,9 @@ k_tc_rowgemm_persistent(const __grid_constant__ TcMaps maps, const Tile* __restr
     }
     if (tid == 0) {
         for (int s = 0; s < PK_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-        // acc_free: the 128 threads of the epilogue group that owns the accumulator set arrive once per item
-        for (int a = 0; a < 2; ++a) { mbar_init(acc_full0 + 8 * a, 1); mbar_init(acc_free0 + 8 * a, 128); mbar_init(res_bar + 8 * a, 1); }
+        // acc_free: every epilogue thread (16 warps) arrives once per item
+        for (int a = 0; a < 2; ++a) { mbar_init(acc_full0 + 8 * a, 1); mbar_init(acc_free0 + 8 * a, 512); }
+        for (int g = 0; g < 4; ++g) mbar_init(res_bar + 8 * g, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), PK_TMEM_COLS);
@@ -706,17 +826,17 @@ k_tc_rowgemm_persistent(const __grid_constant__ TcMaps maps, const Tile* __restr
         }
         __syncwarp();
     } else {
-        // group g (warps 2 + 4g .. 5 + 4g) drains accumulator set g: the items k = g (mod 2) of this CTA
+        // group g (warps 2 + 4g .. 5 + 4g) drains column quarter g of every item
         const int grp = (warp - 2) >> 2;
         EpiSmem es;
-        es.stg = smem_base + PK_PIPE_BYTES + grp * 32768; es.bias = smem_u32(bias_s[grp]); es.res_bar = res_bar + 8 * grp;
-        es.persistent = 1; es.n_groups = 2;
-        es.accum_bar = acc_full0 + 8 * grp; es.free_bar = acc_free0 + 8 * grp; es.res_parity = 0;
+        es.stg = smem_base + PK_PIPE_BYTES + grp * 16384; es.bias = smem_u32(bias_s[grp]); es.res_bar = res_bar + 8 * grp;
+        es.persistent = 1; es.n_groups = 4; es.res_parity = 0;
         uint32_t k = 0, n_res = 0;
         for (int i = blockIdx.x; i < n_items; i += gridDim.x, ++k) {
-            if ((int)(k & 1u) != grp) continue;
+            const uint32_t a = k & 1;
+            es.accum_bar = acc_full0 + 8 * a; es.free_bar = acc_free0 + 8 * a;
             es.acc_parity = (k >> 1) & 1;
-            tc_epilogue_alt(ts[i % n_tiles], bt, br, &maps.o, tmem_base + grp * 128, (i / n_tiles) * TILE_M, B, Bp, split, warp, lane, grp, es, n_res);
+            tc_epilogue_q(ts[i % n_tiles], bt, br, &maps.k, tmem_base + a * 128, (i / n_tiles) * TILE_M, B, Bp, warp, lane, grp, es, n_res);
         }
         if (((warp - 2) & 3) == 0 && lane == 0) tma_store_wait_all();
     }
