@@ -264,7 +264,17 @@ int launch_tc_rowgemm(int kind, const Plan& p, const Launch& L, const BufTable& 
         const int64_t n_items = (int64_t)L.count * (Bp / TILE_M);
         if (n_items > 0x7fffffffLL) return fail(MSHGNN_ERR_ARG, "batch too large for one row-GEMM launch");
         const unsigned grid = (unsigned)(n_items < n_sm ? n_items : n_sm);
-        k_tc_rowgemm_persistent<<<grid, PK_THREADS, PK_SMEM_BYTES, st>>>(wm.tc, p.d_tiles + L.begin, L.count, (int)n_items, bt, br, B, Bp, split);
+        // programmatic stream serialization: the prologue of this grid overlaps the tail of the previous kernel (the
+        // kernel itself waits with griddepcontrol.wait before touching anything that kernel wrote)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(PK_THREADS); cfg.dynamicSmemBytes = PK_SMEM_BYTES; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = g_prof_on ? 0 : 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        const Tile* d_tiles = p.d_tiles + L.begin;
+        const int n_tiles = L.count, n_it = (int)n_items;
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, k_tc_rowgemm_persistent, wm.tc, d_tiles, n_tiles, n_it, bt, br, B, Bp, split));
     }
     LAUNCH_CHECK();
     return 0;

@@ -767,6 +767,11 @@ k_tc_rowgemm_persistent(const __grid_constant__ TcMaps maps, const Tile* __restr
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
     constexpr int SPC = H / TC_KB;                 // pipeline steps per chunk
+    // Programmatic dependent launch: everything above (tile table, barriers, TMEM) ran while the previous kernel of the
+    // stream was still draining; from here on this grid reads what that kernel wrote.  Our own dependents may be scheduled
+    // as soon as every CTA of this grid has passed this point (they start on an SM when its CTA has exited).
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (warp == 0) {
         if (lane == 0) {
