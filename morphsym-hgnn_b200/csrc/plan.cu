@@ -50,11 +50,15 @@ static Tile empty_tile() {
 constexpr int RD_MAX_PAIRS = 4;
 
 // Emit reduce tasks ("units") of at most RD_MAX_PAIRS pairs each; returns false when more than 16 units result.
+// Unit u takes the pairs u, u + U, u + 2U, ... (U = number of units).  Pair lists follow the template's node / edge order,
+// i.e. leg by leg, so with this interleave the p-th pair of EVERY unit of every weight belongs to leg p: the CTAs of a row
+// split, which all walk their pairs at the same pace, read the same few slot tiles at the same time and share them in L2
+// instead of re-reading them from DRAM (ncu: 540 MB of DRAM reads per launch for 336 MB of distinct operands before).
 static bool emit_units(Plan& p, const std::vector<RPair>& prs, int K, int k0, int want_colsum, int* ids, int& n_ids) {
-    for (size_t b = 0; b < prs.size(); b += RD_MAX_PAIRS) {
-        const size_t e = b + RD_MAX_PAIRS < prs.size() ? b + RD_MAX_PAIRS : prs.size();
-        RTask T{}; T.pair_begin = (int)p.rpairs.size(); T.n_pairs = (int)(e - b); T.K = K; T.k0 = k0; T.want_colsum = want_colsum;
-        p.rpairs.insert(p.rpairs.end(), prs.begin() + b, prs.begin() + e);
+    const size_t U = (prs.size() + RD_MAX_PAIRS - 1) / RD_MAX_PAIRS;
+    for (size_t u = 0; u < U; ++u) {
+        RTask T{}; T.pair_begin = (int)p.rpairs.size(); T.n_pairs = 0; T.K = K; T.k0 = k0; T.want_colsum = want_colsum;
+        for (size_t i = u; i < prs.size(); i += U) { p.rpairs.push_back(prs[i]); ++T.n_pairs; }
         if (n_ids >= 16) return false;
         ids[n_ids++] = (int)p.rtasks.size();
         p.rtasks.push_back(T);
