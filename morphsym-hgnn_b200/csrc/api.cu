@@ -210,10 +210,11 @@ int launch_tc_encoder(const Plan& p, const Launch& L, const WsLayout& w, const B
     __half* e_lo = (__half*)(ws + w.wenc16[1]);
     {
         ProfScope ps(K_DERIVE, st);
-        for (int t = 0; t < p.n_types; ++t) {
-            k_derive_enc16<<<32, 256, 0, st>>>(params, p.off_enc_w[t], p.in_w[t], p.enc_kmax, t * H, e_hi, e_lo);
-            LAUNCH_CHECK();
-        }
+        EncImgDesc ed;
+        ed.n_types = p.n_types;
+        for (int t = 0; t < p.n_types; ++t) { ed.w_off[t] = p.off_enc_w[t]; ed.K[t] = p.in_w[t]; }
+        k_derive_enc16<<<dim3(64, (unsigned)p.n_types), 256, 0, st>>>(params, ed, p.enc_kmax, e_hi, e_lo);
+        LAUNCH_CHECK();
     }
     EncMaps maps;
     int rc;
@@ -411,9 +412,12 @@ int mshgnn_forward(const mshgnn_plan* plan, int64_t B, const void* const* x, int
 
     {   // derived weights (transposes, root sums, bias sums) from the current parameters
         ProfScope ps(K_DERIVE, st);
-        dim3 grid(16, (unsigned)p.derive_ops.size());
-        k_derive<<<grid, 256, 0, st>>>(p.d_derive, params, (float*)bt.p[BUF_DERIVED]);
-        LAUNCH_CHECK();
+        const unsigned n_ops = mode == MSHGNN_MODE_FP32 ? (unsigned)p.derive_ops.size() : (unsigned)p.n_derive_bias;
+        if (n_ops > 0) {
+            dim3 grid(mode == MSHGNN_MODE_FP32 ? 16 : 1, n_ops);
+            k_derive<<<grid, 256, 0, st>>>(p.d_derive, params, (float*)bt.p[BUF_DERIVED]);
+            LAUNCH_CHECK();
+        }
     }
     if (mode == MSHGNN_MODE_FP32) {
         if ((rc = launch_rowgemm(K_ENC_FWD, p, train ? p.enc_train : p.enc_launch, bt, B, w.Bp, xf64, st))) return rc;

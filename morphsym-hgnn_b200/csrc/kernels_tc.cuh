@@ -1477,10 +1477,16 @@ k_reduce_enc(const EncDwGroup* __restrict__ groups, const float* __restrict__ pa
         }
 }
 
-// fp16 (hi, lo) image of the encoder weights: [n_types*128][kmax], zero padded beyond each type's in-width
+// fp16 (hi, lo) image of the encoder weights: [n_types*128][kmax], zero padded beyond each type's in-width (blockIdx.y = type)
+struct EncImgDesc {
+    int n_types;
+    int K[4];
+    int64_t w_off[4];
+};
 __global__ void __launch_bounds__(256)
-k_derive_enc16(const float* __restrict__ params, const int64_t w_off, const int K, const int kmax, const int row0,
-               __half* __restrict__ w_hi, __half* __restrict__ w_lo) {
+k_derive_enc16(const float* __restrict__ params, const EncImgDesc ed, const int kmax, __half* __restrict__ w_hi, __half* __restrict__ w_lo) {
+    const int t = blockIdx.y, K = ed.K[t], row0 = t * H;
+    const int64_t w_off = ed.w_off[t];
     for (int e = blockIdx.x * 256 + threadIdx.x; e < H * kmax; e += gridDim.x * 256) {
         const int o = e / kmax, k = e % kmax;
         const float s = k < K ? params[w_off + (int64_t)o * K + k] * TC_W_SCALE : 0.f;

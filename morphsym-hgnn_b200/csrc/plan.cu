@@ -6,6 +6,7 @@
 // weight) contributions, which layers/slots are live (the decoder only reads one node type,
 // so last-layer branches into the others are dead), and the transposed pattern
 // for the backward pass.
+#include <algorithm>
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
@@ -162,6 +163,11 @@ std::string build_plan(const mshgnn_desc* d, Plan& p) {
     if (p.morph_sym)
         for (int i = 0; i < 2; ++i) { p.der_mlpT[i] = q; add_op(q, H, H, 1, {p.off_mlp_w[i]}); q += H * H; }
     p.n_derived = q;
+    // bias sums ([1 x H] ops) first: the tensor-core modes read nothing else from the derived buffer (their weights are
+    // the fp16 images of k_derive16), so they run only this prefix
+    std::stable_partition(p.derive_ops.begin(), p.derive_ops.end(), [](const DeriveOp& o) { return o.rows == 1; });
+    p.n_derive_bias = 0;
+    for (const DeriveOp& o : p.derive_ops) p.n_derive_bias += o.rows == 1;
 
     // ---------------- signs ----------------
     p.sign_off_slot.assign(p.S, -1);

@@ -51,7 +51,8 @@ struct Plan {
     std::vector<int64_t> der_relT;                            // [l*n_etypes+e]
     std::vector<int64_t> der_rootT, der_root, der_bias;       // [l*n_types+t]  (-1 when type has no in-edges)
     int64_t der_mlpT[2] = {-1, -1};
-    std::vector<DeriveOp> derive_ops;
+    std::vector<DeriveOp> derive_ops;                            // bias sums first (n_derive_bias of them): all the tensor-core modes need
+    int n_derive_bias = 0;
     std::vector<Derive16Op> derive16_ops;   // fp16 (hi, lo) weight images for the tensor-core kernels
     int n_mats16 = 0;
 
