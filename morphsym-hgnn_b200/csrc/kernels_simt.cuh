@@ -518,20 +518,21 @@ k_decoder_bwd(const DecoderDesc dd, const float* __restrict__ hslab, const __hal
     }
 #pragma unroll
     for (int c = 0; c < DEC_MAXC; ++c) {
+        if (c >= dd.C) break;                  // only the decoder's C channels carry anything
         red[wid][c][lane * 4 + 0] = gw[c].x; red[wid][c][lane * 4 + 1] = gw[c].y;
         red[wid][c][lane * 4 + 2] = gw[c].z; red[wid][c][lane * 4 + 3] = gw[c].w;
         if (lane == 0) redb[wid][c] = gb[c];   // every lane holds the same gb
     }
     __syncthreads();
     float* pb = part + (int64_t)blockIdx.x * (DEC_MAXC * H + DEC_MAXC);
-    for (int e = threadIdx.x; e < DEC_MAXC * H; e += 256) {
+    for (int e = threadIdx.x; e < dd.C * H; e += 256) {
         const int c = e / H, k = e % H;
         float s = 0.f;
 #pragma unroll
         for (int wv = 0; wv < 8; ++wv) s += red[wv][c][k];
         pb[e] = s;
     }
-    if (threadIdx.x < DEC_MAXC) {
+    if ((int)threadIdx.x < dd.C) {
         float s = 0.f;
 #pragma unroll
         for (int wv = 0; wv < 8; ++wv) s += redb[wv][threadIdx.x];
@@ -612,12 +613,13 @@ k_loss_partial(const int kind, const float* __restrict__ out, const void* __rest
 
 __global__ void k_loss_final(const double* __restrict__ partial, const int n_blocks, const double inv_n,
                              const int round_f32, float* __restrict__ loss_out) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        double s = 0.0;
-        for (int i = 0; i < n_blocks; ++i) s += partial[i];
-        // customMetrics.py:L25: summed_loss.float() / total_num
-        loss_out[0] = round_f32 ? (float)((double)(float)s * inv_n) : (float)(s * inv_n);
-    }
+    // one warp: lane l sums the partials l, l + 32, ... (fixed order), then a fixed shuffle tree
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n_blocks; i += 32) s += partial[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    // customMetrics.py:L25: summed_loss.float() / total_num
+    if (threadIdx.x == 0) loss_out[0] = round_f32 ? (float)((double)(float)s * inv_n) : (float)(s * inv_n);
 }
 
 // ------------------------------------------------------------------------------------------
