@@ -244,11 +244,14 @@ int launch_tc_rowgemm(int kind, const Plan& p, const Launch& L, const BufTable& 
     if (L.count == 0) return 0;
     static bool attr_set = false;
     static bool use_v2 = false;       // MSHGNN_ROWGEMM=tile selects the one-tile-per-CTA kernel (A/B measurements)
+    static bool use_single = false;   // MSHGNN_ROWGEMM=single selects the persistent kernel with one row tile per item
     if (!attr_set) {
         CUDA_TRY(cudaFuncSetAttribute(k_tc_rowgemm, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
         CUDA_TRY(cudaFuncSetAttribute(k_tc_rowgemm_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, PK_SMEM_BYTES));
         const char* e = getenv("MSHGNN_ROWGEMM");
         use_v2 = e && !strcmp(e, "tile");
+        use_single = e && !strcmp(e, "single");
+        CUDA_TRY(cudaFuncSetAttribute(k_tc_rowgemm_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_BYTES));
         attr_set = true;
     }
     for (int i = 0; i < L.count; ++i)
@@ -262,20 +265,24 @@ int launch_tc_rowgemm(int kind, const Plan& p, const Launch& L, const BufTable& 
     } else {
         int n_sm = 0, rc;
         if ((rc = sm_count(&n_sm))) return rc;
-        const int64_t n_items = (int64_t)L.count * (Bp / TILE_M);
+        // two row tiles per item (shared weight stages) only when that still leaves every SM >= 4 items: short launches
+        // (base MLP: 4-8 output tiles) lose more to wave quantisation than they gain from the smaller operand stream
+        const bool pair = !use_single && Bp >= 2 * TILE_M && (int64_t)L.count * ((Bp / TILE_M + 1) / 2) >= 4 * (int64_t)n_sm;
+        const int64_t n_items = (int64_t)L.count * (pair ? (Bp / TILE_M + 1) / 2 : Bp / TILE_M);
         if (n_items > 0x7fffffffLL) return fail(MSHGNN_ERR_ARG, "batch too large for one row-GEMM launch");
         const unsigned grid = (unsigned)(n_items < n_sm ? n_items : n_sm);
         // programmatic stream serialization: the prologue of this grid overlaps the tail of the previous kernel (the
         // kernel itself waits with griddepcontrol.wait before touching anything that kernel wrote)
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(PK_THREADS); cfg.dynamicSmemBytes = PK_SMEM_BYTES; cfg.stream = st;
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(PK_THREADS); cfg.dynamicSmemBytes = pair ? PP_SMEM_BYTES : PK_SMEM_BYTES; cfg.stream = st;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = g_prof_on ? 0 : 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         const Tile* d_tiles = p.d_tiles + L.begin;
         const int n_tiles = L.count, n_it = (int)n_items;
-        CUDA_TRY(cudaLaunchKernelEx(&cfg, k_tc_rowgemm_persistent, wm.tc, d_tiles, n_tiles, n_it, bt, br, B, Bp, split));
+        if (pair) CUDA_TRY(cudaLaunchKernelEx(&cfg, k_tc_rowgemm_pair, wm.tc, d_tiles, n_tiles, n_it, bt, br, B, Bp, split));
+        else CUDA_TRY(cudaLaunchKernelEx(&cfg, k_tc_rowgemm_persistent, wm.tc, d_tiles, n_tiles, n_it, bt, br, B, Bp, split));
     }
     LAUNCH_CHECK();
     return 0;

@@ -854,6 +854,155 @@ k_tc_rowgemm_persistent(const __grid_constant__ TcMaps maps, const Tile* __restr
 }
 
 // ------------------------------------------------------------------------------------------
+// persistent row-GEMM, two row tiles per item ("pair" kernel): every weight K block staged in shared memory feeds TWO
+// 128-row accumulators, so the L2 -> SMEM operand stream per 128x128x128 product drops from 128 KB to 96 KB.  With the
+// 16-warp epilogue the operand stream is the longest leg of an item (352 KB at the ~84 GB/s an SM gets of the chip-wide
+// L2 cap = 4.2 us against 2.2 us of MMAs); the weights are the only operand neighbouring row tiles share.
+//  Item i -> row pair i / n_tiles (rows [256 p, 256 p + 256)), output tile i % n_tiles.  Stage = [A0_hi, A0_lo, A1_hi,
+//  A1_lo, W_hi, W_lo] x 8 KB, 3 stages.  TMEM: 2 accumulator sets x 2 row tiles x 128 columns = 512.  Each epilogue
+//  group drains its column quarter of the two row tiles one after the other.
+// ------------------------------------------------------------------------------------------
+constexpr int PP_STAGES = 3;
+constexpr int PP_STAGE_BYTES = 6 * TC_TILE_BYTES;                          // 48 KB
+constexpr int PP_PIPE_BYTES = PP_STAGES * PP_STAGE_BYTES;                  // 144 KB operand ring
+constexpr int PP_SMEM_BYTES = PP_PIPE_BYTES + 65536 + 1024 /*align*/ + 256 /*barriers*/;
+constexpr uint32_t PP_TMEM_COLS = 512;
+
+__global__ void __launch_bounds__(PK_THREADS, 1)
+k_tc_rowgemm_pair(const __grid_constant__ TcMaps maps, const Tile* __restrict__ tiles, const int n_tiles, const int n_items,
+                        const BufTable bt, const BufRows br, const int64_t B, const int64_t Bp, const int split) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ Tile ts[PK_MAX_TILES];
+    __shared__ __align__(16) float bias_s[4][32];         // one quarter per epilogue group
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PP_PIPE_BYTES + 65536);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + PP_STAGES), acc_full0 = smem_u32(bars + 2 * PP_STAGES),
+                   acc_free0 = smem_u32(bars + 2 * PP_STAGES + 2), res_bar = smem_u32(bars + 2 * PP_STAGES + 4);   // 4 residual barriers
+    const uint32_t smem_base = smem_u32(smem);
+
+    {
+        const int* src = reinterpret_cast<const int*>(tiles);
+        int* dst = reinterpret_cast<int*>(ts);
+        for (int i = tid; i < n_tiles * (int)(sizeof(Tile) / 4); i += PK_THREADS) dst[i] = src[i];
+    }
+    if (tid == 0) {
+        for (int s = 0; s < PP_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        // acc_free: every epilogue thread (16 warps) arrives once per row tile of the item (two row tiles per item)
+        for (int a = 0; a < 2; ++a) { mbar_init(acc_full0 + 8 * a, 1); mbar_init(acc_free0 + 8 * a, 1024); }
+        for (int g = 0; g < 4; ++g) mbar_init(res_bar + 8 * g, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), PP_TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    constexpr int SPC = H / TC_KB;                 // pipeline steps per chunk
+    const int last_tile_row = (int)Bp - TILE_M;    // first row of the last 128-row tile
+    // Programmatic dependent launch: everything above (tile table, barriers, TMEM) ran while the previous kernel of the
+    // stream was still draining; from here on this grid reads what that kernel wrote.  Our own dependents may be scheduled
+    // as soon as every CTA of this grid has passed this point (they start on an SM when its CTA has exited).
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t g = 0;                        // pipeline step counter, runs across items
+            for (int i = blockIdx.x; i < n_items; i += gridDim.x) {
+                const Tile& t = ts[i % n_tiles];
+                const int row0 = (i / n_tiles) * (2 * TILE_M);
+                const bool two = row0 + TILE_M <= last_tile_row;
+                const uint32_t tx_bytes = (uint32_t)((split ? 2 : 1) * (two ? 3 : 2) * TC_TILE_BYTES);
+                const int n_steps = t.n_chunks * SPC;
+                for (int j = 0; j < n_steps; ++j, ++g) {
+                    const uint32_t s = g % PP_STAGES;
+                    mbar_wait(empty0 + 8 * s, ((g / PP_STAGES) & 1) ^ 1);
+                    const Chunk& ch = t.chunks[j / SPC];
+                    const int kcol = (j % SPC) * TC_KB;
+                    const int arow = (int)((int64_t)ch.a_slot * Bp) + row0;
+                    const uint32_t st = smem_base + s * PP_STAGE_BYTES;
+                    const uint32_t fb = full0 + 8 * s;
+                    mbar_expect_tx(fb, tx_bytes);
+                    tma_load_2d(st, &maps.k, fb, kcol, br.hi[ch.a_buf] + arow);
+                    if (two) tma_load_2d(st + 2 * TC_TILE_BYTES, &maps.k, fb, kcol, br.hi[ch.a_buf] + arow + TILE_M);
+                    tma_load_2d(st + 4 * TC_TILE_BYTES, &maps.k, fb, kcol, br.w_hi + ch.w16_row);
+                    if (split) {
+                        tma_load_2d(st + TC_TILE_BYTES, &maps.k, fb, kcol, br.lo[ch.a_buf] + arow);
+                        if (two) tma_load_2d(st + 3 * TC_TILE_BYTES, &maps.k, fb, kcol, br.lo[ch.a_buf] + arow + TILE_M);
+                        tma_load_2d(st + 5 * TC_TILE_BYTES, &maps.k, fb, kcol, br.w_lo + ch.w16_row);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            uint32_t g = 0, k = 0;
+            for (int i = blockIdx.x; i < n_items; i += gridDim.x, ++k) {
+                const int n_steps = ts[i % n_tiles].n_chunks * SPC;
+                const bool two = (i / n_tiles) * (2 * TILE_M) + TILE_M <= last_tile_row;
+                const uint32_t a = k & 1;
+                mbar_wait(acc_free0 + 8 * a, ((k >> 1) & 1) ^ 1);      // the epilogue has drained this accumulator set
+                tc_fence_after();
+                const uint32_t d0 = tmem_base + a * 256, d1 = d0 + 128;
+                for (int j = 0; j < n_steps; ++j, ++g) {
+                    const uint32_t s = g % PP_STAGES;
+                    mbar_wait(full0 + 8 * s, (g / PP_STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t st = smem_base + s * PP_STAGE_BYTES;
+                    const uint64_t a0_hi = smem_desc_sw64(st), a0_lo = smem_desc_sw64(st + TC_TILE_BYTES);
+                    const uint64_t a1_hi = smem_desc_sw64(st + 2 * TC_TILE_BYTES), a1_lo = smem_desc_sw64(st + 3 * TC_TILE_BYTES);
+                    const uint64_t w_hi = smem_desc_sw64(st + 4 * TC_TILE_BYTES), w_lo = smem_desc_sw64(st + 5 * TC_TILE_BYTES);
+#pragma unroll
+                    for (int ks = 0; ks < TC_KB / 16; ++ks) {
+                        const uint64_t adv = (uint64_t)(ks * 2);
+                        const uint32_t acc = (j | ks) ? 1u : 0u;
+                        umma_f16(d0, a0_hi + adv, w_hi + adv, TC_IDESC, acc);
+                        if (two) umma_f16(d1, a1_hi + adv, w_hi + adv, TC_IDESC, acc);
+                        if (split) {
+                            umma_f16(d0, a0_lo + adv, w_hi + adv, TC_IDESC, 1u);
+                            if (two) umma_f16(d1, a1_lo + adv, w_hi + adv, TC_IDESC, 1u);
+                            umma_f16(d0, a0_hi + adv, w_lo + adv, TC_IDESC, 1u);
+                            if (two) umma_f16(d1, a1_hi + adv, w_lo + adv, TC_IDESC, 1u);
+                        }
+                    }
+                    umma_commit(empty0 + 8 * s);
+                }
+                umma_commit(acc_full0 + 8 * a);
+            }
+        }
+        __syncwarp();
+    } else {
+        // group g (warps 2 + 4g .. 5 + 4g) drains column quarter g of every item
+        const int grp = (warp - 2) >> 2;
+        EpiSmem es;
+        es.stg = smem_base + PP_PIPE_BYTES + grp * 16384; es.bias = smem_u32(bias_s[grp]); es.res_bar = res_bar + 8 * grp;
+        es.persistent = 1; es.n_groups = 4; es.res_parity = 0;
+        uint32_t k = 0, n_res = 0;
+        for (int i = blockIdx.x; i < n_items; i += gridDim.x, ++k) {
+            const uint32_t a = k & 1;
+            const int row0 = (i / n_tiles) * (2 * TILE_M);
+            const bool two = row0 + TILE_M <= last_tile_row;
+            es.accum_bar = acc_full0 + 8 * a; es.free_bar = acc_free0 + 8 * a;
+            es.acc_parity = (k >> 1) & 1;
+            tc_epilogue_q(ts[i % n_tiles], bt, br, &maps.k, tmem_base + a * 256, row0, B, Bp, warp, lane, grp, es, n_res);
+            if (two) tc_epilogue_q(ts[i % n_tiles], bt, br, &maps.k, tmem_base + a * 256 + 128, row0 + TILE_M, B, Bp, warp, lane, grp, es, n_res);
+            else mbar_arrive(es.free_bar);         // keeps the arrival count of the set at 1024
+        }
+        if (((warp - 2) & 3) == 0 && lane == 0) tma_store_wait_all();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, PP_TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // reduce-over-rows GEMM on tcgen05 (weight gradients):  dW[128 out, 128 in] = sum_pairs dC[rows,128]^T * A[rows,128]
 // ------------------------------------------------------------------------------------------
 //  The reduction dimension is the graph-row dimension, so both MMA operands are "MN-major": the fp16 images are
