@@ -8,7 +8,7 @@ if [ "${1:-}" != "noprof" ]; then
   # steady-state step = launches [2*LPS, 3*LPS): list every launch of it
   timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 120 -c 70 --csv --log-file gpurun_out/launches.csv \
       python tools/profile_step.py 4 > gpurun_out/launches.log 2>&1
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_tc_rowgemm -s 60 -c 5 -f -o gpurun_out/prof_rowgemm \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_tc_rowgemm -s 30 -c 6 -f -o gpurun_out/prof_rowgemm \
       python tools/profile_step.py 2 > gpurun_out/prof_rowgemm.log 2>&1
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_tc_encoder|k_tc_reducegemm' -s 9 -c 3 -f -o gpurun_out/prof_enc \
       python tools/profile_step.py 2 > gpurun_out/prof_enc.log 2>&1
