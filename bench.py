@@ -169,6 +169,7 @@ def main():
     ap.add_argument("--mode", default="tc", choices=["fp32", "tc", "tc1x"], help="arithmetic mode of the native kernels")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-extra", action="store_true", help="skip the short runs of the other BASELINE.json configs")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -335,6 +336,49 @@ def main():
                     "window_builder_ms": wb_ms,
                     "window_builder_gbs": (150 * 54 * 4 + 43200 + 16) * B / (wb_ms * 1e-3) / 1e9 if wb_ms else None}
 
+    # ---------------- the other BASELINE.json configs, briefly (rank 0, device resident; not the headline) ----------------
+    extra = None
+    if not args.skip_extra and world == 1 and B == PER_GPU_BATCH and args.mode == "tc":
+        from ms_hgnn.synthetic import build_model
+        extra = {}
+
+        def quick(fn, steps=10, warm=3):
+            for _ in range(warm):
+                fn()
+            torch.cuda.synchronize(dev)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(steps):
+                fn()
+            b.record()
+            torch.cuda.synchronize(dev)
+            return a.elapsed_time(b) / steps
+
+        # configs[1]: MS-HGNN C2 Mini Cheetah contact, batch 4096, train step
+        c2 = CONFIGS["mini_cheetah-c2-contact"]
+        m2 = build_model(c2, 128, 8, 1).set_mode(args.mode).to(dev)
+        m2.validate_edges = "cached"
+        b2 = make_batch(c2, 4096, seed=5).to(dev)
+        t2 = FusedTrainer(m2, optimizer="adam", lr=1e-4, process_group=None)
+        t2.world = 1
+        ms = quick(lambda: t2.train_step(b2))
+        extra["mini_cheetah-c2-contact_train_b4096"] = {"graphs_per_s": 4096 / (ms * 1e-3), "ms_per_step": ms}
+        del m2, b2, t2
+        # configs[4]: MS-HGNN K4 Solo12 COM, inference sweep
+        c5 = CONFIGS["solo12-k4-com"]
+        m5 = build_model(c5, 128, 8, 2).set_mode(args.mode).to(dev)
+        m5.validate_edges = "cached"
+        sweep = []
+        for nb in (1 << 10, 1 << 14, 1 << 17, 1 << 20):
+            b5 = make_batch(c5, nb, seed=6).to(dev)
+            with torch.no_grad():
+                ms = quick(lambda: m5(b5.x_dict, b5.edge_index_dict), steps=5 if nb >= (1 << 17) else 20)
+            sweep.append({"graphs": nb, "graphs_per_s": nb / (ms * 1e-3), "ms": ms})
+            del b5
+        extra["solo12-k4-com_inference_sweep"] = sweep
+        del m5
+        torch.cuda.empty_cache()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -413,6 +457,7 @@ def main():
             "peak_gbs": pk["hbm_gbs"], "frac": traffic["step"]["dram_bytes"] / (train_ms / K * 1e-3) / 1e9 / pk["hbm_gbs"],
             "source": "profiles/r1_tc_v6_step_traffic.json (ncu DRAM counters of one step) / this run's step time"},
         "profiled_ms_per_step": prof_ms / K,
+        "other_configs": extra,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
