@@ -682,11 +682,16 @@ int mshgnn_build_windows(const mshgnn_window_desc* d, const void* seq, const voi
     cudaStream_t st = (cudaStream_t)stream;
     const int Tp = T | 1;
     const size_t esz = seq_dtype == MSHGNN_F64 ? 8 : 4;
-    if (C > WIN_THREADS) return fail(MSHGNN_ERR_ARG, "seq_cols exceeds the CTA size");
-    const size_t smem = (size_t)T * C * esz + (size_t)C * Tp * 4;
+    const int vw = (int)(16 / esz);
+    const int Cp = (C + vw - 1) / vw * vw;
+    if (Cp / vw > WIN_THREADS) return fail(MSHGNN_ERR_ARG, "seq_cols exceeds the CTA size");
+    const int nrg = std::min(WIN_THREADS / (Cp / vw), WIN_MAX_RG);
+    // z-scored window [C][T|1] floats, also the scratch of the statistics partials [row groups][Cp][2] doubles
+    const size_t nz_bytes = (std::max((size_t)C * Tp * 4, (size_t)nrg * Cp * 16) + 127) / 128 * 128;
+    const size_t smem = nz_bytes + (size_t)T * Cp * esz;
+    if (smem > 200 * 1024) return fail(MSHGNN_ERR_ARG, "window of %d x %d does not fit in shared memory", T, C);
     // one bulk async copy per window needs 16-byte aligned window starts and sizes
     const int bulk = ((size_t)C * esz) % 16 == 0 && ((uintptr_t)seq % 16) == 0 && ((size_t)T * C * esz) < (1u << 20);
-    if (smem > 200 * 1024) return fail(MSHGNN_ERR_ARG, "window of %d x %d does not fit in shared memory", T, C);
     int dev = 0, sms = 148;
     CUDA_TRY(cudaGetDevice(&dev));
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -695,10 +700,10 @@ int mshgnn_build_windows(const mshgnn_window_desc* d, const void* seq, const voi
     ProfScope ps(K_WINDOWS, st);
     if (seq_dtype == MSHGNN_F64) {
         CUDA_TRY(cudaFuncSetAttribute(k_build_windows<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_build_windows<double><<<grid, WIN_THREADS, smem, st>>>(tb, (const double*)seq, (const double*)label_seq, n_rows, starts, B, out, y, bulk);
+        k_build_windows<double><<<grid, WIN_THREADS, smem, st>>>(tb, (const double*)seq, (const double*)label_seq, n_rows, starts, B, out, y, bulk, (int)nz_bytes);
     } else {
         CUDA_TRY(cudaFuncSetAttribute(k_build_windows<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_build_windows<float><<<grid, WIN_THREADS, smem, st>>>(tb, (const float*)seq, (const float*)label_seq, n_rows, starts, B, out, y, bulk);
+        k_build_windows<float><<<grid, WIN_THREADS, smem, st>>>(tb, (const float*)seq, (const float*)label_seq, n_rows, starts, B, out, y, bulk, (int)nz_bytes);
     }
     LAUNCH_CHECK();
     return 0;

@@ -21,6 +21,7 @@
 #include <stdint.h>
 
 #include <cfloat>
+#include <cstring>
 
 namespace mshgnn {
 
@@ -55,34 +56,49 @@ struct WindowPtrs {
 __device__ __forceinline__ uint32_t win_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // Window pipeline of one CTA (grid-stride over graphs):
-//   (0) the T x C window - one contiguous run of the row-major sequence - lands in shared memory as raw[T][C]: by ONE bulk
+//   (0) the T x C window - one contiguous run of the row-major sequence - lands in shared memory as raw[T][Cp]: by ONE bulk
 //       async copy (cp.async.bulk global -> shared, mbarrier completion) when rows are 16-byte multiples, else by
 //       coalesced element loads;
-//   (1)-(2) thread (column c, row quarter q) accumulates fp64 partial sums / squared deviations (conflict-free: the
-//       threads of a warp read consecutive columns of one row), combined through shared memory;
-//   (3) the same threads write the z-scored values transposed into nz[C][T|1] (odd pitch: conflict-free);
-//       the raw buffer is free from here on, so the NEXT graph's bulk copy is issued now and overlaps (4);
-//   (4) every (node, variable, axis) block is a run of T floats in nz and in the output row: coalesced stores.
+//   (1) thread (column group of 16 bytes, row group) accumulates in ONE pass the fp64 sums of d = v - pivot and d^2 over its
+//       rows (pivot = the column's first row: the shifted sums give mean and Bessel variance without cancellation), one
+//       128-bit shared load per 4 (fp32) / 2 (fp64) columns; partials are combined through shared memory;
+//   (2) the same threads write the z-scored values transposed into nz[C][T|1] (odd pitch); the raw buffer is free from here
+//       on, so the NEXT graph's bulk copy is issued now and overlaps (3);
+//   (3) every (node, variable, axis) block is a run of T floats in nz and in the output row: coalesced stores, block offsets
+//       precomputed once per CTA.
+//  (ncu on the first version: 18 K warp instructions per graph, 52 % issue-bound, three scalar passes with a conversion to
+//  fp64 per element each; this version needs ~4 K.)
+constexpr int WIN_MAX_RG = 16;           // row groups of the statistics pass
+
+template <typename TIn> struct WinVec;
+template <> struct WinVec<float> { static constexpr int W = 4; };
+template <> struct WinVec<double> { static constexpr int W = 2; };
+
 template <typename TIn>
 __global__ void __launch_bounds__(WIN_THREADS)
 k_build_windows(const WindowTable tb, const TIn* __restrict__ seq, const TIn* __restrict__ label_seq, const int64_t n_rows,
-                const int64_t* __restrict__ starts, const int64_t B, const WindowPtrs out, float* __restrict__ y, const int bulk) {
+                const int64_t* __restrict__ starts, const int64_t B, const WindowPtrs out, float* __restrict__ y, const int bulk,
+                const int nz_bytes) {
     extern __shared__ __align__(128) uint8_t win_smem[];
     __shared__ __align__(8) uint64_t bar;
-    __shared__ double part[4][WIN_MAX_COLS];
-    __shared__ double mean_s[WIN_MAX_COLS], rstd_s[WIN_MAX_COLS];
+    __shared__ float dm_s[WIN_MAX_COLS], rstd_s[WIN_MAX_COLS];       // mean - pivot, 1 / std (0: the std == 0 branch)
+    __shared__ int boff_s[WIN_MAX_BLOCKS];                            // element offset of block b inside its graph's rows
+    __shared__ int8_t bty_s[WIN_MAX_BLOCKS];
+    constexpr int VW = WinVec<TIn>::W;
     const int T = tb.T, C = tb.C;
+    const int Cp = (C + VW - 1) / VW * VW;                              // shared-memory row pitch (== C on the bulk path)
     const int Tp = T | 1;
-    TIn* raw = reinterpret_cast<TIn*>(win_smem);                        // [T][C]
-    float* nz = reinterpret_cast<float*>(raw + (size_t)T * C);          // [C][Tp]
+    float* nz = reinterpret_cast<float*>(win_smem);                     // [C][Tp] z-scored window; doubles as the partial-sum scratch
+    double* part = reinterpret_cast<double*>(win_smem);                 // [rg][Cp][2] during the statistics pass
+    TIn* raw = reinterpret_cast<TIn*>(win_smem + nz_bytes);             // [T][Cp]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t bar_a = win_smem_u32(&bar);
     const uint32_t bytes = (uint32_t)((size_t)T * C * sizeof(TIn));
-    // statistics threads: column c = tid % C4, row quarter q = tid / C4 (C4 = columns rounded so that 4 quarters fit)
-    const int nq = (WIN_THREADS / C) < 4 ? (WIN_THREADS / C) : 4;       // 1..4 row ranges
-    const int sc = tid % C, sq = tid / C;
-    const bool stat = sq < nq;
-    const int t0 = stat ? (int)((int64_t)T * sq / nq) : 0, t1 = stat ? (int)((int64_t)T * (sq + 1) / nq) : 0;
+    const int nquad = Cp / VW;
+    const int nrg = (WIN_THREADS / nquad) < WIN_MAX_RG ? (WIN_THREADS / nquad) : WIN_MAX_RG;
+    const int quad = tid % nquad, rg = tid / nquad;
+    const bool stat = rg < nrg;
+    const int c0 = quad * VW;
 
     auto window_start = [&](const int64_t g) {
         int64_t s = starts[g];
@@ -95,14 +111,21 @@ k_build_windows(const WindowTable tb, const TIn* __restrict__ seq, const TIn* __
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      ::"r"(win_smem_u32(raw)), "l"(src), "r"(bytes), "r"(bar_a) : "memory");
     };
-    if (bulk) {
-        if (tid == 0) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a) : "memory");
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncthreads();
-        if (tid == 0 && (int64_t)blockIdx.x < B) issue(blockIdx.x);
+    for (int b = tid; b < tb.n_blocks; b += WIN_THREADS) {
+        int ty = 0;
+#pragma unroll
+        for (int q = 1; q < 4; ++q) if (q < tb.n_types && b >= tb.first_block[q]) ty = q;
+        bty_s[b] = (int8_t)ty;
+        boff_s[b] = (b - tb.first_block[ty]) * tb.blen[ty];             // (node * blocks + k) * len
     }
+    if (!bulk)
+        for (int i = tid; i < T * (Cp - C); i += WIN_THREADS) raw[(i / (Cp - C)) * Cp + C + i % (Cp - C)] = (TIn)0;   // pad columns
+    if (bulk && tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (bulk && tid == 0 && (int64_t)blockIdx.x < B) issue(blockIdx.x);
     uint32_t phase = 0;
     for (int64_t g = blockIdx.x; g < B; g += gridDim.x) {
         const int64_t s = window_start(g);
@@ -116,64 +139,78 @@ k_build_windows(const WindowTable tb, const TIn* __restrict__ seq, const TIn* __
         } else {
             const TIn* src = seq + s * C;
             const int n = T * C;
-            for (int i = tid; i < n; i += WIN_THREADS) raw[i] = __ldg(src + i);
+            for (int i = tid; i < n; i += WIN_THREADS) raw[(i / C) * Cp + (i % C)] = __ldg(src + i);
             __syncthreads();
+        }
+        TIn piv[VW];
+        if (stat) {
+            const uint4 pv = *reinterpret_cast<const uint4*>(raw + c0);
+            memcpy(piv, &pv, 16);
         }
         if (tb.normalize) {
-            if (stat && tb.col_used[sc]) {
-                double a = 0.0;
-                for (int t = t0; t < t1; ++t) a += (double)raw[t * C + sc];
-                part[sq][sc] = a;
+            if (stat) {
+                double sd[VW], sq[VW];
+#pragma unroll
+                for (int e = 0; e < VW; ++e) { sd[e] = 0.0; sq[e] = 0.0; }
+                for (int t = rg; t < T; t += nrg) {
+                    const uint4 pv = *reinterpret_cast<const uint4*>(raw + t * Cp + c0);
+                    TIn v[VW];
+                    memcpy(v, &pv, 16);
+#pragma unroll
+                    for (int e = 0; e < VW; ++e) {
+                        const double d = (double)(v[e] - piv[e]);
+                        sd[e] += d;
+                        sq[e] = fma(d, d, sq[e]);
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < VW; ++e) { part[(rg * Cp + c0 + e) * 2] = sd[e]; part[(rg * Cp + c0 + e) * 2 + 1] = sq[e]; }
             }
             __syncthreads();
-            if (tid < C && tb.col_used[tid]) {
-                double a = 0.0;
-                for (int q = 0; q < nq; ++q) a += part[q][tid];
-                mean_s[tid] = a / (double)T;
-            }
-            __syncthreads();
-            if (stat && tb.col_used[sc]) {
-                const double m = mean_s[sc];
-                double a = 0.0;
-                for (int t = t0; t < t1; ++t) { const double d = (double)raw[t * C + sc] - m; a += d * d; }
-                part[sq][sc] = a;
-            }
-            __syncthreads();
-            if (tid < C && tb.col_used[tid]) {
-                double a = 0.0;
-                for (int q = 0; q < nq; ++q) a += part[q][tid];
-                const double sd = sqrt(a / (double)(T - 1));
-                rstd_s[tid] = sd > 0.0 ? 1.0 / sd : 0.0;                // 0: the (v - mean) / 0 branch below
+            if (tid < C) {
+                double a = 0.0, q2 = 0.0;
+                for (int r = 0; r < nrg; ++r) { a += part[(r * Cp + tid) * 2]; q2 += part[(r * Cp + tid) * 2 + 1]; }
+                const double m = a / (double)T;                                   // mean - pivot
+                double var = (q2 - a * m) / (double)(T - 1);                      // sum (d - m)^2 = sum d^2 - (sum d)^2 / T
+                var = var > 0.0 ? var : 0.0;
+                // a column whose values are all equal has d == 0 everywhere: var == 0 exactly, like the two-pass reference
+                dm_s[tid] = (float)m;
+                rstd_s[tid] = var > 0.0 ? (float)(1.0 / sqrt(var)) : 0.f;
             }
             __syncthreads();
         }
-        if (stat && tb.col_used[sc]) {
-            float* nc = nz + sc * Tp;
-            if (tb.normalize) {
-                const double m = mean_s[sc], r = rstd_s[sc];
-                if (r != 0.0) {
-                    for (int t = t0; t < t1; ++t) nc[t] = (float)(((double)raw[t * C + sc] - m) * r);
-                } else {
-                    // (v - mean) / 0: 0/0 = NaN -> 0 (np.nan_to_num(nan=0.0)); +-x/0 = +-inf -> +-largest finite
-                    for (int t = t0; t < t1; ++t) {
-                        const double d = (double)raw[t * C + sc] - m;
-                        nc[t] = d == 0.0 ? 0.f : (d > 0.0 ? FLT_MAX : -FLT_MAX);
+        if (stat) {
+            float dm[VW], rs[VW];
+#pragma unroll
+            for (int e = 0; e < VW; ++e) {
+                const int c = c0 + e < C ? c0 + e : C - 1;
+                dm[e] = tb.normalize ? dm_s[c] : 0.f;
+                rs[e] = tb.normalize ? rstd_s[c] : 1.f;
+            }
+            for (int t = rg; t < T; t += nrg) {
+                const uint4 pv = *reinterpret_cast<const uint4*>(raw + t * Cp + c0);
+                TIn v[VW];
+                memcpy(v, &pv, 16);
+#pragma unroll
+                for (int e = 0; e < VW; ++e) {
+                    if (c0 + e >= C) continue;
+                    float z;
+                    if (!tb.normalize) z = (float)v[e];
+                    else {
+                        const float d = (float)(v[e] - piv[e]) - dm[e];
+                        // (v - mean) / 0: 0/0 = NaN -> 0 (np.nan_to_num(nan=0.0)); +-x/0 = +-inf -> +-largest finite
+                        z = rs[e] != 0.f ? d * rs[e] : (d == 0.f ? 0.f : (d > 0.f ? FLT_MAX : -FLT_MAX));
                     }
+                    nz[(c0 + e) * Tp + t] = z;
                 }
-            } else {
-                for (int t = t0; t < t1; ++t) nc[t] = (float)raw[t * C + sc];
             }
         }
         __syncthreads();                                               // nz complete, raw free
         if (bulk && tid == 0 && g + gridDim.x < B) issue(g + gridDim.x);
         for (int b = warp; b < tb.n_blocks; b += WIN_THREADS / 32) {
-            int ty = 0;
-#pragma unroll
-            for (int q = 1; q < 4; ++q) if (q < tb.n_types && b >= tb.first_block[q]) ty = q;
-            const int local = b - tb.first_block[ty];
-            const int node = local / tb.blocks[ty], k = local - node * tb.blocks[ty];
+            const int ty = bty_s[b];
             const int len = tb.blen[ty];
-            float* dst = out.x[ty] + ((g * tb.nodes[ty] + node) * (int64_t)tb.blocks[ty] + k) * len;
+            float* dst = out.x[ty] + g * ((int64_t)tb.nodes[ty] * tb.blocks[ty] * len) + boff_s[b];
             const int c = tb.col[b];
             const float f = (float)tb.sign[b];
             if (c >= 0) {
