@@ -130,12 +130,15 @@ k_build_windows(const WindowTable tb, const TIn* __restrict__ seq, const TIn* __
     for (int64_t g = blockIdx.x; g < B; g += gridDim.x) {
         const int64_t s = window_start(g);
         if (bulk) {
-            uint32_t ok = 0;
-            while (!ok) {
-                asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                             : "=r"(ok) : "r"(bar_a), "r"(phase) : "memory");
+            if (warp == 0) {                                           // one warp polls; the others sleep in the CTA barrier
+                uint32_t ok = 0;
+                while (!ok) {
+                    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                                 : "=r"(ok) : "r"(bar_a), "r"(phase) : "memory");
+                }
             }
             phase ^= 1u;
+            __syncthreads();
         } else {
             const TIn* src = seq + s * C;
             const int n = T * C;
@@ -215,7 +218,13 @@ k_build_windows(const WindowTable tb, const TIn* __restrict__ seq, const TIn* __
             const float f = (float)tb.sign[b];
             if (c >= 0) {
                 const float* nc = nz + c * Tp;
-                for (int t = lane; t < len; t += 32) dst[t] = nc[t] * f;
+                for (int t0 = lane; t0 < len; t0 += 160) {            // 5 shared loads in flight, then 5 coalesced stores
+                    float vv[5];
+#pragma unroll
+                    for (int it = 0; it < 5; ++it) vv[it] = t0 + 32 * it < len ? nc[t0 + 32 * it] * f : 0.f;
+#pragma unroll
+                    for (int it = 0; it < 5; ++it) if (t0 + 32 * it < len) dst[t0 + 32 * it] = vv[it];
+                }
             } else {
                 for (int t = lane; t < len; t += 32) dst[t] = f;
             }
