@@ -156,3 +156,73 @@ def test_equivariance_k4_contact():
                               act(base[:, 1], g["permutation_Q_bs"][gi], g["reflection_Q_bs_ang"][gi])), dim=1)
             y1 = nm({k: v.cuda() for k, v in pack(j2, f2, b2).items()}, ei).reshape(B, 4, 2)
             assert rel_err(y1, y0[:, g["permutation_Q_ls"][gi]]) <= TOL_FP32
+
+
+@pytest.mark.parametrize("mode", ["tc", "fp32"])
+def test_full_size_properties_16384_graphs(mode):
+    """BASELINE.json's full batch (16384 K4 Mini Cheetah graphs, L = 8) through size-independent properties, because the fp64
+    oracle takes minutes at this size:
+      (i)   shard invariance - graphs are independent, so the predictions of the full batch equal, bit for bit, the predictions
+            of its two data-parallel shards (different tile / CTA assignment, same per-row arithmetic);
+      (ii)  gradient additivity - the flat gradient of the mean loss over the batch equals the shard gradients weighted by the
+            shard sizes (what the one all-reduce of SURVEY 8e relies on), to 2e-5 norm-wise per tensor (the sums over graphs are
+            split differently);
+      (iii) K4 equivariance of the predictions under gs (LinTzuYaunDataset_Morph.py:L349-408) at the mode's tolerance;
+      (iv)  the first 64 graphs against the fp64 oracle run on those 64 graphs alone."""
+    from ms_hgnn import morphology as M
+    cfg = CONFIGS["mini_cheetah-k4-contact"]
+    B = 16384
+    batch = make_batch(cfg, B, seed=77)
+    om = oracle_model(cfg, layers=8, seed=5)
+    nm = build_model(cfg, layers=8, seed=6)
+    nm.load_state_dict({k: v.float() for k, v in om.state_dict().items()})
+    nm = nm.set_mode(mode).to("cuda:0")
+    nm.validate_edges = "cached"
+
+    def run(b):
+        b = b.to("cuda:0")
+        nm.zero_grad()
+        out = nm(b.x_dict, b.edge_index_dict)
+        eng = nm._last_engine
+        loss, dout = eng.loss(out.detach().contiguous(), b.y, N.LOSS_CE2)
+        out.backward(dout)
+        g = {n: (p.grad.clone() if p.grad is not None else torch.zeros_like(p)) for n, p in nm.named_parameters()}
+        return out.detach().clone(), loss.item(), g
+
+    out_full, loss_full, g_full = run(batch)
+    s0, s1 = batch.shard(0, 2), batch.shard(1, 2)
+    out0, loss0, g0 = run(s0)
+    out1, loss1, g1 = run(s1)
+    assert torch.equal(out_full, torch.cat((out0, out1)))                                   # (i)
+    assert abs(loss_full - 0.5 * (loss0 + loss1)) <= 1e-6 * abs(loss_full)
+    for n in g_full:                                                                        # (ii)
+        ref = 0.5 * (g0[n] + g1[n])
+        if ref.norm() == 0:
+            assert g_full[n].abs().max().item() == 0.0
+        else:
+            assert rel_err(g_full[n], ref) <= 2e-5, n
+    # (iii) gs acts on the packed features as a node permutation + per-column sign (hgnn_k4.py:L198-237 undoes exactly that)
+    g = M.GROUPS["mini_cheetah-k4"]
+    T = 150
+    x = batch.x_dict
+    pj, rj = torch.tensor(g["permutation_Q_js"][0]), torch.tensor(g["reflection_Q_js"][0], dtype=torch.float32)
+    pf, rf = torch.tensor(g["permutation_Q_fs"][0]), torch.tensor(g["reflection_Q_fs"][0], dtype=torch.float32)
+    pb = torch.tensor(g["permutation_Q_bs"][0])
+    rbl, rba = torch.tensor(g["reflection_Q_bs_lin"][0], dtype=torch.float32), torch.tensor(g["reflection_Q_bs_ang"][0], dtype=torch.float32)
+    xj = x["joint"].view(B, 12, 2, T)[:, pj] * rj.view(1, 12, 1, 1)
+    xf = x["foot"].view(B, 4, 2, 3, T).permute(0, 2, 4, 1, 3).reshape(B, 2, T, 12)[..., pf] * rf
+    xf = xf.view(B, 2, T, 4, 3).permute(0, 3, 1, 4, 2).reshape(B * 4, 6 * T)
+    xb = x["base"].view(B, 4, 2, 3, T).permute(0, 2, 4, 1, 3).reshape(B, 2, T, 12)[..., pb]
+    xb = torch.stack((xb[:, 0] * rbl, xb[:, 1] * rba), dim=1).view(B, 2, T, 4, 3).permute(0, 3, 1, 4, 2).reshape(B * 4, 6 * T)
+    from ms_hgnn.synthetic import HeteroBatch
+    gb = HeteroBatch({"base": xb.contiguous(), "joint": xj.reshape(B * 12, 2 * T).contiguous(), "foot": xf.contiguous()},
+                     batch.edge_index_dict, batch.y, B).to("cuda:0")
+    with torch.no_grad():
+        y_g = nm(gb.x_dict, gb.edge_index_dict).reshape(B, 4, 2)
+    y_ref = out_full.reshape(B, 4, 2)[:, g["permutation_Q_ls"][0]]
+    assert rel_err(y_g, y_ref) <= TOL_FP32
+    # (iv) oracle on the first 64 graphs
+    from helpers import oracle_run
+    head = batch.shard(0, 256)
+    out_o, _, _ = oracle_run(cfg, om, head)
+    assert rel_err(out_full[: 64 * 4], out_o) <= TOL_FP32
