@@ -202,8 +202,13 @@ int launch_tc_encoder(const Plan& p, const Launch& L, const WsLayout& w, const B
                       const float* params, int64_t B, int xf64, int split, cudaStream_t st) {
     if (L.count == 0) return 0;
     static bool attr_set = false;
+    static bool use_v1 = false;       // MSHGNN_ENCODER=v1 selects the one-CTA-per-SM kernel with 64-column K blocks (A/B measurements)
     if (!attr_set) {
         CUDA_TRY(cudaFuncSetAttribute(k_tc_encoder, cudaFuncAttributeMaxDynamicSharedMemorySize, ENC_SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(k_tc_encoder2, cudaFuncAttributeMaxDynamicSharedMemorySize, ENC2_SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(k_tc_encoder2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        const char* e = getenv("MSHGNN_ENCODER");
+        use_v1 = e && !strcmp(e, "v1");
         attr_set = true;
     }
     __half* e_hi = (__half*)(ws + w.wenc16[0]);
@@ -218,12 +223,15 @@ int launch_tc_encoder(const Plan& p, const Launch& L, const WsLayout& w, const B
     }
     EncMaps maps;
     int rc;
-    if ((rc = make_map_2d(&maps.w_hi, e_hi, (int64_t)p.n_types * H, p.enc_kmax, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-    if ((rc = make_map_2d(&maps.w_lo, e_lo, (int64_t)p.n_types * H, p.enc_kmax, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    const int kb = use_v1 ? 64 : ENC2_KB;
+    const CUtensorMapSwizzle sw = use_v1 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    if ((rc = make_map_2d(&maps.w_hi, e_hi, (int64_t)p.n_types * H, p.enc_kmax, kb, 128, sw))) return rc;
+    if ((rc = make_map_2d(&maps.w_lo, e_lo, (int64_t)p.n_types * H, p.enc_kmax, kb, 128, sw))) return rc;
     maps.o = wm.tc.o;
     ProfScope ps(K_ENC_FWD, st);
     dim3 grid((unsigned)(w.Bp / TILE_M), (unsigned)L.count);
-    k_tc_encoder<<<grid, ENC_THREADS, ENC_SMEM_BYTES, st>>>(maps, p.d_tiles + L.begin, bt, br, B, w.Bp, xf64, split);
+    if (use_v1) k_tc_encoder<<<grid, ENC_THREADS, ENC_SMEM_BYTES, st>>>(maps, p.d_tiles + L.begin, bt, br, B, w.Bp, xf64, split);
+    else k_tc_encoder2<<<grid, ENC_THREADS, ENC2_SMEM_BYTES, st>>>(maps, p.d_tiles + L.begin, bt, br, B, w.Bp, xf64, split);
     LAUNCH_CHECK();
     return 0;
 }
@@ -302,7 +310,7 @@ void fill_rows16(const Plan& p, const WsLayout& w, BufRows& br) {
     br.w_hi = at(w.w16[0]); br.w_lo = at(w.w16[1]);
 }
 
-int launch_tc_dw(int kind, const Plan& p, const Launch& L, const WsLayout& w, const BufRows& br, const WsMaps& wm, int64_t B, int split,
+int launch_tc_dw(int kind, const Plan& p, int layer, const Launch& L, const WsLayout& w, const BufRows& br, const WsMaps& wm, int64_t B, int split,
                  float* part_w, float* part_b, cudaStream_t st) {
     if (L.count == 0) return 0;
     static bool attr_set = false;
@@ -317,8 +325,8 @@ int launch_tc_dw(int kind, const Plan& p, const Launch& L, const WsLayout& w, co
             if (p.rpairs[T.pair_begin + j].a_kind != A_SLAB) return fail(MSHGNN_ERR_ARG, "internal: tensor-core weight-gradient task must read slabs");
     }
     ProfScope ps(kind, st);
-    dim3 grid((unsigned)L.count, (unsigned)w.n_splits_tc);
-    k_tc_reducegemm<<<grid, TC_THREADS, DW_SMEM_BYTES, st>>>(wm.dw, p.d_rtasks, p.d_rpairs, L.begin, br, B, w.Bp, w.rows_per_tc, w.n_splits_tc,
+    dim3 grid((unsigned)L.count, (unsigned)w.dw_ns[layer]);          // wave-fitted row splits of this layer (ws_layout)
+    k_tc_reducegemm<<<grid, TC_THREADS, DW_SMEM_BYTES, st>>>(wm.dw, p.d_rtasks, p.d_rpairs, L.begin, br, B, w.Bp, w.dw_rows[layer], w.part_stride,
                                                              split, part_w, part_b);
     LAUNCH_CHECK();
     return 0;
@@ -381,7 +389,13 @@ int mshgnn_param_offset(const mshgnn_plan* plan, int32_t kind, int32_t layer, in
 
 int64_t mshgnn_workspace_bytes(const mshgnn_plan* plan, int64_t B, int32_t train, int32_t mode) {
     if (!plan || B < 1) return -1;
-    return ws_layout(plan->p, B, train, mode).total;
+    const WsLayout w = ws_layout(plan->p, B, train, mode);
+    if (train && mode != MSHGNN_MODE_FP32 && getenv("MSHGNN_DEBUG_LAYOUT")) {   // weight-gradient row splits per layer launch
+        fprintf(stderr, "mshgnn layout B=%lld: dW default %d x %d rows, partial stride %d;", (long long)B, w.n_splits_tc, w.rows_per_tc, w.part_stride);
+        for (size_t l = 0; l < plan->p.dw_layer.size(); ++l) fprintf(stderr, " L%zu[%d tasks]: %d x %d", l, plan->p.dw_layer[l].count, w.dw_ns[l], w.dw_rows[l]);
+        fprintf(stderr, "\n");
+    }
+    return w.total;
 }
 
 int64_t mshgnn_out_rows(const mshgnn_plan* plan, int64_t B) { return plan ? B * plan->p.nodes[plan->p.dec_type] : -1; }
@@ -565,7 +579,7 @@ int mshgnn_backward(const mshgnn_plan* plan, int64_t B, const void* const* x, in
         if (tc) {
             if ((rc = launch_tc_rowgemm(K_MLP_BWD, p, p.bwd_m1[l], bt, br, wm, B, w.Bp, split, st))) return rc;
             if ((rc = launch_tc_rowgemm(K_MLP_BWD, p, p.bwd_m2[l], bt, br, wm, B, w.Bp, split, st))) return rc;
-            if ((rc = launch_tc_dw(K_DW_LAYER, p, p.dw_layer[l], w, br, wm, B, split, part_w, part_b, st))) return rc;
+            if ((rc = launch_tc_dw(K_DW_LAYER, p, l, p.dw_layer[l], w, br, wm, B, split, part_w, part_b, st))) return rc;
             if ((rc = launch_tc_rowgemm(K_DX_BWD, p, p.bwd_dx[l], bt, br, wm, B, w.Bp, split, st))) return rc;
         } else {
             if ((rc = launch_rowgemm(K_MLP_BWD, p, p.bwd_m1[l], bt, B, w.Bp, 0, st))) return rc;
@@ -600,16 +614,24 @@ int mshgnn_backward(const mshgnn_plan* plan, int64_t B, const void* const* x, in
     } else if ((rc = launch_dw(K_DW_ENC, p.dw_enc))) return rc;
     // layer-stack groups were produced with the split count of the kernel that ran them, encoder groups with the SIMT one
     const int ngl = p.n_groups_layers, nge = (int)p.groups.size() - ngl;
+    if (p.rtasks.size() > (size_t)MAX_RTASKS) return fail(MSHGNN_ERR_ARG, "internal: more than %d weight-gradient tasks", MAX_RTASKS);
+    TaskSplits ts;
+    const int ns_uniform = tc ? w.n_splits_tc : w.n_splits;
+    for (size_t i = 0; i < p.rtasks.size(); ++i) ts.ns[i] = (unsigned char)ns_uniform;
+    if (tc)
+        for (size_t l = 0; l < p.dw_layer.size(); ++l)
+            for (int i = 0; i < p.dw_layer[l].count; ++i) ts.ns[p.dw_layer[l].begin + i] = (unsigned char)w.dw_ns[l];
+    const int stride = tc ? w.part_stride : w.n_splits;
     if (ngl > 0) {
         dim3 grid((unsigned)ngl, 32);
         ProfScope ps(K_REDUCE, st);
-        k_reduce_partials<<<grid, 256, 0, st>>>(p.d_groups, part_w, part_b, tc ? w.n_splits_tc : w.n_splits, grads, 1.f / G);
+        k_reduce_partials<<<grid, 256, 0, st>>>(p.d_groups, part_w, part_b, stride, ts, grads, 1.f / G);
         LAUNCH_CHECK();
     }
     if (nge > 0 && !tc) {
         dim3 grid((unsigned)nge, 32);
         ProfScope ps(K_REDUCE, st);
-        k_reduce_partials<<<grid, 256, 0, st>>>(p.d_groups + ngl, part_w, part_b, w.n_splits, grads, 1.f / G);
+        k_reduce_partials<<<grid, 256, 0, st>>>(p.d_groups + ngl, part_w, part_b, stride, ts, grads, 1.f / G);
         LAUNCH_CHECK();
     }
     return 0;

@@ -80,6 +80,12 @@ struct RTask {
     int pad[3];
 };
 
+// How many row-split partials each weight-gradient task wrote (launches of different sizes use different split counts).
+constexpr int MAX_RTASKS = 1024;
+struct TaskSplits {
+    unsigned char ns[MAX_RTASKS];
+};
+
 // Final reduction of split partials into the flat gradient buffer.
 struct OutGroup {
     int kind;                         // 0: weight tile, 1: bias (colsum)

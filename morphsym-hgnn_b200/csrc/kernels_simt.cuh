@@ -365,7 +365,8 @@ k_reducegemm(const RTask* __restrict__ tasks, const RPair* __restrict__ pairs, c
 // sum the split partials of a group of tasks into the flat gradient buffer (fixed order => deterministic)
 __global__ void __launch_bounds__(256)
 k_reduce_partials(const OutGroup* __restrict__ groups, const float* __restrict__ part_w,
-                  const float* __restrict__ part_b, const int n_splits, float* __restrict__ grads, const float rscale) {
+                  const float* __restrict__ part_b, const int stride /*partial slots per task*/, const __grid_constant__ TaskSplits ts,
+                  float* __restrict__ grads, const float rscale) {
     const OutGroup g = groups[blockIdx.x];
     if (g.kind == 0) {
         const int per = (H * H) / gridDim.y;
@@ -374,7 +375,8 @@ k_reduce_partials(const OutGroup* __restrict__ groups, const float* __restrict__
             if (g.k0 + i >= g.K) continue;
             double sd = 0.0;
             for (int ti = 0; ti < g.n_tasks; ++ti) {
-                const float* p = part_w + (int64_t)g.tasks[ti] * n_splits * (H * H) + e;
+                const float* p = part_w + (int64_t)g.tasks[ti] * stride * (H * H) + e;
+                const int n_splits = ts.ns[g.tasks[ti]];
                 int sp = 0;
                 for (; sp + 8 <= n_splits; sp += 8) {      // 8 independent loads in flight, summed in the fixed order
                     float v[8];
@@ -393,7 +395,8 @@ k_reduce_partials(const OutGroup* __restrict__ groups, const float* __restrict__
         for (int e = threadIdx.x; e < H; e += 256) {
             double sd = 0.0;
             for (int ti = 0; ti < g.n_tasks; ++ti) {
-                const float* p = part_b + (int64_t)g.tasks[ti] * n_splits * H + e;
+                const float* p = part_b + (int64_t)g.tasks[ti] * stride * H + e;
+                const int n_splits = ts.ns[g.tasks[ti]];
                 for (int sp = 0; sp < n_splits; ++sp) sd += (double)p[(int64_t)sp * H];
             }
             const float s = (float)(sd * (double)g.scale * (double)rscale);

@@ -1235,11 +1235,11 @@ __device__ __forceinline__ float4 x_factors(const float* __restrict__ signs, con
     return f;
 }
 
-// v[it] = x[min(row_first + 8*it, row_last)][k .. k+3] (columns clamped into [0, K)).  Every load is issued unconditionally
+// v[it] = x[min(row_first + RS*it, row_last)][k .. k+3] (columns clamped into [0, K)).  Every load is issued unconditionally
 // on a clamped (always valid) address, so all N loads are in flight together; columns outside [0, K) are zeroed later by
 // their factor, rows beyond the batch alias the last row and only ever meet zero partners (dead accumulator rows in
 // the forward pass, zero dC rows in the weight gradient).
-template <int N>
+template <int N, int RS = 8>
 __device__ __forceinline__ void load_x_block(float4 (&v)[N], const XRows& x, const int64_t row_first, const int64_t row_last, const int k) {
     const int K = x.K;
     const int kc = k < K ? k : 0;
@@ -1249,14 +1249,14 @@ __device__ __forceinline__ void load_x_block(float4 (&v)[N], const XRows& x, con
         if (x.vec == 4) {
 #pragma unroll
             for (int it = 0; it < N; ++it) {
-                const int64_t r = min(row_first + it * 8, row_last);
+                const int64_t r = min(row_first + it * RS, row_last);
                 v[it] = __ldg(reinterpret_cast<const float4*>(b + r * x.lda + kc));
             }
         } else if (x.vec == 2) {
             const int kd = min(kc + 2, K - 2);
 #pragma unroll
             for (int it = 0; it < N; ++it) {
-                const int64_t r = min(row_first + it * 8, row_last);
+                const int64_t r = min(row_first + it * RS, row_last);
                 const float2 p = __ldg(reinterpret_cast<const float2*>(b + r * x.lda + kc));
                 const float2 q = __ldg(reinterpret_cast<const float2*>(b + r * x.lda + kd));
                 v[it] = make_float4(p.x, p.y, q.x, q.y);
@@ -1264,7 +1264,7 @@ __device__ __forceinline__ void load_x_block(float4 (&v)[N], const XRows& x, con
         } else {
 #pragma unroll
             for (int it = 0; it < N; ++it) {
-                const float* pr = b + min(row_first + it * 8, row_last) * x.lda;
+                const float* pr = b + min(row_first + it * RS, row_last) * x.lda;
                 v[it] = make_float4(__ldg(pr + kc), __ldg(pr + c1), __ldg(pr + c2), __ldg(pr + c3));
             }
         }
@@ -1274,7 +1274,7 @@ __device__ __forceinline__ void load_x_block(float4 (&v)[N], const XRows& x, con
             const int kd = min(kc + 2, K - 2);
 #pragma unroll
             for (int it = 0; it < N; ++it) {
-                const int64_t r = min(row_first + it * 8, row_last);
+                const int64_t r = min(row_first + it * RS, row_last);
                 const double2 p = __ldg(reinterpret_cast<const double2*>(b + r * x.lda + kc));
                 const double2 q = __ldg(reinterpret_cast<const double2*>(b + r * x.lda + kd));
                 v[it] = make_float4((float)p.x, (float)p.y, (float)q.x, (float)q.y);
@@ -1282,7 +1282,7 @@ __device__ __forceinline__ void load_x_block(float4 (&v)[N], const XRows& x, con
         } else {
 #pragma unroll
             for (int it = 0; it < N; ++it) {
-                const double* pr = b + min(row_first + it * 8, row_last) * x.lda;
+                const double* pr = b + min(row_first + it * RS, row_last) * x.lda;
                 v[it] = make_float4((float)__ldg(pr + kc), (float)__ldg(pr + c1), (float)__ldg(pr + c2), (float)__ldg(pr + c3));
             }
         }
@@ -1394,6 +1394,156 @@ k_tc_encoder(const __grid_constant__ EncMaps maps, const Tile* __restrict__ tile
                 const int r = half * 64 + it * 8 + rsub;
                 const uint32_t off = (uint32_t)(r * 128 + ((((kq >> 1) ^ (r & 7))) << 4) + ((kq & 1) << 3));
                 split_to_smem(st + off, st + ENC_TILE_BYTES + off, v[it], f);
+            }
+            if (half) {
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full0 + 8 * s);
+            }
+        };
+        load(va, 0);
+        load(vb, 1);
+        for (int n = 0; n < n_units; n += 3) {
+            load(vc, n + 2); convert(va, n);
+            load(va, n + 3); convert(vb, n + 1);
+            load(vb, n + 4); convert(vc, n + 2);
+        }
+        {
+            // ---------------- epilogue: warps 2..5 take columns 0..63, warps 6..9 columns 64..127 ----------------
+            EpiSmem es;
+            es.stg = smem_base; es.bias = smem_u32(bias_s); es.res_bar = res_bar; es.accum_bar = accum_bar;
+            es.free_bar = 0; es.acc_parity = 0; es.res_parity = 0; es.persistent = 0; es.n_groups = 2;
+            tc_epilogue(t, bt, br, &maps.o, tmem_base, row0, B, Bp, split, warp, lane, es);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TC_TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// encoder, two CTAs per SM (default; MSHGNN_ENCODER=v1 selects k_tc_encoder)
+// ------------------------------------------------------------------------------------------
+//  Same program as k_tc_encoder with 32-column K blocks (64B-swizzled, the row-GEMM's operand shape): a stage is 32 KB, the
+//  3-stage ring 96 KB, and the loaders keep three rotating sets of FOUR 128-bit loads (64 rows x 32 columns per unit), so
+//  two CTAs fit an SM (<= 102 registers, 2 x 128 TMEM columns).  The same number of bytes is in flight per SM as with one
+//  CTA, but the prologue (tile read, barrier init, TMEM allocation), the first-load latency and the whole epilogue of one
+//  CTA now overlap the feature stream of the other instead of idling the SM's share of HBM: with one CTA per SM those
+//  fixed ~9 us per tile were as long as the stream itself (3.5 us for a 300-wide joint tile, 10.5 us for a 900-wide one).
+constexpr int ENC2_KB = 32;
+constexpr int ENC2_STAGES = 3;
+constexpr int ENC2_TILE_BYTES = 128 * ENC2_KB * 2;            // 128 rows x 32 fp16 = 8 KB
+constexpr int ENC2_STAGE_BYTES = 4 * ENC2_TILE_BYTES;         // A_hi, A_lo, W_hi, W_lo = 32 KB
+constexpr int ENC2_SMEM_BYTES = ENC2_STAGES * ENC2_STAGE_BYTES + 1024 + 256;
+static_assert(ENC2_STAGES * ENC2_STAGE_BYTES >= 65536, "the epilogue stages 64 KB of output tiles in the drained operand ring");
+
+__global__ void __launch_bounds__(ENC_THREADS, 2)
+k_tc_encoder2(const __grid_constant__ EncMaps maps, const Tile* __restrict__ tiles, const BufTable bt, const BufRows br,
+              const int64_t B, const int64_t Bp, const int x_f64, const int split) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ Tile t;
+    __shared__ __align__(16) float bias_s[H];
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ENC2_STAGES * ENC2_STAGE_BYTES);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + ENC2_STAGES), accum_bar = smem_u32(bars + 2 * ENC2_STAGES),
+                   res_bar = smem_u32(bars + 2 * ENC2_STAGES + 1);
+    const uint32_t smem_base = smem_u32(smem);
+    {
+        const int* src = reinterpret_cast<const int*>(tiles + blockIdx.y);
+        int* dst = reinterpret_cast<int*>(&t);
+        for (int i = tid; i < (int)(sizeof(Tile) / 4); i += ENC_THREADS) dst[i] = src[i];
+    }
+    if (tid == 0) {
+        for (int s = 0; s < ENC2_STAGES; ++s) { mbar_init(full0 + 8 * s, 1 + ENC_LOADER_WARPS); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(accum_bar, 1);
+        mbar_init(res_bar, 1);
+        mbar_init(res_bar + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), TC_TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    const int row0 = blockIdx.x * TILE_M;
+    const int K = t.chunks[0].K;
+    const int n_kb = (K + ENC2_KB - 1) / ENC2_KB;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint32_t tx_bytes = split ? 2 * ENC2_TILE_BYTES : ENC2_TILE_BYTES;
+            const int wrow = t.chunks[0].w16_row;
+            for (int i = 0; i < n_kb; ++i) {
+                const int s = i % ENC2_STAGES;
+                mbar_wait(empty0 + 8 * s, ((i / ENC2_STAGES) & 1) ^ 1);
+                const uint32_t st = smem_base + s * ENC2_STAGE_BYTES;
+                const uint32_t fb = full0 + 8 * s;
+                mbar_expect_tx(fb, tx_bytes);
+                tma_load_2d(st + 2 * ENC2_TILE_BYTES, &maps.w_hi, fb, i * ENC2_KB, wrow);
+                if (split) tma_load_2d(st + 3 * ENC2_TILE_BYTES, &maps.w_lo, fb, i * ENC2_KB, wrow);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            for (int i = 0; i < n_kb; ++i) {
+                const int s = i % ENC2_STAGES;
+                mbar_wait(full0 + 8 * s, (i / ENC2_STAGES) & 1);
+                tc_fence_after();
+                const uint32_t st = smem_base + s * ENC2_STAGE_BYTES;
+                const uint64_t a_hi = smem_desc_sw64(st), a_lo = smem_desc_sw64(st + ENC2_TILE_BYTES);
+                const uint64_t w_hi = smem_desc_sw64(st + 2 * ENC2_TILE_BYTES), w_lo = smem_desc_sw64(st + 3 * ENC2_TILE_BYTES);
+#pragma unroll
+                for (int ks = 0; ks < ENC2_KB / 16; ++ks) {
+                    const uint64_t adv = (uint64_t)(ks * 2);      // +32 bytes (16 fp16) along K inside the swizzle atom
+                    umma_f16(tmem_base, a_hi + adv, w_hi + adv, TC_IDESC, (i | ks) ? 1u : 0u);
+                    if (split) {
+                        umma_f16(tmem_base, a_lo + adv, w_hi + adv, TC_IDESC, 1u);
+                        umma_f16(tmem_base, a_hi + adv, w_lo + adv, TC_IDESC, 1u);
+                    }
+                }
+                umma_commit(empty0 + 8 * s);
+            }
+            umma_commit(accum_bar);
+        }
+        __syncwarp();
+    } else {
+        // ---------------- loaders: group g takes the K blocks kb = g (mod 2) ----------------
+        const int g = (warp - 2) / ENC_LOADER_WARPS;
+        const int gt = tid - 64 - g * (ENC_LOADER_WARPS * 32);
+        const Chunk& ch = t.chunks[0];
+        const XRows xr = make_xrows(bt.p[ch.a_buf], x_f64, ch.lda, ch.a_off, K);
+        const float* signs = (const float*)bt.p[2];
+        const int kq = gt & 7;                                    // which 4-column group of the 32-column block
+        const int rsub = gt >> 3;                                 // 0..15
+        const int64_t row_first = (int64_t)row0 + rsub;
+        // Work units of 64 rows x 32 columns (half a K block, four 128-bit loads per thread); three register sets rotate
+        // so that the loads of units n + 1 and n + 2 are in flight while unit n is converted and written to shared memory.
+        const int n_units = kb_count(g, n_kb) * 2;
+        float4 va[4], vb[4], vc[4];
+        auto load = [&](float4 (&v)[4], const int n) {
+            if (n < n_units) load_x_block<4, 16>(v, xr, row_first + (n & 1) * 64, B - 1, (g + 2 * (n >> 1)) * ENC2_KB + kq * 4);
+        };
+        auto convert = [&](const float4 (&v)[4], const int n) {
+            if (n >= n_units) return;
+            const int kb = g + 2 * (n >> 1), half = n & 1;
+            const float4 f = x_factors(signs, ch.sign_off, kb * ENC2_KB + kq * 4, K);
+            const int s = kb % ENC2_STAGES;
+            if (!half) mbar_wait(empty0 + 8 * s, ((kb / ENC2_STAGES) & 1) ^ 1);
+            const uint32_t st = smem_base + s * ENC2_STAGE_BYTES;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int r = half * 64 + it * 16 + rsub;
+                // 64-byte rows, SWIZZLE_64B: 16-byte chunk index ^= address bits [7, 9) = (r >> 1) & 3
+                const uint32_t off = (uint32_t)(r * 64 + ((((kq >> 1) ^ ((r >> 1) & 3))) << 4) + ((kq & 1) << 3));
+                split_to_smem(st + off, st + ENC2_TILE_BYTES + off, v[it], f);
             }
             if (half) {
                 fence_proxy_async_smem();

@@ -470,6 +470,33 @@ WsLayout ws_layout(const Plan& p, int64_t B, int train, int mode) {
         target = target < 1 ? 1 : (target > 64 ? 64 : target);
         w.rows_per_tc = (int)round_up((B + target - 1) / target, 64);
         w.n_splits_tc = (int)((B + w.rows_per_tc - 1) / w.rows_per_tc);
+        // Per layer launch: a CTA (one task x one row split, one CTA per SM) takes time ~ rows + a fixed ~96 rows' worth, and a
+        // launch takes ceil(tasks x splits / 148) waves of that.  The pruned last layers have 2 / 5 / 8 / 11 tasks instead of
+        // 17 (dead branches), so the default 16 splits left them at 32 / 80 / 128 / 176 CTAs - a quarter-filled wave, or one
+        // full wave plus a 19 % one (ncu: 57 / 58 / 61 / 114 us against 121 us for the full 272-CTA layer).  Pick the split
+        // that minimises waves x (rows + 96) under the same row cap; keep the default unless the model gains > 10 %.
+        static const bool fit = [] { const char* e = getenv("MSHGNN_DW_FIT"); return !(e && !strcmp(e, "0")); }();
+        const int64_t cap = dw_rows > w.rows_per_tc ? dw_rows : w.rows_per_tc;
+        for (int l = 0; l < MAX_LAYERS; ++l) { w.dw_ns[l] = w.n_splits_tc; w.dw_rows[l] = w.rows_per_tc; }
+        w.part_stride = w.n_splits > w.n_splits_tc ? w.n_splits : w.n_splits_tc;
+        for (size_t l = 0; l < p.dw_layer.size() && l < (size_t)MAX_LAYERS; ++l) {
+            const int64_t count = p.dw_layer[l].count;
+            if (count < 1 || !fit) continue;
+            auto cost = [&](int64_t rows) {
+                const int64_t ns = (B + rows - 1) / rows;
+                return (double)((count * ns + 147) / 148) * (double)(rows + 96);
+            };
+            int64_t best = w.rows_per_tc;
+            double best_c = 0.9 * cost(best);
+            for (int64_t rows = 64; rows <= cap; rows += 64) {
+                if ((B + rows - 1) / rows > 64) continue;
+                const double c = cost(rows);
+                if (c < best_c) { best_c = c; best = rows; }
+            }
+            w.dw_rows[l] = (int)best;
+            w.dw_ns[l] = (int)((B + best - 1) / best);
+            if (w.dw_ns[l] > w.part_stride) w.part_stride = w.dw_ns[l];
+        }
     }
     int64_t o = 0;
     auto take = [&](int64_t bytes) { int64_t at = o; o += round_up(bytes, 256); return at; };
@@ -492,7 +519,7 @@ WsLayout ws_layout(const Plan& p, int64_t B, int train, int mode) {
             w.dh[0] = take(slab); w.dh[1] = take(slab); w.dc[0] = take(slab); w.dc[1] = take(slab);
             if (p.morph_sym) w.du = take((int64_t)p.nm * w.Bp * H * 4);
         }
-        const int ns_max = w.n_splits > w.n_splits_tc ? w.n_splits : w.n_splits_tc;
+        const int ns_max = w.part_stride;
         w.part_w = take((int64_t)p.rtasks.size() * ns_max * H * H * 4);
         w.part_b = take((int64_t)p.rtasks.size() * ns_max * H * 4);
         w.dec_part = take((int64_t)DEC_BLOCKS * (DEC_MAXC * H + DEC_MAXC) * 4);

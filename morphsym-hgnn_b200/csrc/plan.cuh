@@ -101,7 +101,9 @@ struct Plan {
 struct WsLayout {
     int64_t Bp = 0;
     int n_splits = 1;                  // row splits of the SIMT reduce-GEMM (<= 512 rows each)
-    int n_splits_tc = 1, rows_per_tc = 64;   // row splits of the tcgen05 reduce-GEMM (multiples of 64 rows)
+    int n_splits_tc = 1, rows_per_tc = 64;   // default row splits of the tcgen05 reduce-GEMM (multiples of 64 rows)
+    int dw_ns[MAX_LAYERS], dw_rows[MAX_LAYERS];   // per layer launch: row splits actually used (wave-fitted, see ws_layout)
+    int part_stride = 1;               // partial slots reserved per weight-gradient task (>= every split count in use)
     int64_t derived = 0;
     int64_t h[MAX_LAYERS + 1];
     int64_t ct[MAX_LAYERS];
