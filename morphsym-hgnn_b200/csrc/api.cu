@@ -202,11 +202,10 @@ int launch_tc_encoder(const Plan& p, const Launch& L, const WsLayout& w, const B
                       const float* params, int64_t B, int xf64, int split, cudaStream_t st) {
     if (L.count == 0) return 0;
     static bool attr_set = false;
-    static bool use_v1 = false;       // MSHGNN_ENCODER=v1 selects the one-CTA-per-SM kernel with 64-column K blocks (A/B measurements)
+    static bool use_v1 = false;       // MSHGNN_ENCODER=v1 selects the kernel with one row tile per CTA (A/B measurements)
     if (!attr_set) {
         CUDA_TRY(cudaFuncSetAttribute(k_tc_encoder, cudaFuncAttributeMaxDynamicSharedMemorySize, ENC_SMEM_BYTES));
-        CUDA_TRY(cudaFuncSetAttribute(k_tc_encoder2, cudaFuncAttributeMaxDynamicSharedMemorySize, ENC2_SMEM_BYTES));
-        CUDA_TRY(cudaFuncSetAttribute(k_tc_encoder2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CUDA_TRY(cudaFuncSetAttribute(k_tc_encoder_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, ENCP_SMEM_BYTES));
         const char* e = getenv("MSHGNN_ENCODER");
         use_v1 = e && !strcmp(e, "v1");
         attr_set = true;
@@ -223,15 +222,13 @@ int launch_tc_encoder(const Plan& p, const Launch& L, const WsLayout& w, const B
     }
     EncMaps maps;
     int rc;
-    const int kb = use_v1 ? 64 : ENC2_KB;
-    const CUtensorMapSwizzle sw = use_v1 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-    if ((rc = make_map_2d(&maps.w_hi, e_hi, (int64_t)p.n_types * H, p.enc_kmax, kb, 128, sw))) return rc;
-    if ((rc = make_map_2d(&maps.w_lo, e_lo, (int64_t)p.n_types * H, p.enc_kmax, kb, 128, sw))) return rc;
+    if ((rc = make_map_2d(&maps.w_hi, e_hi, (int64_t)p.n_types * H, p.enc_kmax, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    if ((rc = make_map_2d(&maps.w_lo, e_lo, (int64_t)p.n_types * H, p.enc_kmax, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
     maps.o = wm.tc.o;
     ProfScope ps(K_ENC_FWD, st);
-    dim3 grid((unsigned)(w.Bp / TILE_M), (unsigned)L.count);
-    if (use_v1) k_tc_encoder<<<grid, ENC_THREADS, ENC_SMEM_BYTES, st>>>(maps, p.d_tiles + L.begin, bt, br, B, w.Bp, xf64, split);
-    else k_tc_encoder2<<<grid, ENC_THREADS, ENC2_SMEM_BYTES, st>>>(maps, p.d_tiles + L.begin, bt, br, B, w.Bp, xf64, split);
+    const unsigned n_row_tiles = (unsigned)(w.Bp / TILE_M);
+    if (use_v1) k_tc_encoder<<<dim3(n_row_tiles, (unsigned)L.count), ENC_THREADS, ENC_SMEM_BYTES, st>>>(maps, p.d_tiles + L.begin, bt, br, B, w.Bp, xf64, split);
+    else k_tc_encoder_pair<<<dim3((n_row_tiles + 1) / 2, (unsigned)L.count), ENC_THREADS, ENCP_SMEM_BYTES, st>>>(maps, p.d_tiles + L.begin, bt, br, B, w.Bp, xf64, split);
     LAUNCH_CHECK();
     return 0;
 }

@@ -1182,6 +1182,7 @@ k_tc_reducegemm(const __grid_constant__ CUtensorMap map, const RTask* __restrict
 constexpr int ENC_THREADS = 320;
 constexpr int ENC_LOADER_WARPS = 4;               // per group
 constexpr int ENC_STAGES = 3;
+constexpr int ENC_SETS = 3;                       // rotating register sets of the loaders (a fourth one spills at 168 registers and measured slower)
 constexpr int ENC_TILE_BYTES = 128 * 128;         // 128 rows x 64 fp16 (one 128B-swizzled K block)
 constexpr int ENC_STAGE_BYTES = 4 * ENC_TILE_BYTES;   // A_hi, A_lo, W_hi, W_lo = 64 KB
 constexpr int ENC_SMEM_BYTES = ENC_STAGES * ENC_STAGE_BYTES + 1024 + 256;
@@ -1233,6 +1234,24 @@ __device__ __forceinline__ float4 x_factors(const float* __restrict__ signs, con
         f.x *= __ldg(sp + kc); f.y *= __ldg(sp + min(kc + 1, K - 1)); f.z *= __ldg(sp + min(kc + 2, K - 1)); f.w *= __ldg(sp + min(kc + 3, K - 1));
     }
     return f;
+}
+
+// The same factors from a per-CTA shared-memory table (fac[k] = sign or 0, staged once in the prologue).  Used by the encoder
+// weight gradient, whose CTAs loop over many row blocks (-5 %).  The forward kernels keep x_factors(): there the staging is a
+// dependent global round trip in front of every (short-lived) CTA and measured 15 % slower.
+__device__ __forceinline__ float4 col_factors(const uint32_t fac_addr, const float* __restrict__ signs, const int sign_off, const int k, const int K) {
+    if (!fac_addr) return x_factors(signs, sign_off, k, K);
+    float4 f;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f.x), "=f"(f.y), "=f"(f.z), "=f"(f.w) : "r"(fac_addr + 4u * (uint32_t)k));
+    return f;
+}
+// fac[k] for k in [0, n_cols): +-1 symmetry sign (1 without a sign vector) for k < K, 0 beyond
+__device__ __forceinline__ void stage_factors(float* fac, const float* __restrict__ signs, const int sign_off, const int k0, const int K,
+                                              const int n_cols, const int tid, const int n_threads) {
+    for (int c = tid; c < n_cols; c += n_threads) {
+        const int k = k0 + c;
+        fac[c] = k < K ? (sign_off >= 0 ? __ldg(signs + sign_off + k) : 1.f) : 0.f;
+    }
 }
 
 // v[it] = x[min(row_first + RS*it, row_last)][k .. k+3] (columns clamped into [0, K)).  Every load is issued unconditionally
@@ -1375,10 +1394,10 @@ k_tc_encoder(const __grid_constant__ EncMaps maps, const Tile* __restrict__ tile
         const int kq = gt & 15;                                   // which 4-column group of the 64-column block
         const int rsub = gt >> 4;                                 // 0..7
         const int64_t row_first = (int64_t)row0 + rsub;
-        // Work units of 64 rows x 64 columns (half a K block); three register sets rotate so that the loads of units
-        // n + 1 and n + 2 are in flight while unit n is converted and written to shared memory.
+        // Work units of 64 rows x 64 columns (half a K block); ENC_SETS register sets rotate so that the loads of units
+        // n + 1 .. n + ENC_SETS - 1 are in flight while unit n is converted and written to shared memory.
         const int n_units = kb_count(g, n_kb) * 2;
-        float4 va[8], vb[8], vc[8];
+        float4 v[ENC_SETS][8];
         auto load = [&](float4 (&v)[8], const int n) {
             if (n < n_units) load_x_block<8>(v, xr, row_first + (n & 1) * 64, B - 1, (g + 2 * (n >> 1)) * 64 + kq * 4);
         };
@@ -1401,12 +1420,14 @@ k_tc_encoder(const __grid_constant__ EncMaps maps, const Tile* __restrict__ tile
                 if (lane == 0) mbar_arrive(full0 + 8 * s);
             }
         };
-        load(va, 0);
-        load(vb, 1);
-        for (int n = 0; n < n_units; n += 3) {
-            load(vc, n + 2); convert(va, n);
-            load(va, n + 3); convert(vb, n + 1);
-            load(vb, n + 4); convert(vc, n + 2);
+#pragma unroll
+        for (int j = 0; j < ENC_SETS - 1; ++j) load(v[j], j);
+        for (int n = 0; n < n_units; n += ENC_SETS) {
+#pragma unroll
+            for (int j = 0; j < ENC_SETS; ++j) {
+                load(v[(j + ENC_SETS - 1) % ENC_SETS], n + j + ENC_SETS - 1);
+                convert(v[j], n + j);
+            }
         }
         {
             // ---------------- epilogue: warps 2..5 take columns 0..63, warps 6..9 columns 64..127 ----------------
@@ -1425,24 +1446,24 @@ k_tc_encoder(const __grid_constant__ EncMaps maps, const Tile* __restrict__ tile
 }
 
 // ------------------------------------------------------------------------------------------
-// encoder, two CTAs per SM (default; MSHGNN_ENCODER=v1 selects k_tc_encoder)
+// encoder, two row tiles per CTA (default; MSHGNN_ENCODER=v1 selects k_tc_encoder)
 // ------------------------------------------------------------------------------------------
-//  Same program as k_tc_encoder with 32-column K blocks (64B-swizzled, the row-GEMM's operand shape): a stage is 32 KB, the
-//  3-stage ring 96 KB, and the loaders keep three rotating sets of FOUR 128-bit loads (64 rows x 32 columns per unit), so
-//  two CTAs fit an SM (<= 102 registers, 2 x 128 TMEM columns).  The same number of bytes is in flight per SM as with one
-//  CTA, but the prologue (tile read, barrier init, TMEM allocation), the first-load latency and the whole epilogue of one
-//  CTA now overlap the feature stream of the other instead of idling the SM's share of HBM: with one CTA per SM those
-//  fixed ~9 us per tile were as long as the stream itself (3.5 us for a 300-wide joint tile, 10.5 us for a 900-wide one).
-constexpr int ENC2_KB = 32;
-constexpr int ENC2_STAGES = 3;
-constexpr int ENC2_TILE_BYTES = 128 * ENC2_KB * 2;            // 128 rows x 32 fp16 = 8 KB
-constexpr int ENC2_STAGE_BYTES = 4 * ENC2_TILE_BYTES;         // A_hi, A_lo, W_hi, W_lo = 32 KB
-constexpr int ENC2_SMEM_BYTES = ENC2_STAGES * ENC2_STAGE_BYTES + 1024 + 256;
-static_assert(ENC2_STAGES * ENC2_STAGE_BYTES >= 65536, "the epilogue stages 64 KB of output tiles in the drained operand ring");
+//  ncu of k_tc_encoder: 46.7 M L2->SM read sectors (1.49 GB) for 708 MB of features - a 128-row x 64-column fp32 block
+//  of x is 32 KB and so is the (hi, lo) weight K block it meets, i.e. every CTA pulled as many weight bytes out of L2 as
+//  feature bytes, and the kernel ran at the ~4.6 TB/s L2->SM ceiling the weight-gradient kernel also sits at, not at an
+//  HBM or issue limit (two CTAs per SM with 32-column K blocks hid the per-CTA prologue / epilogue but was 5 % SLOWER:
+//  same bytes through the same pipe).  Here a CTA owns TWO row tiles (256 graphs of one node slot): every weight stage
+//  is used by both, the weight stream halves (L2->SM bytes -25 %), and the fixed per-CTA cost is paid once per 256 rows.
+//  Stage = A0_hi, A0_lo, A1_hi, A1_lo, W_hi, W_lo = 96 KB, two stages (loader group g owns stage g), accumulators of the
+//  two tiles in TMEM columns [0,128) and [128,256); the epilogue drains them one after the other through the drained ring.
+constexpr int ENCP_STAGES = 2;
+constexpr int ENCP_STAGE_BYTES = 6 * ENC_TILE_BYTES;          // 96 KB
+constexpr int ENCP_SMEM_BYTES = ENCP_STAGES * ENCP_STAGE_BYTES + 1024 + 256;
+constexpr uint32_t ENCP_TMEM_COLS = 256;
 
-__global__ void __launch_bounds__(ENC_THREADS, 2)
-k_tc_encoder2(const __grid_constant__ EncMaps maps, const Tile* __restrict__ tiles, const BufTable bt, const BufRows br,
-              const int64_t B, const int64_t Bp, const int x_f64, const int split) {
+__global__ void __launch_bounds__(ENC_THREADS, 1)
+k_tc_encoder_pair(const __grid_constant__ EncMaps maps, const Tile* __restrict__ tiles, const BufTable bt, const BufRows br,
+                  const int64_t B, const int64_t Bp, const int x_f64, const int split) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ Tile t;
     __shared__ __align__(16) float bias_s[H];
@@ -1451,9 +1472,9 @@ k_tc_encoder2(const __grid_constant__ EncMaps maps, const Tile* __restrict__ til
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ENC2_STAGES * ENC2_STAGE_BYTES);
-    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + ENC2_STAGES), accum_bar = smem_u32(bars + 2 * ENC2_STAGES),
-                   res_bar = smem_u32(bars + 2 * ENC2_STAGES + 1);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ENCP_STAGES * ENCP_STAGE_BYTES);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + ENCP_STAGES), accum_bar = smem_u32(bars + 2 * ENCP_STAGES),
+                   res_bar = smem_u32(bars + 2 * ENCP_STAGES + 1);
     const uint32_t smem_base = smem_u32(smem);
     {
         const int* src = reinterpret_cast<const int*>(tiles + blockIdx.y);
@@ -1461,52 +1482,56 @@ k_tc_encoder2(const __grid_constant__ EncMaps maps, const Tile* __restrict__ til
         for (int i = tid; i < (int)(sizeof(Tile) / 4); i += ENC_THREADS) dst[i] = src[i];
     }
     if (tid == 0) {
-        for (int s = 0; s < ENC2_STAGES; ++s) { mbar_init(full0 + 8 * s, 1 + ENC_LOADER_WARPS); mbar_init(empty0 + 8 * s, 1); }
+        for (int s = 0; s < ENCP_STAGES; ++s) { mbar_init(full0 + 8 * s, 1 + ENC_LOADER_WARPS); mbar_init(empty0 + 8 * s, 1); }
         mbar_init(accum_bar, 1);
         mbar_init(res_bar, 1);
         mbar_init(res_bar + 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), TC_TMEM_COLS);
+    if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), ENCP_TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
 
-    const int row0 = blockIdx.x * TILE_M;
+    const int row0 = blockIdx.x * (2 * TILE_M);
+    const int n_tiles = (int64_t)row0 + TILE_M < Bp ? 2 : 1;     // Bp is a multiple of 128, not of 256
     const int K = t.chunks[0].K;
-    const int n_kb = (K + ENC2_KB - 1) / ENC2_KB;
+    const int n_kb = (K + 63) / 64;
 
     if (warp == 0) {
         if (lane == 0) {
-            const uint32_t tx_bytes = split ? 2 * ENC2_TILE_BYTES : ENC2_TILE_BYTES;
+            const uint32_t tx_bytes = split ? 2 * ENC_TILE_BYTES : ENC_TILE_BYTES;
             const int wrow = t.chunks[0].w16_row;
             for (int i = 0; i < n_kb; ++i) {
-                const int s = i % ENC2_STAGES;
-                mbar_wait(empty0 + 8 * s, ((i / ENC2_STAGES) & 1) ^ 1);
-                const uint32_t st = smem_base + s * ENC2_STAGE_BYTES;
+                const int s = i % ENCP_STAGES;
+                mbar_wait(empty0 + 8 * s, ((i / ENCP_STAGES) & 1) ^ 1);
+                const uint32_t st = smem_base + s * ENCP_STAGE_BYTES;
                 const uint32_t fb = full0 + 8 * s;
                 mbar_expect_tx(fb, tx_bytes);
-                tma_load_2d(st + 2 * ENC2_TILE_BYTES, &maps.w_hi, fb, i * ENC2_KB, wrow);
-                if (split) tma_load_2d(st + 3 * ENC2_TILE_BYTES, &maps.w_lo, fb, i * ENC2_KB, wrow);
+                tma_load_2d(st + 4 * ENC_TILE_BYTES, &maps.w_hi, fb, i * 64, wrow);
+                if (split) tma_load_2d(st + 5 * ENC_TILE_BYTES, &maps.w_lo, fb, i * 64, wrow);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             for (int i = 0; i < n_kb; ++i) {
-                const int s = i % ENC2_STAGES;
-                mbar_wait(full0 + 8 * s, (i / ENC2_STAGES) & 1);
+                const int s = i % ENCP_STAGES;
+                mbar_wait(full0 + 8 * s, (i / ENCP_STAGES) & 1);
                 tc_fence_after();
-                const uint32_t st = smem_base + s * ENC2_STAGE_BYTES;
-                const uint64_t a_hi = smem_desc_sw64(st), a_lo = smem_desc_sw64(st + ENC2_TILE_BYTES);
-                const uint64_t w_hi = smem_desc_sw64(st + 2 * ENC2_TILE_BYTES), w_lo = smem_desc_sw64(st + 3 * ENC2_TILE_BYTES);
+                const uint32_t st = smem_base + s * ENCP_STAGE_BYTES;
+                const uint64_t w_hi = smem_desc_sw128(st + 4 * ENC_TILE_BYTES), w_lo = smem_desc_sw128(st + 5 * ENC_TILE_BYTES);
+                for (int tl = 0; tl < n_tiles; ++tl) {
+                    const uint64_t a_hi = smem_desc_sw128(st + (2 * tl) * ENC_TILE_BYTES), a_lo = smem_desc_sw128(st + (2 * tl + 1) * ENC_TILE_BYTES);
+                    const uint32_t acc = tmem_base + (uint32_t)tl * 128u;
 #pragma unroll
-                for (int ks = 0; ks < ENC2_KB / 16; ++ks) {
-                    const uint64_t adv = (uint64_t)(ks * 2);      // +32 bytes (16 fp16) along K inside the swizzle atom
-                    umma_f16(tmem_base, a_hi + adv, w_hi + adv, TC_IDESC, (i | ks) ? 1u : 0u);
-                    if (split) {
-                        umma_f16(tmem_base, a_lo + adv, w_hi + adv, TC_IDESC, 1u);
-                        umma_f16(tmem_base, a_hi + adv, w_lo + adv, TC_IDESC, 1u);
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint64_t adv = (uint64_t)(ks * 2);
+                        umma_f16(acc, a_hi + adv, w_hi + adv, TC_IDESC, (i | ks) ? 1u : 0u);
+                        if (split) {
+                            umma_f16(acc, a_lo + adv, w_hi + adv, TC_IDESC, 1u);
+                            umma_f16(acc, a_hi + adv, w_lo + adv, TC_IDESC, 1u);
+                        }
                     }
                 }
                 umma_commit(empty0 + 8 * s);
@@ -1515,62 +1540,64 @@ k_tc_encoder2(const __grid_constant__ EncMaps maps, const Tile* __restrict__ til
         }
         __syncwarp();
     } else {
-        // ---------------- loaders: group g takes the K blocks kb = g (mod 2) ----------------
+        // ---------------- loaders: group g takes the K blocks kb = g (mod 2), i.e. always stage g ----------------
         const int g = (warp - 2) / ENC_LOADER_WARPS;
         const int gt = tid - 64 - g * (ENC_LOADER_WARPS * 32);
         const Chunk& ch = t.chunks[0];
         const XRows xr = make_xrows(bt.p[ch.a_buf], x_f64, ch.lda, ch.a_off, K);
         const float* signs = (const float*)bt.p[2];
-        const int kq = gt & 7;                                    // which 4-column group of the 32-column block
-        const int rsub = gt >> 3;                                 // 0..15
+        const int kq = gt & 15;                                   // which 4-column group of the 64-column block
+        const int rsub = gt >> 4;                                 // 0..7
         const int64_t row_first = (int64_t)row0 + rsub;
-        // Work units of 64 rows x 32 columns (half a K block, four 128-bit loads per thread); three register sets rotate
-        // so that the loads of units n + 1 and n + 2 are in flight while unit n is converted and written to shared memory.
-        const int n_units = kb_count(g, n_kb) * 2;
-        float4 va[4], vb[4], vc[4];
-        auto load = [&](float4 (&v)[4], const int n) {
-            if (n < n_units) load_x_block<4, 16>(v, xr, row_first + (n & 1) * 64, B - 1, (g + 2 * (n >> 1)) * ENC2_KB + kq * 4);
+        // Work units of 64 rows x 64 columns (a quarter of a K block of the row pair); three register sets rotate so
+        // that the loads of units n + 1 and n + 2 are in flight while unit n is converted and written to shared memory.
+        const int upb = 2 * n_tiles;                              // units per K block
+        const int n_units = kb_count(g, n_kb) * upb;
+        float4 v[ENC_SETS][8];
+        auto load = [&](float4 (&v)[8], const int n) {
+            if (n < n_units) load_x_block<8>(v, xr, row_first + (n % upb) * 64, B - 1, (g + 2 * (n / upb)) * 64 + kq * 4);
         };
-        auto convert = [&](const float4 (&v)[4], const int n) {
+        auto convert = [&](const float4 (&v)[8], const int n) {
             if (n >= n_units) return;
-            const int kb = g + 2 * (n >> 1), half = n & 1;
-            const float4 f = x_factors(signs, ch.sign_off, kb * ENC2_KB + kq * 4, K);
-            const int s = kb % ENC2_STAGES;
-            if (!half) mbar_wait(empty0 + 8 * s, ((kb / ENC2_STAGES) & 1) ^ 1);
-            const uint32_t st = smem_base + s * ENC2_STAGE_BYTES;
+            const int kb = g + 2 * (n / upb), q = n % upb;
+            const float4 f = x_factors(signs, ch.sign_off, kb * 64 + kq * 4, K);
+            const int s = kb % ENCP_STAGES;
+            if (q == 0) mbar_wait(empty0 + 8 * s, ((kb / ENCP_STAGES) & 1) ^ 1);
+            const uint32_t st = smem_base + s * ENCP_STAGE_BYTES + (uint32_t)(q >> 1) * (2 * ENC_TILE_BYTES);
 #pragma unroll
-            for (int it = 0; it < 4; ++it) {
-                const int r = half * 64 + it * 16 + rsub;
-                // 64-byte rows, SWIZZLE_64B: 16-byte chunk index ^= address bits [7, 9) = (r >> 1) & 3
-                const uint32_t off = (uint32_t)(r * 64 + ((((kq >> 1) ^ ((r >> 1) & 3))) << 4) + ((kq & 1) << 3));
-                split_to_smem(st + off, st + ENC2_TILE_BYTES + off, v[it], f);
+            for (int it = 0; it < 8; ++it) {
+                const int r = (q & 1) * 64 + it * 8 + rsub;
+                const uint32_t off = (uint32_t)(r * 128 + ((((kq >> 1) ^ (r & 7))) << 4) + ((kq & 1) << 3));
+                split_to_smem(st + off, st + ENC_TILE_BYTES + off, v[it], f);
             }
-            if (half) {
+            if (q == upb - 1) {
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(full0 + 8 * s);
             }
         };
-        load(va, 0);
-        load(vb, 1);
-        for (int n = 0; n < n_units; n += 3) {
-            load(vc, n + 2); convert(va, n);
-            load(va, n + 3); convert(vb, n + 1);
-            load(vb, n + 4); convert(vc, n + 2);
+#pragma unroll
+        for (int j = 0; j < ENC_SETS - 1; ++j) load(v[j], j);
+        for (int n = 0; n < n_units; n += ENC_SETS) {
+#pragma unroll
+            for (int j = 0; j < ENC_SETS; ++j) {
+                load(v[(j + ENC_SETS - 1) % ENC_SETS], n + j + ENC_SETS - 1);
+                convert(v[j], n + j);
+            }
         }
-        {
-            // ---------------- epilogue: warps 2..5 take columns 0..63, warps 6..9 columns 64..127 ----------------
+        // ---------------- epilogue: warps 2..5 take columns 0..63, warps 6..9 columns 64..127, tile after tile ----------------
+        for (int tl = 0; tl < n_tiles; ++tl) {
             EpiSmem es;
-            es.stg = smem_base; es.bias = smem_u32(bias_s); es.res_bar = res_bar; es.accum_bar = accum_bar;
+            es.stg = smem_base + (uint32_t)tl * 65536u; es.bias = smem_u32(bias_s); es.res_bar = res_bar; es.accum_bar = accum_bar;
             es.free_bar = 0; es.acc_parity = 0; es.res_parity = 0; es.persistent = 0; es.n_groups = 2;
-            tc_epilogue(t, bt, br, &maps.o, tmem_base, row0, B, Bp, split, warp, lane, es);
+            tc_epilogue(t, bt, br, &maps.o, tmem_base + (uint32_t)tl * 128u, row0 + tl * TILE_M, B, Bp, split, warp, lane, es);
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, TC_TMEM_COLS);
+        tmem_dealloc(tmem_base, ENCP_TMEM_COLS);
     }
 }
 
@@ -1594,6 +1621,7 @@ k_tc_encoder_dw(const __grid_constant__ CUtensorMap map, const EncDwUnit* __rest
     extern __shared__ uint8_t smem_raw[];
     __shared__ EncDwUnit u;
     __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) float fac_s[4][EDW_NMAX];     // per-slot column factors of this unit's columns (see col_factors)
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -1604,6 +1632,11 @@ k_tc_encoder_dw(const __grid_constant__ CUtensorMap map, const EncDwUnit* __rest
     const uint32_t smem_base = smem_u32(smem);
 
     if (tid < (int)(sizeof(EncDwUnit) / 4)) reinterpret_cast<int*>(&u)[tid] = reinterpret_cast<const int*>(units + blockIdx.x)[tid];
+    {
+        const EncDwUnit* gu = units + blockIdx.x;
+        const int g_slots = __ldg(&gu->n_slots), g_k0 = __ldg(&gu->k0), g_K = __ldg(&gu->K), g_cols = __ldg(&gu->nkb) * 64;
+        for (int j = 0; j < g_slots; ++j) stage_factors(fac_s[j], (const float*)bt.p[2], __ldg(&gu->sign_off[j]), g_k0, g_K, g_cols, tid, ENC_THREADS);
+    }
     for (int i = tid; i < DW_ONES_BYTES / 4; i += ENC_THREADS) reinterpret_cast<uint32_t*>(ones)[i] = 0x3C003C00u;
     fence_proxy_async_smem();
     if (tid == 0) {
@@ -1694,7 +1727,7 @@ k_tc_encoder_dw(const __grid_constant__ CUtensorMap map, const EncDwUnit* __rest
 #pragma unroll
             for (int jb = 0; jb < 3; ++jb)
                 if (jb < nkb) {
-                    const float4 f = x_factors(signs, u.sign_off[j], u.k0 + jb * 64 + kq * 4, u.K);
+                    const float4 f = col_factors(smem_u32(fac_s[j]), signs, u.sign_off[j], jb * 64 + kq * 4, u.K);
 #pragma unroll
                     for (int it = 0; it < 8; ++it) {
                         const int r = it * 8 + rsub;

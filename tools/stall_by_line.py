@@ -37,7 +37,8 @@ for l in lines:
     if m:
         insts.append((int(m.group(1), 16), m.group(2).strip(), cur))
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout.split("\n")
-starts = [i for i, l in enumerate(raw) if l.startswith('"Kernel Name"') and kname in l]
+nname = os.environ.get("NCU_KERNEL", kname)      # demangled name in the report when it differs from the mangled substring
+starts = [i for i, l in enumerate(raw) if l.startswith('"Kernel Name"') and nname in l]
 a = starts[which]
 b = next((i for i in range(a + 1, len(raw)) if raw[i].startswith('"Kernel Name"')), len(raw))
 rd = csv.reader(io.StringIO("\n".join(raw[a + 1:b])))
