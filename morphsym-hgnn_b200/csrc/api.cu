@@ -323,7 +323,7 @@ int launch_tc_dw(int kind, const Plan& p, int layer, const Launch& L, const WsLa
     }
     ProfScope ps(kind, st);
     dim3 grid((unsigned)L.count, (unsigned)w.dw_ns[layer]);          // wave-fitted row splits of this layer (ws_layout)
-    k_tc_reducegemm<<<grid, TC_THREADS, DW_SMEM_BYTES, st>>>(wm.dw, p.d_rtasks, p.d_rpairs, L.begin, br, B, w.Bp, w.dw_rows[layer], w.part_stride,
+    k_tc_reducegemm<<<grid, TC_THREADS, DW_SMEM_BYTES, st>>>(wm.dw, p.d_rtasks, p.d_rpairs, L.begin, br, B, w.Bp, w.dw_rows[layer], w.dw_slot0[layer],
                                                              split, part_w, part_b);
     LAUNCH_CHECK();
     return 0;
@@ -388,8 +388,10 @@ int64_t mshgnn_workspace_bytes(const mshgnn_plan* plan, int64_t B, int32_t train
     if (!plan || B < 1) return -1;
     const WsLayout w = ws_layout(plan->p, B, train, mode);
     if (train && mode != MSHGNN_MODE_FP32 && getenv("MSHGNN_DEBUG_LAYOUT")) {   // weight-gradient row splits per layer launch
-        fprintf(stderr, "mshgnn layout B=%lld: dW default %d x %d rows, partial stride %d;", (long long)B, w.n_splits_tc, w.rows_per_tc, w.part_stride);
+        fprintf(stderr, "mshgnn layout B=%lld: dW default %d x %d rows, %lld partial slots;", (long long)B, w.n_splits_tc, w.rows_per_tc, (long long)w.part_slots);
         for (size_t l = 0; l < plan->p.dw_layer.size(); ++l) fprintf(stderr, " L%zu[%d tasks]: %d x %d", l, plan->p.dw_layer[l].count, w.dw_ns[l], w.dw_rows[l]);
+        fprintf(stderr, "; segments");
+        for (int i = 0; i < w.segs.n; ++i) fprintf(stderr, " [tasks %d..%d) x %d @ slot %d", w.segs.begin[i], w.segs.begin[i + 1], w.segs.ns[i], w.segs.base[i]);
         fprintf(stderr, "\n");
     }
     return w.total;
@@ -611,24 +613,16 @@ int mshgnn_backward(const mshgnn_plan* plan, int64_t B, const void* const* x, in
     } else if ((rc = launch_dw(K_DW_ENC, p.dw_enc))) return rc;
     // layer-stack groups were produced with the split count of the kernel that ran them, encoder groups with the SIMT one
     const int ngl = p.n_groups_layers, nge = (int)p.groups.size() - ngl;
-    if (p.rtasks.size() > (size_t)MAX_RTASKS) return fail(MSHGNN_ERR_ARG, "internal: more than %d weight-gradient tasks", MAX_RTASKS);
-    TaskSplits ts;
-    const int ns_uniform = tc ? w.n_splits_tc : w.n_splits;
-    for (size_t i = 0; i < p.rtasks.size(); ++i) ts.ns[i] = (unsigned char)ns_uniform;
-    if (tc)
-        for (size_t l = 0; l < p.dw_layer.size(); ++l)
-            for (int i = 0; i < p.dw_layer[l].count; ++i) ts.ns[p.dw_layer[l].begin + i] = (unsigned char)w.dw_ns[l];
-    const int stride = tc ? w.part_stride : w.n_splits;
     if (ngl > 0) {
         dim3 grid((unsigned)ngl, 32);
         ProfScope ps(K_REDUCE, st);
-        k_reduce_partials<<<grid, 256, 0, st>>>(p.d_groups, part_w, part_b, stride, ts, grads, 1.f / G);
+        k_reduce_partials<<<grid, 256, 0, st>>>(p.d_groups, part_w, part_b, w.segs, grads, 1.f / G);
         LAUNCH_CHECK();
     }
     if (nge > 0 && !tc) {
         dim3 grid((unsigned)nge, 32);
         ProfScope ps(K_REDUCE, st);
-        k_reduce_partials<<<grid, 256, 0, st>>>(p.d_groups + ngl, part_w, part_b, stride, ts, grads, 1.f / G);
+        k_reduce_partials<<<grid, 256, 0, st>>>(p.d_groups + ngl, part_w, part_b, w.segs, grads, 1.f / G);
         LAUNCH_CHECK();
     }
     return 0;

@@ -80,11 +80,24 @@ struct RTask {
     int pad[3];
 };
 
-// How many row-split partials each weight-gradient task wrote (launches of different sizes use different split counts).
-constexpr int MAX_RTASKS = 1024;
-struct TaskSplits {
-    unsigned char ns[MAX_RTASKS];
+// Partial-slot layout of the weight-gradient tasks.  Launches of different sizes use different row-split counts (ws_layout
+// fits them to whole waves), so the fp32 partials are packed segment by segment: the tasks [begin[s], begin[s+1]) of one
+// launch wrote ns[s] partials each, task t's first slot is base[s] + (t - begin[s]) * ns[s].
+constexpr int MAX_PART_SEGS = 20;
+struct PartSegs {
+    int n;
+    int begin[MAX_PART_SEGS + 1];
+    int ns[MAX_PART_SEGS];
+    int base[MAX_PART_SEGS];
 };
+#ifdef __CUDACC__
+__device__ __forceinline__ void part_lookup(const PartSegs& ps, const int task, int64_t& slot0, int& ns) {
+    int s = 0;
+    while (s + 1 < ps.n && task >= ps.begin[s + 1]) ++s;
+    ns = ps.ns[s];
+    slot0 = (int64_t)ps.base[s] + (int64_t)(task - ps.begin[s]) * ns;
+}
+#endif
 
 // Final reduction of split partials into the flat gradient buffer.
 struct OutGroup {

@@ -365,7 +365,7 @@ k_reducegemm(const RTask* __restrict__ tasks, const RPair* __restrict__ pairs, c
 // sum the split partials of a group of tasks into the flat gradient buffer (fixed order => deterministic)
 __global__ void __launch_bounds__(256)
 k_reduce_partials(const OutGroup* __restrict__ groups, const float* __restrict__ part_w,
-                  const float* __restrict__ part_b, const int stride /*partial slots per task*/, const __grid_constant__ TaskSplits ts,
+                  const float* __restrict__ part_b, const __grid_constant__ PartSegs segs,
                   float* __restrict__ grads, const float rscale) {
     const OutGroup g = groups[blockIdx.x];
     if (g.kind == 0) {
@@ -375,10 +375,18 @@ k_reduce_partials(const OutGroup* __restrict__ groups, const float* __restrict__
             if (g.k0 + i >= g.K) continue;
             double sd = 0.0;
             for (int ti = 0; ti < g.n_tasks; ++ti) {
-                const float* p = part_w + (int64_t)g.tasks[ti] * stride * (H * H) + e;
-                const int n_splits = ts.ns[g.tasks[ti]];
+                int64_t slot0; int n_splits;
+                part_lookup(segs, g.tasks[ti], slot0, n_splits);
+                const float* p = part_w + slot0 * (H * H) + e;
                 int sp = 0;
-                for (; sp + 8 <= n_splits; sp += 8) {      // 8 independent loads in flight, summed in the fixed order
+                for (; sp + 16 <= n_splits; sp += 16) {    // 16 independent loads in flight, summed in the fixed order
+                    float v[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = __ldg(p + (int64_t)(sp + j) * (H * H));
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) sd += (double)v[j];
+                }
+                for (; sp + 8 <= n_splits; sp += 8) {
                     float v[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) v[j] = __ldg(p + (int64_t)(sp + j) * (H * H));
@@ -395,8 +403,9 @@ k_reduce_partials(const OutGroup* __restrict__ groups, const float* __restrict__
         for (int e = threadIdx.x; e < H; e += 256) {
             double sd = 0.0;
             for (int ti = 0; ti < g.n_tasks; ++ti) {
-                const float* p = part_b + (int64_t)g.tasks[ti] * stride * H + e;
-                const int n_splits = ts.ns[g.tasks[ti]];
+                int64_t slot0; int n_splits;
+                part_lookup(segs, g.tasks[ti], slot0, n_splits);
+                const float* p = part_b + slot0 * H + e;
                 for (int sp = 0; sp < n_splits; ++sp) sd += (double)p[(int64_t)sp * H];
             }
             const float s = (float)(sd * (double)g.scale * (double)rscale);

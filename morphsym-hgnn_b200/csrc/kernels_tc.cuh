@@ -1037,7 +1037,7 @@ constexpr uint32_t DW_IDESC_CS = (1u << 4) | (1u << 15) | ((16u >> 3) << 17) | (
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_tc_reducegemm(const __grid_constant__ CUtensorMap map, const RTask* __restrict__ tasks, const RPair* __restrict__ pairs,
-                const int task0, const BufRows br, const int64_t B, const int64_t Bp, const int rows_per, const int n_splits,
+                const int task0, const BufRows br, const int64_t B, const int64_t Bp, const int rows_per, const int slot0 /*first partial slot of this launch*/,
                 const int split, float* __restrict__ part_w, float* __restrict__ part_b) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ RTask t;
@@ -1141,7 +1141,7 @@ k_tc_reducegemm(const __grid_constant__ CUtensorMap map, const RTask* __restrict
         tc_fence_after();
         const int q = warp & 3;
         const int o = q * 32 + lane;
-        const int64_t slot = (int64_t)task * n_splits + sp;
+        const int64_t slot = (int64_t)slot0 + (int64_t)blockIdx.x * gridDim.y + sp;      // gridDim.y = row splits of this launch
         float* pw = part_w + slot * (H * H) + (int64_t)o * H;
 #pragma unroll 1
         for (int cc = 0; cc < 4; ++cc) {

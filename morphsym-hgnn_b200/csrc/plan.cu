@@ -11,6 +11,8 @@
 #include <cstdio>
 #include <cstring>
 #include <sstream>
+#include <utility>
+#include <vector>
 
 #include "plan.cuh"
 
@@ -478,7 +480,6 @@ WsLayout ws_layout(const Plan& p, int64_t B, int train, int mode) {
         static const bool fit = [] { const char* e = getenv("MSHGNN_DW_FIT"); return !(e && !strcmp(e, "0")); }();
         const int64_t cap = dw_rows > w.rows_per_tc ? dw_rows : w.rows_per_tc;
         for (int l = 0; l < MAX_LAYERS; ++l) { w.dw_ns[l] = w.n_splits_tc; w.dw_rows[l] = w.rows_per_tc; }
-        w.part_stride = w.n_splits > w.n_splits_tc ? w.n_splits : w.n_splits_tc;
         for (size_t l = 0; l < p.dw_layer.size() && l < (size_t)MAX_LAYERS; ++l) {
             const int64_t count = p.dw_layer[l].count;
             if (count < 1 || !fit) continue;
@@ -495,8 +496,28 @@ WsLayout ws_layout(const Plan& p, int64_t B, int train, int mode) {
             }
             w.dw_rows[l] = (int)best;
             w.dw_ns[l] = (int)((B + best - 1) / best);
-            if (w.dw_ns[l] > w.part_stride) w.part_stride = w.dw_ns[l];
         }
+    }
+    {   // partial slots, packed launch by launch in task order (the SIMT kernels use one split count for every task)
+        std::vector<std::pair<int, int>> seg;          // (first task, split count)
+        for (size_t l = 0; l < p.dw_layer.size() && l < (size_t)MAX_LAYERS; ++l)
+            if (p.dw_layer[l].count > 0) seg.push_back({p.dw_layer[l].begin, tc ? w.dw_ns[l] : w.n_splits});
+        if (p.dw_enc.count > 0) seg.push_back({p.dw_enc.begin, tc ? 0 : w.n_splits});   // the tensor-core encoder gradient has its own partials
+        std::sort(seg.begin(), seg.end());
+        w.segs.n = 0;
+        int base = 0;
+        for (size_t i = 0; i < seg.size() && i < (size_t)MAX_PART_SEGS; ++i) {
+            const int end = i + 1 < seg.size() ? seg[i + 1].first : (int)p.rtasks.size();
+            w.segs.begin[i] = seg[i].first; w.segs.ns[i] = seg[i].second; w.segs.base[i] = base;
+            base += (end - seg[i].first) * seg[i].second;
+            w.segs.begin[i + 1] = end;
+            w.segs.n = (int)i + 1;
+        }
+        w.part_slots = base > 0 ? base : 1;
+        for (int l = 0; l < MAX_LAYERS; ++l) w.dw_slot0[l] = 0;
+        for (size_t l = 0; l < p.dw_layer.size() && l < (size_t)MAX_LAYERS; ++l)
+            for (int i = 0; i < w.segs.n; ++i)
+                if (w.segs.begin[i] == p.dw_layer[l].begin && p.dw_layer[l].count > 0) w.dw_slot0[l] = w.segs.base[i];
     }
     int64_t o = 0;
     auto take = [&](int64_t bytes) { int64_t at = o; o += round_up(bytes, 256); return at; };
@@ -519,9 +540,8 @@ WsLayout ws_layout(const Plan& p, int64_t B, int train, int mode) {
             w.dh[0] = take(slab); w.dh[1] = take(slab); w.dc[0] = take(slab); w.dc[1] = take(slab);
             if (p.morph_sym) w.du = take((int64_t)p.nm * w.Bp * H * 4);
         }
-        const int ns_max = w.part_stride;
-        w.part_w = take((int64_t)p.rtasks.size() * ns_max * H * H * 4);
-        w.part_b = take((int64_t)p.rtasks.size() * ns_max * H * 4);
+        w.part_w = take(w.part_slots * H * H * 4);
+        w.part_b = take(w.part_slots * H * 4);
         w.dec_part = take((int64_t)DEC_BLOCKS * (DEC_MAXC * H + DEC_MAXC) * 4);
     } else if (!tc) {
         const int64_t a = take(slab), b = take(slab);

@@ -103,7 +103,9 @@ struct WsLayout {
     int n_splits = 1;                  // row splits of the SIMT reduce-GEMM (<= 512 rows each)
     int n_splits_tc = 1, rows_per_tc = 64;   // default row splits of the tcgen05 reduce-GEMM (multiples of 64 rows)
     int dw_ns[MAX_LAYERS], dw_rows[MAX_LAYERS];   // per layer launch: row splits actually used (wave-fitted, see ws_layout)
-    int part_stride = 1;               // partial slots reserved per weight-gradient task (>= every split count in use)
+    PartSegs segs;                     // packed partial slots of the weight-gradient tasks (common.cuh)
+    int dw_slot0[MAX_LAYERS];          // first partial slot of each layer launch
+    int64_t part_slots = 0;            // total slots ([128][128] fp32 weight partial + [128] bias partial each)
     int64_t derived = 0;
     int64_t h[MAX_LAYERS + 1];
     int64_t ct[MAX_LAYERS];
