@@ -172,6 +172,12 @@ int make_map_2d(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, in
     EncodeTiledFn enc;
     int rc = get_encode_fn(&enc);
     if (rc) return rc;
+    // cuTensorMapEncodeTiled is a driver call and needs a context current on THIS thread.  The runtime binds the primary
+    // context lazily: a thread that has not yet made a context-binding runtime call - PyTorch's autograd worker when the
+    // caching allocator serves every allocation of its first backward from cached blocks - fails here with
+    // CUDA_ERROR_INVALID_CONTEXT (201).  cudaFree(0) binds it; once per thread.
+    static thread_local bool ctx_bound = false;
+    if (!ctx_bound) { CUDA_TRY(cudaFree(0)); ctx_bound = true; }
     if (!base || rows < 1) return fail(MSHGNN_ERR_ARG, "internal: bad fp16 tensor for a TMA map");
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)cols * 2};

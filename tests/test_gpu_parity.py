@@ -73,6 +73,13 @@ def test_forward_loss_backward_parity_tensor_core_mode(name, B, layers):
     check_gradients(CONFIGS[name], B, layers, mode="tc")
 
 
+def test_mid_size_batch_with_per_layer_weight_gradient_splits():
+    """2400 graphs: 19 row tiles (the two-tile encoder CTAs end on a single tile) and a different wave-fitted row-split
+    count in each of the pruned last layers' weight-gradient launches (ws_layout), against the oracle at the same 1e-4."""
+    check_gradients(CONFIGS["mini_cheetah-k4-contact"], 2400, 8, mode="tc")
+    check_gradients(CONFIGS["mini_cheetah-c2-contact"], 1100, 8, mode="tc")
+
+
 def test_single_pass_fp16_mode_predictions_within_1e3():
     """MODE_TC_1X (one fp16 MMA per product) is an inference mode: predictions within the stated 1e-3."""
     cfg = CONFIGS["mini_cheetah-k4-contact"]
