@@ -55,7 +55,7 @@ ALG = {
 
 def recorded_traffic():
     """DRAM bytes from the committed ncu captures (profiles/): per launch of the dominant kernels and per train step."""
-    p = os.path.join(ROOT, "profiles", "r1_tc_v6_dominant_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r1_tc_v7_dominant_traffic.json")
     return json.load(open(p)) if os.path.exists(p) else {}
 
 
@@ -474,7 +474,7 @@ def main():
         "hbm_step": None if not (traffic.get("step") and B == PER_GPU_BATCH and args.mode == "tc") else {
             "dram_bytes_per_step": traffic["step"]["dram_bytes"], "achieved_gbs": traffic["step"]["dram_bytes"] / (train_ms / K * 1e-3) / 1e9,
             "peak_gbs": pk["hbm_gbs"], "frac": traffic["step"]["dram_bytes"] / (train_ms / K * 1e-3) / 1e9 / pk["hbm_gbs"],
-            "source": "profiles/r1_tc_v6_step_traffic.json (ncu DRAM counters of one step) / this run's step time"},
+            "source": "profiles/r1_tc_v7_step_traffic.json (ncu DRAM counters of one step) / this run's step time"},
         "profiled_ms_per_step": prof_ms / K,
         "other_configs": extra,
     }

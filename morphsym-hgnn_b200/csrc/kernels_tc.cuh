@@ -1454,7 +1454,7 @@ k_tc_encoder(const __grid_constant__ EncMaps maps, const Tile* __restrict__ tile
 //  HBM or issue limit (two CTAs per SM with 32-column K blocks hid the per-CTA prologue / epilogue but was 5 % SLOWER:
 //  same bytes through the same pipe).  Here a CTA owns TWO row tiles (256 graphs of one node slot): every weight stage
 //  is used by both, the weight stream halves (L2->SM bytes -25 %), and the fixed per-CTA cost is paid once per 256 rows.
-//  Stage = A0_hi, A0_lo, A1_hi, A1_lo, W_hi, W_lo = 96 KB, two stages (loader group g owns stage g), accumulators of the
+//  Stage = A0_hi, A0_lo, A1_hi, A1_lo, W_hi, W_lo = 96 KB, two stages (loader group g fills row tile g), accumulators of the
 //  two tiles in TMEM columns [0,128) and [128,256); the epilogue drains them one after the other through the drained ring.
 constexpr int ENCP_STAGES = 2;
 constexpr int ENCP_STAGE_BYTES = 6 * ENC_TILE_BYTES;          // 96 KB
@@ -1481,8 +1481,11 @@ k_tc_encoder_pair(const __grid_constant__ EncMaps maps, const Tile* __restrict__
         int* dst = reinterpret_cast<int*>(&t);
         for (int i = tid; i < (int)(sizeof(Tile) / 4); i += ENC_THREADS) dst[i] = src[i];
     }
+    const int row0 = blockIdx.x * (2 * TILE_M);
+    const int n_tiles = (int64_t)row0 + TILE_M < Bp ? 2 : 1;     // Bp is a multiple of 128, not of 256
     if (tid == 0) {
-        for (int s = 0; s < ENCP_STAGES; ++s) { mbar_init(full0 + 8 * s, 1 + ENC_LOADER_WARPS); mbar_init(empty0 + 8 * s, 1); }
+        // a stage is full when the weight TMA and the four loader warps of every live row tile have arrived
+        for (int s = 0; s < ENCP_STAGES; ++s) { mbar_init(full0 + 8 * s, 1 + ENC_LOADER_WARPS * n_tiles); mbar_init(empty0 + 8 * s, 1); }
         mbar_init(accum_bar, 1);
         mbar_init(res_bar, 1);
         mbar_init(res_bar + 8, 1);
@@ -1494,8 +1497,6 @@ k_tc_encoder_pair(const __grid_constant__ EncMaps maps, const Tile* __restrict__
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
 
-    const int row0 = blockIdx.x * (2 * TILE_M);
-    const int n_tiles = (int64_t)row0 + TILE_M < Bp ? 2 : 1;     // Bp is a multiple of 128, not of 256
     const int K = t.chunks[0].K;
     const int n_kb = (K + 63) / 64;
 
@@ -1540,7 +1541,9 @@ k_tc_encoder_pair(const __grid_constant__ EncMaps maps, const Tile* __restrict__
         }
         __syncwarp();
     } else {
-        // ---------------- loaders: group g takes the K blocks kb = g (mod 2), i.e. always stage g ----------------
+        // ---------------- loaders: group g fills row tile g of EVERY K block; stages alternate ----------------
+        //  (with the K blocks split between the groups a group always refilled the stage the MMA warp was still reading:
+        //  6.5 % of the warp samples sat in that empty-barrier wait; now both groups write stage kb + 1 while stage kb is consumed)
         const int g = (warp - 2) / ENC_LOADER_WARPS;
         const int gt = tid - 64 - g * (ENC_LOADER_WARPS * 32);
         const Chunk& ch = t.chunks[0];
@@ -1548,29 +1551,28 @@ k_tc_encoder_pair(const __grid_constant__ EncMaps maps, const Tile* __restrict__
         const float* signs = (const float*)bt.p[2];
         const int kq = gt & 15;                                   // which 4-column group of the 64-column block
         const int rsub = gt >> 4;                                 // 0..7
-        const int64_t row_first = (int64_t)row0 + rsub;
-        // Work units of 64 rows x 64 columns (a quarter of a K block of the row pair); three register sets rotate so
-        // that the loads of units n + 1 and n + 2 are in flight while unit n is converted and written to shared memory.
-        const int upb = 2 * n_tiles;                              // units per K block
-        const int n_units = kb_count(g, n_kb) * upb;
+        const int64_t row_first = (int64_t)row0 + g * TILE_M + rsub;
+        // Work units of 64 rows x 64 columns (half a K block of this group's row tile); ENC_SETS register sets rotate so that
+        // the loads of units n + 1 .. n + ENC_SETS - 1 are in flight while unit n is converted and written to shared memory.
+        const int n_units = g < n_tiles ? n_kb * 2 : 0;
         float4 v[ENC_SETS][8];
         auto load = [&](float4 (&v)[8], const int n) {
-            if (n < n_units) load_x_block<8>(v, xr, row_first + (n % upb) * 64, B - 1, (g + 2 * (n / upb)) * 64 + kq * 4);
+            if (n < n_units) load_x_block<8>(v, xr, row_first + (n & 1) * 64, B - 1, (n >> 1) * 64 + kq * 4);
         };
         auto convert = [&](const float4 (&v)[8], const int n) {
             if (n >= n_units) return;
-            const int kb = g + 2 * (n / upb), q = n % upb;
+            const int kb = n >> 1, half = n & 1;
             const float4 f = x_factors(signs, ch.sign_off, kb * 64 + kq * 4, K);
             const int s = kb % ENCP_STAGES;
-            if (q == 0) mbar_wait(empty0 + 8 * s, ((kb / ENCP_STAGES) & 1) ^ 1);
-            const uint32_t st = smem_base + s * ENCP_STAGE_BYTES + (uint32_t)(q >> 1) * (2 * ENC_TILE_BYTES);
+            if (!half) mbar_wait(empty0 + 8 * s, ((kb / ENCP_STAGES) & 1) ^ 1);
+            const uint32_t st = smem_base + s * ENCP_STAGE_BYTES + (uint32_t)g * (2 * ENC_TILE_BYTES);
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
-                const int r = (q & 1) * 64 + it * 8 + rsub;
+                const int r = half * 64 + it * 8 + rsub;
                 const uint32_t off = (uint32_t)(r * 128 + ((((kq >> 1) ^ (r & 7))) << 4) + ((kq & 1) << 3));
                 split_to_smem(st + off, st + ENC_TILE_BYTES + off, v[it], f);
             }
-            if (q == upb - 1) {
+            if (half) {
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(full0 + 8 * s);
