@@ -213,6 +213,11 @@ const char* mshgnn_kernel_kind_name(int32_t kind);
 int mshgnn_relu_mask_offset(const mshgnn_plan* plan, int64_t B, int32_t mode, int32_t layer,
                             int64_t* byte_off, int64_t* n_slots, int64_t* rows_padded);
 
+/* Introspection for the host tests: how a training-mode backward of B graphs splits the layer-stack weight-gradient work.
+ * For layer launch l (0..L-1) writes out[4*l .. 4*l+3] = {tasks, row splits, rows per split, first partial slot}; returns L
+ * (or -1).  One CTA = one task x one row split; partial slots are packed launch by launch in task order.  Host-only. */
+int64_t mshgnn_dw_layout(const mshgnn_plan* plan, int64_t B, int32_t mode, int32_t* out, int64_t cap);
+
 int64_t mshgnn_launch_count(void);
 const char* mshgnn_last_error(void);
 const char* mshgnn_version(void);

@@ -403,6 +403,20 @@ int64_t mshgnn_workspace_bytes(const mshgnn_plan* plan, int64_t B, int32_t train
     return w.total;
 }
 
+int64_t mshgnn_dw_layout(const mshgnn_plan* plan, int64_t B, int32_t mode, int32_t* out, int64_t cap) {
+    if (!plan || B < 1 || !out) return -1;
+    const Plan& p = plan->p;
+    const WsLayout w = ws_layout(p, B, 1, mode);
+    const bool tc = mode != MSHGNN_MODE_FP32;
+    for (int l = 0; l < p.L && 4 * (int64_t)l + 3 < cap; ++l) {
+        out[4 * l] = p.dw_layer[l].count;
+        out[4 * l + 1] = tc ? w.dw_ns[l] : w.n_splits;
+        out[4 * l + 2] = tc ? w.dw_rows[l] : (int32_t)round_up((B + w.n_splits - 1) / w.n_splits, RG_BK);   // as k_reducegemm rounds it
+        out[4 * l + 3] = w.dw_slot0[l];
+    }
+    return p.L;
+}
+
 int64_t mshgnn_out_rows(const mshgnn_plan* plan, int64_t B) { return plan ? B * plan->p.nodes[plan->p.dec_type] : -1; }
 
 int64_t mshgnn_plan_describe(const mshgnn_plan* plan, char* buf, int64_t cap) {

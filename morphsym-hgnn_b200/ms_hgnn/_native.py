@@ -28,7 +28,7 @@ EXPORTS = (
     "mshgnn_workspace_bytes", "mshgnn_out_rows", "mshgnn_forward", "mshgnn_loss", "mshgnn_backward",
     "mshgnn_adam_step", "mshgnn_sgd_step", "mshgnn_plan_describe", "mshgnn_launch_count",
     "mshgnn_last_error", "mshgnn_version", "mshgnn_profile_enable", "mshgnn_profile_read", "mshgnn_kernel_kind_name",
-    "mshgnn_relu_mask_offset", "mshgnn_build_windows", "mshgnn_step_metrics",
+    "mshgnn_relu_mask_offset", "mshgnn_build_windows", "mshgnn_step_metrics", "mshgnn_dw_layout",
 )
 
 
@@ -94,6 +94,7 @@ def lib() -> C.CDLL:
     L.mshgnn_param_count.argtypes = [vp]; L.mshgnn_param_count.restype = i64
     L.mshgnn_param_offset.argtypes = [vp, i32, i32, i32, C.POINTER(i64), C.POINTER(i64)]; L.mshgnn_param_offset.restype = C.c_int
     L.mshgnn_workspace_bytes.argtypes = [vp, i64, i32, i32]; L.mshgnn_workspace_bytes.restype = i64
+    L.mshgnn_dw_layout.argtypes = [vp, i64, i32, C.POINTER(C.c_int32), i64]; L.mshgnn_dw_layout.restype = i64
     L.mshgnn_out_rows.argtypes = [vp, i64]; L.mshgnn_out_rows.restype = i64
     L.mshgnn_forward.argtypes = [vp, i64, C.POINTER(vp), i32, vp, vp, vp, i64, i32, i32, vp]; L.mshgnn_forward.restype = C.c_int
     L.mshgnn_loss.argtypes = [vp, i64, i32, vp, vp, i32, f32, vp, vp, vp, i64, vp]; L.mshgnn_loss.restype = C.c_int
@@ -200,6 +201,14 @@ class NativePlan:
         if n < 0:
             raise RuntimeError("mshgnn_workspace_bytes failed")
         return n
+
+    def dw_layout(self, B: int, mode: int = MODE_TC):
+        """Per layer launch of the weight-gradient GEMM: (tasks, row splits, rows per split, first partial slot)."""
+        buf = (C.c_int32 * 64)()
+        n = int(lib().mshgnn_dw_layout(self.handle, B, mode, buf, 64))
+        if n < 0:
+            raise RuntimeError("mshgnn_dw_layout failed")
+        return [tuple(buf[4 * l + k] for k in range(4)) for l in range(n)]
 
     def out_rows(self, B: int) -> int:
         return int(lib().mshgnn_out_rows(self.handle, B))

@@ -70,6 +70,30 @@ def test_live_row_gemv_counts():
     assert com["need"][8] == [1] * 4 + [0] * 12
 
 
+def test_weight_gradient_launch_layout():
+    """ws_layout (csrc/plan.cu): row splits fitted per layer launch to whole waves of 148 CTAs, partial slots packed."""
+    k4 = N.NativePlan(_spec(M.K4_MINI_CHEETAH, {"base": 900, "joint": 300, "foot": 900}, True, "foot", 2))
+    lay = k4.dw_layout(16384, N.MODE_TC)
+    assert [t for t, _, _, _ in lay] == [17, 17, 17, 17, 11, 8, 5, 2]          # dead branches prune the last four layers
+    assert lay[0][1:3] == (16, 1024)                                             # full layers: the measured default
+    assert [(ns, rows) for _, ns, rows, _ in lay[4:]] == [(26, 640), (16, 1024), (29, 576), (64, 256)]
+    for B in (1, 96, 257, 1100, 2400, 4096, 16384, 65536, 100000):
+        for plan_mode in (N.MODE_TC, N.MODE_FP32):
+            lay = k4.dw_layout(B, plan_mode)
+            used = []
+            for tasks, ns, rows, slot0 in lay:
+                assert 1 <= ns <= 64 and B <= ns * rows                             # all rows covered
+                if plan_mode == N.MODE_TC:
+                    assert rows % 64 == 0 and (ns - 1) * rows < B                   # no empty split
+                used.append((slot0, slot0 + tasks * ns))
+            used.sort()
+            assert used[0][0] == 0 and all(a[1] == b[0] for a, b in zip(used, used[1:]))   # packed, no overlap
+    # a pruned launch never takes more waves than the default split would
+    for tasks, ns, rows, _ in k4.dw_layout(16384, N.MODE_TC):
+        waves = lambda n: -(-tasks * n // 148)
+        assert waves(ns) * (rows + 96) <= waves(16) * (1024 + 96)
+
+
 def test_plan_rejects_unsupported():
     tpl = M.K4_MINI_CHEETAH
     spec = _spec(tpl, {"base": 900, "joint": 300, "foot": 900}, True, "foot", 2)
