@@ -1,7 +1,7 @@
 #!/bin/bash
 # same-box A/B, alternating, three repeats each.  usage: gpu_enc_ab.sh "ENV=a" "ENV=b" ...
 mkdir -p gpurun_out
-for r in 1 2 3; do
+for r in ${REPEATS:-1 2 3}; do
   i=0
   for envs in "$@"; do
     i=$((i+1))
