@@ -73,6 +73,13 @@ def test_forward_loss_backward_parity_tensor_core_mode(name, B, layers):
     check_gradients(CONFIGS[name], B, layers, mode="tc")
 
 
+@pytest.mark.parametrize("name,B,layers", [("a1-c2-grf", 300, 8), ("solo12-k4-com", 700, 8), ("mi-contact", 400, 8)])
+def test_several_row_tiles_with_narrow_inputs_tensor_core_mode(name, B, layers):
+    """3-6 row tiles (two-tile encoder CTAs: full pairs plus a single last tile) for the input widths that take the scalar /
+    2-wide load paths (A1 foot width 1, A1 joint 450, Solo 6 / 2) and for the baseline model without the base MLP."""
+    check_gradients(CONFIGS[name], B, layers, mode="tc")
+
+
 def test_mid_size_batch_with_per_layer_weight_gradient_splits():
     """2400 graphs: 19 row tiles (the two-tile encoder CTAs end on a single tile) and a different wave-fitted row-split
     count in each of the pruned last layers' weight-gradient launches (ws_layout), against the oracle at the same 1e-4."""
