@@ -1449,11 +1449,12 @@ k_tc_encoder(const __grid_constant__ EncMaps maps, const Tile* __restrict__ tile
 // encoder, two row tiles per CTA (default; MSHGNN_ENCODER=v1 selects k_tc_encoder)
 // ------------------------------------------------------------------------------------------
 //  ncu of k_tc_encoder: 46.7 M L2->SM read sectors (1.49 GB) for 708 MB of features - a 128-row x 64-column fp32 block
-//  of x is 32 KB and so is the (hi, lo) weight K block it meets, i.e. every CTA pulled as many weight bytes out of L2 as
-//  feature bytes, and the kernel ran at the ~4.6 TB/s L2->SM ceiling the weight-gradient kernel also sits at, not at an
-//  HBM or issue limit (two CTAs per SM with 32-column K blocks hid the per-CTA prologue / epilogue but was 5 % SLOWER:
-//  same bytes through the same pipe).  Here a CTA owns TWO row tiles (256 graphs of one node slot): every weight stage
-//  is used by both, the weight stream halves (L2->SM bytes -25 %), and the fixed per-CTA cost is paid once per 256 rows.
+//  of x is 32 KB and so is the (hi, lo) weight K block it meets, i.e. every CTA pulls as many weight bytes out of L2 as
+//  feature bytes.  Here a CTA owns TWO row tiles (256 graphs of one node slot): every weight stage is used by both, the
+//  weight stream halves (L2->SM bytes -25 %) and the fixed per-CTA cost is paid once per 256 rows.  Measured on one box,
+//  alternating runs: 0.359-0.365 ms against 0.372-0.378 ms for k_tc_encoder (DESIGN 3.1a lists what did NOT help: two
+//  CTAs per SM, a fourth register set, staged or prefetched sign factors - the kernel is bound by the latency of the
+//  strided 256-byte row fragments, not by L2 bytes, issue slots or per-CTA overhead).
 //  Stage = A0_hi, A0_lo, A1_hi, A1_lo, W_hi, W_lo = 96 KB, two stages (loader group g fills row tile g), accumulators of the
 //  two tiles in TMEM columns [0,128) and [128,256); the epilogue drains them one after the other through the drained ring.
 constexpr int ENCP_STAGES = 2;
