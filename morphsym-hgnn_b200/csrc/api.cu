@@ -634,7 +634,9 @@ int mshgnn_backward(const mshgnn_plan* plan, int64_t B, const void* const* x, in
     // layer-stack groups were produced with the split count of the kernel that ran them, encoder groups with the SIMT one
     const int ngl = p.n_groups_layers, nge = (int)p.groups.size() - ngl;
     if (ngl > 0) {
-        dim3 grid((unsigned)ngl, 32);
+        // 64 blocks per group = one element per thread: the groups of the shared base_transform weights sum up to 16 tasks x
+        // 16..64 splits per element, and that serial chain (not the 117 MB of partials) sets the launch time
+        dim3 grid((unsigned)ngl, 64);
         ProfScope ps(K_REDUCE, st);
         k_reduce_partials<<<grid, 256, 0, st>>>(p.d_groups, part_w, part_b, w.segs, grads, 1.f / G);
         LAUNCH_CHECK();
