@@ -94,6 +94,33 @@ def test_weight_gradient_launch_layout():
         assert waves(ns) * (rows + 96) <= waves(16) * (1024 + 96)
 
 
+def test_weight_gradient_launch_layout_any_batch_size():
+    """Same invariants for arbitrary batch sizes and the other morphologies (hypothesis)."""
+    from hypothesis import given, settings, strategies as st
+    plans = [N.NativePlan(_spec(M.K4_MINI_CHEETAH, {"base": 900, "joint": 300, "foot": 900}, True, "foot", 2)),
+             N.NativePlan(_spec(M.C2_A1, {"base": 900, "joint": 450, "foot": 1}, True, "foot", 3)),
+             N.NativePlan(_spec(M.K4_SOLO_COM, {"base": 6, "joint": 2}, True, "base", 6)),
+             N.NativePlan(_spec(M.MI_QUADRUPED, {"base": 6, "joint": 3, "foot": 1}, False, "foot", 1, L=3))]
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(0, len(plans) - 1), st.integers(1, 1 << 21), st.sampled_from([N.MODE_TC, N.MODE_TC_1X, N.MODE_FP32]))
+    def check(pi, B, mode):
+        lay = plans[pi].dw_layout(B, mode)
+        used = []
+        for tasks, ns, rows, slot0 in lay:
+            if tasks == 0:
+                continue
+            assert 1 <= ns <= 64 and B <= ns * rows
+            if mode != N.MODE_FP32:
+                assert rows % 64 == 0 and (ns - 1) * rows < B
+            used.append((slot0, slot0 + tasks * ns))
+        used.sort()
+        assert used and used[0][0] == 0 and all(a[1] == b[0] for a, b in zip(used, used[1:]))
+        assert plans[pi].workspace_bytes(B, True, mode) > 0
+
+    check()
+
+
 def test_plan_rejects_unsupported():
     tpl = M.K4_MINI_CHEETAH
     spec = _spec(tpl, {"base": 900, "joint": 300, "foot": 900}, True, "foot", 2)
