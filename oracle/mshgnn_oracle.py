@@ -29,15 +29,21 @@ Reference call sites this follows (paths relative to /root/reference/src/ms_hgnn
 
 Pinning
 -------
-``tests/test_oracle_anchor.py`` checks this file against the reference's own known-answer
-test (tests/testGnnLightning.py:L214-216: MSE 6.33834 / RMSE 2.51761 / L1 2.31058 for the
-shipped checkpoint ``tests/test_models/epoch=48-val_MSE_loss=6.33834.ckpt`` on its 20
-graphs), through fixtures extracted by ``tools/make_golden.py``.  That pins GraphConv /
-HeteroConv / encoder / decoder / ReLU semantics, the state-dict naming, the batch layout and
-the MSE head.  PARITY UNPINNED for the MS-HGNN-specific parts (sign tables, base_transform +
-residual, mean-aggregated gt/gs/center_bb, output sign decoders) and for all gradients: the
-reference has no test or fixture for them; evidence there is line-by-line correspondence,
-exact C2/K4 equivariance in float64 and ``torch.autograd.gradcheck``.
+PINNED against the reference's own code, three ways:
+
+1. ``tests/test_reference_pin.py``: the reference's UNMODIFIED model files (``hgnn.py``, ``hgnn_k4.py``, ``hgnn_c2.py``,
+   ``hgnn_k4_com.py``, ``hgnn_c2_com.py``, ``hgnn_s4_com.py``) are imported from /root/reference against
+   ``oracle/pyg_shim`` (the four ``torch_geometric.nn`` classes they use, restated from torch_geometric 2.5.0) and run
+   in fp64; every class of this file equals them on every ``CONFIGS`` entry at L = 8 - outputs, loss and EVERY
+   gradient tensor - to fp64 rounding (<= 1e-12 norm-wise; summation order only), with identical
+   ``named_parameters()`` order and identical dead-gradient sets.  That covers the sign tables, ``base_transform`` +
+   residual, the mean relations, the output sign decoders and all gradients.  The same reference runs are stored as
+   ``tests/golden/reference_models.pt`` (``tools/make_golden.py``) for machines without /root/reference.
+2. ``tests/test_oracle_anchor.py``: the reference's known-answer test (tests/testGnnLightning.py:L214-216: MSE 6.33834 /
+   RMSE 2.51761 / L1 2.31058 for the shipped checkpoint ``tests/test_models/epoch=48-val_MSE_loss=6.33834.ckpt`` on
+   its 20 graphs), through fixtures extracted by ``tools/make_golden.py``; this one anchors the shim's GraphConv /
+   HeteroConv / HeteroDictLinear semantics to numbers produced by the real torch_geometric.
+3. Loss / metric literals and graph-template pins of the reference's tests (same file).
 """
 from __future__ import annotations
 

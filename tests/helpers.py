@@ -120,7 +120,7 @@ def native_relu_pattern(model, B):
     return out
 
 
-def gradient_check_under_native_pattern(cfg, model, batch, native_model, native_grads, fwd_rel_err, tol=TOL_FP32):
+def gradient_check_under_native_pattern(cfg, model, batch, native_model, native_grads, fwd_rel_err, tol=TOL_FP32, plain_grads=None):
     """Returns (ok, info).  ReLU makes d(loss)/d(params) discontinuous in the forward numerics: an implementation whose
     forward is accurate to 1e-6 may put a pre-activation of +-1e-7 on the other side of zero, which moves whole gradient
     tensors by 1e-4..1e-2 (plain PyTorch fp32 does the same against fp64).  So the native gradient is compared, strictly
@@ -162,4 +162,16 @@ def gradient_check_under_native_pattern(cfg, model, batch, native_model, native_
         e = rel_err(native_grads[n], g[n])
         if e > worst:
             worst, worst_name = e, n
-    return worst <= tol, {"flips": flips, "err": worst, "tensor": worst_name, "worst |x| / threshold": worst_ratio}
+    info = {"flips": flips, "err": worst, "tensor": worst_name, "worst |x| / threshold": worst_ratio}
+    if plain_grads is not None:
+        # the PLAIN error too (oracle's own ReLU pattern, nothing forced): reported next to the forced one so that the
+        # size of the sign-flip effect is visible; it equals the forced error when no pre-activation flipped
+        pw, pn = 0.0, None
+        for n in names:
+            if plain_grads[n].norm().item() == 0.0:
+                continue
+            e = rel_err(native_grads[n], plain_grads[n])
+            if e > pw:
+                pw, pn = e, n
+        info["plain_err"], info["plain_tensor"] = pw, pn
+    return worst <= tol, info

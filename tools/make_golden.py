@@ -5,6 +5,10 @@
    the fp64 oracle output on exactly those numbers, and the pinned metrics.
 2. seeded.pt       - oracle outputs / losses / gradient norms of every model class on seeded synthetic batches
    (weights and inputs are regenerated from the seeds by the tests; only the expected numbers are stored).
+3. reference_models.pt - outputs, loss and per-tensor gradient digests of the reference's UNMODIFIED model files
+   (/root/reference/src/ms_hgnn/lightning_py/hgnn*.py, imported against oracle/pyg_shim by oracle/reference_pin.py) for
+   every CONFIGS entry at L = 8 on a seeded 5-graph batch with seeded weights - the pin of the MS-HGNN-specific oracle
+   semantics (sign tables, base_transform + residual, mean relations, output decoders) and of all gradients.
 """
 import os
 import sys
@@ -21,6 +25,7 @@ from ms_hgnn.synthetic import CONFIGS, make_batch  # noqa: E402
 GOLD = os.path.join(ROOT, "tests", "golden")
 CKPT = "/root/reference/tests/test_models/epoch=48-val_MSE_loss=6.33834.ckpt"
 SEEDED_CASES = [(n, 3, 2) for n in CONFIGS]   # (config, B, layers)
+RP_B, RP_LAYERS, RP_BATCH_SEED, RP_WEIGHT_SEED = 5, 8, 11, 4
 
 
 def main():
@@ -55,6 +60,22 @@ def main():
                         "x_checksum": {k: v.double().sum().item() for k, v in b.x_dict.items()},
                         "w_checksum": sum(p.double().sum().item() for p in om.parameters())}
     torch.save(seeded, os.path.join(GOLD, "seeded.pt"))
+    import reference_pin as RP
+    from helpers import oracle_loss
+    ref = {}
+    for name, cfg in CONFIGS.items():
+        b = make_batch(cfg, RP_B, seed=RP_BATCH_SEED)
+        rm = RP.build_reference_model(cfg, RP_LAYERS, 1)
+        RP.materialize(rm, b)
+        rm.load_state_dict(RP.seeded_state_dict(rm, RP_WEIGHT_SEED))
+        o, l, g = RP.reference_run(cfg, rm, b, oracle_loss)
+        ref[name] = {"B": RP_B, "layers": RP_LAYERS, "batch_seed": RP_BATCH_SEED, "weight_seed": RP_WEIGHT_SEED,
+                     "keys": list(rm.state_dict().keys()), "shapes": [tuple(v.shape) for v in rm.state_dict().values()],
+                     "out": o, "loss": l, "grad_digest": RP.grad_digest(g),
+                     "grad_is_none": sorted(n for n, p in rm.named_parameters() if p.grad is None)}
+        print("reference", name, tuple(o.shape), float(l))
+    torch.save({"cases": ref, "source": "unmodified /root/reference/src/ms_hgnn/lightning_py/hgnn*.py @ 9e55c68 run against "
+                "oracle/pyg_shim (torch_geometric 2.5.0 semantics), fp64, CPU"}, os.path.join(GOLD, "reference_models.pt"))
     for f in os.listdir(GOLD):
         print(f, os.path.getsize(os.path.join(GOLD, f)))
 
