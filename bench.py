@@ -48,6 +48,8 @@ ALG = {
     "base_mlp_fwd": 2 * (8 * 7 * 128 * 128),
     "dx_bwd": 2 * (_LAY_MAC - 8 * 7 * 128 * 128),
     "base_mlp_bwd": 2 * (8 * 7 * 128 * 128),
+    "stack_fwd": 2 * _LAY_MAC,                                  # cross-layer kernel: conv + chained base MLP of all layers
+    "stack_bwd": 2 * _LAY_MAC,                                  # dX chain + chained base MLP backward of all layers
     "dw_layers": 2 * _LAY_MAC,
     "dw_encoder": 2 * _ENC_MAC,
 }

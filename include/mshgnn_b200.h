@@ -199,7 +199,7 @@ int64_t mshgnn_plan_describe(const mshgnn_plan* plan, char* buf, int64_t cap);
  * stream it is launched on.  mshgnn_profile_read synchronises those events, adds the elapsed
  * milliseconds and launch counts per kernel kind into ms_out / launches_out (n entries each, n >=
  * MSHGNN_NUM_KERNEL_KINDS) and clears the record.  Used by bench.py for the roofline figures. */
-#define MSHGNN_NUM_KERNEL_KINDS 16
+#define MSHGNN_NUM_KERNEL_KINDS 19
 int mshgnn_profile_enable(int32_t on);
 int mshgnn_profile_read(double* ms_out, int64_t* launches_out, int32_t n);
 const char* mshgnn_kernel_kind_name(int32_t kind);
@@ -217,6 +217,25 @@ int mshgnn_relu_mask_offset(const mshgnn_plan* plan, int64_t B, int32_t mode, in
  * For layer launch l (0..L-1) writes out[4*l .. 4*l+3] = {tasks, row splits, rows per split, first partial slot}; returns L
  * (or -1).  One CTA = one task x one row split; partial slots are packed launch by launch in task order.  Host-only. */
 int64_t mshgnn_dw_layout(const mshgnn_plan* plan, int64_t B, int32_t mode, int32_t* out, int64_t cap);
+
+/* ---- batching-layout check ------------------------------------------------------
+ * The kernels never read edge_index (the template is compiled into the plan); this verifies, in ONE launch and without a
+ * host synchronisation, that the caller's batch is that template tiled over B graphs, bit-exactly (PyG
+ * Batch.from_data_list).  edge_index[e]: device int64 [2][edge_count[e] * B], row-major (row 0 sources, row 1
+ * destinations), metadata order.  On a mismatch the kernel stores 1 + (edge type) into *flag - pinned host memory
+ * (readable by the host at any later time) or device memory.  Replaces nothing in the reference (PyG trusts the batch);
+ * it is the guard that makes "no edge_index on the device" safe. */
+int mshgnn_check_edges(const mshgnn_plan* plan, int64_t B, const int64_t* const* edge_index, int32_t* flag, void* stream);
+
+/* ---- switches and status --------------------------------------------------------------------
+ * Option "stack" (default 1, environment MSHGNN_STACK=0 turns it off): run the layer loop of the tensor-core modes
+ * (hgnn_k4.py:L170-186 and its backward) as ONE persistent cross-layer kernel over L2-resident row chunks instead of one
+ * launch per layer.  It changes the workspace layout: query mshgnn_workspace_bytes again after switching.
+ * mshgnn_stack_status copies one word back (synchronising): *status_out = 1 when a dependency wait inside the last stack
+ * launch on this workspace timed out (its results are then invalid); used by the tests. */
+int mshgnn_set_option(const char* name, int32_t value);
+int32_t mshgnn_get_option(const char* name);
+int mshgnn_stack_status(const mshgnn_plan* plan, int64_t B, int32_t train, int32_t mode, const void* workspace, int32_t* status_out);
 
 int64_t mshgnn_launch_count(void);
 const char* mshgnn_last_error(void);

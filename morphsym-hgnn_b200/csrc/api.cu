@@ -12,6 +12,7 @@
 
 #include "kernels_simt.cuh"
 #include "kernels_tc.cuh"
+#include "kernels_stack.cuh"
 #include "plan.cuh"
 #include "windows.cuh"
 #include "metrics.cuh"
@@ -44,11 +45,12 @@ int fail(int code, const char* fmt, ...) {
 
 // ---- per-kernel event profiling ----
 enum Kind : int { K_DERIVE = 0, K_ENC_FWD, K_CONV_FWD, K_MLP_FWD, K_DEC_FWD, K_LOSS, K_DEC_BWD, K_MLP_BWD, K_DX_BWD,
-                  K_DW_LAYER, K_DW_ENC, K_REDUCE, K_OPTIM, K_MEMSET, K_WINDOWS, K_METRICS, K_NKINDS };
+                  K_DW_LAYER, K_DW_ENC, K_REDUCE, K_OPTIM, K_MEMSET, K_WINDOWS, K_METRICS, K_STACK_FWD, K_STACK_BWD, K_EDGES, K_NKINDS };
+static_assert(K_NKINDS == MSHGNN_NUM_KERNEL_KINDS, "kernel kind table out of sync with the header");
 const char* const kKindNames[MSHGNN_NUM_KERNEL_KINDS] = {
     "derive_weights", "encoder_fwd", "conv_fwd", "base_mlp_fwd", "decoder_fwd", "loss",
     "decoder_bwd", "base_mlp_bwd", "dx_bwd", "dw_layers", "dw_encoder",
-    "reduce_partials", "optimizer", "memset", "window_builder", "step_metrics"};
+    "reduce_partials", "optimizer", "memset", "window_builder", "step_metrics", "stack_fwd", "stack_bwd", "check_edges"};
 struct ProfRec { int kind; cudaEvent_t a, b; };
 std::mutex g_prof_mu;
 bool g_prof_on = false;
@@ -99,6 +101,13 @@ int ensure_uploaded(const Plan& p) {
     }
     int rc;
     if ((rc = upload(p.tiles, &p.d_tiles))) return rc;
+    if ((rc = upload(p.stack_items, &p.d_stack_items))) return rc;
+    {
+        std::vector<int> tpl;
+        for (int e = 0; e < p.n_etypes; ++e) { tpl.insert(tpl.end(), p.e_src[e].begin(), p.e_src[e].end()); tpl.insert(tpl.end(), p.e_dst[e].begin(), p.e_dst[e].end()); }
+        if (tpl.empty()) tpl.push_back(0);
+        if ((rc = upload(tpl, &p.d_edge_tpl))) return rc;
+    }
     if ((rc = upload(p.rtasks, &p.d_rtasks))) return rc;
     if ((rc = upload(p.rpairs, &p.d_rpairs))) return rc;
     if ((rc = upload(p.groups, &p.d_groups))) return rc;
@@ -117,9 +126,10 @@ void fill_bufs(const Plan& p, const WsLayout& w, char* ws, BufTable& bt) {
     bt.p[BUF_DERIVED] = ws + w.derived;
     bt.p[BUF_SIGNS] = p.d_signs;
     auto at = [&](int64_t off) -> void* { return off < 0 ? nullptr : (void*)(ws + off); };
-    bt.p[BUF_DH0] = at(w.dh[0]); bt.p[BUF_DH1] = at(w.dh[1]);
-    bt.p[BUF_DC0] = at(w.dc[0]); bt.p[BUF_DC1] = at(w.dc[1]);
-    bt.p[BUF_DU] = at(w.du);
+    // per-layer backward ids alias the two ping-pong slabs (fp32 SIMT mode; the tensor-core modes carry fp16 images only)
+    for (int l = 0; l <= p.L; ++l) bt.p[BUF_DHL0 + l] = at(w.dh[l & 1]);
+    for (int l = -1; l < p.L; ++l) bt.p[BUF_DCL0 + l] = at(w.dc[(l + 2) & 1]);
+    for (int l = 0; l < p.L; ++l) bt.p[BUF_DUL0 + l] = at(w.du);
     bt.p[BUF_MASKE] = at(w.maske);
     for (int l = 0; l <= p.L; ++l) bt.p[BUF_H0 + l] = at(w.h[l]);
     for (int l = 0; l < p.L; ++l) { bt.p[BUF_CT0 + l] = at(w.ct[l]); bt.p[BUF_MASK0 + l] = at(w.mask[l]); }
@@ -128,11 +138,15 @@ void fill_bufs(const Plan& p, const WsLayout& w, char* ws, BufTable& bt) {
 void fill_bufs16(const Plan& p, const WsLayout& w, char* ws, BufTable16& bh) {
     memset(&bh, 0, sizeof bh);
     auto at = [&](int64_t off) -> __half* { return off < 0 ? nullptr : (__half*)(ws + off); };
-    for (int b = 0; b < 2; ++b) {
-        bh.hi[BUF_DH0 + b] = at(w.dh16[b][0]); bh.lo[BUF_DH0 + b] = at(w.dh16[b][1]);
-        bh.hi[BUF_DC0 + b] = at(w.dc16[b][0]); bh.lo[BUF_DC0 + b] = at(w.dc16[b][1]);
+    for (int l = 0; l <= p.L; ++l) {
+        bh.hi[BUF_DHL0 + l] = at(w.stack ? w.dhL16[l][0] : w.dh16[l & 1][0]); bh.lo[BUF_DHL0 + l] = at(w.stack ? w.dhL16[l][1] : w.dh16[l & 1][1]);
     }
-    bh.hi[BUF_DU] = at(w.du16[0]); bh.lo[BUF_DU] = at(w.du16[1]);
+    for (int l = -1; l < p.L; ++l) {
+        bh.hi[BUF_DCL0 + l] = at(w.stack ? w.dcL16[l + 1][0] : w.dc16[(l + 2) & 1][0]); bh.lo[BUF_DCL0 + l] = at(w.stack ? w.dcL16[l + 1][1] : w.dc16[(l + 2) & 1][1]);
+    }
+    for (int l = 0; l < p.L; ++l) {
+        bh.hi[BUF_DUL0 + l] = at(w.stack ? w.duL16[l][0] : w.du16[0]); bh.lo[BUF_DUL0 + l] = at(w.stack ? w.duL16[l][1] : w.du16[1]);
+    }
     for (int l = 0; l <= p.L; ++l) { bh.hi[BUF_H0 + l] = at(w.h16[l][0]); bh.lo[BUF_H0 + l] = at(w.h16[l][1]); }
     for (int l = 0; l < p.L; ++l) { bh.hi[BUF_CT0 + l] = at(w.ct16[l][0]); bh.lo[BUF_CT0 + l] = at(w.ct16[l][1]); }
 }
@@ -204,17 +218,35 @@ int make_ws_maps(WsMaps* m, const void* ws, const WsLayout& w) {
     return 0;
 }
 
+// per-device state: a process may drive several GPUs (one plan / model per device)
+constexpr int MAX_DEVICES = 64;
+int sm_count(int* out) {
+    static std::atomic<int> n[MAX_DEVICES];
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    int v = dev < MAX_DEVICES ? n[dev].load(std::memory_order_relaxed) : 0;
+    if (!v) {
+        CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
+        if (dev < MAX_DEVICES) n[dev].store(v, std::memory_order_relaxed);
+    }
+    *out = v;
+    return 0;
+}
+// true the first time it is called on the current device for this flag set (cudaFuncSetAttribute is per device)
+bool first_on_device(std::atomic<bool> (&flags)[MAX_DEVICES]) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) return true;
+    return !flags[dev].exchange(true);
+}
+
 int launch_tc_encoder(const Plan& p, const Launch& L, const WsLayout& w, const BufTable& bt, const BufRows& br, const WsMaps& wm, char* ws,
                       const float* params, int64_t B, int xf64, int split, cudaStream_t st) {
     if (L.count == 0) return 0;
-    static bool attr_set = false;
-    static bool use_v1 = false;       // MSHGNN_ENCODER=v1 selects the kernel with one row tile per CTA (A/B measurements)
-    if (!attr_set) {
+    static std::atomic<bool> attr_set[64];
+    static const bool use_v1 = [] { const char* e = getenv("MSHGNN_ENCODER"); return e && !strcmp(e, "v1"); }();   // one row tile per CTA (A/B measurements)
+    if (first_on_device(attr_set)) {
         CUDA_TRY(cudaFuncSetAttribute(k_tc_encoder, cudaFuncAttributeMaxDynamicSharedMemorySize, ENC_SMEM_BYTES));
         CUDA_TRY(cudaFuncSetAttribute(k_tc_encoder_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, ENCP_SMEM_BYTES));
-        const char* e = getenv("MSHGNN_ENCODER");
-        use_v1 = e && !strcmp(e, "v1");
-        attr_set = true;
     }
     __half* e_hi = (__half*)(ws + w.wenc16[0]);
     __half* e_lo = (__half*)(ws + w.wenc16[1]);
@@ -239,31 +271,16 @@ int launch_tc_encoder(const Plan& p, const Launch& L, const WsLayout& w, const B
     return 0;
 }
 
-int sm_count(int* out) {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        CUDA_TRY(cudaGetDevice(&dev));
-        CUDA_TRY(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
-    }
-    *out = n;
-    return 0;
-}
-
 int launch_tc_rowgemm(int kind, const Plan& p, const Launch& L, const BufTable& bt, const BufRows& br, const WsMaps& wm,
                       int64_t B, int64_t Bp, int split, cudaStream_t st) {
     if (L.count == 0) return 0;
-    static bool attr_set = false;
-    static bool use_v2 = false;       // MSHGNN_ROWGEMM=tile selects the one-tile-per-CTA kernel (A/B measurements)
-    static bool use_single = false;   // MSHGNN_ROWGEMM=single selects the persistent kernel with one row tile per item
-    if (!attr_set) {
+    static std::atomic<bool> attr_set[64];
+    static const bool use_v2 = [] { const char* e = getenv("MSHGNN_ROWGEMM"); return e && !strcmp(e, "tile"); }();       // one-tile-per-CTA kernel (A/B measurements)
+    static const bool use_single = [] { const char* e = getenv("MSHGNN_ROWGEMM"); return e && !strcmp(e, "single"); }(); // persistent kernel, one row tile per item
+    if (first_on_device(attr_set)) {
         CUDA_TRY(cudaFuncSetAttribute(k_tc_rowgemm, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
         CUDA_TRY(cudaFuncSetAttribute(k_tc_rowgemm_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, PK_SMEM_BYTES));
-        const char* e = getenv("MSHGNN_ROWGEMM");
-        use_v2 = e && !strcmp(e, "tile");
-        use_single = e && !strcmp(e, "single");
         CUDA_TRY(cudaFuncSetAttribute(k_tc_rowgemm_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_BYTES));
-        attr_set = true;
     }
     for (int i = 0; i < L.count; ++i)
         for (int c = 0; c < p.tiles[L.begin + i].n_chunks; ++c)
@@ -303,11 +320,15 @@ int launch_tc_rowgemm(int kind, const Plan& p, const Launch& L, const BufTable& 
 void fill_rows16(const Plan& p, const WsLayout& w, BufRows& br) {
     for (int i = 0; i < MAX_BUFS; ++i) br.hi[i] = br.lo[i] = 0;
     auto at = [&](int64_t off) -> int { return off < 0 ? 0 : (int)(off / 256); };
-    for (int b = 0; b < 2; ++b) {
-        br.hi[BUF_DH0 + b] = at(w.dh16[b][0]); br.lo[BUF_DH0 + b] = at(w.dh16[b][1]);
-        br.hi[BUF_DC0 + b] = at(w.dc16[b][0]); br.lo[BUF_DC0 + b] = at(w.dc16[b][1]);
+    for (int l = 0; l <= p.L; ++l) {
+        br.hi[BUF_DHL0 + l] = at(w.stack ? w.dhL16[l][0] : w.dh16[l & 1][0]); br.lo[BUF_DHL0 + l] = at(w.stack ? w.dhL16[l][1] : w.dh16[l & 1][1]);
     }
-    br.hi[BUF_DU] = at(w.du16[0]); br.lo[BUF_DU] = at(w.du16[1]);
+    for (int l = -1; l < p.L; ++l) {
+        br.hi[BUF_DCL0 + l] = at(w.stack ? w.dcL16[l + 1][0] : w.dc16[(l + 2) & 1][0]); br.lo[BUF_DCL0 + l] = at(w.stack ? w.dcL16[l + 1][1] : w.dc16[(l + 2) & 1][1]);
+    }
+    for (int l = 0; l < p.L; ++l) {
+        br.hi[BUF_DUL0 + l] = at(w.stack ? w.duL16[l][0] : w.du16[0]); br.lo[BUF_DUL0 + l] = at(w.stack ? w.duL16[l][1] : w.du16[1]);
+    }
     for (int l = 0; l <= p.L; ++l) { br.hi[BUF_H0 + l] = at(w.h16[l][0]); br.lo[BUF_H0 + l] = at(w.h16[l][1]); }
     for (int l = 0; l < p.L; ++l) { br.hi[BUF_CT0 + l] = at(w.ct16[l][0]); br.lo[BUF_CT0 + l] = at(w.ct16[l][1]); }
     br.w_hi = at(w.w16[0]); br.w_lo = at(w.w16[1]);
@@ -316,11 +337,8 @@ void fill_rows16(const Plan& p, const WsLayout& w, BufRows& br) {
 int launch_tc_dw(int kind, const Plan& p, int layer, const Launch& L, const WsLayout& w, const BufRows& br, const WsMaps& wm, int64_t B, int split,
                  float* part_w, float* part_b, cudaStream_t st) {
     if (L.count == 0) return 0;
-    static bool attr_set = false;
-    if (!attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute(k_tc_reducegemm, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM_BYTES));
-        attr_set = true;
-    }
+    static std::atomic<bool> attr_set[64];
+    if (first_on_device(attr_set)) CUDA_TRY(cudaFuncSetAttribute(k_tc_reducegemm, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM_BYTES));
     for (int i = 0; i < L.count; ++i) {
         const RTask& T = p.rtasks[L.begin + i];
         if (T.n_pairs > DW_MAX_PAIRS) return fail(MSHGNN_ERR_ARG, "internal: weight-gradient task with more than %d pairs", DW_MAX_PAIRS);
@@ -331,6 +349,62 @@ int launch_tc_dw(int kind, const Plan& p, int layer, const Launch& L, const WsLa
     dim3 grid((unsigned)L.count, (unsigned)w.dw_ns[layer]);          // wave-fitted row splits of this layer (ws_layout)
     k_tc_reducegemm<<<grid, TC_THREADS, DW_SMEM_BYTES, st>>>(wm.dw, p.d_rtasks, p.d_rpairs, L.begin, br, B, w.Bp, w.dw_rows[layer], w.dw_slot0[layer],
                                                              split, part_w, part_b);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+// ---- cross-layer stack kernel (kernels_stack.cuh) ----
+// Row tiles per chunk: the slabs one layer reads and writes for a chunk (2 x S slots x 128 rows x 512 B per row tile) must
+// stay in L2 until the next layer has consumed them - 64 MB of the 126 MB - and the chunk must be long enough that the
+// items of layer l + 1 of a row tile are handed out >= ~300 items (two rounds of 148 CTAs) after those of layer l.
+int stack_rows_per_chunk(const Plan& p) {
+    static const int env = [] { const char* e = getenv("MSHGNN_STACK_RC"); return e ? atoi(e) : 0; }();
+    if (env > 0) return env;
+    const int64_t per_row_tile = (int64_t)2 * p.S * TILE_M * H * 4;
+    int rc = (int)((int64_t)64 * 1024 * 1024 / per_row_tile);
+    return rc < 16 ? 16 : (rc > 64 ? 64 : rc);
+}
+
+int stack_sync_reset(const WsLayout& w, char* ws, cudaStream_t st) {
+    if (!w.stack) return 0;
+    ProfScope ps(K_MEMSET, st);
+    CUDA_TRY(cudaMemsetAsync(ws + w.stack_sync, 0, (size_t)w.stack_sync_bytes, st));
+    return 0;
+}
+
+int launch_stack(int kind, const Plan& p, const Plan::Stack& sp, const WsLayout& w, const BufTable& bt, const BufRows& br, const WsMaps& wm,
+                 char* ws, int64_t B, int split, cudaStream_t st) {
+    if (sp.prog.n_phases == 0) return 0;
+    static std::atomic<bool> attr_set[64];
+    if (first_on_device(attr_set)) CUDA_TRY(cudaFuncSetAttribute(k_tc_stack, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM_BYTES));
+    for (int i = 0; i < sp.tiles.count; ++i) {
+        const Tile& T = p.tiles[sp.tiles.begin + i];
+        for (int c = 0; c < T.n_chunks; ++c)
+            if (T.chunks[c].a_kind != A_SLAB) return fail(MSHGNN_ERR_ARG, "internal: a stack program must read slab buffers");
+    }
+    StackArgs a;
+    a.prog = sp.prog;
+    a.n_row_tiles = (int)(w.Bp / TILE_M);
+    a.rows_per_chunk = stack_rows_per_chunk(p);
+    const int64_t n_total = (int64_t)a.n_row_tiles * sp.prog.items_per_row;
+    if (n_total > 0x7fffffffLL) return fail(MSHGNN_ERR_ARG, "batch too large for one stack launch");
+    a.n_total = (int)n_total;
+    a.split = split; a.B = B; a.Bp = w.Bp;
+    a.sync = (uint32_t*)(ws + w.stack_sync);
+    a.err = (uint32_t*)(ws + w.stack_sync + w.stack_sync_bytes - 4);
+    if ((int64_t)sp.prog.n_phases * a.n_row_tiles + 1 > w.stack_sync_bytes / 4) return fail(MSHGNN_ERR_WORKSPACE, "internal: stack counters do not fit");
+    int n_sm = 0, rc;
+    if ((rc = sm_count(&n_sm))) return rc;
+    ProfScope ps(kind, st);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(n_total < n_sm ? n_total : n_sm)); cfg.blockDim = dim3(SK_THREADS); cfg.dynamicSmemBytes = SK_SMEM_BYTES; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = g_prof_on ? 0 : 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    const Tile* d_tiles = p.d_tiles + sp.tiles.begin;
+    const StackItem* d_items = p.d_stack_items + sp.item0;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, k_tc_stack, wm.tc, d_tiles, d_items, a, bt, br));
     LAUNCH_CHECK();
     return 0;
 }
@@ -363,7 +437,7 @@ void mshgnn_plan_destroy(mshgnn_plan* plan) {
     if (!plan) return;
     Plan& p = plan->p;
     if (p.uploaded) {
-        cudaFree(p.d_tiles); cudaFree(p.d_rtasks); cudaFree(p.d_rpairs);
+        cudaFree(p.d_tiles); cudaFree(p.d_stack_items); cudaFree(p.d_edge_tpl); cudaFree(p.d_rtasks); cudaFree(p.d_rpairs);
         cudaFree(p.d_groups); cudaFree(p.d_derive); cudaFree(p.d_derive16); cudaFree(p.d_signs); cudaFree(p.d_enc_units); cudaFree(p.d_enc_groups);
     }
     delete plan;
@@ -481,7 +555,12 @@ int mshgnn_forward(const mshgnn_plan* plan, int64_t B, const void* const* x, int
             k_derive16<<<grid, 256, 0, st>>>(p.d_derive16, params, w_hi, w_lo);
             LAUNCH_CHECK();
         }
+        if ((rc = stack_sync_reset(w, (char*)workspace, st))) return rc;
         if ((rc = launch_tc_encoder(p, train ? p.enc_train : p.enc_launch, w, bt, br, wm, (char*)workspace, params, B, xf64, split, st))) return rc;
+        if (w.stack) {
+            // all layers (conv + chained base_transform) in one persistent launch over L2-resident row chunks
+            if ((rc = launch_stack(K_STACK_FWD, p, train ? p.stack_train : p.stack_infer, w, bt, br, wm, (char*)workspace, B, split, st))) return rc;
+        } else
         for (int l = 0; l < p.L; ++l) {
             if ((rc = launch_tc_rowgemm(K_CONV_FWD, p, train ? p.conv_train[l] : p.conv_infer[l], bt, br, wm, B, w.Bp, split, st))) return rc;
             if ((rc = launch_tc_rowgemm(K_MLP_FWD, p, train ? p.mlp1_train[l] : p.mlp1[l], bt, br, wm, B, w.Bp, split, st))) return rc;
@@ -565,18 +644,19 @@ int mshgnn_backward(const mshgnn_plan* plan, int64_t B, const void* const* x, in
     if (tc) { int e = 0; std::frexp((double)(B * p.dec.n_dec), &e); G = (float)std::ldexp(1.0, e - 1); }
 
     { ProfScope ps(K_MEMSET, st); CUDA_TRY(cudaMemsetAsync(grads, 0, (size_t)p.n_params * 4, st)); }
+    if (tc && (rc = stack_sync_reset(w, ws, st))) return rc;
 
     {   // decoder backward: dH_L on the decoded slots (+ masked copy = dc_{L-1}), dW_dec, db_dec
         const int L = p.L;
         float* dh = nullptr; float* dc = nullptr; int mk = MK_NONE; const void* mbuf = nullptr;
         if (p.morph_sym) {
-            dh = (float*)bt.p[BUF_DH0 + (L & 1)];
-            if (p.dec_type != p.mlp_type) { dc = (float*)bt.p[BUF_DC0 + ((L - 1) & 1)]; mk = MK_BITS; mbuf = bt.p[BUF_MASK0 + L - 1]; }
+            dh = (float*)bt.p[BUF_DHL0 + L];
+            if (p.dec_type != p.mlp_type) { dc = (float*)bt.p[BUF_DCL0 + L - 1]; mk = MK_BITS; mbuf = bt.p[BUF_MASK0 + L - 1]; }
         } else {
-            dc = (float*)bt.p[BUF_DC0 + ((L - 1) & 1)]; mk = MK_BITS; mbuf = bt.p[BUF_MASK0 + L - 1];
+            dc = (float*)bt.p[BUF_DCL0 + L - 1]; mk = MK_BITS; mbuf = bt.p[BUF_MASK0 + L - 1];
         }
         ProfScope ps(K_DEC_BWD, st);
-        const int dhb = BUF_DH0 + (L & 1), dcb = BUF_DC0 + ((L - 1) & 1);
+        const int dhb = BUF_DHL0 + L, dcb = BUF_DCL0 + L - 1;
         const bool want_dh = p.morph_sym, want_dc = !p.morph_sym || p.dec_type != p.mlp_type;
         k_decoder_bwd<<<DEC_BLOCKS, 256, 0, st>>>(p.dec, tc ? nullptr : (const float*)bt.p[BUF_H0 + L], tc ? bh.hi[BUF_H0 + L] : nullptr,
                                                   tc ? bh.lo[BUF_H0 + L] : nullptr, params, p.d_signs, dout, tc ? nullptr : dh, tc ? nullptr : dc, mk, mbuf,
@@ -594,6 +674,13 @@ int mshgnn_backward(const mshgnn_plan* plan, int64_t B, const void* const* x, in
         LAUNCH_CHECK();
         return 0;
     };
+    if (tc && w.stack) {
+        // the whole dX chain (with the base_transform backward chained on chip) in one launch over per-layer dh / dc / du
+        // images, then the weight gradients of every layer (they only read what the chain and the forward pass stored)
+        if ((rc = launch_stack(K_STACK_BWD, p, p.stack_bwd, w, bt, br, wm, ws, B, split, st))) return rc;
+        for (int l = p.L - 1; l >= 0; --l)
+            if ((rc = launch_tc_dw(K_DW_LAYER, p, l, p.dw_layer[l], w, br, wm, B, split, part_w, part_b, st))) return rc;
+    } else
     for (int l = p.L - 1; l >= 0; --l) {
         if (tc) {
             if ((rc = launch_tc_rowgemm(K_MLP_BWD, p, p.bwd_m1[l], bt, br, wm, B, w.Bp, split, st))) return rc;
@@ -609,11 +696,8 @@ int mshgnn_backward(const mshgnn_plan* plan, int64_t B, const void* const* x, in
     }
     if (tc) {
         if (!p.enc_units.empty()) {
-            static bool attr_set = false;
-            if (!attr_set) {
-                CUDA_TRY(cudaFuncSetAttribute(k_tc_encoder_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, EDW_SMEM_BYTES));
-                attr_set = true;
-            }
+            static std::atomic<bool> attr_set[64];
+            if (first_on_device(attr_set)) CUDA_TRY(cudaFuncSetAttribute(k_tc_encoder_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, EDW_SMEM_BYTES));
             float* pe_w = (float*)(ws + w.part_enc_w);
             float* pe_b = (float*)(ws + w.part_enc_b);
             {
@@ -799,6 +883,55 @@ int mshgnn_relu_mask_offset(const mshgnn_plan* plan, int64_t B, int32_t mode, in
     *byte_off = layer < 0 ? w.maske : w.mask[layer];
     *n_slots = layer < 0 ? p.S : p.S + p.nm;
     *rows_padded = w.Bp;
+    return 0;
+}
+
+int mshgnn_check_edges(const mshgnn_plan* plan, int64_t B, const int64_t* const* edge_index, int32_t* flag, void* stream) {
+    if (!plan || !edge_index || !flag || B < 1) return fail(MSHGNN_ERR_ARG, "bad argument");
+    const Plan& p = plan->p;
+    int rc;
+    if ((rc = ensure_uploaded(p))) return rc;
+    EdgeCheck ec;
+    memset(&ec, 0, sizeof ec);
+    ec.n_etypes = p.n_etypes;
+    int off = 0;
+    int64_t most = 0;
+    for (int e = 0; e < p.n_etypes; ++e) {
+        ec.E[e] = (int)p.e_src[e].size();
+        ec.n_src[e] = p.nodes[p.e_src_t[e]]; ec.n_dst[e] = p.nodes[p.e_dst_t[e]];
+        ec.tpl_off[e] = off; off += 2 * ec.E[e];
+        if (ec.E[e] > 0 && !edge_index[e]) return fail(MSHGNN_ERR_ARG, "edge_index[%d] is NULL", e);
+        ec.ei[e] = (const long long*)edge_index[e];
+        most = std::max<int64_t>(most, (int64_t)ec.E[e] * B);
+    }
+    if (most == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned blocks = (unsigned)std::min<int64_t>((most + 1023) / 1024, 148 * 4);
+    ProfScope ps(K_EDGES, st);
+    k_check_edges<<<dim3(blocks, (unsigned)p.n_etypes), 256, 0, st>>>(ec, p.d_edge_tpl, (long long)B, flag);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+int mshgnn_set_option(const char* name, int32_t value) {
+    if (!name) return fail(MSHGNN_ERR_ARG, "option name is NULL");
+    if (!strcmp(name, "stack")) { set_stack_enabled(value); return 0; }
+    return fail(MSHGNN_ERR_ARG, "unknown option '%s'", name);
+}
+
+int32_t mshgnn_get_option(const char* name) {
+    if (name && !strcmp(name, "stack")) return stack_enabled() ? 1 : 0;
+    return -1;
+}
+
+int mshgnn_stack_status(const mshgnn_plan* plan, int64_t B, int32_t train, int32_t mode, const void* workspace, int32_t* status_out) {
+    if (!plan || !workspace || !status_out || B < 1) return fail(MSHGNN_ERR_ARG, "bad argument");
+    const WsLayout w = ws_layout(plan->p, B, train, mode);
+    *status_out = 0;
+    if (!w.stack) return 0;
+    uint32_t word = 0;      // last word of the counter region: set by a stack launch whose dependency wait timed out
+    CUDA_TRY(cudaMemcpy(&word, (const char*)workspace + w.stack_sync + w.stack_sync_bytes - 4, 4, cudaMemcpyDeviceToHost));
+    *status_out = word ? 1 : 0;
     return 0;
 }
 

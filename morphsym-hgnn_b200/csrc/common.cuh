@@ -16,7 +16,7 @@ namespace mshgnn {
 
 constexpr int H = 128;
 constexpr int MAX_CHUNKS = 8;
-constexpr int MAX_BUFS = 64;
+constexpr int MAX_BUFS = 128;
 constexpr int TILE_M = 128;
 constexpr int DEC_MAXC = 8;     // max decoder width
 constexpr float LO_SCALE = 1.f; // scale of the low half of a (hi, lo) fp16 pair: lo = fp16((v - hi) * LO_SCALE)
@@ -61,7 +61,27 @@ struct Tile {
     int out2_buf, out2_slot;          // secondary output = result (*) mask (-1: none)
     int out2_mask_kind, out2_mask_buf, out2_mask_slot;
     int mask_out_slot;
+    // chained steps of the cross-layer stack kernel (kernels_stack.cuh); zero in every per-layer launch table
+    int a_stage;                      // chunk 0 reads its A operand from the staging tiles the previous step of the item left on chip
+    int stage_out;                    // the epilogue leaves the (hi, lo) result in the staging tiles for the next step of the item
+    int pad_;
     Chunk chunks[MAX_CHUNKS];
+};
+
+// ---- cross-layer stack program (kernels_stack.cuh) ----
+// A program is a sequence of phases (one per layer); phase p of row tile r may start once every item of phase p - 1 of
+// the same row tile has signalled.  An item is 1..3 chained steps (Tile entries, contiguous in the tile table) on one
+// 128-row tile; the steps after the first take their A operand from on-chip staging.
+constexpr int STACK_MAX_PHASES = 20;
+struct StackItem {
+    int tile;                         // first step (index relative to the program's first tile)
+    int n_steps;                      // 1..3
+};
+struct StackProg {
+    int n_phases;
+    int items_per_row;                // sum of n_items over the phases
+    int first_item[STACK_MAX_PHASES]; // index into the item table
+    int n_items[STACK_MAX_PHASES];
 };
 
 // One (dC, A) pair of a reduce-over-rows GEMM: dW[128, K] += dC[rows,128]^T * A[rows,K]

@@ -11,6 +11,7 @@
 //                hgnn_k4_com.py:L157-165) and its backward.
 //  k_loss_*    : MSE / per-row 2-way CE heads (gnnLightning.py:L124-139, customMetrics.py:L6-25).
 #pragma once
+#include "../../include/mshgnn_b200.h"
 #include "common.cuh"
 
 namespace mshgnn {
@@ -655,6 +656,39 @@ k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m
 __global__ void __launch_bounds__(256)
 k_sgd(float* __restrict__ p, const float* __restrict__ g, const int64_t n, const float lr) {
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) p[i] -= lr * g[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// edge_index validation (SURVEY 3.4 batching layout; modules.py "validate_edges")
+// ------------------------------------------------------------------------------------------
+//  The kernels never read edge_index: the morphology template is compiled into the plan.  What has to hold is that the
+//  caller's edge_index_dict IS that template tiled over the batch, bit-exactly (PyG Batch.from_data_list: graph g's edges
+//  are the template's plus g * nodes_per_graph).  One launch checks every edge type; a mismatch raises `flag` (pinned host
+//  memory or device memory), which the host reads without synchronising.
+struct EdgeCheck {
+    int n_etypes;
+    int E[MSHGNN_MAX_EDGE_TYPES];              // edges per graph
+    int n_src[MSHGNN_MAX_EDGE_TYPES], n_dst[MSHGNN_MAX_EDGE_TYPES];
+    int tpl_off[MSHGNN_MAX_EDGE_TYPES];        // offset of [src E | dst E] in the template table
+    const long long* ei[MSHGNN_MAX_EDGE_TYPES];   // [2][E * B] int64, row-major
+};
+__global__ void __launch_bounds__(256)
+k_check_edges(const EdgeCheck ec, const int* __restrict__ tpl, const long long B, int* __restrict__ flag) {
+    const int e = blockIdx.y;
+    const int E = ec.E[e];
+    const long long n = (long long)E * B;
+    const long long* src = ec.ei[e];
+    const long long* dst = src + n;
+    const int* ts = tpl + ec.tpl_off[e];
+    const int* td = ts + E;
+    bool bad = false;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        const long long g = i / E;
+        const int j = (int)(i - g * E);
+        bad |= __ldg(src + i) != (long long)ts[j] + g * ec.n_src[e];
+        bad |= __ldg(dst + i) != (long long)td[j] + g * ec.n_dst[e];
+    }
+    if (bad) *reinterpret_cast<volatile int*>(flag) = 1 + e;
 }
 
 }  // namespace mshgnn

@@ -1013,7 +1013,7 @@ k_tc_rowgemm_pair(const __grid_constant__ TcMaps maps, const Tile* __restrict__ 
 //  Accumulators (TMEM columns): D0 [0,128) hi*hi, D1 [128,256) cross terms (x 2^11), D2 [256,272) colsum hi,
 //  D3 [288,304) colsum lo (x 2^11).  One CTA = one task (<= 4 pairs) x one row split; fp32 partials go to part_w /
 //  part_b and are summed in double by k_reduce_partials (deterministic, no atomics).
-constexpr int BUF_DC1_ID = 11;     // plan.cuh BUF_DC1: dpre of the encoder lives there after the layer-0 dX launch
+constexpr int BUF_DC1_ID = 80;     // plan.cuh BUF_DCL0 - 1: dpre of the encoder (dc_{-1}), written by the layer-0 dX tiles
 
 constexpr int DW_STAGES = 3;
 constexpr int DW_KB = 64;                              // graph rows (MMA K) per pipeline stage

@@ -7,6 +7,7 @@
 // so last-layer branches into the others are dead), and the transposed pattern
 // for the backward pass.
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
@@ -67,6 +68,116 @@ static bool emit_units(Plan& p, const std::vector<RPair>& prs, int K, int k0, in
         p.rtasks.push_back(T);
     }
     return true;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Cross-layer stack programs (kernels_stack.cuh), derived from the per-layer tables built above: the same tiles, copied
+// into one contiguous range per program, with the base_transform steps chained behind the tile that produces their input
+// (forward: conv(l) of an MLP-type node -> Linear -> ReLU -> Linear + residual, hgnn_k4.py:L133-137,175-186; backward:
+// dX(l) of an MLP-type node -> dpre(l-1) -> dc(l-1)), so the intermediate tiles never leave the SM in inference and are
+// read back from shared memory, not from HBM, in training.
+// ------------------------------------------------------------------------------------------------------------------
+static std::string build_stack_programs(Plan& p) {
+    auto begin_prog = [&](Plan::Stack& st) { st.tiles.begin = (int)p.tiles.size(); st.item0 = (int)p.stack_items.size(); st.prog = StackProg{}; };
+    auto begin_phase = [&](Plan::Stack& st) -> std::string {
+        if (st.prog.n_phases >= STACK_MAX_PHASES) return "too many layers for the cross-layer stack kernel";
+        st.prog.first_item[st.prog.n_phases] = (int)p.stack_items.size() - st.item0;
+        st.prog.n_items[st.prog.n_phases] = 0;
+        return "";
+    };
+    auto end_phase = [&](Plan::Stack& st) {
+        if (st.prog.n_items[st.prog.n_phases] > 0) { st.prog.items_per_row += st.prog.n_items[st.prog.n_phases]; st.prog.n_phases++; }
+    };
+    auto emit = [&](Plan::Stack& st, const std::vector<Tile>& steps) {
+        StackItem it{(int)p.tiles.size() - st.tiles.begin, (int)steps.size()};
+        p.tiles.insert(p.tiles.end(), steps.begin(), steps.end());
+        p.stack_items.push_back(it);
+        st.prog.n_items[st.prog.n_phases]++;
+    };
+    auto end_prog = [&](Plan::Stack& st) { st.tiles.count = (int)p.tiles.size() - st.tiles.begin; };
+    auto find_by_a = [&](const Launch& L, int a_buf, int a_slot) -> int {
+        for (int i = 0; i < L.count; ++i) {
+            const Tile& T = p.tiles[L.begin + i];
+            if (T.n_chunks == 1 && T.chunks[0].a_buf == a_buf && T.chunks[0].a_slot == a_slot) return L.begin + i;
+        }
+        return -1;
+    };
+
+    // ---- forward (inference / training) ----
+    for (int train = 0; train < 2; ++train) {
+        Plan::Stack& st = train ? p.stack_train : p.stack_infer;
+        begin_prog(st);
+        for (int l = 0; l < p.L; ++l) {
+            std::string e = begin_phase(st);
+            if (!e.empty()) return e;
+            const Launch& conv = train ? p.conv_train[l] : p.conv_infer[l];
+            const Launch& m1 = train ? p.mlp1_train[l] : p.mlp1[l];
+            for (int i = 0; i < conv.count; ++i) {
+                Tile T = p.tiles[conv.begin + i];
+                if (p.morph_sym && T.out_buf == BUF_CT0 + l) {
+                    const int n = T.out_slot;
+                    const int ia = find_by_a(m1, BUF_CT0 + l, n), ib = find_by_a(p.mlp2[l], BUF_CT0 + l, p.nm + n);
+                    if (ia < 0 || ib < 0) return "internal: base_transform tiles missing for a conv tile";
+                    Tile A = p.tiles[ia], Bt = p.tiles[ib];
+                    T.stage_out = 1; A.a_stage = 1; A.stage_out = 1; Bt.a_stage = 1;
+                    if (!train) { T.out_buf = -1; A.out_buf = -1; }     // the intermediates only exist on chip
+                    emit(st, {T, A, Bt});
+                } else {
+                    emit(st, {T});
+                }
+            }
+            end_phase(st);
+        }
+        end_prog(st);
+    }
+    // ---- backward dX chain ----
+    {
+        Plan::Stack& st = p.stack_bwd;
+        begin_prog(st);
+        if (p.morph_sym && p.bwd_m1[p.L - 1].count > 0) {       // the decoder reads the MLP type (COM models): dh_L -> dpre -> dc_{L-1}
+            std::string e = begin_phase(st);
+            if (!e.empty()) return e;
+            const Launch& m1 = p.bwd_m1[p.L - 1];
+            for (int i = 0; i < m1.count; ++i) {
+                Tile A = p.tiles[m1.begin + i];
+                const int ib = find_by_a(p.bwd_m2[p.L - 1], BUF_DUL0 + p.L - 1, A.out_slot);
+                if (ib < 0) return "internal: base_transform backward tiles do not pair up";
+                Tile Bt = p.tiles[ib];
+                A.stage_out = 1; Bt.a_stage = 1;
+                emit(st, {A, Bt});
+            }
+            end_phase(st);
+        }
+        for (int l = p.L - 1; l >= 0; --l) {
+            std::string e = begin_phase(st);
+            if (!e.empty()) return e;
+            const Launch& dx = p.bwd_dx[l];
+            for (int i = 0; i < dx.count; ++i) {
+                Tile T = p.tiles[dx.begin + i];
+                int ia = -1;
+                if (p.morph_sym && l >= 1 && T.out_buf == BUF_DHL0 + l && T.out2_buf < 0) ia = find_by_a(p.bwd_m1[l - 1], BUF_DHL0 + l, T.out_slot);
+                if (ia >= 0) {
+                    Tile A = p.tiles[ia];
+                    const int ib = find_by_a(p.bwd_m2[l - 1], BUF_DUL0 + l - 1, A.out_slot);
+                    if (ib < 0) return "internal: base_transform backward tiles do not pair up";
+                    Tile Bt = p.tiles[ib];
+                    T.stage_out = 1; A.a_stage = 1; A.stage_out = 1; Bt.a_stage = 1;
+                    emit(st, {T, A, Bt});
+                } else {
+                    emit(st, {T});
+                }
+            }
+            end_phase(st);
+        }
+        end_prog(st);
+        // every base_transform backward tile must have been chained somewhere
+        int chained = 0, want = 0;
+        for (int i = 0; i < st.tiles.count; ++i) chained += p.tiles[st.tiles.begin + i].a_stage;
+        for (int l = 0; l < p.L; ++l) want += p.bwd_m1[l].count + p.bwd_m2[l].count;
+        const int heads = (p.morph_sym && p.bwd_m1[p.L - 1].count > 0) ? p.bwd_m1[p.L - 1].count : 0;     // pre-phase m1 tiles read global memory
+        if (chained != want - heads) return "internal: base_transform backward tiles left out of the stack program";
+    }
+    return "";
 }
 
 std::string build_plan(const mshgnn_desc* d, Plan& p) {
@@ -293,8 +404,10 @@ std::string build_plan(const mshgnn_desc* d, Plan& p) {
     p.bwd_m1.resize(p.L); p.bwd_m2.resize(p.L); p.bwd_dx.resize(p.L); p.dw_layer.resize(p.L);
     std::vector<int> mlp_tasks[2];
     for (int l = p.L - 1; l >= 0; --l) {
-        const int DHn = BUF_DH0 + ((l + 1) & 1), DHo = BUF_DH0 + (l & 1);
-        const int DCc = BUF_DC0 + (l & 1), DCp = BUF_DC0 + ((l + 1) & 1);   // dc_l lives in DCc, dc_{l-1} goes to DCp
+        // per-layer buffer ids (plan.cuh): the per-layer launch sequence aliases them onto ping-pong buffers
+        const int DHn = BUF_DHL0 + l + 1, DHo = BUF_DHL0 + l;
+        const int DCc = BUF_DCL0 + l, DCp = BUF_DCL0 + l - 1;   // dc_l lives in DCc, dc_{l-1} goes to DCp
+        const int DUc = BUF_DUL0 + l;
         std::vector<Tile> b1, b2, dx;
         if (p.morph_sym)
             for (int n = 0; n < p.nm; ++n) {
@@ -303,10 +416,10 @@ std::string build_plan(const mshgnn_desc* d, Plan& p) {
                 Tile A = empty_tile();   // dpre = (du * W2) (*) (t > 0)
                 A.chunks[A.n_chunks++] = slab_chunk(DHn, s, BUF_PARAMS, p.off_mlp_w[1], mat16(p, {p.off_mlp_w[1]}, true));
                 A.posmask_buf = BUF_MASK0 + l; A.posmask_slot = p.S + n;
-                A.out_buf = BUF_DU; A.out_slot = n;
+                A.out_buf = DUc; A.out_slot = n;
                 b1.push_back(A);
                 Tile Bt = empty_tile();  // dc_base = dpre * W1
-                Bt.chunks[Bt.n_chunks++] = slab_chunk(BUF_DU, n, BUF_PARAMS, p.off_mlp_w[0], mat16(p, {p.off_mlp_w[0]}, true));
+                Bt.chunks[Bt.n_chunks++] = slab_chunk(DUc, n, BUF_PARAMS, p.off_mlp_w[0], mat16(p, {p.off_mlp_w[0]}, true));
                 Bt.out_buf = DCc; Bt.out_slot = s;
                 b2.push_back(Bt);
             }
@@ -376,7 +489,7 @@ std::string build_plan(const mshgnn_desc* d, Plan& p) {
             for (int n = 0; n < p.nm; ++n) {
                 const int s = p.slot_of(p.mlp_type, n);
                 if (!p.need[l + 1][s]) continue;
-                p1.push_back(slab_pair(BUF_DU, n, BUF_CT0 + l, n));
+                p1.push_back(slab_pair(DUc, n, BUF_CT0 + l, n));
                 p2.push_back(slab_pair(DHn, s, BUF_CT0 + l, p.nm + n));
             }
             if (!p1.empty()) {
@@ -409,7 +522,7 @@ std::string build_plan(const mshgnn_desc* d, Plan& p) {
         for (int n = 0; n < p.nodes[t]; ++n) {
             const int s = p.slot_of(t, n);
             if (!p.need[0][s]) continue;
-            RPair r{}; r.d_buf = BUF_DC1; r.d_slot = s; r.a_kind = A_EXT; r.a_buf = BUF_X0 + t; r.a_slot = 0;
+            RPair r{}; r.d_buf = BUF_DCL0 - 1; r.d_slot = s; r.a_kind = A_EXT; r.a_buf = BUF_X0 + t; r.a_slot = 0;
             r.lda = p.nodes[t] * p.in_w[t]; r.a_off = n * p.in_w[t]; r.sign_off = p.sign_off_slot[s];
             prs.push_back(r);
         }
@@ -449,12 +562,26 @@ std::string build_plan(const mshgnn_desc* d, Plan& p) {
             p.enc_groups.push_back(g);
         }
     }
+    { std::string e = build_stack_programs(p); if (!e.empty()) return e; }
     return "";
 }
+
+static std::atomic<int> g_stack_on{-1};
+bool stack_enabled() {
+    int v = g_stack_on.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char* e = getenv("MSHGNN_STACK");
+        v = !(e && !strcmp(e, "0"));
+        g_stack_on.store(v, std::memory_order_relaxed);
+    }
+    return v != 0;
+}
+void set_stack_enabled(int on) { g_stack_on.store(on ? 1 : 0, std::memory_order_relaxed); }
 
 WsLayout ws_layout(const Plan& p, int64_t B, int train, int mode) {
     const bool tc = mode != MSHGNN_MODE_FP32;
     WsLayout w{};
+    w.stack = tc && stack_enabled() && p.stack_infer.prog.n_phases > 0;
     w.Bp = round_up(B < 1 ? 1 : B, TILE_M);
     int ns = (int)((B + 511) / 512);
     w.n_splits = ns < 1 ? 1 : (ns > 64 ? 64 : ns);
@@ -551,14 +678,26 @@ WsLayout ws_layout(const Plan& p, int64_t B, int train, int mode) {
     for (int l = 0; l <= MAX_LAYERS; ++l) w.h16[l][0] = w.h16[l][1] = -1;
     for (int l = 0; l < MAX_LAYERS; ++l) w.ct16[l][0] = w.ct16[l][1] = -1;
     for (int i = 0; i < 2; ++i) { w.dh16[i][0] = w.dh16[i][1] = w.dc16[i][0] = w.dc16[i][1] = -1; w.du16[i] = -1; w.w16[i] = -1; }
+    for (int l = 0; l <= MAX_LAYERS; ++l) for (int i = 0; i < 2; ++i) { w.dhL16[l][i] = -1; w.dcL16[l][i] = -1; }
+    for (int l = 0; l < MAX_LAYERS; ++l) for (int i = 0; i < 2; ++i) w.duL16[l][i] = -1;
     if (tc) {
         for (int i = 0; i < 2; ++i) w.w16[i] = take((int64_t)p.n_mats16 * H * H * 2);
         if (train) {
             for (int l = 0; l <= p.L; ++l) for (int i = 0; i < 2; ++i) w.h16[l][i] = take(slab / 2);
             if (p.morph_sym)
                 for (int l = 0; l < p.L; ++l) for (int i = 0; i < 2; ++i) w.ct16[l][i] = take(ctb / 2);
-            for (int b = 0; b < 2; ++b) for (int i = 0; i < 2; ++i) { w.dh16[b][i] = take(slab / 2); w.dc16[b][i] = take(slab / 2); }
-            if (p.morph_sym) for (int i = 0; i < 2; ++i) w.du16[i] = take((int64_t)p.nm * w.Bp * H * 2);
+            if (!w.stack) {
+                for (int b = 0; b < 2; ++b) for (int i = 0; i < 2; ++i) { w.dh16[b][i] = take(slab / 2); w.dc16[b][i] = take(slab / 2); }
+                if (p.morph_sym) for (int i = 0; i < 2; ++i) w.du16[i] = take((int64_t)p.nm * w.Bp * H * 2);
+            } else {
+                // the dX chain of all layers runs in ONE launch ahead of the weight-gradient kernels: every layer keeps its own
+                // dh / dc / du images (dh_l only where a residual or base_transform reads it: MS-HGNN models)
+                for (int l = 0; l <= p.L; ++l) for (int i = 0; i < 2; ++i) {
+                    if (p.morph_sym && l >= 1) w.dhL16[l][i] = take(slab / 2);
+                    w.dcL16[l][i] = take(slab / 2);                       // index l + 1: dc_{-1} (encoder dpre) .. dc_{L-1}
+                }
+                if (p.morph_sym) for (int l = 0; l < p.L; ++l) for (int i = 0; i < 2; ++i) w.duL16[l][i] = take((int64_t)p.nm * w.Bp * H * 2);
+            }
         } else {
             int64_t a[2], b[2], c[2] = {-1, -1};
             for (int i = 0; i < 2; ++i) { a[i] = take(slab / 2); b[i] = take(slab / 2); }
@@ -575,6 +714,10 @@ WsLayout ws_layout(const Plan& p, int64_t B, int train, int mode) {
             w.part_enc_w = take((int64_t)p.enc_units.size() * w.n_splits_enc * H * 192 * 4);
             w.part_enc_b = take((int64_t)p.enc_units.size() * w.n_splits_enc * H * 4);
         }
+    }
+    if (w.stack) {
+        w.stack_sync_bytes = ((int64_t)STACK_MAX_PHASES * (w.Bp / TILE_M) + 64) * 4;
+        w.stack_sync = take(w.stack_sync_bytes);
     }
     w.loss_part = take(LOSS_BLOCKS * 8);
     w.total = o;

@@ -14,14 +14,20 @@ namespace mshgnn {
 enum : int {
     BUF_PARAMS = 0, BUF_DERIVED = 1, BUF_SIGNS = 2, BUF_GRADS = 3,
     BUF_X0 = 4,                       // +type
-    BUF_DH0 = 8, BUF_DH1 = 9, BUF_DC0 = 10, BUF_DC1 = 11, BUF_DU = 12,
     BUF_MASKE = 13,                   // ReLU bitmask of the encoder output
 
     BUF_H0 = 16,                      // +layer (0..L)
     BUF_CT0 = 32,                     // +layer
-    BUF_MASK0 = 48                    // +layer: ReLU bitmasks, slots [0,S) conv outputs, [S,S+nm) base-MLP hidden
+    BUF_MASK0 = 48,                   // +layer: ReLU bitmasks, slots [0,S) conv outputs, [S,S+nm) base-MLP hidden
+    // backward quantities, one id per layer.  The per-layer launch sequence aliases them onto two ping-pong buffers
+    // (dh_l -> dh[l & 1], dc_l -> dc[l & 1], du_l -> du); the cross-layer stack kernel runs the whole dX chain in one
+    // launch, before the weight-gradient kernels, so there every layer keeps its own buffer.
+    BUF_DHL0 = 64,                    // +l (0..L):  dL/dh_l
+    BUF_DCL0 = 81,                    // +l (-1..L-1, i.e. BUF_DCL0 - 1 = dpre of the encoder): dL/dc_l (pre-activation gradients)
+    BUF_DUL0 = 96                     // +l (0..L-1): gradient at the hidden ReLU of base_transform
 };
 constexpr int MAX_LAYERS = 15;
+static_assert(BUF_DCL0 - 1 == 80, "kernels_tc.cuh BUF_DC1_ID names the encoder dpre buffer by number");
 
 struct Launch { int begin = 0, count = 0; };
 
@@ -69,6 +75,10 @@ struct Plan {
     Launch enc_launch, enc_train;
     std::vector<Launch> conv_train, conv_infer, mlp1, mlp1_train, mlp2;      // per layer
     std::vector<Launch> bwd_m1, bwd_m2, bwd_dx;                  // per layer
+    // cross-layer stack programs (kernels_stack.cuh): tiles [tiles.begin, +count) of `tiles`, items in stack_items
+    struct Stack { Launch tiles; int item0 = 0; StackProg prog{}; };
+    Stack stack_infer, stack_train, stack_bwd;
+    std::vector<StackItem> stack_items;
     std::vector<RTask> rtasks;
     std::vector<RPair> rpairs;
     std::vector<Launch> dw_layer;                                // per layer (task ranges)
@@ -86,6 +96,8 @@ struct Plan {
     mutable bool uploaded = false;
     mutable int device = -1;
     mutable Tile* d_tiles = nullptr;
+    mutable StackItem* d_stack_items = nullptr;
+    mutable int* d_edge_tpl = nullptr;   // per edge type [src E | dst E] local node indices (k_check_edges)
     mutable RTask* d_rtasks = nullptr;
     mutable RPair* d_rpairs = nullptr;
     mutable OutGroup* d_groups = nullptr;
@@ -118,6 +130,11 @@ struct WsLayout {
     int64_t wenc16[2] = {-1, -1};                      // encoder weight images [n_types*128][enc_kmax] fp16 (hi, lo)
     // tensor-core modes: (hi, lo) fp16 images; index [0] = hi, [1] = lo; -1 when absent
     int64_t h16[MAX_LAYERS + 1][2], ct16[MAX_LAYERS][2], dh16[2][2], dc16[2][2], du16[2], w16[2];
+    // stack mode (training, tensor-core modes): per-layer backward images, -1 when the ping-pong layout is used
+    int stack = 0;
+    int64_t dhL16[MAX_LAYERS + 1][2], dcL16[MAX_LAYERS + 1][2] /* index l + 1 */, duL16[MAX_LAYERS][2];
+    int64_t stack_sync = -1;           // dependency counters of the stack kernel (uint32 [phases][row tiles]) + error word
+    int64_t stack_sync_bytes = 0;
     int64_t total = 0;
 };
 
@@ -126,6 +143,8 @@ constexpr int LOSS_BLOCKS = 592;
 
 std::string build_plan(const mshgnn_desc* d, Plan& p);            // returns error text ("" = ok)
 WsLayout ws_layout(const Plan& p, int64_t B, int train, int mode);
+bool stack_enabled();                 // cross-layer stack kernel on (default) / off (MSHGNN_STACK=0 or mshgnn_set_option)
+void set_stack_enabled(int on);
 std::string describe_plan(const Plan& p);
 
 }  // namespace mshgnn

@@ -29,6 +29,7 @@ EXPORTS = (
     "mshgnn_adam_step", "mshgnn_sgd_step", "mshgnn_plan_describe", "mshgnn_launch_count",
     "mshgnn_last_error", "mshgnn_version", "mshgnn_profile_enable", "mshgnn_profile_read", "mshgnn_kernel_kind_name",
     "mshgnn_relu_mask_offset", "mshgnn_build_windows", "mshgnn_step_metrics", "mshgnn_dw_layout",
+    "mshgnn_check_edges", "mshgnn_set_option", "mshgnn_get_option", "mshgnn_stack_status",
 )
 
 
@@ -113,6 +114,10 @@ def lib() -> C.CDLL:
     L.mshgnn_build_windows.argtypes = [C.POINTER(WindowDesc), vp, vp, i32, i64, vp, i64, C.POINTER(vp), vp, vp]
     L.mshgnn_build_windows.restype = C.c_int
     L.mshgnn_step_metrics.argtypes = [i32, i64, i32, vp, vp, i32, vp, vp, vp, vp]; L.mshgnn_step_metrics.restype = C.c_int
+    L.mshgnn_check_edges.argtypes = [vp, i64, C.POINTER(vp), vp, vp]; L.mshgnn_check_edges.restype = C.c_int
+    L.mshgnn_set_option.argtypes = [C.c_char_p, i32]; L.mshgnn_set_option.restype = C.c_int
+    L.mshgnn_get_option.argtypes = [C.c_char_p]; L.mshgnn_get_option.restype = i32
+    L.mshgnn_stack_status.argtypes = [vp, i64, i32, i32, vp, C.POINTER(i32)]; L.mshgnn_stack_status.restype = C.c_int
     _lib = L
     return L
 
@@ -122,7 +127,7 @@ def check(rc: int, what: str) -> None:
         raise RuntimeError(f"{what} failed (code {rc}): {lib().mshgnn_last_error().decode()}")
 
 
-NUM_KERNEL_KINDS = 16
+NUM_KERNEL_KINDS = 19
 
 
 def profile_enable(on: bool) -> None:
@@ -144,6 +149,15 @@ def profile_read() -> dict:
 
 def launch_count() -> int:
     return int(lib().mshgnn_launch_count())
+
+
+def set_option(name: str, value: int) -> None:
+    """Library switches: 'stack' (1 = cross-layer persistent kernel for the layer loop, 0 = one launch per layer)."""
+    check(lib().mshgnn_set_option(name.encode(), int(value)), "mshgnn_set_option")
+
+
+def get_option(name: str) -> int:
+    return int(lib().mshgnn_get_option(name.encode()))
 
 
 class NativePlan:
@@ -225,6 +239,17 @@ class NativePlan:
         buf = C.create_string_buffer(n)
         lib().mshgnn_plan_describe(self.handle, buf, n)
         return json.loads(buf.value.decode())
+
+    def check_edges(self, B, ei_ptrs: Sequence[int], flag_ptr, stream):
+        """One launch: raises *flag when an edge_index is not the plan's template tiled over B graphs (no host sync)."""
+        arr = (C.c_void_p * len(ei_ptrs))(*ei_ptrs)
+        check(lib().mshgnn_check_edges(self.handle, B, arr, flag_ptr, stream), "mshgnn_check_edges")
+
+    def stack_status(self, B, train, mode, ws_ptr) -> int:
+        """1 when a dependency wait of the last cross-layer launch on this workspace timed out (synchronises)."""
+        out = C.c_int32()
+        check(lib().mshgnn_stack_status(self.handle, B, int(train), mode, ws_ptr, C.byref(out)), "mshgnn_stack_status")
+        return out.value
 
     # ---- compute (raw device pointers) ----
     def forward(self, B, x_ptrs: Sequence[int], x_dtype, params_ptr, out_ptr, ws_ptr, ws_bytes, train, mode, stream):

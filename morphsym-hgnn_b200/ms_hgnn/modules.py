@@ -159,8 +159,9 @@ class NativeHGNN(nn.Module):
         self._flat: Optional[torch.Tensor] = None
         self._views: List[Tuple[int, int, Tuple[int, ...]]] = []
         self._flat_params: List[nn.Parameter] = []
-        self._edge_ok: Dict[tuple, bool] = {}
-        self._expected_edges: Dict[tuple, torch.Tensor] = {}
+        self._edge_ok: Dict[tuple, tuple] = {}
+        self._edge_first: set = set()
+        self._edge_flag: Optional[torch.Tensor] = None
         self._fwd_token = None
 
     _MODES = {"fp32": N.MODE_FP32, "tc": N.MODE_TC, "tc1x": N.MODE_TC_1X}
@@ -183,7 +184,8 @@ class NativeHGNN(nn.Module):
         d["_views"] = []
         d["_flat_params"] = []
         d["_edge_ok"] = {}
-        d["_expected_edges"] = {}
+        d["_edge_first"] = set()
+        d["_edge_flag"] = None
         d["_fwd_token"] = None
         d.pop("_last_engine", None)
         return d
@@ -304,39 +306,71 @@ class NativeHGNN(nn.Module):
             edges[et] = (src, dst)
         return edges
 
+    def _raise_deferred_edge_error(self) -> None:
+        """The native edge check raises a flag in pinned host memory; it is read here without synchronising, so a
+        mismatch in step n is reported at the latest by the forward call of step n + 1 (or by assert_edges_valid())."""
+        flag = self._edge_flag
+        if flag is not None and int(flag[0]) != 0:
+            code = int(flag[0])
+            flag.zero_()
+            raise ValueError(f"edge_index of edge type #{code - 1} in an EARLIER batch was not the morphology template tiled over "
+                             "the batch (graph-major PyG batch layout); the results of that step are invalid.  The B200-native "
+                             "path only runs fixed-template batches and has no fallback")
+
+    def assert_edges_valid(self) -> None:
+        """Synchronises and raises if any batch validated so far failed the native edge_index check."""
+        if self._edge_flag is not None:
+            torch.cuda.synchronize()
+            self._raise_deferred_edge_error()
+
     def _edges_match(self, edge_index_dict, B: int, eng: Engine, device) -> bool:
-        """True iff every edge_index equals the engine's template tiled B times (bit-exact)."""
+        """True iff every edge_index equals the engine's template tiled B times (bit-exact).
+
+        Shapes / dtypes are checked on the host; the values by ONE native kernel launch (mshgnn_check_edges) that raises a
+        flag in pinned host memory.  The first batch of every (template, B, device) is checked synchronously - a wrong
+        template fails right here - later batches without a host sync ('always': every call; 'cached': only tensor objects
+        not seen before); a late mismatch raises at the next forward."""
         if self.validate_edges == "never":
             return True
+        eis = []
         for et in self.edge_types:
             if et not in edge_index_dict:
                 raise KeyError(f"edge_index_dict is missing edge type {et}")
             ei = edge_index_dict[et]
-            key = (id(eng), et, B, ei.data_ptr(), ei._version, tuple(ei.shape))
-            if self.validate_edges == "cached" and self._edge_ok.get(key):
-                continue
             if ei.device != device:
                 raise ValueError("edge_index tensors must live on the same device as the node features")
-            ek = (id(eng), et, B, str(device))
-            exp = self._expected_edges.get(ek)
-            if exp is None:
-                src, dst = eng._edges[et]
-                t = torch.tensor([src, dst], dtype=torch.long, device=device)
-                E = t.shape[1]
-                g = torch.arange(B, dtype=torch.long, device=device).repeat_interleave(E)
-                t = t.repeat(1, B)
-                exp = torch.stack((t[0] + g * eng._npg[et[0]], t[1] + g * eng._npg[et[2]]))
-                if len(self._expected_edges) > 64:
-                    self._expected_edges.clear()
-                self._expected_edges[ek] = exp
-            if tuple(ei.shape) != tuple(exp.shape) or not torch.equal(ei.to(torch.long), exp):
+            E = len(eng._edges[et][0])
+            if ei.dim() != 2 or tuple(ei.shape) != (2, E * B):
                 return False
-            if len(self._edge_ok) > 256:
+            eis.append(ei)
+        if self.validate_edges == "cached":
+            key = (id(eng), B, tuple((id(e), e._version) for e in eis))
+            hit = self._edge_ok.get(key)
+            if hit is not None and all(a is b for a, b in zip(hit, eis)):      # the cache holds the tensors: ids cannot be reused
+                return True
+        if self._edge_flag is None:
+            self._edge_flag = torch.zeros(1, dtype=torch.int32).pin_memory()
+        eis_c = [e if (e.dtype == torch.long and e.is_contiguous()) else e.to(torch.long).contiguous() for e in eis]
+        stream = torch.cuda.current_stream(device).cuda_stream
+        with torch.cuda.device(device):
+            eng.plan.check_edges(B, [e.data_ptr() for e in eis_c], self._edge_flag.data_ptr(), stream)
+        first = (id(eng), B, str(device))
+        if first not in self._edge_first:
+            torch.cuda.current_stream(device).synchronize()
+            if int(self._edge_flag[0]) != 0:
+                self._edge_flag.zero_()
+                return False
+            if len(self._edge_first) > 256:
+                self._edge_first.clear()
+            self._edge_first.add(first)
+        if self.validate_edges == "cached":
+            if len(self._edge_ok) > 64:
                 self._edge_ok.clear()
-            self._edge_ok[key] = True
+            self._edge_ok[key] = tuple(eis)
         return True
 
     def _engine_for(self, x_dict, edge_index_dict) -> Tuple[Engine, int]:
+        self._raise_deferred_edge_error()
         B, npg = self._nodes_per_graph(x_dict)
         in_dims = {t: int(x_dict[t].shape[1]) for t in self.node_types}
         device = x_dict[self.node_types[0]].device
