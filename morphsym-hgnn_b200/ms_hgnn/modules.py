@@ -128,7 +128,10 @@ class NativeHGNN(nn.Module):
     mean_relations: Tuple[str, ...] = ()
     fixed_nodes_per_graph: Optional[Dict[str, int]] = None
     mode = N.MODE_FP32
-    validate_edges = "always"    # "always" | "cached" (re-validate only new tensor objects) | "never"
+    # edge_index validation (one native launch, mshgnn_check_edges): "always" = every call, mismatch reported without a host
+    # sync (raises at the latest at the next forward / assert_edges_valid()); "sync" = every call, raises immediately (one
+    # stream synchronisation per forward); "cached" = only tensor objects not seen before; "never"
+    validate_edges = "always"
 
     def __init__(self, hidden_channels: int, num_layers: int, data_metadata, out_channels: int,
                  activation_fn=None, in_dims: Optional[Dict[str, int]] = None,
@@ -355,7 +358,7 @@ class NativeHGNN(nn.Module):
         with torch.cuda.device(device):
             eng.plan.check_edges(B, [e.data_ptr() for e in eis_c], self._edge_flag.data_ptr(), stream)
         first = (id(eng), B, str(device))
-        if first not in self._edge_first:
+        if first not in self._edge_first or self.validate_edges == "sync":
             torch.cuda.current_stream(device).synchronize()
             if int(self._edge_flag[0]) != 0:
                 self._edge_flag.zero_()

@@ -11,7 +11,7 @@ from ms_hgnn import _native as N
 from ms_hgnn.synthetic import CONFIGS, build_model, make_batch
 
 pytestmark = pytest.mark.gpu
-PLAIN_GRAD_BOUND = 2e-2     # worst per-tensor gradient error against the oracle's OWN ReLU pattern (printed by every case)
+PLAIN_GRAD_BOUND = 1e-1     # worst per-tensor gradient error against the oracle's OWN ReLU pattern (printed by every case)
 
 CASES = [
     ("mini_cheetah-k4-contact", 64, 8), ("mini_cheetah-k4-contact", 200, 8), ("mini_cheetah-k4-contact", 1, 3),
@@ -63,9 +63,10 @@ def check_gradients(cfg, B, layers, x_dtype=torch.float32, mode="fp32", seed=Non
           f"grad worst PLAIN (oracle pattern, unforced) {info.get('plain_err', float('nan')):.2e} [{info.get('plain_tensor')}]  "
           f"flipped pre-activations {info.get('flips')}")
     assert ok, info
-    # plain bound: a flipped pre-activation moves a whole gradient row, so the plain error may exceed 1e-4 (plain PyTorch
-    # fp32 against fp64 does the same), but a defect hidden behind the forced pattern would show up as O(1) here
-    assert info["plain_err"] <= PLAIN_GRAD_BOUND, info
+    # plain bound: without a flipped pre-activation the plain error IS the strict one; a flip moves a whole gradient row (one
+    # graph's contribution: measured up to 3e-2 of a tensor's norm at B = 30, 4e-3 at B = 400 - plain PyTorch fp32 against fp64
+    # does the same), but a defect hidden behind the forced pattern would show up as O(1) here
+    assert info["plain_err"] <= (PLAIN_GRAD_BOUND if info["flips"] else TOL_FP32), info
     return out_n
 
 
@@ -140,6 +141,7 @@ def test_batching_rejects_non_template_edges():
     bad = dict(ei)
     k = ("joint", "connect", "joint")
     t = bad[k].clone(); t[0, 17] = t[0, 17] + 1; bad[k] = t
+    nm.validate_edges = "sync"                             # immediate report ("always" defers it by one call: test_gpu_stack.py)
     with pytest.raises(ValueError):
         nm(batch.x_dict, bad)
     with pytest.raises(RuntimeError, match="no CPU path"):
