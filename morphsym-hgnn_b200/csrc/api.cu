@@ -376,7 +376,11 @@ int launch_stack(int kind, const Plan& p, const Plan::Stack& sp, const WsLayout&
                  char* ws, int64_t B, int split, cudaStream_t st) {
     if (sp.prog.n_phases == 0) return 0;
     static std::atomic<bool> attr_set[64];
-    if (first_on_device(attr_set)) CUDA_TRY(cudaFuncSetAttribute(k_tc_stack, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM_BYTES));
+    static const bool timing = [] { const char* e = getenv("MSHGNN_STACK_TIMING"); return e && !strcmp(e, "1"); }();
+    if (first_on_device(attr_set)) {
+        CUDA_TRY(cudaFuncSetAttribute(k_tc_stack<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(k_tc_stack<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM_BYTES));
+    }
     for (int i = 0; i < sp.tiles.count; ++i) {
         const Tile& T = p.tiles[sp.tiles.begin + i];
         for (int c = 0; c < T.n_chunks; ++c)
@@ -392,6 +396,7 @@ int launch_stack(int kind, const Plan& p, const Plan::Stack& sp, const WsLayout&
     a.split = split; a.B = B; a.Bp = w.Bp;
     a.sync = (uint32_t*)(ws + w.stack_sync);
     a.err = (uint32_t*)(ws + w.stack_sync + w.stack_sync_bytes - 4);
+    a.timing = (unsigned long long*)(ws + w.stack_timing);
     if ((int64_t)sp.prog.n_phases * a.n_row_tiles + 1 > w.stack_sync_bytes / 4) return fail(MSHGNN_ERR_WORKSPACE, "internal: stack counters do not fit");
     int n_sm = 0, rc;
     if ((rc = sm_count(&n_sm))) return rc;
@@ -404,7 +409,8 @@ int launch_stack(int kind, const Plan& p, const Plan::Stack& sp, const WsLayout&
     cfg.attrs = at; cfg.numAttrs = 1;
     const Tile* d_tiles = p.d_tiles + sp.tiles.begin;
     const StackItem* d_items = p.d_stack_items + sp.item0;
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, k_tc_stack, wm.tc, d_tiles, d_items, a, bt, br));
+    if (timing) CUDA_TRY(cudaLaunchKernelEx(&cfg, k_tc_stack<true>, wm.tc, d_tiles, d_items, a, bt, br));
+    else CUDA_TRY(cudaLaunchKernelEx(&cfg, k_tc_stack<false>, wm.tc, d_tiles, d_items, a, bt, br));
     LAUNCH_CHECK();
     return 0;
 }
@@ -933,6 +939,12 @@ int mshgnn_stack_status(const mshgnn_plan* plan, int64_t B, int32_t train, int32
     CUDA_TRY(cudaMemcpy(&word, (const char*)workspace + w.stack_sync + w.stack_sync_bytes - 4, 4, cudaMemcpyDeviceToHost));
     *status_out = word ? 1 : 0;
     return 0;
+}
+
+int64_t mshgnn_stack_timing_offset(const mshgnn_plan* plan, int64_t B, int32_t train, int32_t mode) {
+    if (!plan || B < 1) return -1;
+    const WsLayout w = ws_layout(plan->p, B, train, mode);
+    return w.stack ? w.stack_timing : -1;
 }
 
 int64_t mshgnn_launch_count(void) { return g_launches.load(); }

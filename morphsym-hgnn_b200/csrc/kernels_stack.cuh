@@ -46,6 +46,7 @@ struct StackArgs {
     int64_t B, Bp;
     uint32_t* sync;              // [n_phases][n_row_tiles] completion counters
     uint32_t* err;               // error word (a dependency wait timed out)
+    unsigned long long* timing;  // TIMING instantiation only: per CTA 8 cycle counters (see k_tc_stack)
 };
 
 struct ItemRef { int phase, row_tile, item; };
@@ -139,7 +140,8 @@ struct StackEpi {
 __device__ __forceinline__ void stack_epilogue(const TileHdr& t, const BufTable& bt, const BufRows& br, const CUtensorMap* map_k,
                                                const uint32_t tmem_acc, const int row0, const int64_t B, const int64_t Bp,
                                                const int warp, const int lane, const int grp, const StackEpi es, uint32_t& res_count,
-                                               uint32_t*& pend, uint32_t* sig, const volatile int* dep_ok, const int dep_need) {
+                                               uint32_t*& pend, uint32_t* sig, const volatile int* dep_ok, const int dep_need,
+                                               unsigned long long* t_wait_acc = nullptr) {
     const int q = warp & 3;                        // TMEM lane quarter this warp may access (hardware rule: warp index mod 4)
     const bool leader = q == 2 && lane == 0;       // first warp of the group (warps 2 + 4g .. 5 + 4g): warp index = 2 mod 4
     const int rl = q * 32 + lane;                  // row inside the tile
@@ -191,7 +193,8 @@ __device__ __forceinline__ void stack_epilogue(const TileHdr& t, const BufTable&
         stack_signal(pend);
         pend = nullptr;
     }
-    mbar_wait(es.accum_bar, es.acc_parity);
+    if (t_wait_acc) { const long long t0 = clock64(); mbar_wait(es.accum_bar, es.acc_parity); *t_wait_acc += (unsigned long long)(clock64() - t0); }
+    else mbar_wait(es.accum_bar, es.acc_parity);
     tc_fence_after();
     uint32_t raw[32];
     tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + col0, raw);
@@ -287,6 +290,11 @@ __device__ __forceinline__ void stack_epilogue(const TileHdr& t, const BufTable&
     }
 }
 
+// TIMING = true is a diagnostic instantiation (MSHGNN_STACK_TIMING=1): the single-thread roles accumulate the cycles they
+// spend in each kind of wait into args.timing[blockIdx.x * 8 + {0: producer/ring slot, 1: producer/dependency, 2: MMA/operands,
+// 3: MMA/accumulator free, 4: MMA/staged operand, 5: epilogue group 0/accumulator, 6: kernel, 7: steps}].
+#define SK_TIMED(slot, stmt) do { if (TIMING) { const long long t0_ = clock64(); stmt; tim[slot] += (unsigned long long)(clock64() - t0_); } else { stmt; } } while (0)
+template <bool TIMING>
 __global__ void __launch_bounds__(SK_THREADS, 1)
 k_tc_stack(const __grid_constant__ TcMaps maps, const Tile* __restrict__ tiles, const StackItem* __restrict__ items,
            const __grid_constant__ StackArgs args, const BufTable bt, const BufRows br) {
@@ -319,6 +327,8 @@ k_tc_stack(const __grid_constant__ TcMaps maps, const Tile* __restrict__ tiles, 
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
     constexpr int SPC = H / TC_KB;                 // pipeline steps (K blocks) per chunk
+    unsigned long long tim[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long t_begin = TIMING ? clock64() : 0;
     const StackProg& pg = args.prog;
     const int NT = args.n_row_tiles, RC = args.rows_per_chunk, n_total = args.n_total, split = args.split;
     const int64_t B = args.B, Bp = args.Bp;
@@ -345,7 +355,7 @@ k_tc_stack(const __grid_constant__ TcMaps maps, const Tile* __restrict__ tiles, 
                         asm volatile("fence.acq_rel.gpu;" ::: "memory");
                         asm volatile("fence.proxy.async.global;" ::: "memory");
                     } else {
-                        stack_wait(args.sync + (size_t)(ir.phase - 1) * NT + ir.row_tile, target, err);
+                        SK_TIMED(1, stack_wait(args.sync + (size_t)(ir.phase - 1) * NT + ir.row_tile, target, err));
                     }
                 }
                 __threadfence_block();
@@ -368,7 +378,7 @@ k_tc_stack(const __grid_constant__ TcMaps maps, const Tile* __restrict__ tiles, 
                         const uint32_t tx_bytes = (uint32_t)((from_stage ? 1 : 2) * (split ? 2 : 1) * TC_TILE_BYTES);
                         for (int kb = 0; kb < SPC; ++kb, ++g) {
                             const uint32_t s4 = g % SK_STAGES;
-                            mbar_wait(empty0 + 8 * s4, ((g / SK_STAGES) & 1) ^ 1);
+                            SK_TIMED(0, mbar_wait(empty0 + 8 * s4, ((g / SK_STAGES) & 1) ^ 1));
                             const int kcol = kb * TC_KB;
                             const uint32_t st = smem_base + s4 * TC_STAGE_BYTES;
                             const uint32_t fb = full0 + 8 * s4;
@@ -383,6 +393,7 @@ k_tc_stack(const __grid_constant__ TcMaps maps, const Tile* __restrict__ tiles, 
                     }
                 }
             }
+            if (TIMING) { args.timing[(size_t)blockIdx.x * 8] = tim[0]; args.timing[(size_t)blockIdx.x * 8 + 1] = tim[1]; }
         }
     } else if (warp == 1) {
         if (lane == 0) {
@@ -394,19 +405,20 @@ k_tc_stack(const __grid_constant__ TcMaps maps, const Tile* __restrict__ tiles, 
                     const Tile* t = tiles + it.tile + s;
                     const int n_chunks = __ldg(&t->n_chunks), a_stage = __ldg(&t->a_stage);
                     const uint32_t a = k & 1;
-                    mbar_wait(acc_free0 + 8 * a, ((k >> 1) & 1) ^ 1);      // the epilogue has drained this accumulator
+                    SK_TIMED(3, mbar_wait(acc_free0 + 8 * a, ((k >> 1) & 1) ^ 1));      // the epilogue has drained this accumulator
                     tc_fence_after();
+                    if (TIMING) tim[7] += 1;
                     const uint32_t d0 = tmem_base + a * 128;
                     for (int c = 0; c < n_chunks; ++c) {
                         const bool from_stage = a_stage && c == 0;
                         if (from_stage) {
-                            mbar_wait(stage_bar, n_staged & 1);              // the four quarters of the previous step's result are staged
+                            SK_TIMED(4, mbar_wait(stage_bar, n_staged & 1));   // the four quarters of the previous step's result are staged
                             ++n_staged;
                             tc_fence_after();
                         }
                         for (int kb = 0; kb < SPC; ++kb, ++g) {
                             const uint32_t s4 = g % SK_STAGES;
-                            mbar_wait(full0 + 8 * s4, (g / SK_STAGES) & 1);
+                            SK_TIMED(2, mbar_wait(full0 + 8 * s4, (g / SK_STAGES) & 1));
                             tc_fence_after();
                             const uint32_t st = smem_base + s4 * TC_STAGE_BYTES;
                             const uint32_t a_base = from_stage ? stg_base + (uint32_t)kb * 16384u : st;
@@ -426,6 +438,10 @@ k_tc_stack(const __grid_constant__ TcMaps maps, const Tile* __restrict__ tiles, 
                     }
                     umma_commit(acc_full0 + 8 * a);
                 }
+            }
+            if (TIMING) {
+                tim[6] = (unsigned long long)(clock64() - t_begin);
+                for (int j = 2; j < 8; ++j) if (j != 5) args.timing[(size_t)blockIdx.x * 8 + j] = tim[j];
             }
         }
         __syncwarp();
@@ -448,13 +464,14 @@ k_tc_stack(const __grid_constant__ TcMaps maps, const Tile* __restrict__ tiles, 
                 es.accum_bar = acc_full0 + 8 * a; es.free_bar = acc_free0 + 8 * a;
                 es.acc_parity = (k >> 1) & 1;
                 stack_epilogue(t, bt, br, &maps.k, tmem_base + a * 128, ir.row_tile * TILE_M, B, Bp, warp, lane, grp, es, n_res, pend,
-                               s == it.n_steps - 1 ? ctr : nullptr, &dep_ok_s, ir.phase > 0 ? n_item : 0);
+                               s == it.n_steps - 1 ? ctr : nullptr, &dep_ok_s, ir.phase > 0 ? n_item : 0, (TIMING && warp == 2 && lane == 0) ? &tim[5] : nullptr);
             }
         }
         if ((warp & 3) == 2 && lane == 0) {
             tma_store_wait_all();
             if (pend) stack_signal(pend);
         }
+        if (TIMING && warp == 2 && lane == 0) args.timing[(size_t)blockIdx.x * 8 + 5] = tim[5];
     }
     tc_fence_before();
     __syncthreads();

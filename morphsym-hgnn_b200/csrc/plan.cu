@@ -718,6 +718,7 @@ WsLayout ws_layout(const Plan& p, int64_t B, int train, int mode) {
     if (w.stack) {
         w.stack_sync_bytes = ((int64_t)STACK_MAX_PHASES * (w.Bp / TILE_M) + 64) * 4;
         w.stack_sync = take(w.stack_sync_bytes);
+        w.stack_timing = take(256 * 8 * 8);
     }
     w.loss_part = take(LOSS_BLOCKS * 8);
     w.total = o;

@@ -135,6 +135,7 @@ struct WsLayout {
     int64_t dhL16[MAX_LAYERS + 1][2], dcL16[MAX_LAYERS + 1][2] /* index l + 1 */, duL16[MAX_LAYERS][2];
     int64_t stack_sync = -1;           // dependency counters of the stack kernel (uint32 [phases][row tiles]) + error word
     int64_t stack_sync_bytes = 0;
+    int64_t stack_timing = -1;         // diagnostic cycle counters of the TIMING instantiation: [CTA][8] uint64
     int64_t total = 0;
 };
 

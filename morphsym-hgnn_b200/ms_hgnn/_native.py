@@ -29,7 +29,7 @@ EXPORTS = (
     "mshgnn_adam_step", "mshgnn_sgd_step", "mshgnn_plan_describe", "mshgnn_launch_count",
     "mshgnn_last_error", "mshgnn_version", "mshgnn_profile_enable", "mshgnn_profile_read", "mshgnn_kernel_kind_name",
     "mshgnn_relu_mask_offset", "mshgnn_build_windows", "mshgnn_step_metrics", "mshgnn_dw_layout",
-    "mshgnn_check_edges", "mshgnn_set_option", "mshgnn_get_option", "mshgnn_stack_status",
+    "mshgnn_check_edges", "mshgnn_set_option", "mshgnn_get_option", "mshgnn_stack_status", "mshgnn_stack_timing_offset",
 )
 
 
@@ -118,6 +118,7 @@ def lib() -> C.CDLL:
     L.mshgnn_set_option.argtypes = [C.c_char_p, i32]; L.mshgnn_set_option.restype = C.c_int
     L.mshgnn_get_option.argtypes = [C.c_char_p]; L.mshgnn_get_option.restype = i32
     L.mshgnn_stack_status.argtypes = [vp, i64, i32, i32, vp, C.POINTER(i32)]; L.mshgnn_stack_status.restype = C.c_int
+    L.mshgnn_stack_timing_offset.argtypes = [vp, i64, i32, i32]; L.mshgnn_stack_timing_offset.restype = i64
     _lib = L
     return L
 
@@ -250,6 +251,9 @@ class NativePlan:
         out = C.c_int32()
         check(lib().mshgnn_stack_status(self.handle, B, int(train), mode, ws_ptr, C.byref(out)), "mshgnn_stack_status")
         return out.value
+
+    def stack_timing_offset(self, B, train, mode) -> int:
+        return int(lib().mshgnn_stack_timing_offset(self.handle, B, int(train), mode))
 
     # ---- compute (raw device pointers) ----
     def forward(self, B, x_ptrs: Sequence[int], x_dtype, params_ptr, out_ptr, ws_ptr, ws_bytes, train, mode, stream):
