@@ -237,7 +237,7 @@ int mshgnn_set_option(const char* name, int32_t value);
 int32_t mshgnn_get_option(const char* name);
 int mshgnn_stack_status(const mshgnn_plan* plan, int64_t B, int32_t train, int32_t mode, const void* workspace, int32_t* status_out);
 /* Diagnostics (MSHGNN_STACK_TIMING=1 selects an instrumented build of the stack kernel): byte offset in the workspace of
- * uint64 [CTA][8] cycle counters of the LAST stack launch - producer waiting for a ring slot / for a dependency, MMA
+ * uint64 [CTA][16] cycle counters of the LAST stack launch - producer waiting for a ring slot / for a dependency, MMA
  * issuer waiting for operands / a free accumulator / a staged operand, epilogue group 0 waiting for an accumulator,
  * kernel cycles, steps.  -1 when the stack kernel is off. */
 int64_t mshgnn_stack_timing_offset(const mshgnn_plan* plan, int64_t B, int32_t train, int32_t mode);

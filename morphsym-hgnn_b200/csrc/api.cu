@@ -354,15 +354,29 @@ int launch_tc_dw(int kind, const Plan& p, int layer, const Launch& L, const WsLa
 }
 
 // ---- cross-layer stack kernel (kernels_stack.cuh) ----
-// Row tiles per chunk: the slabs one layer reads and writes for a chunk (2 x S slots x 128 rows x 512 B per row tile) must
-// stay in L2 until the next layer has consumed them - 64 MB of the 126 MB - and the chunk must be long enough that the
-// items of layer l + 1 of a row tile are handed out >= ~300 items (two rounds of 148 CTAs) after those of layer l.
+// Item order of the stack kernel (kernels_stack.cuh).  Default: CHUNKED - row chunks of RC row tiles, walked phase by phase.
+// RC trades the two things the kernel is sensitive to (tools/stack_timing.py, 16384 graphs, K4 Mini Cheetah):
+//   * dependency distance: the items of layer l + 1 of a row tile are handed out RC x (items per row tile and layer) items
+//     after those of layer l; below ~2 x 148 items in flight + the latency of the slowest item (a base_transform chain) the
+//     scheduler warps wait (RC = 24: 22 % of the kernel in queue waits, RC = 32: 9 %, RC = 48: 7 %);
+//   * L2 residency: a chunk's input and output slabs of one layer are RC x 2 x S x 128 x 512 B (RC = 32: 84 MB of 126 MB).
+// MSHGNN_STACK_ORDER=diag selects the diagonal wavefront (uniform distance D x items per slot, MSHGNN_STACK_DELAY); measured
+// 5 % slower at equal footprint (all layers' weights and buffers are live at once).
 int stack_rows_per_chunk(const Plan& p) {
     static const int env = [] { const char* e = getenv("MSHGNN_STACK_RC"); return e ? atoi(e) : 0; }();
     if (env > 0) return env;
     const int64_t per_row_tile = (int64_t)2 * p.S * TILE_M * H * 4;
-    int rc = (int)((int64_t)64 * 1024 * 1024 / per_row_tile);
+    int rc = (int)((int64_t)84 * 1024 * 1024 / per_row_tile);
     return rc < 16 ? 16 : (rc > 64 ? 64 : rc);
+}
+int stack_delay(const Plan::Stack& sp, int n_row_tiles, int n_sm) {
+    static const int env = [] { const char* e = getenv("MSHGNN_STACK_DELAY"); return e ? atoi(e) : 0; }();
+    if (env > 0) return env;
+    const int per_slot = sp.prog.items_per_row > 0 ? sp.prog.items_per_row : 1;
+    int d = (4 * n_sm + per_slot - 1) / per_slot;
+    const int most = n_row_tiles / (sp.prog.n_phases > 0 ? sp.prog.n_phases : 1);      // short batches: do not stretch the pipeline beyond the rows there are
+    if (d > most) d = most;
+    return d < 1 ? 1 : d;
 }
 
 int stack_sync_reset(const WsLayout& w, char* ws, cudaStream_t st) {
@@ -389,17 +403,23 @@ int launch_stack(int kind, const Plan& p, const Plan::Stack& sp, const WsLayout&
     StackArgs a;
     a.prog = sp.prog;
     a.n_row_tiles = (int)(w.Bp / TILE_M);
-    a.rows_per_chunk = stack_rows_per_chunk(p);
     const int64_t n_total = (int64_t)a.n_row_tiles * sp.prog.items_per_row;
     if (n_total > 0x7fffffffLL) return fail(MSHGNN_ERR_ARG, "batch too large for one stack launch");
     a.n_total = (int)n_total;
-    a.split = split; a.B = B; a.Bp = w.Bp;
+    a.split = split; a.B = B; a.Bp = w.Bp; a.n_slots = p.S;
     a.sync = (uint32_t*)(ws + w.stack_sync);
     a.err = (uint32_t*)(ws + w.stack_sync + w.stack_sync_bytes - 4);
+    a.next = (uint32_t*)(ws + w.stack_sync + w.stack_sync_bytes - 8);
     a.timing = (unsigned long long*)(ws + w.stack_timing);
-    if ((int64_t)sp.prog.n_phases * a.n_row_tiles + 1 > w.stack_sync_bytes / 4) return fail(MSHGNN_ERR_WORKSPACE, "internal: stack counters do not fit");
+    if ((int64_t)sp.prog.n_phases * a.n_row_tiles * p.S + 2 > w.stack_sync_bytes / 4) return fail(MSHGNN_ERR_WORKSPACE, "internal: stack counters do not fit");
     int n_sm = 0, rc;
     if ((rc = sm_count(&n_sm))) return rc;
+    static const bool chunked = [] { const char* e = getenv("MSHGNN_STACK_ORDER"); return !(e && !strcmp(e, "diag")); }();
+    // an item drawn long before it runs delays its dependents: the scheduler warp stays one item ahead of the producer
+    static const int env_la = [] { const char* e = getenv("MSHGNN_STACK_LOOKAHEAD"); return e ? atoi(e) : 0; }();
+    a.lookahead = env_la > 0 ? (env_la > 4 ? 4 : env_la) : 1;
+    a.chunked = chunked ? 1 : 0;
+    a.delay = chunked ? stack_rows_per_chunk(p) : stack_delay(sp, a.n_row_tiles, n_sm);
     ProfScope ps(kind, st);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(n_total < n_sm ? n_total : n_sm)); cfg.blockDim = dim3(SK_THREADS); cfg.dynamicSmemBytes = SK_SMEM_BYTES; cfg.stream = st;

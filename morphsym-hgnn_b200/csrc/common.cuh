@@ -69,13 +69,18 @@ struct Tile {
 };
 
 // ---- cross-layer stack program (kernels_stack.cuh) ----
-// A program is a sequence of phases (one per layer); phase p of row tile r may start once every item of phase p - 1 of
-// the same row tile has signalled.  An item is 1..3 chained steps (Tile entries, contiguous in the tile table) on one
+// A program is a sequence of phases (one per layer).  An item of phase p on row tile r may start once the items of phase
+// p - 1 of the same row tile that produce the node slots in its dep_mask have signalled (the dependency structure IS the
+// morphology graph: a thigh tile waits for hip, thigh and calf, not for the slow base_transform chains).  An item is 1..3 chained steps (Tile entries, contiguous in the tile table) on one
 // 128-row tile; the steps after the first take their A operand from on-chip staging.
 constexpr int STACK_MAX_PHASES = 20;
 struct StackItem {
     int tile;                         // first step (index relative to the program's first tile)
     int n_steps;                      // 1..3
+    int out_slot;                     // node slot whose outputs (h / dh / dc) this item completes in its phase
+    int pad_;
+    unsigned long long dep_mask;      // node slots of the PREVIOUS phase (same row tile) that must be complete before it starts:
+                                      // the slots it reads (operands, residual) and, where buffers ping-pong, the readers of the slot it overwrites
 };
 struct StackProg {
     int n_phases;

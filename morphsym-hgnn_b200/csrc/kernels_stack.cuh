@@ -7,14 +7,15 @@
 //  images is 1.3 MB - it cannot be resident in one SM's 227 KB of shared memory (and five 128-row role tiles, the
 //  smallest closed set under the morphology's edges, are 320 KB) - so this kernel keeps it resident one level up:
 //
-//   * ONE persistent launch walks all layers.  Work items are ordered (row chunk, layer, row tile, output tile); a chunk
-//     is a few thousand graphs, sized so that the slabs a layer reads and writes for it stay in the 126 MB L2 until the
-//     next layer has consumed them.  In inference the two ping-pong slabs of a chunk never reach HBM at all; in
-//     training every h_l is written once (the backward pass needs it) and never read back from DRAM by the forward.
+//   * ONE persistent launch walks all layers.  Work items are ordered as a diagonal wavefront (stack_decode): a row tile
+//     of 128 graphs advances one layer every D time slots, so only ~L x D row tiles (a few thousand graphs) are between
+//     their first and last layer at any time and the slabs a layer reads were written a few hundred items earlier - they
+//     are still in the 126 MB L2.  In inference the ping-pong slabs never reach HBM at all; in training every h_l is
+//     written once (the backward pass needs it) and never read back from DRAM by the forward.
 //   * No grid-wide barrier: layer l + 1 of row tile r starts as soon as every item of layer l of row tile r has
-//     signalled a global counter (release / acquire at gpu scope, bounded spin).  Items are handed out round-robin in
-//     that order, so the dependency distance ((rows per chunk - 1) x items per row tile) is kept above the number of
-//     items in flight and the waits are normally already satisfied.
+//     signalled a global counter (release / acquire at gpu scope, bounded spin).  Items are drawn from one atomic work
+//     counter in wavefront order, so no CTA falls behind and the dependency distance (D x items per slot) stays above
+//     the number of items in flight: the waits are normally already satisfied.
 //   * base_transform (Linear -> ReLU -> Linear, + residual) is CHAINED behind the conv tile of its node inside one item:
 //     the epilogue leaves the (hi, lo) result in its staging tiles, which have exactly the operand K-block layout
 //     (128 rows x 32 fp16, SWIZZLE_64B), and the MMA warp issues the next GEMM straight from them.  The same chain runs
@@ -29,30 +30,53 @@
 
 namespace mshgnn {
 
-constexpr int SK_STAGES = 4;
-constexpr int SK_THREADS = 576;
-constexpr int SK_PIPE_BYTES = SK_STAGES * TC_STAGE_BYTES;                  // 128 KB operand ring
+// Operand K blocks are 64 fp16 wide (128-byte rows, SWIZZLE_128B): with the 32-column blocks of the per-layer kernels the
+// MMA warp spent 40-50 % of the kernel waiting for operands while the producer rarely waited for a ring slot - the
+// L2 -> SM stream of 64-byte row segments was the bottleneck (tools/stack_timing.py), not the bytes in flight.
+constexpr int SK_KB = 64;
+constexpr int SK_TILE_BYTES = 128 * SK_KB * 2;                            // 16 KB
+constexpr int SK_STAGE_BYTES = 4 * SK_TILE_BYTES;                         // A_hi, A_lo, W_hi, W_lo = 64 KB
+constexpr int SK_STAGES = 2;
+constexpr int SK_QUEUE = 16;                                              // in-CTA item queue (the scheduler runs <= 2 items ahead of the producer)
+constexpr int SK_THREADS = 608;                                           // TMA warp, MMA warp, 16 epilogue warps, scheduler warp
+constexpr int SK_PIPE_BYTES = SK_STAGES * SK_STAGE_BYTES;                  // 128 KB operand ring
 constexpr int SK_STG_BYTES = 65536;                                       // 4 groups x (hi | lo) x 8 KB
 constexpr int SK_SMEM_BYTES = SK_PIPE_BYTES + SK_STG_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-constexpr uint32_t SK_TMEM_COLS = 256;
+constexpr uint32_t SK_TMEM_COLS = 512;                                    // four 128-column accumulators: the MMA warp runs up to three steps ahead of the epilogue
+constexpr int SK_ACCS = 4;
 constexpr unsigned SK_SPIN_LIMIT = 1u << 22;                              // ~ seconds: a broken dependency must not hang the GPU
 
 struct StackArgs {
     StackProg prog;
     int n_row_tiles;             // Bp / 128
-    int rows_per_chunk;          // row tiles per L2-resident chunk
+    int delay;                   // D: time slots between consecutive phases of a row tile (see stack_decode); chunked order: row tiles per chunk
+    int chunked;                 // 1: chunked order (stack_decode_chunked)
+    int lookahead;               // items the scheduler warp may draw ahead of the TMA producer
+    int n_slots;                 // node slots per graph: the completion counters are [phase][row tile][slot]
     int n_total;                 // n_row_tiles * prog.items_per_row
     int split;                   // 1: (hi, lo) operands, 3 MMAs per product; 0: hi only
     int64_t B, Bp;
-    uint32_t* sync;              // [n_phases][n_row_tiles] completion counters
+    uint32_t* sync;              // [n_phases][n_row_tiles][n_slots] completion counters (4 = the four epilogue groups of the producing item)
     uint32_t* err;               // error word (a dependency wait timed out)
+    uint32_t* next;              // work counter: the next item index to hand out (zeroed with the completion counters)
     unsigned long long* timing;  // TIMING instantiation only: per CTA 8 cycle counters (see k_tc_stack)
 };
 
 struct ItemRef { int phase, row_tile, item; };
 
-// item index -> (phase, row tile, item): chunks of rows_per_chunk row tiles, phase-major inside a chunk
-__device__ __forceinline__ ItemRef stack_decode(const StackProg& pg, const int NT, const int RC, const int i) {
+// Item order: a DIAGONAL wavefront.  Time slot t holds, for every phase p, the items of row tile r = t - p * D (when
+// 0 <= r < NT): row tiles enter phase 0 one per slot and advance one phase every D slots.  The items of (p, r) are therefore
+// handed out D slots - D x (items per slot) items - after those of (p - 1, r), for EVERY phase (with row chunks walked phase
+// by phase the pruned last layers, which have few items per row tile, followed their producers too closely and a quarter
+// of the kernel was spent in dependency waits), while only P x D row tiles are between their first and last phase at any
+// time - the L2-resident working set.
+__device__ __forceinline__ int stack_count(const StackProg& pg, const int NT, const int D, const int t) {   // items in slots [0, t)
+    int c = 0;
+    for (int p = 0; p < pg.n_phases; ++p) c += pg.n_items[p] * min(max(t - p * D, 0), NT);
+    return c;
+}
+// chunked order: chunks of RC row tiles, phase-major inside a chunk (MSHGNN_STACK_ORDER=chunk, for A/B measurements)
+__device__ __forceinline__ ItemRef stack_decode_chunked(const StackProg& pg, const int NT, const int RC, const int i) {
     const int chunk_items = RC * pg.items_per_row;
     const int c = i / chunk_items;
     int j = i - c * chunk_items;
@@ -68,15 +92,42 @@ __device__ __forceinline__ ItemRef stack_decode(const StackProg& pg, const int N
     r.phase = p; r.row_tile = c * RC + j / n; r.item = pg.first_item[p] + j % n;
     return r;
 }
+__device__ __forceinline__ ItemRef stack_decode(const StackProg& pg, const int NT, const int D, const int i) {
+    int lo = 0, hi = NT + (pg.n_phases - 1) * D;          // count(lo) <= i < count(hi)
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (stack_count(pg, NT, D, mid) <= i) lo = mid; else hi = mid;
+    }
+    int j = i - stack_count(pg, NT, D, lo);
+    ItemRef r;
+    r.phase = 0; r.row_tile = 0; r.item = 0;
+    for (int p = 0; p < pg.n_phases; ++p) {
+        const int row = lo - p * D;
+        if (row < 0 || row >= NT) continue;
+        const int n = pg.n_items[p];
+        if (j < n) { r.phase = p; r.row_tile = row; r.item = pg.first_item[p] + j; break; }
+        j -= n;
+    }
+    return r;
+}
 
-// Bounded acquire-spin on a completion counter.  On timeout (or when another CTA already timed out) the error word is
-// set and the wait gives up: the results are then garbage, but the kernel terminates and the host reports the error.
-__device__ __forceinline__ void stack_wait(const uint32_t* ctr, const uint32_t target, uint32_t* err) {
+// Bounded acquire-spin of a whole warp on the completion counters of the node slots in `mask` (lane l polls slots l and
+// l + 32).  On timeout (or when another CTA already timed out) the error word is set and the wait gives up: the results
+// are then garbage, but the kernel terminates and the host reports the error (mshgnn_stack_status).
+__device__ __forceinline__ void stack_wait(const uint32_t* ctr, const unsigned long long mask, const int lane, uint32_t* err) {
     unsigned spins = 0;
     for (;;) {
-        uint32_t v;
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-        if (v >= target) break;
+        bool ok = true;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int sl = lane + 32 * h;
+            if ((mask >> sl) & 1ull) {
+                uint32_t v;
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr + sl) : "memory");
+                ok = ok && v >= 4u;
+            }
+        }
+        if (__all_sync(0xffffffffu, ok)) break;
         ++spins;
         if ((spins & 1023u) == 0) {
             uint32_t e;
@@ -85,8 +136,6 @@ __device__ __forceinline__ void stack_wait(const uint32_t* ctr, const uint32_t t
         }
         __nanosleep(40);
     }
-    // what the producers wrote with TMA stores (async proxy) is read here with TMA loads (async proxy)
-    asm volatile("fence.proxy.async.global;" ::: "memory");
 }
 
 __device__ __forceinline__ void stack_signal(uint32_t* ctr) {
@@ -135,13 +184,11 @@ struct StackEpi {
     uint32_t acc_parity;
 };
 
-// One step of an item through one epilogue group (cf. tc_epilogue_q).  `pend` (leader only) is the completion counter of
-// the last item whose TMA stores this leader has committed but not yet published.
+// One step of an item through one epilogue group (cf. tc_epilogue_q).  `sig`: completion counter of the item (last step only).
 __device__ __forceinline__ void stack_epilogue(const TileHdr& t, const BufTable& bt, const BufRows& br, const CUtensorMap* map_k,
                                                const uint32_t tmem_acc, const int row0, const int64_t B, const int64_t Bp,
                                                const int warp, const int lane, const int grp, const StackEpi es, uint32_t& res_count,
-                                               uint32_t*& pend, uint32_t* sig, const volatile int* dep_ok, const int dep_need,
-                                               unsigned long long* t_wait_acc = nullptr) {
+                                               uint32_t* sig, unsigned long long* t_wait_acc = nullptr) {
     const int q = warp & 3;                        // TMEM lane quarter this warp may access (hardware rule: warp index mod 4)
     const bool leader = q == 2 && lane == 0;       // first warp of the group (warps 2 + 4g .. 5 + 4g): warp index = 2 mod 4
     const int rl = q * 32 + lane;                  // row inside the tile
@@ -162,17 +209,10 @@ __device__ __forceinline__ void stack_epilogue(const TileHdr& t, const BufTable&
     };
     if (leader) {
         tma_store_wait_read();                     // the staging tiles may still feed this group's previous TMA stores
+        // early fetch (hidden behind the MMAs of this step); the item is only published to this warp once its input
+        // dependency - the residual is an output of the previous phase - has been seen satisfied by the producer warp
         if (has_res && !t.a_stage) {
-            // early fetch (hidden behind the MMAs of this step).  The residual is an output of the previous phase: the
-            // producer warp publishes, per item, that it has seen those outputs complete.
-            if (dep_need > 0) {
-                if (*dep_ok < dep_need) {
-                    // about to wait on other CTAs: publish our own pending completion first (it may be what they wait for)
-                    if (pend) { tma_store_wait_all(); stack_signal(pend); pend = nullptr; }
-                    while (*dep_ok < dep_need) { }
-                }
-                asm volatile("fence.proxy.async.global;" ::: "memory");
-            }
+            asm volatile("fence.proxy.async.global;" ::: "memory");
             fetch_residual();
         }
     }
@@ -186,13 +226,6 @@ __device__ __forceinline__ void stack_epilogue(const TileHdr& t, const BufTable&
         m2 = __ldg(reinterpret_cast<const uint32_t*>(bt.p[t.out2_mask_buf]) + ((int64_t)t.out2_mask_slot * Bp + row) * 4 + grp);
     group_bar_sync(grp);
 
-    if (leader && pend && !mbar_test(es.accum_bar, es.acc_parity)) {
-        // about to block on the tensor pipe: publish what is still pending first (a CTA that waits never withholds a signal
-        // another CTA's producer may be spinning on)
-        tma_store_wait_all();
-        stack_signal(pend);
-        pend = nullptr;
-    }
     if (t_wait_acc) { const long long t0 = clock64(); mbar_wait(es.accum_bar, es.acc_parity); *t_wait_acc += (unsigned long long)(clock64() - t0); }
     else mbar_wait(es.accum_bar, es.acc_parity);
     tc_fence_after();
@@ -242,7 +275,6 @@ __device__ __forceinline__ void stack_epilogue(const TileHdr& t, const BufTable&
     }
     fence_proxy_async_smem();
     group_bar_sync(grp);
-    int committed = 0;
     if (leader) {
         const int ob = has_out ? t.out_buf : t.out2_buf, os = has_out ? t.out_slot : t.out2_slot;
         if (ob >= 0) {
@@ -250,7 +282,6 @@ __device__ __forceinline__ void stack_epilogue(const TileHdr& t, const BufTable&
             tma_store_2d(map_k, es.stg, col0, br.hi[ob] + o);
             tma_store_2d(map_k, es.stg + 8192u, col0, br.lo[ob] + o);
             tma_store_commit();
-            ++committed;
         }
         if (t.stage_out) mbar_arrive(es.stage_bar);        // this quarter of the next step's A operand is in place
     }
@@ -272,21 +303,16 @@ __device__ __forceinline__ void stack_epilogue(const TileHdr& t, const BufTable&
             tma_store_2d(map_k, es.stg, col0, br.hi[t.out2_buf] + o);
             tma_store_2d(map_k, es.stg + 8192u, col0, br.lo[t.out2_buf] + o);
             tma_store_commit();
-            ++committed;
         }
     }
     if (live && t.mask_out_buf >= 0)
         *(reinterpret_cast<uint32_t*>(bt.p[t.mask_out_buf]) + ((int64_t)t.mask_out_slot * Bp + row) * 4 + grp) = mask;
-    if (leader) {
-        if (pend) {
-            // everything committed BEFORE this step has landed once at most this step's groups are still in flight
-            if (committed == 0) tma_store_wait_pending<0>();
-            else if (committed == 1) tma_store_wait_pending<1>();
-            else tma_store_wait_pending<2>();
-            stack_signal(pend);
-            pend = nullptr;
-        }
-        if (sig) pend = sig;
+    if (leader && sig) {
+        // Publish the item as soon as its stores have landed.  (Deferring the signal to the next step of this CTA saved the
+        // store round trip here, but it added a whole item time to every dependency chain - the scheduler warps of the
+        // dependent items then waited for it two thirds of the time; the epilogue groups have the slack, the chains do not.)
+        tma_store_wait_all();
+        stack_signal(sig);
     }
 }
 
@@ -301,24 +327,30 @@ k_tc_stack(const __grid_constant__ TcMaps maps, const Tile* __restrict__ tiles, 
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(16) float bias_s[4][32];         // one quarter per epilogue group
     __shared__ uint32_t tmem_base_s;
-    __shared__ volatile int dep_ok_s;                     // items whose input dependency the producer warp has seen satisfied
+    // Items are handed out dynamically: the scheduler warp (warp 18) draws the next global item index from an atomic counter
+    // (so no CTA falls behind: the dependency of an item always points at items that are finished or running), decodes it,
+    // waits for its input dependency and then publishes the decoded item to the other roles through this queue.  Decode,
+    // dependency round trips and descriptor loads are thereby off the critical path of the single-thread TMA / MMA roles.
+    __shared__ int4 q_ent[SK_QUEUE][2];                   // {row tile, phase, first tile, steps}, {per step one byte: chunks | a_stage << 4, -, -, -}
+    __shared__ volatile int q_count;                      // entries published
+    __shared__ volatile int q_prod;                       // entries the TMA producer has started
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SK_PIPE_BYTES + SK_STG_BYTES);
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + SK_STAGES), acc_full0 = smem_u32(bars + 2 * SK_STAGES),
-                   acc_free0 = smem_u32(bars + 2 * SK_STAGES + 2), res_bar = smem_u32(bars + 2 * SK_STAGES + 4),   // 4 residual barriers
-                   stage_bar = smem_u32(bars + 2 * SK_STAGES + 8);
+                   acc_free0 = smem_u32(bars + 2 * SK_STAGES + SK_ACCS), res_bar = smem_u32(bars + 2 * SK_STAGES + 2 * SK_ACCS),   // 4 residual barriers
+                   stage_bar = smem_u32(bars + 2 * SK_STAGES + 2 * SK_ACCS + 4);
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t stg_base = smem_base + SK_PIPE_BYTES;
 
     if (tid == 0) {
         for (int s = 0; s < SK_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(acc_full0 + 8 * a, 1); mbar_init(acc_free0 + 8 * a, 512); }
+        for (int a = 0; a < SK_ACCS; ++a) { mbar_init(acc_full0 + 8 * a, 1); mbar_init(acc_free0 + 8 * a, 512); }
         for (int g = 0; g < 4; ++g) mbar_init(res_bar + 8 * g, 1);
         mbar_init(stage_bar, 4);
-        dep_ok_s = 0;
+        q_count = 0; q_prod = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), SK_TMEM_COLS);
@@ -326,86 +358,108 @@ k_tc_stack(const __grid_constant__ TcMaps maps, const Tile* __restrict__ tiles, 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
-    constexpr int SPC = H / TC_KB;                 // pipeline steps (K blocks) per chunk
-    unsigned long long tim[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    constexpr int SPC = H / SK_KB;                 // pipeline steps (K blocks) per chunk
+    unsigned long long tim[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     const long long t_begin = TIMING ? clock64() : 0;
     const StackProg& pg = args.prog;
-    const int NT = args.n_row_tiles, RC = args.rows_per_chunk, n_total = args.n_total, split = args.split;
+    const int NT = args.n_row_tiles, RC = args.delay, n_total = args.n_total, split = args.split;
     const int64_t B = args.B, Bp = args.Bp;
     uint32_t* const err = args.err;
     // Programmatic dependent launch: everything above ran while the previous kernel of the stream was still draining
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-    if (warp == 0) {
-        if (lane == 0) {
-            uint32_t g = 0;                        // pipeline step counter, runs across items
-            int n_done = 0;
-            // the completion counter of the NEXT item is polled one item ahead (relaxed load, consumed an item later), so
-            // the L2 round trip of the dependency check hides behind the operand stream of the current item
-            uint32_t pre = 0;
-            bool have_pre = false;
-            ItemRef ir = stack_decode(pg, NT, RC, blockIdx.x < n_total ? blockIdx.x : 0);
-            for (int i = blockIdx.x; i < n_total; i += gridDim.x) {
+    // consumer side of the queue: the n-th item of this CTA (a.w = 0 steps: no more work)
+    auto next_item = [&](const int n, int4& a, int4& b) {
+        if (lane == 0) { while (q_count <= n) { } }
+        __syncwarp();
+        a = q_ent[n % SK_QUEUE][0];
+        b = q_ent[n % SK_QUEUE][1];
+    };
+
+    if (warp == 18) {
+        int n_pub = 0;
+        for (;;) {
+            int cur = 0;
+            if (lane == 0) {
+                while (n_pub - q_prod >= args.lookahead) { }       // stay close to the producer: a drawn item blocks its dependents
+                cur = (int)atomicAdd(args.next, 1u);
+            }
+            cur = __shfl_sync(0xffffffffu, cur, 0);
+            int4 a = make_int4(0, 0, 0, 0), b = make_int4(0, 0, 0, 0);
+            if (cur < n_total) {
+                const ItemRef ir = args.chunked ? stack_decode_chunked(pg, NT, RC, cur) : stack_decode(pg, NT, RC, cur);
                 const StackItem it = items[ir.item];
-                const int row0 = ir.row_tile * TILE_M;
-                if (ir.phase > 0) {
-                    const uint32_t target = 4u * (uint32_t)pg.n_items[ir.phase - 1];
-                    if (have_pre && pre >= target) {
-                        asm volatile("fence.acq_rel.gpu;" ::: "memory");
-                        asm volatile("fence.proxy.async.global;" ::: "memory");
-                    } else {
-                        SK_TIMED(1, stack_wait(args.sync + (size_t)(ir.phase - 1) * NT + ir.row_tile, target, err));
-                    }
-                }
+                int meta = 0;                             // per step one byte: chunks | a_stage << 4
+                for (int s = 0; s < it.n_steps && s < 4; ++s) meta |= (__ldg(&tiles[it.tile + s].n_chunks) | (__ldg(&tiles[it.tile + s].a_stage) << 4)) << (8 * s);
+                if (ir.phase > 0 && it.dep_mask)
+                    SK_TIMED(1, stack_wait(args.sync + ((size_t)(ir.phase - 1) * NT + ir.row_tile) * args.n_slots, it.dep_mask, lane, err));
+                a = make_int4(ir.row_tile, ir.phase, it.tile, it.n_steps);
+                b = make_int4(meta, it.out_slot, 0, 0);
+            }
+            if (lane == 0) {
+                q_ent[n_pub % SK_QUEUE][0] = a;
+                q_ent[n_pub % SK_QUEUE][1] = b;
                 __threadfence_block();
-                dep_ok_s = ++n_done;
-                have_pre = false;
-                if (i + (int)gridDim.x < n_total) {
-                    ir = stack_decode(pg, NT, RC, i + (int)gridDim.x);
-                    if (ir.phase > 0) {
-                        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(pre) : "l"(args.sync + (size_t)(ir.phase - 1) * NT + ir.row_tile) : "memory");
-                        have_pre = true;
-                    }
-                }
-                for (int s = 0; s < it.n_steps; ++s) {
-                    const Tile* t = tiles + it.tile + s;
-                    const int n_chunks = __ldg(&t->n_chunks), a_stage = __ldg(&t->a_stage);
+                q_count = n_pub + 1;
+            }
+            ++n_pub;
+            if (cur >= n_total) break;
+        }
+        if (TIMING && lane == 0) args.timing[(size_t)blockIdx.x * 16 + 1] = tim[1];
+    } else if (warp == 0) {
+        uint32_t g = 0;                        // pipeline step counter, runs across items
+        for (int n = 0;; ++n) {
+            int4 qa, qb;
+            SK_TIMED(11, next_item(n, qa, qb));
+            if (qa.w == 0) break;
+            if (lane == 0) {
+                q_prod = n + 1;
+                // the scheduler warp has acquired the completion of this item's inputs; they were written with TMA stores
+                // (async proxy) and are read below with TMA loads (async proxy)
+                asm volatile("fence.proxy.async.global;" ::: "memory");
+                const int row0 = qa.x * TILE_M;
+                for (int s = 0; s < qa.w; ++s) {
+                    const Tile* t = tiles + qa.z + s;
+                    const int n_chunks = (qb.x >> (8 * s)) & 0xf, a_stage = (qb.x >> (8 * s + 4)) & 1;
                     for (int c = 0; c < n_chunks; ++c) {
                         const bool from_stage = a_stage && c == 0;
                         const int a_buf = __ldg(&t->chunks[c].a_buf), a_slot = __ldg(&t->chunks[c].a_slot), w16_row = __ldg(&t->chunks[c].w16_row);
                         const int arow = (int)((int64_t)a_slot * Bp) + row0;
-                        const uint32_t tx_bytes = (uint32_t)((from_stage ? 1 : 2) * (split ? 2 : 1) * TC_TILE_BYTES);
+                        const uint32_t tx_bytes = (uint32_t)((from_stage ? 1 : 2) * (split ? 2 : 1) * SK_TILE_BYTES);
                         for (int kb = 0; kb < SPC; ++kb, ++g) {
                             const uint32_t s4 = g % SK_STAGES;
                             SK_TIMED(0, mbar_wait(empty0 + 8 * s4, ((g / SK_STAGES) & 1) ^ 1));
-                            const int kcol = kb * TC_KB;
-                            const uint32_t st = smem_base + s4 * TC_STAGE_BYTES;
+                            const int kcol = kb * SK_KB;
+                            const uint32_t st = smem_base + s4 * SK_STAGE_BYTES;
                             const uint32_t fb = full0 + 8 * s4;
+                            const long long t_tma = TIMING ? clock64() : 0;
                             mbar_expect_tx(fb, tx_bytes);
-                            if (!from_stage) tma_load_2d(st, &maps.k, fb, kcol, br.hi[a_buf] + arow);
-                            tma_load_2d(st + 2 * TC_TILE_BYTES, &maps.k, fb, kcol, br.w_hi + w16_row);
+                            if (!from_stage) tma_load_2d(st, &maps.o, fb, kcol, br.hi[a_buf] + arow);
+                            tma_load_2d(st + 2 * SK_TILE_BYTES, &maps.o, fb, kcol, br.w_hi + w16_row);
                             if (split) {
-                                if (!from_stage) tma_load_2d(st + TC_TILE_BYTES, &maps.k, fb, kcol, br.lo[a_buf] + arow);
-                                tma_load_2d(st + 3 * TC_TILE_BYTES, &maps.k, fb, kcol, br.w_lo + w16_row);
+                                if (!from_stage) tma_load_2d(st + SK_TILE_BYTES, &maps.o, fb, kcol, br.lo[a_buf] + arow);
+                                tma_load_2d(st + 3 * SK_TILE_BYTES, &maps.o, fb, kcol, br.w_lo + w16_row);
                             }
+                            if (TIMING) tim[10] += (unsigned long long)(clock64() - t_tma);
                         }
                     }
                 }
             }
-            if (TIMING) { args.timing[(size_t)blockIdx.x * 8] = tim[0]; args.timing[(size_t)blockIdx.x * 8 + 1] = tim[1]; }
+            __syncwarp();
         }
+        if (TIMING && lane == 0) { args.timing[(size_t)blockIdx.x * 16] = tim[0]; args.timing[(size_t)blockIdx.x * 16 + 10] = tim[10]; args.timing[(size_t)blockIdx.x * 16 + 11] = tim[11]; }
     } else if (warp == 1) {
-        if (lane == 0) {
-            uint32_t g = 0, k = 0, n_staged = 0;
-            for (int i = blockIdx.x; i < n_total; i += gridDim.x) {
-                const ItemRef ir = stack_decode(pg, NT, RC, i);
-                const StackItem it = items[ir.item];
-                for (int s = 0; s < it.n_steps; ++s, ++k) {
-                    const Tile* t = tiles + it.tile + s;
-                    const int n_chunks = __ldg(&t->n_chunks), a_stage = __ldg(&t->a_stage);
-                    const uint32_t a = k & 1;
-                    SK_TIMED(3, mbar_wait(acc_free0 + 8 * a, ((k >> 1) & 1) ^ 1));      // the epilogue has drained this accumulator
+        uint32_t g = 0, k = 0, n_staged = 0;
+        for (int n = 0;; ++n) {
+            int4 qa, qb;
+            SK_TIMED(8, next_item(n, qa, qb));
+            if (qa.w == 0) break;
+            if (lane == 0) {
+                for (int s = 0; s < qa.w; ++s, ++k) {
+                    const int n_chunks = (qb.x >> (8 * s)) & 0xf, a_stage = (qb.x >> (8 * s + 4)) & 1;
+                    const uint32_t a = k % SK_ACCS;
+                    SK_TIMED(3, mbar_wait(acc_free0 + 8 * a, ((k / SK_ACCS) & 1) ^ 1));      // the epilogue has drained this accumulator
                     tc_fence_after();
                     if (TIMING) tim[7] += 1;
                     const uint32_t d0 = tmem_base + a * 128;
@@ -420,58 +474,63 @@ k_tc_stack(const __grid_constant__ TcMaps maps, const Tile* __restrict__ tiles, 
                             const uint32_t s4 = g % SK_STAGES;
                             SK_TIMED(2, mbar_wait(full0 + 8 * s4, (g / SK_STAGES) & 1));
                             tc_fence_after();
-                            const uint32_t st = smem_base + s4 * TC_STAGE_BYTES;
-                            const uint32_t a_base = from_stage ? stg_base + (uint32_t)kb * 16384u : st;
-                            const uint64_t a_hi = smem_desc_sw64(a_base), a_lo = smem_desc_sw64(a_base + (from_stage ? 8192u : (uint32_t)TC_TILE_BYTES));
-                            const uint64_t w_hi = smem_desc_sw64(st + 2 * TC_TILE_BYTES), w_lo = smem_desc_sw64(st + 3 * TC_TILE_BYTES);
+                            const long long t_issue = TIMING ? clock64() : 0;
+                            const uint32_t st = smem_base + s4 * SK_STAGE_BYTES;
+                            const uint64_t w_hi = smem_desc_sw128(st + 2 * SK_TILE_BYTES), w_lo = smem_desc_sw128(st + 3 * SK_TILE_BYTES);
 #pragma unroll
-                            for (int ks = 0; ks < TC_KB / 16; ++ks) {
-                                const uint64_t adv = (uint64_t)(ks * 2);
-                                umma_f16(d0, a_hi + adv, w_hi + adv, TC_IDESC, (c | kb | ks) ? 1u : 0u);
+                            for (int ks = 0; ks < SK_KB / 16; ++ks) {
+                                uint64_t a_hi, a_lo;
+                                if (from_stage) {
+                                    // the staged operand keeps the epilogue's layout: four 32-column SWIZZLE_64B blocks (one per group)
+                                    const uint32_t blk = stg_base + (uint32_t)(kb * (SK_KB / 32) + (ks >> 1)) * 16384u;
+                                    a_hi = smem_desc_sw64(blk) + (uint64_t)((ks & 1) * 2);
+                                    a_lo = smem_desc_sw64(blk + 8192u) + (uint64_t)((ks & 1) * 2);
+                                } else {
+                                    a_hi = smem_desc_sw128(st) + (uint64_t)(ks * 2);
+                                    a_lo = smem_desc_sw128(st + SK_TILE_BYTES) + (uint64_t)(ks * 2);
+                                }
+                                const uint64_t adv = (uint64_t)(ks * 2);      // +32 bytes (16 fp16) along K inside the swizzle atom
+                                umma_f16(d0, a_hi, w_hi + adv, TC_IDESC, (c | kb | ks) ? 1u : 0u);
                                 if (split) {
-                                    umma_f16(d0, a_lo + adv, w_hi + adv, TC_IDESC, 1u);
-                                    umma_f16(d0, a_hi + adv, w_lo + adv, TC_IDESC, 1u);
+                                    umma_f16(d0, a_lo, w_hi + adv, TC_IDESC, 1u);
+                                    umma_f16(d0, a_hi, w_lo + adv, TC_IDESC, 1u);
                                 }
                             }
                             umma_commit(empty0 + 8 * s4);
+                            if (TIMING) tim[9] += (unsigned long long)(clock64() - t_issue);
                         }
                     }
                     umma_commit(acc_full0 + 8 * a);
                 }
             }
-            if (TIMING) {
-                tim[6] = (unsigned long long)(clock64() - t_begin);
-                for (int j = 2; j < 8; ++j) if (j != 5) args.timing[(size_t)blockIdx.x * 8 + j] = tim[j];
-            }
+            __syncwarp();
         }
-        __syncwarp();
+        if (TIMING && lane == 0) {
+            tim[6] = (unsigned long long)(clock64() - t_begin);
+            for (int j = 2; j < 10; ++j) if (j != 5) args.timing[(size_t)blockIdx.x * 16 + j] = tim[j];
+        }
     } else {
         // group g (warps 2 + 4g .. 5 + 4g) drains column quarter g of every step
         const int grp = (warp - 2) >> 2;
         StackEpi es;
         es.stg = stg_base + grp * 16384; es.bias = smem_u32(bias_s[grp]); es.res_bar = res_bar + 8 * grp; es.stage_bar = stage_bar;
         uint32_t k = 0, n_res = 0;
-        uint32_t* pend = nullptr;
-        int n_item = 0;
-        for (int i = blockIdx.x; i < n_total; i += gridDim.x) {
-            const ItemRef ir = stack_decode(pg, NT, RC, i);
-            const StackItem it = items[ir.item];
-            ++n_item;
-            uint32_t* const ctr = args.sync + (size_t)ir.phase * NT + ir.row_tile;
-            for (int s = 0; s < it.n_steps; ++s, ++k) {
-                const TileHdr t = load_hdr(tiles + it.tile + s);
-                const uint32_t a = k & 1;
+        for (int n = 0;; ++n) {
+            int4 qa, qb;
+            next_item(n, qa, qb);
+            if (qa.w == 0) break;
+            uint32_t* const ctr = args.sync + ((size_t)qa.y * NT + qa.x) * args.n_slots + qb.y;
+            for (int s = 0; s < qa.w; ++s, ++k) {
+                const TileHdr t = load_hdr(tiles + qa.z + s);
+                const uint32_t a = k % SK_ACCS;
                 es.accum_bar = acc_full0 + 8 * a; es.free_bar = acc_free0 + 8 * a;
-                es.acc_parity = (k >> 1) & 1;
-                stack_epilogue(t, bt, br, &maps.k, tmem_base + a * 128, ir.row_tile * TILE_M, B, Bp, warp, lane, grp, es, n_res, pend,
-                               s == it.n_steps - 1 ? ctr : nullptr, &dep_ok_s, ir.phase > 0 ? n_item : 0, (TIMING && warp == 2 && lane == 0) ? &tim[5] : nullptr);
+                es.acc_parity = (k / SK_ACCS) & 1;
+                stack_epilogue(t, bt, br, &maps.k, tmem_base + a * 128, qa.x * TILE_M, B, Bp, warp, lane, grp, es, n_res,
+                               s == qa.w - 1 ? ctr : nullptr, (TIMING && warp == 2 && lane == 0) ? &tim[5] : nullptr);
             }
         }
-        if ((warp & 3) == 2 && lane == 0) {
-            tma_store_wait_all();
-            if (pend) stack_signal(pend);
-        }
-        if (TIMING && warp == 2 && lane == 0) args.timing[(size_t)blockIdx.x * 8 + 5] = tim[5];
+        if ((warp & 3) == 2 && lane == 0) tma_store_wait_all();
+        if (TIMING && warp == 2 && lane == 0) args.timing[(size_t)blockIdx.x * 16 + 5] = tim[5];
     }
     tc_fence_before();
     __syncthreads();

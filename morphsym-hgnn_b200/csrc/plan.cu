@@ -77,6 +77,11 @@ static bool emit_units(Plan& p, const std::vector<RPair>& prs, int K, int k0, in
 // dX(l) of an MLP-type node -> dpre(l-1) -> dc(l-1)), so the intermediate tiles never leave the SM in inference and are
 // read back from shared memory, not from HBM, in training.
 // ------------------------------------------------------------------------------------------------------------------
+// activation / gradient buffers written by the phases of a stack program (as opposed to forward state a backward phase reads)
+static bool is_phase_buffer(int buf) {
+    return (buf >= BUF_H0 && buf < BUF_H0 + MAX_LAYERS + 1) || (buf >= BUF_DHL0 && buf < BUF_DUL0 + MAX_LAYERS);
+}
+
 static std::string build_stack_programs(Plan& p) {
     auto begin_prog = [&](Plan::Stack& st) { st.tiles.begin = (int)p.tiles.size(); st.item0 = (int)p.stack_items.size(); st.prog = StackProg{}; };
     auto begin_phase = [&](Plan::Stack& st) -> std::string {
@@ -88,13 +93,47 @@ static std::string build_stack_programs(Plan& p) {
     auto end_phase = [&](Plan::Stack& st) {
         if (st.prog.n_items[st.prog.n_phases] > 0) { st.prog.items_per_row += st.prog.n_items[st.prog.n_phases]; st.prog.n_phases++; }
     };
+    // reads[i] = slots of the previous phase item i reads from global memory (operands of non-staged chunks whose buffer the
+    // previous phase wrote, and residuals); filled per item, turned into dep_mask by end_prog
+    std::vector<unsigned long long> reads;
     auto emit = [&](Plan::Stack& st, const std::vector<Tile>& steps) {
-        StackItem it{(int)p.tiles.size() - st.tiles.begin, (int)steps.size()};
+        StackItem it{};
+        it.tile = (int)p.tiles.size() - st.tiles.begin; it.n_steps = (int)steps.size();
+        const Tile& last = steps.back();
+        it.out_slot = last.out_buf >= 0 ? last.out_slot : last.out2_slot;
+        unsigned long long rd = 0;
+        for (const Tile& T : steps) {
+            for (int c = 0; c < T.n_chunks; ++c)
+                if (!(T.a_stage && c == 0) && is_phase_buffer(T.chunks[c].a_buf)) rd |= 1ull << T.chunks[c].a_slot;
+            if (T.res_buf >= 0 && is_phase_buffer(T.res_buf)) rd |= 1ull << T.res_slot;
+        }
         p.tiles.insert(p.tiles.end(), steps.begin(), steps.end());
         p.stack_items.push_back(it);
+        reads.push_back(rd);
         st.prog.n_items[st.prog.n_phases]++;
     };
-    auto end_prog = [&](Plan::Stack& st) { st.tiles.count = (int)p.tiles.size() - st.tiles.begin; };
+    // ping_pong: the buffers of phase p + 1's outputs are those phase p READ (inference): an item may only overwrite slot d
+    // once every phase-p item that reads slot d has finished
+    auto end_prog = [&](Plan::Stack& st, bool ping_pong) {
+        st.tiles.count = (int)p.tiles.size() - st.tiles.begin;
+        const size_t r0 = reads.size() - (p.stack_items.size() - st.item0);
+        for (int ph = 0; ph < st.prog.n_phases; ++ph)
+            for (int i = 0; i < st.prog.n_items[ph]; ++i) {
+                StackItem& it = p.stack_items[st.item0 + st.prog.first_item[ph] + i];
+                it.dep_mask = 0;
+                if (ph == 0) continue;
+                it.dep_mask = reads[r0 + st.prog.first_item[ph] + i];
+                if (ping_pong)
+                    for (int j = 0; j < st.prog.n_items[ph - 1]; ++j) {
+                        const StackItem& prev = p.stack_items[st.item0 + st.prog.first_item[ph - 1] + j];
+                        if (reads[r0 + st.prog.first_item[ph - 1] + j] >> it.out_slot & 1ull) it.dep_mask |= 1ull << prev.out_slot;
+                    }
+                // only slots the previous phase actually produces can be waited for
+                unsigned long long produced = 0;
+                for (int j = 0; j < st.prog.n_items[ph - 1]; ++j) produced |= 1ull << p.stack_items[st.item0 + st.prog.first_item[ph - 1] + j].out_slot;
+                it.dep_mask &= produced;
+            }
+    };
     auto find_by_a = [&](const Launch& L, int a_buf, int a_slot) -> int {
         for (int i = 0; i < L.count; ++i) {
             const Tile& T = p.tiles[L.begin + i];
@@ -128,7 +167,7 @@ static std::string build_stack_programs(Plan& p) {
             }
             end_phase(st);
         }
-        end_prog(st);
+        end_prog(st, !train);
     }
     // ---- backward dX chain ----
     {
@@ -169,7 +208,7 @@ static std::string build_stack_programs(Plan& p) {
             }
             end_phase(st);
         }
-        end_prog(st);
+        end_prog(st, false);
         // every base_transform backward tile must have been chained somewhere
         int chained = 0, want = 0;
         for (int i = 0; i < st.tiles.count; ++i) chained += p.tiles[st.tiles.begin + i].a_stage;
@@ -716,9 +755,9 @@ WsLayout ws_layout(const Plan& p, int64_t B, int train, int mode) {
         }
     }
     if (w.stack) {
-        w.stack_sync_bytes = ((int64_t)STACK_MAX_PHASES * (w.Bp / TILE_M) + 64) * 4;
+        w.stack_sync_bytes = ((int64_t)(p.L + 2) * (w.Bp / TILE_M) * p.S + 64) * 4;      // per (phase, row tile, node slot) completion counters + work counter + error word
         w.stack_sync = take(w.stack_sync_bytes);
-        w.stack_timing = take(256 * 8 * 8);
+        w.stack_timing = take(256 * 16 * 8);
     }
     w.loss_part = take(LOSS_BLOCKS * 8);
     w.total = o;

@@ -18,18 +18,22 @@ dev = torch.device("cuda:0")
 nm = build_model(cfg, layers=8, seed=3).set_mode(mode).to(dev)
 nm.validate_edges = "cached"
 b = make_batch(cfg, B, seed=1).to(dev)
-NAMES = ["producer: ring slot", "producer: dependency", "MMA: operands", "MMA: accumulator free", "MMA: staged operand",
-         "epilogue g0: accumulator", "kernel", "steps"]
+NAMES = ["producer: ring slot", "scheduler: dependency", "MMA: operands", "MMA: accumulator free", "MMA: staged operand",
+         "epilogue g0: accumulator", "kernel", "steps", "MMA: item queue", "MMA: issuing a K block", "producer: issuing TMA", "producer: item queue"]
 
 
 def show(tag, train):
     eng = nm._last_engine
     off = eng.plan.stack_timing_offset(B, train, eng.mode)
     torch.cuda.synchronize()
-    t = eng._ws[off:off + 148 * 64].view(torch.int64).view(148, 8).double().cpu()
+    t = eng._ws[off:off + 148 * 128].view(torch.int64).view(148, 16).double().cpu()
     tot = t[:, 6].mean().item()
+    if os.environ.get("STACK_TIMING_COMPACT"):
+        short = {1: "sched:dep", 11: "prod:queue", 0: "prod:ring", 8: "mma:queue", 2: "mma:operands", 4: "mma:staged", 3: "mma:accfree", 9: "mma:issue", 5: "epi:acc"}
+        print(f"{tag:18s} {tot / 1e6:.3f} Mcyc | " + "  ".join(f"{v} {100 * t[:, j].mean().item() / tot:4.1f}" for j, v in short.items()))
+        return
     print(f"--- {tag}: kernel {tot / 1e6:.3f} Mcycles per CTA (mean), {t[:, 7].mean().item():.1f} steps per CTA")
-    for j in range(6):
+    for j in (1, 11, 0, 10, 8, 2, 3, 4, 9, 5):
         print(f"   {NAMES[j]:28s} {100 * t[:, j].mean().item() / tot:5.1f} % of kernel cycles (min {100 * t[:, j].min().item() / tot:4.1f}, max {100 * t[:, j].max().item() / tot:4.1f})")
 
 
