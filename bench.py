@@ -31,6 +31,7 @@ import torch  # noqa: E402
 
 WORKLOAD = "mini_cheetah-k4-contact"      # BASELINE.json configs[2]: MS-HGNN K4 Mini Cheetah contact, batch 16384 per GPU
 PER_GPU_BATCH = 16384
+REFERENCE_SAMPLE = 4096                    # graphs per step of the CPU arm (bounded sample, see run_reference)
 METRIC = "train-step graphs/s (MS-HGNN K4 Mini Cheetah contact, H=128, L=8, fwd+loss+bwd+allreduce+Adam)"
 
 # Algorithmic work per graph, SURVEY 8d (minimum: zero aggregates skipped, roots pre-summed, dead last layer):
@@ -55,9 +56,12 @@ ALG = {
 }
 
 
+TRAFFIC_FILE = "r2_dominant_traffic.json"   # ncu DRAM bytes of THIS round's kernels (tools/launch_traffic.py); keyed by kernel kind
+
+
 def recorded_traffic():
     """DRAM bytes from the committed ncu captures (profiles/): per launch of the dominant kernels and per train step."""
-    p = os.path.join(ROOT, "profiles", "r1_tc_v7_dominant_traffic.json")
+    p = os.path.join(ROOT, "profiles", TRAFFIC_FILE)
     return json.load(open(p)) if os.path.exists(p) else {}
 
 
@@ -144,17 +148,23 @@ def run_reference(args, rank):
         return
     cores = os.cpu_count()
     torch.set_num_threads(cores)
-    B = 1024
+    # bounded sample of the 16384-graph step: 4096 graphs per CPU step (8.7 GB of fp64 autograd state, ~1 s per step on 16
+    # cores; the full 16384 would need ~35 GB and 25 x 3.5 s).  Throughput is per graph, so the sample size only matters
+    # through cache effects: 1024 / 4096 graphs per step measured within 10 % of each other.
+    B = REFERENCE_SAMPLE
     mean_rate, best_rate = oracle_train_rate(B, args.steps, args.warmup)
     ms = 1e3 * B / mean_rate
     line = {
         "impl": "reference", "metric": METRIC, "value": mean_rate, "unit": "graphs/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "per_step_graphs": B, "note": "CPU oracle = pure-PyTorch restatement of the reference's "
-                   "torch_geometric op sequence (the reference itself is not installable offline); fp64 like the reference"},
+        "config": {"workload": WORKLOAD, "per_gpu_batch": PER_GPU_BATCH, "global_batch": PER_GPU_BATCH * max(args.gpus, 1), "hidden": 128, "layers": 8,
+                   "sample_graphs_per_step": B,
+                   "note": "CPU oracle = pure-PyTorch restatement of the reference's torch_geometric op sequence, pinned to the reference's "
+                           "unmodified model files (tests/test_reference_pin.py); the reference itself is not installable offline.  fp64 like "
+                           "the reference.  Each step is a bounded 4096-graph sample of the 16384-graph batch (graphs/s is per graph)"},
         "cpu_baseline": {"value": mean_rate, "unit": "graphs/s", "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"{args.steps} train steps of {B} graphs, fp64, torch threads={torch.get_num_threads()}"},
+                         "sample": f"{args.steps} train steps of {B} graphs (of the 16384-graph batch), fp64, torch threads={torch.get_num_threads()}"},
         "e2e": {"value": mean_rate, "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -172,6 +182,7 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-extra", action="store_true", help="skip the short runs of the other BASELINE.json configs")
+    ap.add_argument("--skip-strong", action="store_true", help="skip the strong-scaling block (16384 graphs global)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -254,6 +265,48 @@ def main():
         trainer.infer(resident)
     infer_ms = timed(lambda: trainer.infer(resident), K)
     clocks = sampler.stop() if sampler else {}          # sampled across the three device-resident timed regions above
+
+    # ---------------- strong scaling: BASELINE.json configs[2] as written = 16384 graphs GLOBAL over the N GPUs ----------------
+    # Every rank trains PER_GPU_BATCH / N graphs per step (eager launches, and with the forward + loss + backward replayed from
+    # one CUDA graph: at 2048 graphs per GPU the step is launch bound).  Efficiency = T(16384 on one GPU, no collective) /
+    # (N x T(16384 / N per GPU, with the all-reduce)), both measured in THIS run on the same GPUs.
+    strong = None
+    if B == PER_GPU_BATCH and not args.skip_strong:
+        trainer.skip_allreduce = True
+        for _ in range(W):
+            trainer.train_step(resident)
+        t1_ms = timed(lambda: trainer.train_step(resident), K) / K        # one GPU's 16384-graph step without the collective
+        trainer.skip_allreduce = False
+
+        def small(bs):
+            hb = make_batch(cfg, bs, seed=300 + rank).to(dev)
+            for _ in range(W):
+                trainer.train_step(hb)
+            eager = timed(lambda: trainer.train_step(hb), K) / K
+            for _ in range(W):
+                trainer.train_step_graphed(hb)
+            graphed = timed(lambda: trainer.train_step_graphed(hb), K) / K
+            return eager, graphed
+
+        if world > 1:
+            bs = PER_GPU_BATCH // world
+            eager, graphed = small(bs)
+            best = min(eager, graphed)
+            strong = {"global_batch": PER_GPU_BATCH, "per_gpu_batch": bs, "n_gpus": world, "ms_per_step": eager, "ms_per_step_cuda_graph": graphed,
+                      "value": PER_GPU_BATCH / (best * 1e-3), "unit": "graphs/s", "single_gpu_ms_per_step": t1_ms,
+                      "efficiency": t1_ms / (world * best), "efficiency_eager": t1_ms / (world * eager),
+                      "note": "16384 graphs global; efficiency = T1 / (N x TN) with T1 = this run's 16384-graph step on one GPU without the collective"}
+        else:
+            # one GPU: what each rank of an N-GPU strong-scaling run computes (no collective here, so an upper bound on the
+            # N-GPU efficiency; the N-GPU runs of this script report the measured one)
+            rows = []
+            for n in (2, 4, 8):
+                eager, graphed = small(PER_GPU_BATCH // n)
+                rows.append({"n_gpus_emulated": n, "per_gpu_batch": PER_GPU_BATCH // n, "ms_per_step": eager, "ms_per_step_cuda_graph": graphed,
+                             "compute_efficiency_bound": t1_ms / (n * min(eager, graphed))})
+            strong = {"global_batch": PER_GPU_BATCH, "n_gpus": 1, "single_gpu_ms_per_step": t1_ms, "efficiency": 1.0,
+                      "per_rank_compute_at_n_gpus": rows,
+                      "note": "per-rank compute of a 16384-graph global batch split over N GPUs, measured on this one GPU (no collective)"}
 
     # ---------------- end to end: pinned host buffers -> H2D -> train step -> D2H loss ----------------
     e2e_ms = None
@@ -457,6 +510,9 @@ def main():
         "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world, "hidden": 128, "layers": 8,
                    "parallelism": f"dp{world}", "mode": {"fp32": "fp32 SIMT FMA", "tc": "tcgen05 split-fp16 x3 (fp32-class accuracy): encoder, layers, dX, dW all on tensor cores", "tc1x": "tcgen05 fp16 x1"}[args.mode], "l2": "inputs (708 MB/step/GPU) exceed the 126 MB L2; no flush needed"},
         "inference": {"value": total_graphs / (infer_ms * 1e-3), "unit": "graphs/s", "ms_per_step": infer_ms / K},
+        "strong": strong,
+        "allreduce": None if world == 1 else {"overlapped": bool(trainer.overlap_allreduce), "skipped": bool(trainer.skip_allreduce),
+                                              "note": "two buckets: layer-stack gradients on a side stream under the encoder weight gradient, encoder block at the end"},
         "e2e": None if e2e_ms is None else {"value": total_graphs / (e2e_ms * 1e-3), "unit": "graphs/s", "ms_per_step": e2e_ms / K,
                                             "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                                             "note": "pinned host batch -> H2D (copy stream, double-buffered) -> train step -> D2H loss"},
@@ -476,7 +532,7 @@ def main():
         "hbm_step": None if not (traffic.get("step") and B == PER_GPU_BATCH and args.mode == "tc") else {
             "dram_bytes_per_step": traffic["step"]["dram_bytes"], "achieved_gbs": traffic["step"]["dram_bytes"] / (train_ms / K * 1e-3) / 1e9,
             "peak_gbs": pk["hbm_gbs"], "frac": traffic["step"]["dram_bytes"] / (train_ms / K * 1e-3) / 1e9 / pk["hbm_gbs"],
-            "source": "profiles/r1_tc_v7_step_traffic.json (ncu DRAM counters of one step) / this run's step time"},
+            "source": "profiles/" + TRAFFIC_FILE + " (ncu DRAM counters of one step) / this run's step time"},
         "profiled_ms_per_step": prof_ms / K,
         "other_configs": extra,
     }

@@ -132,6 +132,16 @@ int mshgnn_backward(const mshgnn_plan* plan, int64_t B,
                     void* workspace, int64_t workspace_bytes,
                     int32_t mode, void* stream);
 
+/* Same, for data-parallel training: every gradient OUTSIDE the encoder block (the encoder parameters come first in the flat
+ * buffer; everything from the first convs.* offset on) is final when `layers_ready_event` (a cudaEvent_t, may be NULL) is
+ * recorded on `stream` - before the encoder weight gradient, the last launch of the step, runs - so that segment can be
+ * all-reduced on another stream underneath it.  Replaces: DDP's bucketed gradient hooks (gnnLightning.py:L1396-1400, devices). */
+int mshgnn_backward_staged(const mshgnn_plan* plan, int64_t B,
+                           const void* const* x, int32_t x_dtype,
+                           const float* params, const float* dout, float* grads,
+                           void* workspace, int64_t workspace_bytes,
+                           int32_t mode, void* stream, void* layers_ready_event);
+
 /* Fused Adam on flat buffers (torch.optim.Adam defaults semantics, gnnLightning.py:L258-265):
  * step is the 1-based step count after this update. */
 int mshgnn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,

@@ -636,6 +636,12 @@ int mshgnn_loss(const mshgnn_plan* plan, int64_t B, int32_t loss_kind, const flo
 
 int mshgnn_backward(const mshgnn_plan* plan, int64_t B, const void* const* x, int32_t x_dtype, const float* params,
                     const float* dout, float* grads, void* workspace, int64_t workspace_bytes, int32_t mode, void* stream) {
+    return mshgnn_backward_staged(plan, B, x, x_dtype, params, dout, grads, workspace, workspace_bytes, mode, stream, nullptr);
+}
+
+int mshgnn_backward_staged(const mshgnn_plan* plan, int64_t B, const void* const* x, int32_t x_dtype, const float* params,
+                           const float* dout, float* grads, void* workspace, int64_t workspace_bytes, int32_t mode, void* stream,
+                           void* layers_ready_event) {
     if (!plan) return fail(MSHGNN_ERR_ARG, "plan is NULL");
     const Plan& p = plan->p;
     if (mode != MSHGNN_MODE_FP32 && mode != MSHGNN_MODE_TC && mode != MSHGNN_MODE_TC_1X) return fail(MSHGNN_ERR_ARG, "unknown mode %d", mode);
@@ -720,7 +726,24 @@ int mshgnn_backward(const mshgnn_plan* plan, int64_t B, const void* const* x, in
             if ((rc = launch_rowgemm(K_DX_BWD, p, p.bwd_dx[l], bt, B, w.Bp, 0, st))) return rc;
         }
     }
+    // layer-stack groups were produced with the split count of the kernel that ran them, encoder groups with the SIMT one
+    const int ngl = p.n_groups_layers, nge = (int)p.groups.size() - ngl;
+    auto reduce_layers = [&]() -> int {
+        if (ngl > 0) {
+            // 64 blocks per group = one element per thread: the groups of the shared base_transform weights sum up to 16 tasks x
+            // 16..64 splits per element, and that serial chain (not the 117 MB of partials) sets the launch time
+            dim3 grid((unsigned)ngl, 64);
+            ProfScope ps(K_REDUCE, st);
+            k_reduce_partials<<<grid, 256, 0, st>>>(p.d_groups, part_w, part_b, w.segs, grads, 1.f / G);
+            LAUNCH_CHECK();
+        }
+        return 0;
+    };
     if (tc) {
+        // Every gradient outside the encoder is final here - before the encoder weight gradient, the last 8 % of the step, has
+        // even started: the caller's event lets a data-parallel trainer all-reduce that 7.5 MB segment underneath it.
+        if ((rc = reduce_layers())) return rc;
+        if (layers_ready_event) CUDA_TRY(cudaEventRecord((cudaEvent_t)layers_ready_event, st));
         if (!p.enc_units.empty()) {
             static std::atomic<bool> attr_set[64];
             if (first_on_device(attr_set)) CUDA_TRY(cudaFuncSetAttribute(k_tc_encoder_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, EDW_SMEM_BYTES));
@@ -741,22 +764,14 @@ int mshgnn_backward(const mshgnn_plan* plan, int64_t B, const void* const* x, in
             }
         }
     } else if ((rc = launch_dw(K_DW_ENC, p.dw_enc))) return rc;
-    // layer-stack groups were produced with the split count of the kernel that ran them, encoder groups with the SIMT one
-    const int ngl = p.n_groups_layers, nge = (int)p.groups.size() - ngl;
-    if (ngl > 0) {
-        // 64 blocks per group = one element per thread: the groups of the shared base_transform weights sum up to 16 tasks x
-        // 16..64 splits per element, and that serial chain (not the 117 MB of partials) sets the launch time
-        dim3 grid((unsigned)ngl, 64);
-        ProfScope ps(K_REDUCE, st);
-        k_reduce_partials<<<grid, 256, 0, st>>>(p.d_groups, part_w, part_b, w.segs, grads, 1.f / G);
-        LAUNCH_CHECK();
-    }
+    if (!tc && (rc = reduce_layers())) return rc;
     if (nge > 0 && !tc) {
         dim3 grid((unsigned)nge, 32);
         ProfScope ps(K_REDUCE, st);
         k_reduce_partials<<<grid, 256, 0, st>>>(p.d_groups + ngl, part_w, part_b, w.segs, grads, 1.f / G);
         LAUNCH_CHECK();
     }
+    if (!tc && layers_ready_event) CUDA_TRY(cudaEventRecord((cudaEvent_t)layers_ready_event, st));
     return 0;
 }
 

@@ -30,6 +30,7 @@ EXPORTS = (
     "mshgnn_last_error", "mshgnn_version", "mshgnn_profile_enable", "mshgnn_profile_read", "mshgnn_kernel_kind_name",
     "mshgnn_relu_mask_offset", "mshgnn_build_windows", "mshgnn_step_metrics", "mshgnn_dw_layout",
     "mshgnn_check_edges", "mshgnn_set_option", "mshgnn_get_option", "mshgnn_stack_status", "mshgnn_stack_timing_offset",
+    "mshgnn_backward_staged",
 )
 
 
@@ -100,6 +101,7 @@ def lib() -> C.CDLL:
     L.mshgnn_forward.argtypes = [vp, i64, C.POINTER(vp), i32, vp, vp, vp, i64, i32, i32, vp]; L.mshgnn_forward.restype = C.c_int
     L.mshgnn_loss.argtypes = [vp, i64, i32, vp, vp, i32, f32, vp, vp, vp, i64, vp]; L.mshgnn_loss.restype = C.c_int
     L.mshgnn_backward.argtypes = [vp, i64, C.POINTER(vp), i32, vp, vp, vp, vp, i64, i32, vp]; L.mshgnn_backward.restype = C.c_int
+    L.mshgnn_backward_staged.argtypes = [vp, i64, C.POINTER(vp), i32, vp, vp, vp, vp, i64, i32, vp, vp]; L.mshgnn_backward_staged.restype = C.c_int
     L.mshgnn_adam_step.argtypes = [vp, vp, vp, vp, i64, i64, f32, f32, f32, f32, f32, vp]; L.mshgnn_adam_step.restype = C.c_int
     L.mshgnn_sgd_step.argtypes = [vp, vp, i64, f32, vp]; L.mshgnn_sgd_step.restype = C.c_int
     L.mshgnn_plan_describe.argtypes = [vp, C.c_char_p, i64]; L.mshgnn_plan_describe.restype = i64
@@ -265,10 +267,10 @@ class NativePlan:
         check(lib().mshgnn_loss(self.handle, B, kind, out_ptr, labels_ptr, label_dtype, loss_scale, loss_ptr, dout_ptr,
                                 ws_ptr, ws_bytes, stream), "mshgnn_loss")
 
-    def backward(self, B, x_ptrs, x_dtype, params_ptr, dout_ptr, grads_ptr, ws_ptr, ws_bytes, mode, stream):
+    def backward(self, B, x_ptrs, x_dtype, params_ptr, dout_ptr, grads_ptr, ws_ptr, ws_bytes, mode, stream, layers_ready_event=None):
         arr = (C.c_void_p * len(x_ptrs))(*x_ptrs)
-        check(lib().mshgnn_backward(self.handle, B, arr, x_dtype, params_ptr, dout_ptr, grads_ptr, ws_ptr, ws_bytes, mode, stream),
-              "mshgnn_backward")
+        check(lib().mshgnn_backward_staged(self.handle, B, arr, x_dtype, params_ptr, dout_ptr, grads_ptr, ws_ptr, ws_bytes, mode, stream,
+                                           layers_ready_event), "mshgnn_backward")
 
 
 METRIC_SLOTS, METRIC_SCRATCH = 32, 296 * 32

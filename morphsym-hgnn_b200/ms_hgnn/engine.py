@@ -149,7 +149,12 @@ class Engine:
                            dout.data_ptr() if want_grad else None, ws.data_ptr(), ws.numel(), stream)
         return loss, dout
 
-    def backward(self, dout: torch.Tensor, flat_params: torch.Tensor, grads: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def encoder_param_end(self) -> int:
+        """Flat offset of the first non-encoder parameter (the encoder block comes first, reference named_parameters() order)."""
+        return min(o for (name, o, _) in self.param_layout() if not name.startswith("encoder."))
+
+    def backward(self, dout: torch.Tensor, flat_params: torch.Tensor, grads: Optional[torch.Tensor] = None,
+                 layers_ready: Optional[torch.cuda.Event] = None) -> torch.Tensor:
         if self._train_ctx is None:
             raise RuntimeError("backward() needs a preceding forward(train=True) on the same engine")
         B, x, xd = self._train_ctx
@@ -164,6 +169,11 @@ class Engine:
         ws = self.workspace(B, True, dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
         with torch.cuda.device(dev):
+            if layers_ready is not None:
+                # torch creates the CUDA event lazily at its first record(): make sure the handle exists
+                if layers_ready.cuda_event == 0:
+                    layers_ready.record(torch.cuda.current_stream(dev))
             self.plan.backward(B, [t.data_ptr() for t in x], xd, flat_params.data_ptr(), dout.data_ptr(), grads.data_ptr(),
-                               ws.data_ptr(), ws.numel(), self.mode, stream)
+                               ws.data_ptr(), ws.numel(), self.mode, stream,
+                               layers_ready.cuda_event if layers_ready is not None else None)
         return grads
