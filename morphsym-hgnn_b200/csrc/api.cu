@@ -710,8 +710,15 @@ int mshgnn_backward_staged(const mshgnn_plan* plan, int64_t B, const void* const
         // the whole dX chain (with the base_transform backward chained on chip) in one launch over per-layer dh / dc / du
         // images, then the weight gradients of every layer (they only read what the chain and the forward pass stored)
         if ((rc = launch_stack(K_STACK_BWD, p, p.stack_bwd, w, bt, br, wm, ws, B, split, st))) return rc;
-        for (int l = p.L - 1; l >= 0; --l)
-            if ((rc = launch_tc_dw(K_DW_LAYER, p, l, p.dw_layer[l], w, br, wm, B, split, part_w, part_b, st))) return rc;
+        if (w.dw_merged) {
+            // tasks are laid out layer L-1 first, contiguously: one launch covers them all (ws_layout fitted one split count)
+            Launch all{p.dw_layer[p.L - 1].begin, 0};
+            for (int l = 0; l < p.L; ++l) all.count += p.dw_layer[l].count;
+            if ((rc = launch_tc_dw(K_DW_LAYER, p, p.L - 1, all, w, br, wm, B, split, part_w, part_b, st))) return rc;
+        } else {
+            for (int l = p.L - 1; l >= 0; --l)
+                if ((rc = launch_tc_dw(K_DW_LAYER, p, l, p.dw_layer[l], w, br, wm, B, split, part_w, part_b, st))) return rc;
+        }
     } else
     for (int l = p.L - 1; l >= 0; --l) {
         if (tc) {

@@ -663,6 +663,30 @@ WsLayout ws_layout(const Plan& p, int64_t B, int train, int mode) {
             w.dw_rows[l] = (int)best;
             w.dw_ns[l] = (int)((B + best - 1) / best);
         }
+        // Stack mode: the dX chain of every layer has already run when the weight gradients start, so ALL layers' tasks go
+        // into ONE launch (K4: 94 tasks) with one row split count fitted to whole waves by the same cost model - 8 launches
+        // fewer, and at small batches (2048 graphs: 136 CTAs of 256 rows per layer launch) CTAs long enough to amortise
+        // their fixed prologue / partial write-out (94 x 3 splits of 704 rows).
+        if (w.stack && train && fit) {
+            int64_t count = 0;
+            for (size_t l = 0; l < p.dw_layer.size(); ++l) count += p.dw_layer[l].count;
+            if (count > 0) {
+                auto cost = [&](int64_t rows) {
+                    const int64_t ns = (B + rows - 1) / rows;
+                    return (double)((count * ns + 147) / 148) * (double)(rows + 96);
+                };
+                int64_t best = w.rows_per_tc;
+                double best_c = cost(best);
+                const int64_t cap2 = round_up(B < 2048 ? B : 2048, 64);
+                for (int64_t rows = 64; rows <= cap2; rows += 64) {
+                    if ((B + rows - 1) / rows > 64) continue;
+                    const double c = cost(rows);
+                    if (c < best_c) { best_c = c; best = rows; }
+                }
+                for (size_t l = 0; l < p.dw_layer.size() && l < (size_t)MAX_LAYERS; ++l) { w.dw_rows[l] = (int)best; w.dw_ns[l] = (int)((B + best - 1) / best); }
+                w.dw_merged = 1;
+            }
+        }
     }
     {   // partial slots, packed launch by launch in task order (the SIMT kernels use one split count for every task)
         std::vector<std::pair<int, int>> seg;          // (first task, split count)
@@ -748,7 +772,22 @@ WsLayout ws_layout(const Plan& p, int64_t B, int train, int mode) {
     if (tc) {
         for (int i = 0; i < 2; ++i) w.wenc16[i] = take((int64_t)p.n_types * H * p.enc_kmax * 2);
         if (train) {
+            // row splits of the encoder weight gradient, fitted to whole waves like the layer-stack ones (16 units for the K4 model:
+            // 512-row splits gave 64 CTAs on 148 SMs at 2048 graphs)
             w.rows_per_enc = 512;
+            {
+                const int64_t units = (int64_t)p.enc_units.size();
+                auto cost = [&](int64_t rows) {
+                    const int64_t ns = (B + rows - 1) / rows;
+                    return (double)((units * ns + 147) / 148) * (double)(rows + 96);
+                };
+                double best_c = cost(512);
+                for (int64_t rows = 128; rows <= 1024 && units > 0; rows += 64) {
+                    if ((B + rows - 1) / rows > 64) continue;
+                    const double c = cost(rows);
+                    if (c < 0.97 * best_c) { best_c = c; w.rows_per_enc = (int)rows; }
+                }
+            }
             w.n_splits_enc = (int)((B + w.rows_per_enc - 1) / w.rows_per_enc);
             w.part_enc_w = take((int64_t)p.enc_units.size() * w.n_splits_enc * H * 192 * 4);
             w.part_enc_b = take((int64_t)p.enc_units.size() * w.n_splits_enc * H * 4);

@@ -117,6 +117,7 @@ struct WsLayout {
     int dw_ns[MAX_LAYERS], dw_rows[MAX_LAYERS];   // per layer launch: row splits actually used (wave-fitted, see ws_layout)
     PartSegs segs;                     // packed partial slots of the weight-gradient tasks (common.cuh)
     int dw_slot0[MAX_LAYERS];          // first partial slot of each layer launch
+    int dw_merged = 0;                 // stack mode: one weight-gradient launch for all layers (uniform row splits)
     int64_t part_slots = 0;            // total slots ([128][128] fp32 weight partial + [128] bias partial each)
     int64_t derived = 0;
     int64_t h[MAX_LAYERS + 1];

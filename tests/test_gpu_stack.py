@@ -1,8 +1,9 @@
 """GPU tests of the cross-layer stack kernel (csrc/kernels_stack.cuh) and the native edge_index check.
 
 The stack kernel runs the same tiles as the per-layer launch sequence - same operands, same MMA order, same epilogue
-arithmetic - so predictions AND every gradient must be bit-identical between the two paths; the oracle parity of the stack
-path itself is what tests/test_gpu_parity.py checks (the stack path is the default there).
+arithmetic - so predictions and loss must be bit-identical between the two paths (and the gradients equal up to the
+summation order of the weight-gradient row splits); the oracle parity of the stack path itself is what
+tests/test_gpu_parity.py checks (the stack path is the default there).
 """
 import pytest
 import torch
@@ -61,8 +62,13 @@ def test_stack_kernel_is_bit_identical_to_the_per_layer_launches(name, B, layers
     assert torch.equal(out_s, out_l)
     assert torch.equal(inf_s, inf_l) and torch.equal(inf_s, out_s)
     assert loss_s == loss_l
+    # gradients: the dX chain is bit-identical too, but the stack path sums the weight gradients of ALL layers in one launch
+    # with its own row-split count (ws_layout), i.e. in a different fp32 summation order over the graphs
     for k in g_l:
-        assert torch.equal(g_s[k], g_l[k]), k
+        if g_l[k].norm() == 0:
+            assert g_s[k].abs().max().item() == 0.0, k
+        else:
+            assert rel_err(g_s[k], g_l[k]) <= 2e-6, (k, rel_err(g_s[k], g_l[k]))
     print(f"stack[{name} B={B} L={layers}]: {launches_stack} launches per train step with the stack kernel, {launches_layer} per layer")
     assert launches_stack < launches_layer or layers < 2
 

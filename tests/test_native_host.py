@@ -73,6 +73,29 @@ def test_live_row_gemv_counts():
 def test_weight_gradient_launch_layout():
     """ws_layout (csrc/plan.cu): row splits fitted per layer launch to whole waves of 148 CTAs, partial slots packed."""
     k4 = N.NativePlan(_spec(M.K4_MINI_CHEETAH, {"base": 900, "joint": 300, "foot": 900}, True, "foot", 2))
+    before = N.get_option("stack")
+    try:
+        # stack mode (default): ONE launch for all 94 tasks, one split count fitted to whole waves
+        N.set_option("stack", 1)
+        for B in (1, 257, 2048, 4096, 16384, 100000):
+            lay = k4.dw_layout(B, N.MODE_TC)
+            assert len({(ns, rows) for _, ns, rows, _ in lay}) == 1
+            tasks, (ns, rows) = sum(t for t, _, _, _ in lay), lay[0][1:3]
+            assert tasks == 94 and rows % 64 == 0 and (ns - 1) * rows < B <= ns * rows
+            waves = lambda n: -(-tasks * n // 148)
+            default_ns = -(-B // 1024)
+            assert waves(ns) * (rows + 96) <= waves(default_ns) * (1024 + 96) or B < 1024
+            # partial slots of the merged launch are contiguous in task order (layer L-1 first)
+            order = sorted(lay, key=lambda e: e[3])
+            assert order[0][3] == 0 and all(a[3] + a[0] * a[1] == b[3] for a, b in zip(order, order[1:]))
+        assert k4.dw_layout(2048, N.MODE_TC)[0][1:3] == (3, 704)                 # 94 x 3 = 282 CTAs: two waves (was 8 launches of 136 x 256 rows)
+        N.set_option("stack", 0)
+        _per_layer_layout_checks(k4)
+    finally:
+        N.set_option("stack", before)
+
+
+def _per_layer_layout_checks(k4):
     lay = k4.dw_layout(16384, N.MODE_TC)
     assert [t for t, _, _, _ in lay] == [17, 17, 17, 17, 11, 8, 5, 2]          # dead branches prune the last four layers
     assert lay[0][1:3] == (16, 1024)                                             # full layers: the measured default
