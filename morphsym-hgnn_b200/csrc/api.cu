@@ -13,6 +13,7 @@
 #include "kernels_simt.cuh"
 #include "kernels_tc.cuh"
 #include "kernels_stack.cuh"
+#include "kernels_stack2.cuh"
 #include "plan.cuh"
 #include "windows.cuh"
 #include "metrics.cuh"
@@ -400,6 +401,14 @@ int launch_stack(int kind, const Plan& p, const Plan::Stack& sp, const WsLayout&
         for (int c = 0; c < T.n_chunks; ++c)
             if (T.chunks[c].a_kind != A_SLAB) return fail(MSHGNN_ERR_ARG, "internal: a stack program must read slab buffers");
     }
+    int n_prog_items = 0;
+    for (int ph = 0; ph < sp.prog.n_phases; ++ph) n_prog_items = std::max(n_prog_items, sp.prog.first_item[ph] + sp.prog.n_items[ph]);
+    for (int i = 0; i < n_prog_items; ++i) {
+        const StackItem& it = p.stack_items[sp.item0 + i];
+        int chunks = 0;
+        for (int st_ = 0; st_ < it.n_steps; ++st_) chunks += p.tiles[sp.tiles.begin + it.tile + st_].n_chunks;
+        if (chunks > SK_QCHUNKS || it.n_steps > SK_QSTEPS) return fail(MSHGNN_ERR_ARG, "internal: stack item with %d chunks / %d steps (queue holds %d / %d)", chunks, it.n_steps, SK_QCHUNKS, SK_QSTEPS);
+    }
     StackArgs a;
     a.prog = sp.prog;
     a.n_row_tiles = (int)(w.Bp / TILE_M);
@@ -411,6 +420,9 @@ int launch_stack(int kind, const Plan& p, const Plan::Stack& sp, const WsLayout&
     a.err = (uint32_t*)(ws + w.stack_sync + w.stack_sync_bytes - 4);
     a.next = (uint32_t*)(ws + w.stack_sync + w.stack_sync_bytes - 8);
     a.timing = (unsigned long long*)(ws + w.stack_timing);
+    static const int env_dbg = [] { const char* e = getenv("MSHGNN_STACK_DEBUG"); return e ? atoi(e) : 0; }();
+    a.debug = env_dbg;
+    a.epilogue = stack_epilogue_choice() >= 0 ? stack_epilogue_choice() : (kind == K_STACK_FWD ? 1 : 0);
     if ((int64_t)sp.prog.n_phases * a.n_row_tiles * p.S + 2 > w.stack_sync_bytes / 4) return fail(MSHGNN_ERR_WORKSPACE, "internal: stack counters do not fit");
     int n_sm = 0, rc;
     if ((rc = sm_count(&n_sm))) return rc;
@@ -420,6 +432,42 @@ int launch_stack(int kind, const Plan& p, const Plan::Stack& sp, const WsLayout&
     a.lookahead = env_la > 0 ? (env_la > 4 ? 4 : env_la) : 1;
     a.chunked = chunked ? 1 : 0;
     a.delay = chunked ? stack_rows_per_chunk(p) : stack_delay(sp, a.n_row_tiles, n_sm);
+    if (w.stack_pair && !timing) {
+        // CTA-pair kernel: items are (phase, row-tile pair, node slot); one cluster of two CTAs per TPC
+        if (a.n_row_tiles & 1) return fail(MSHGNN_ERR_ARG, "internal: the CTA-pair stack kernel needs an even number of row tiles");
+        static std::atomic<bool> attr2_set[64];
+        static std::atomic<int> max_clusters[64];
+        int dev = 0;
+        CUDA_TRY(cudaGetDevice(&dev));
+        if (first_on_device(attr2_set)) CUDA_TRY(cudaFuncSetAttribute(k_tc_stack2, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_SMEM_BYTES));
+        const int64_t n_pairs_total = (int64_t)(a.n_row_tiles / 2) * sp.prog.items_per_row;
+        a.n_total = (int)n_pairs_total;
+        if (a.chunked) { a.delay = a.delay / 2; if (a.delay < 1) a.delay = 1; }
+        else a.delay = stack_delay(sp, a.n_row_tiles / 2, n_sm / 2);
+        cudaLaunchConfig_t cfg = {};
+        cfg.blockDim = dim3(SK_THREADS); cfg.dynamicSmemBytes = S2_SMEM_BYTES; cfg.stream = st;
+        cudaLaunchAttribute at[2];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[1].val.programmaticStreamSerializationAllowed = g_prof_on ? 0 : 1;
+        cfg.attrs = at; cfg.numAttrs = 2;
+        int mc = dev < 64 ? max_clusters[dev].load(std::memory_order_relaxed) : 0;
+        if (!mc) {
+            cfg.gridDim = dim3((unsigned)n_sm);
+            CUDA_TRY(cudaOccupancyMaxActiveClusters(&mc, k_tc_stack2, &cfg));
+            if (mc < 1) return fail(MSHGNN_ERR_CUDA, "the CTA-pair stack kernel does not fit on this device (0 active clusters)");
+            if (dev < 64) max_clusters[dev].store(mc, std::memory_order_relaxed);
+        }
+        const int64_t clusters = n_pairs_total < mc ? n_pairs_total : mc;
+        cfg.gridDim = dim3((unsigned)(2 * clusters));
+        const Tile* d_tiles = p.d_tiles + sp.tiles.begin;
+        const StackItem* d_items = p.d_stack_items + sp.item0;
+        ProfScope ps(kind, st);
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, k_tc_stack2, wm.tc, wm.dw, d_tiles, d_items, a, bt, br));
+        LAUNCH_CHECK();
+        return 0;
+    }
     ProfScope ps(kind, st);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(n_total < n_sm ? n_total : n_sm)); cfg.blockDim = dim3(SK_THREADS); cfg.dynamicSmemBytes = SK_SMEM_BYTES; cfg.stream = st;
@@ -964,11 +1012,15 @@ int mshgnn_check_edges(const mshgnn_plan* plan, int64_t B, const int64_t* const*
 int mshgnn_set_option(const char* name, int32_t value) {
     if (!name) return fail(MSHGNN_ERR_ARG, "option name is NULL");
     if (!strcmp(name, "stack")) { set_stack_enabled(value); return 0; }
+    if (!strcmp(name, "stack_pair")) { set_stack_pair_enabled(value); return 0; }
+    if (!strcmp(name, "stack_epilogue")) { set_stack_epilogue_choice(value); return 0; }
     return fail(MSHGNN_ERR_ARG, "unknown option '%s'", name);
 }
 
 int32_t mshgnn_get_option(const char* name) {
     if (name && !strcmp(name, "stack")) return stack_enabled() ? 1 : 0;
+    if (name && !strcmp(name, "stack_pair")) return stack_pair_enabled() ? 1 : 0;
+    if (name && !strcmp(name, "stack_epilogue")) return stack_epilogue_choice();
     return -1;
 }
 

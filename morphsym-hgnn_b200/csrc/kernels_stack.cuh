@@ -38,6 +38,9 @@ constexpr int SK_TILE_BYTES = 128 * SK_KB * 2;                            // 16 
 constexpr int SK_STAGE_BYTES = 4 * SK_TILE_BYTES;                         // A_hi, A_lo, W_hi, W_lo = 64 KB
 constexpr int SK_STAGES = 2;
 constexpr int SK_QUEUE = 16;                                              // in-CTA item queue (the scheduler runs <= 2 items ahead of the producer)
+constexpr int SK_QSTEPS = 3;                                              // steps per item (StackItem::n_steps)
+constexpr int SK_HDR16 = 5;                                               // sizeof(TileHdr) / 16
+constexpr int SK_QCHUNKS = 16;                                            // chunk descriptors per queued item (all steps of the item together)
 constexpr int SK_THREADS = 608;                                           // TMA warp, MMA warp, 16 epilogue warps, scheduler warp
 constexpr int SK_PIPE_BYTES = SK_STAGES * SK_STAGE_BYTES;                  // 128 KB operand ring
 constexpr int SK_STG_BYTES = 65536;                                       // 4 groups x (hi | lo) x 8 KB
@@ -60,6 +63,10 @@ struct StackArgs {
     uint32_t* err;               // error word (a dependency wait timed out)
     uint32_t* next;              // work counter: the next item index to hand out (zeroed with the completion counters)
     unsigned long long* timing;  // TIMING instantiation only: per CTA 8 cycle counters (see k_tc_stack)
+    int epilogue;                // CTA-pair kernel: 0 = epilogue with headers from the queue, deferred completion signal (backward: epilogue-bound,
+                                 // -2..5 %); 1 = first version (forward: bound by the MMA side, where the longer scheduler chain of 0 costs 3 %)
+    int debug;                   // ablation switches for timing experiments (MSHGNN_STACK_DEBUG; results are then garbage): 1 no A loads,
+                                 // 2 no W loads, 4 no MMAs, 8 epilogue reduced to its handshakes (CTA-pair kernel only)
 };
 
 struct ItemRef { int phase, row_tile, item; };
@@ -161,6 +168,25 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
 template <int N>
 __device__ __forceinline__ void tma_store_wait_pending() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 
+// Operand rows of one chunk of an item, resolved by the scheduler warp (lane l = l-th chunk of the item, steps in order) so
+// that the single-thread TMA producer never waits for a descriptor load: {first row of the A hi image of the node slot,
+// same for the lo image, first row of the weight image, -}.  `meta` holds one byte per step: chunks | a_stage << 4.
+__device__ __forceinline__ int4 stack_chunk_desc(const Tile* tiles, const int first_tile, const int n_steps, const int meta, const int lane,
+                                                 const BufRows& br, const int64_t Bp) {
+    int cum = 0;
+    int4 d = make_int4(0, 0, 0, 0);
+    for (int s = 0; s < n_steps && s < 4; ++s) {
+        const int nc = (meta >> (8 * s)) & 0xf;
+        if (lane >= cum && lane < cum + nc) {
+            const Chunk* c = &tiles[first_tile + s].chunks[lane - cum];
+            const int a_buf = __ldg(&c->a_buf), a_slot = __ldg(&c->a_slot);
+            d = make_int4(br.hi[a_buf] + (int)((int64_t)a_slot * Bp), br.lo[a_buf] + (int)((int64_t)a_slot * Bp), __ldg(&c->w16_row), 0);
+        }
+        cum += nc;
+    }
+    return d;
+}
+
 // header of a Tile (everything but the chunk list), fetched once per step into registers
 struct TileHdr {
     int n_chunks, out_buf, out_slot, bias_buf, bias_off, relu, posmask_buf, posmask_slot, res_buf, res_slot, mask_out_buf,
@@ -175,19 +201,194 @@ __device__ __forceinline__ TileHdr load_hdr(const Tile* t) {
     for (int i = 0; i < (int)(sizeof(TileHdr) / 16); ++i) dst[i] = __ldg(src + i);
     return h;
 }
+static_assert(sizeof(TileHdr) == 16 * SK_HDR16, "queue header slots must hold a TileHdr");
 static_assert(sizeof(TileHdr) % 16 == 0 && sizeof(Tile) % 16 == 0, "Tile entries are read with 128-bit loads");
 
 struct StackEpi {
     uint32_t stg;            // this group's staging pair: hi tile (8 KB) | lo tile (8 KB)
-    uint32_t bias;           // 128 B of shared memory: bias of this group's column quarter
+    uint32_t bias;           // 128 B of shared memory private to this WARP: bias of the group's column quarter
     uint32_t res_bar, accum_bar, free_bar, stage_bar;
     uint32_t acc_parity;
 };
+
+// L1 prefetches of what the epilogue of one step reads from global memory (bias quarter lines, stored ReLU bit masks of the
+// 128 rows): issued by the scheduler warp when the item is published, one or two items before the epilogue gets there.
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void stack_prefetch_step(const TileHdr& t, const BufTable& bt, const int row0, const int64_t Bp, const int lane) {
+    if (t.bias_buf >= 0 && lane < 4) prefetch_l1((const float*)bt.p[t.bias_buf] + t.bias_off + 32 * lane);
+    if (t.posmask_buf >= 0 && lane < 16)
+        prefetch_l1(reinterpret_cast<const uint32_t*>(bt.p[t.posmask_buf]) + ((int64_t)t.posmask_slot * Bp + row0) * 4 + 32 * lane);
+    if (t.out2_buf >= 0 && t.out2_mask_kind == MK_BITS && lane >= 16)
+        prefetch_l1(reinterpret_cast<const uint32_t*>(bt.p[t.out2_mask_buf]) + ((int64_t)t.out2_mask_slot * Bp + row0) * 4 + 32 * (lane - 16));
+}
+
+// Completion signal of an item, deferred by its group leader: waiting for the item's last TMA stores to land costs a store
+// round trip (~1.5 k cycles) that nothing in the group overlaps.  The leader therefore keeps the counter address and publishes
+// it (a) at once when it would idle anyway - the next step's accumulator is not complete yet, or the item queue is empty -
+// and (b) otherwise right after the next step's accumulator read-back, when the stores have long landed.  (Deferring to
+// the END of the next step was measured before: it added an item time to every dependency chain.)
+__device__ __forceinline__ void stack_flush_signal(uint32_t*& pending) {
+    if (pending) {
+        tma_store_wait_all();
+        stack_signal(pending);
+        pending = nullptr;
+    }
+}
 
 // One step of an item through one epilogue group (cf. tc_epilogue_q).  `sig`: completion counter of the item (last step only).
 __device__ __forceinline__ void stack_epilogue(const TileHdr& t, const BufTable& bt, const BufRows& br, const CUtensorMap* map_k,
                                                const uint32_t tmem_acc, const int row0, const int64_t B, const int64_t Bp,
                                                const int warp, const int lane, const int grp, const StackEpi es, uint32_t& res_count,
+                                               uint32_t* sig, uint32_t*& pending, unsigned long long* t_wait_acc = nullptr,
+                                               const bool dbg_bare = false, const int dbg = 0) {
+    const int q = warp & 3;                        // TMEM lane quarter this warp may access (hardware rule: warp index mod 4)
+    const bool leader = q == 2 && lane == 0;       // first warp of the group (warps 2 + 4g .. 5 + 4g): warp index = 2 mod 4
+    const int rl = q * 32 + lane;                  // row inside the tile
+    const int64_t row = (int64_t)row0 + rl;
+    const bool live = row < B;
+    const bool all_live = (int64_t)row0 + TILE_M <= B;
+    const uint32_t rsw = (uint32_t)((rl >> 1) & 3);     // SWIZZLE_64B: 16-byte chunk index ^= address bits [7, 9)
+    const uint32_t tile = es.stg + (uint32_t)rl * 64u;
+    const bool has_out = t.out_buf >= 0, has_out2 = t.out2_buf >= 0, has_res = t.res_buf >= 0 && !dbg_bare;
+    const bool want_mask = t.relu || t.mask_out_buf >= 0;
+    const bool writes_stage = has_out || has_out2 || t.stage_out;
+    const int col0 = grp * 32;
+    if (dbg_bare) {                                // ablation: accumulator handshake, staged-operand handshake and completion signal only
+        mbar_wait(es.accum_bar, es.acc_parity);
+        tc_fence_after();
+        tc_fence_before();
+        mbar_arrive(es.free_bar);
+        group_bar_sync(grp);
+        if (leader && t.stage_out) mbar_arrive(es.stage_bar);
+        if (leader && sig) stack_signal(sig);
+        return;
+    }
+
+    auto fetch_residual = [&]() {
+        const int r_hi = br.hi[t.res_buf] + (int)((int64_t)t.res_slot * Bp) + row0, r_lo = br.lo[t.res_buf] + (int)((int64_t)t.res_slot * Bp) + row0;
+        mbar_expect_tx(es.res_bar, 2u * 8192u);
+        tma_load_2d(es.stg, map_k, es.res_bar, col0, r_hi);
+        tma_load_2d(es.stg + 8192, map_k, es.res_bar, col0, r_lo);
+    };
+    if (leader) {
+        tma_store_wait_read();                     // the staging tiles may still feed this group's previous TMA stores
+        // early fetch (hidden behind the MMAs of this step); the item is only published to this warp once its input
+        // dependency - the residual is an output of the previous phase - has been seen satisfied by the producer warp
+        if (has_res && !t.a_stage) {
+            asm volatile("fence.proxy.async.global;" ::: "memory");
+            fetch_residual();
+        }
+    }
+    // global reads of this step (L1-prefetched by the scheduler warp), issued before the accumulator wait.  Bias: lane j of
+    // EVERY warp fetches column col0 + j and the warp keeps its own 128-byte copy in shared memory (read back as broadcasts):
+    // no barrier between warps, no dependent global round trip in front of the arithmetic.  Measured alternatives: per-lane
+    // values + 32 shuffles per warp and step (slower: SHFL shares the crossbar the MMA operand reads saturate), eight
+    // warp-uniform 128-bit global loads inside the loop (slower in the forward pass, which has the biases).
+    const bool has_bias = t.bias_buf >= 0;
+    const float bias_l = has_bias ? __ldg((const float*)bt.p[t.bias_buf] + t.bias_off + col0 + lane) : 0.f;
+    uint32_t pm = ~0u, m2 = ~0u;
+    if (live && t.posmask_buf >= 0) pm = __ldg(reinterpret_cast<const uint32_t*>(bt.p[t.posmask_buf]) + ((int64_t)t.posmask_slot * Bp + row) * 4 + grp);
+    if (live && has_out2 && t.out2_mask_kind == MK_BITS)
+        m2 = __ldg(reinterpret_cast<const uint32_t*>(bt.p[t.out2_mask_buf]) + ((int64_t)t.out2_mask_slot * Bp + row) * 4 + grp);
+    if (leader && pending && !mbar_test(es.accum_bar, es.acc_parity)) stack_flush_signal(pending);     // idle anyway
+
+    if (t_wait_acc) { const long long t0 = clock64(); mbar_wait(es.accum_bar, es.acc_parity); *t_wait_acc += (unsigned long long)(clock64() - t0); }
+    else mbar_wait(es.accum_bar, es.acc_parity);
+    tc_fence_after();
+    uint32_t raw[32];
+    tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + col0, raw);
+    tmem_ld_wait();
+    tc_fence_before();
+    mbar_arrive(es.free_bar);                      // this thread's part of the accumulator is in registers
+    if (leader) stack_flush_signal(pending);       // the previous item's stores landed long ago
+    if (has_res) {
+        // chained step: the staging tiles were the A operand of THIS step's MMAs, which have completed by now
+        if (t.a_stage && leader) fetch_residual();
+        mbar_wait(es.res_bar, res_count & 1u);
+        ++res_count;
+    }
+    float v[32];
+    unsigned mask = 0;
+    if (has_bias) {
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(es.bias + 4u * lane), "f"(bias_l) : "memory");
+        __syncwarp();
+    }
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has_bias) asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(es.bias + 16u * j4));
+        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int j = j4 * 4 + e;
+            float x = fmaf(__uint_as_float(raw[j]), TC_W_UNSCALE, bb[e]);
+            if (want_mask && x > 0.f) mask |= 1u << j;
+            if (t.relu) x = fmaxf(x, 0.f);
+            v[j] = x;
+        }
+    }
+    if (t.posmask_buf >= 0) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = ((pm >> j) & 1u) ? v[j] : 0.f;
+    }
+    // the leader has seen the previous stores of this group read the staging tiles (has_res: the residual has landed in them)
+    if (!has_res || (dbg & 32)) group_bar_sync(grp);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const uint32_t a = tile + ((((uint32_t)g) ^ rsw) << 4);
+        if (has_res) join8_add(v + g * 8, lds128(a), lds128(a + 8192));
+        if (writes_stage) {
+            uint4 hi, lo;
+            split8(v + g * 8, hi, lo);
+            if (!has_out && has_out2) { hi = mask8(hi, m2 >> (g * 8)); lo = mask8(lo, m2 >> (g * 8)); }
+            if (!all_live && !live) { hi = make_uint4(0u, 0u, 0u, 0u); lo = hi; }     // rows [B, Bp) of every image stay zero
+            sts128(a, hi);
+            sts128(a + 8192, lo);
+        }
+    }
+    fence_proxy_async_smem();
+    group_bar_sync(grp);
+    if (leader) {
+        const int ob = has_out ? t.out_buf : t.out2_buf, os = has_out ? t.out_slot : t.out2_slot;
+        if (ob >= 0) {
+            const int o = (int)((int64_t)os * Bp) + row0;
+            tma_store_2d(map_k, es.stg, col0, br.hi[ob] + o);
+            tma_store_2d(map_k, es.stg + 8192u, col0, br.lo[ob] + o);
+            tma_store_commit();
+        }
+        if (t.stage_out) mbar_arrive(es.stage_bar);        // this quarter of the next step's A operand is in place
+    }
+    if (has_out && has_out2) {
+        // second output = first output with the masked-off lanes cleared, made in place once the first store has read the tile
+        if (leader) tma_store_wait_read();
+        group_bar_sync(grp);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const uint32_t a = tile + ((((uint32_t)c) ^ rsw) << 4);
+            const uint32_t m = m2 >> (c * 8);
+            sts128(a, mask8(lds128(a), m));
+            sts128(a + 8192, mask8(lds128(a + 8192), m));
+        }
+        fence_proxy_async_smem();
+        group_bar_sync(grp);
+        if (leader) {
+            const int o = (int)((int64_t)t.out2_slot * Bp) + row0;
+            tma_store_2d(map_k, es.stg, col0, br.hi[t.out2_buf] + o);
+            tma_store_2d(map_k, es.stg + 8192u, col0, br.lo[t.out2_buf] + o);
+            tma_store_commit();
+        }
+    }
+    if (live && t.mask_out_buf >= 0)
+        *(reinterpret_cast<uint32_t*>(bt.p[t.mask_out_buf]) + ((int64_t)t.mask_out_slot * Bp + row) * 4 + grp) = mask;
+    if (leader && sig) pending = sig;              // published by stack_flush_signal (see there)
+    if (leader && (dbg & 16)) stack_flush_signal(pending);
+}
+
+// Round-2 first version of the epilogue, kept for same-box A/B runs (MSHGNN_STACK_DEBUG bit 128): header from global memory,
+// bias through shared memory behind a step-start barrier, completion signal published at once.  `sig`: completion counter of the item (last step only).
+__device__ __forceinline__ void stack_epilogue_v1(const TileHdr& t, const BufTable& bt, const BufRows& br, const CUtensorMap* map_k,
+                                               const uint32_t tmem_acc, const int row0, const int64_t B, const int64_t Bp,
+                                               const int warp, const int lane, const int grp, const StackEpi es, const uint32_t bias_smem, uint32_t& res_count,
                                                uint32_t* sig, unsigned long long* t_wait_acc = nullptr) {
     const int q = warp & 3;                        // TMEM lane quarter this warp may access (hardware rule: warp index mod 4)
     const bool leader = q == 2 && lane == 0;       // first warp of the group (warps 2 + 4g .. 5 + 4g): warp index = 2 mod 4
@@ -218,7 +419,7 @@ __device__ __forceinline__ void stack_epilogue(const TileHdr& t, const BufTable&
     }
     if (rl < 32) {
         const float bv = t.bias_buf >= 0 ? __ldg((const float*)bt.p[t.bias_buf] + t.bias_off + col0 + rl) : 0.f;
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(es.bias + 4u * rl), "f"(bv) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_smem + 4u * rl), "f"(bv) : "memory");
     }
     uint32_t pm = ~0u, m2 = ~0u;
     if (live && t.posmask_buf >= 0) pm = __ldg(reinterpret_cast<const uint32_t*>(bt.p[t.posmask_buf]) + ((int64_t)t.posmask_slot * Bp + row) * 4 + grp);
@@ -245,7 +446,7 @@ __device__ __forceinline__ void stack_epilogue(const TileHdr& t, const BufTable&
 #pragma unroll
     for (int j4 = 0; j4 < 8; ++j4) {
         float4 b4;
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(es.bias + 16u * j4));
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(bias_smem + 16u * j4));
         const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -325,13 +526,15 @@ __global__ void __launch_bounds__(SK_THREADS, 1)
 k_tc_stack(const __grid_constant__ TcMaps maps, const Tile* __restrict__ tiles, const StackItem* __restrict__ items,
            const __grid_constant__ StackArgs args, const BufTable bt, const BufRows br) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(16) float bias_s[4][32];         // one quarter per epilogue group
     __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) float bias_w[16][32];        // one copy per epilogue warp
     // Items are handed out dynamically: the scheduler warp (warp 18) draws the next global item index from an atomic counter
     // (so no CTA falls behind: the dependency of an item always points at items that are finished or running), decodes it,
     // waits for its input dependency and then publishes the decoded item to the other roles through this queue.  Decode,
     // dependency round trips and descriptor loads are thereby off the critical path of the single-thread TMA / MMA roles.
     __shared__ int4 q_ent[SK_QUEUE][2];                   // {row tile, phase, first tile, steps}, {per step one byte: chunks | a_stage << 4, -, -, -}
+    __shared__ int4 q_chunk[SK_QUEUE][SK_QCHUNKS];        // operand rows of the item's chunks (stack_chunk_desc)
+    __shared__ int4 q_hdr[SK_QUEUE][SK_QSTEPS][SK_HDR16]; // tile headers of the item's steps: the epilogue never waits for a descriptor load
     __shared__ volatile int q_count;                      // entries published
     __shared__ volatile int q_prod;                       // entries the TMA producer has started
 
@@ -397,6 +600,10 @@ k_tc_stack(const __grid_constant__ TcMaps maps, const Tile* __restrict__ tiles, 
                 a = make_int4(ir.row_tile, ir.phase, it.tile, it.n_steps);
                 b = make_int4(meta, it.out_slot, 0, 0);
             }
+            if (lane < SK_QCHUNKS && a.w) q_chunk[n_pub % SK_QUEUE][lane] = stack_chunk_desc(tiles, a.z, a.w, b.x, lane, br, Bp);
+            if (lane < a.w * SK_HDR16) q_hdr[n_pub % SK_QUEUE][lane / SK_HDR16][lane % SK_HDR16] = __ldg(reinterpret_cast<const int4*>(tiles + a.z + lane / SK_HDR16) + lane % SK_HDR16);
+            __syncwarp();
+            for (int s = 0; s < a.w; ++s) stack_prefetch_step(*reinterpret_cast<const TileHdr*>(q_hdr[n_pub % SK_QUEUE][s]), bt, a.x * TILE_M, Bp, lane);
             if (lane == 0) {
                 q_ent[n_pub % SK_QUEUE][0] = a;
                 q_ent[n_pub % SK_QUEUE][1] = b;
@@ -419,13 +626,13 @@ k_tc_stack(const __grid_constant__ TcMaps maps, const Tile* __restrict__ tiles, 
                 // (async proxy) and are read below with TMA loads (async proxy)
                 asm volatile("fence.proxy.async.global;" ::: "memory");
                 const int row0 = qa.x * TILE_M;
+                const int4* qc = q_chunk[n % SK_QUEUE];
                 for (int s = 0; s < qa.w; ++s) {
-                    const Tile* t = tiles + qa.z + s;
                     const int n_chunks = (qb.x >> (8 * s)) & 0xf, a_stage = (qb.x >> (8 * s + 4)) & 1;
                     for (int c = 0; c < n_chunks; ++c) {
                         const bool from_stage = a_stage && c == 0;
-                        const int a_buf = __ldg(&t->chunks[c].a_buf), a_slot = __ldg(&t->chunks[c].a_slot), w16_row = __ldg(&t->chunks[c].w16_row);
-                        const int arow = (int)((int64_t)a_slot * Bp) + row0;
+                        const int4 d = *qc++;
+                        const int arow_hi = d.x + row0, arow_lo = d.y + row0, w16_row = d.z;
                         const uint32_t tx_bytes = (uint32_t)((from_stage ? 1 : 2) * (split ? 2 : 1) * SK_TILE_BYTES);
                         for (int kb = 0; kb < SPC; ++kb, ++g) {
                             const uint32_t s4 = g % SK_STAGES;
@@ -435,10 +642,10 @@ k_tc_stack(const __grid_constant__ TcMaps maps, const Tile* __restrict__ tiles, 
                             const uint32_t fb = full0 + 8 * s4;
                             const long long t_tma = TIMING ? clock64() : 0;
                             mbar_expect_tx(fb, tx_bytes);
-                            if (!from_stage) tma_load_2d(st, &maps.o, fb, kcol, br.hi[a_buf] + arow);
+                            if (!from_stage) tma_load_2d(st, &maps.o, fb, kcol, arow_hi);
                             tma_load_2d(st + 2 * SK_TILE_BYTES, &maps.o, fb, kcol, br.w_hi + w16_row);
                             if (split) {
-                                if (!from_stage) tma_load_2d(st + SK_TILE_BYTES, &maps.o, fb, kcol, br.lo[a_buf] + arow);
+                                if (!from_stage) tma_load_2d(st + SK_TILE_BYTES, &maps.o, fb, kcol, arow_lo);
                                 tma_load_2d(st + 3 * SK_TILE_BYTES, &maps.o, fb, kcol, br.w_lo + w16_row);
                             }
                             if (TIMING) tim[10] += (unsigned long long)(clock64() - t_tma);
@@ -512,24 +719,31 @@ k_tc_stack(const __grid_constant__ TcMaps maps, const Tile* __restrict__ tiles, 
     } else {
         // group g (warps 2 + 4g .. 5 + 4g) drains column quarter g of every step
         const int grp = (warp - 2) >> 2;
+        const bool sig_leader = (warp & 3) == 2 && lane == 0;
         StackEpi es;
-        es.stg = stg_base + grp * 16384; es.bias = smem_u32(bias_s[grp]); es.res_bar = res_bar + 8 * grp; es.stage_bar = stage_bar;
+        es.stg = stg_base + grp * 16384; es.bias = smem_u32(bias_w[warp - 2]); es.res_bar = res_bar + 8 * grp; es.stage_bar = stage_bar;
         uint32_t k = 0, n_res = 0;
+        uint32_t* pending = nullptr;               // group leader: completion counter of the last item, not yet published
         for (int n = 0;; ++n) {
             int4 qa, qb;
-            next_item(n, qa, qb);
+            if (lane == 0) { while (q_count <= n) { if (sig_leader) stack_flush_signal(pending); } }
+            __syncwarp();
+            qa = q_ent[n % SK_QUEUE][0];
+            qb = q_ent[n % SK_QUEUE][1];
             if (qa.w == 0) break;
             uint32_t* const ctr = args.sync + ((size_t)qa.y * NT + qa.x) * args.n_slots + qb.y;
             for (int s = 0; s < qa.w; ++s, ++k) {
-                const TileHdr t = load_hdr(tiles + qa.z + s);
+                TileHdr t;
+#pragma unroll
+                for (int i = 0; i < SK_HDR16; ++i) reinterpret_cast<int4*>(&t)[i] = q_hdr[n % SK_QUEUE][s][i];
                 const uint32_t a = k % SK_ACCS;
                 es.accum_bar = acc_full0 + 8 * a; es.free_bar = acc_free0 + 8 * a;
                 es.acc_parity = (k / SK_ACCS) & 1;
                 stack_epilogue(t, bt, br, &maps.k, tmem_base + a * 128, qa.x * TILE_M, B, Bp, warp, lane, grp, es, n_res,
-                               s == qa.w - 1 ? ctr : nullptr, (TIMING && warp == 2 && lane == 0) ? &tim[5] : nullptr);
+                               s == qa.w - 1 ? ctr : nullptr, pending, (TIMING && warp == 2 && lane == 0) ? &tim[5] : nullptr);
             }
         }
-        if ((warp & 3) == 2 && lane == 0) tma_store_wait_all();
+        if (sig_leader) { stack_flush_signal(pending); tma_store_wait_all(); }
         if (TIMING && warp == 2 && lane == 0) args.timing[(size_t)blockIdx.x * 16 + 5] = tim[5];
     }
     tc_fence_before();

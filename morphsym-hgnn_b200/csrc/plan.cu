@@ -617,11 +617,38 @@ bool stack_enabled() {
 }
 void set_stack_enabled(int on) { g_stack_on.store(on ? 1 : 0, std::memory_order_relaxed); }
 
+// CTA-pair variant of the stack kernel (kernels_stack2.cuh): on by default, MSHGNN_STACK_2CTA=0 / option "stack_pair" turn it off
+static std::atomic<int> g_stack_pair{-1};
+bool stack_pair_enabled() {
+    int v = g_stack_pair.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char* e = getenv("MSHGNN_STACK_2CTA");
+        v = !(e && !strcmp(e, "0"));
+        g_stack_pair.store(v, std::memory_order_relaxed);
+    }
+    return v != 0;
+}
+void set_stack_pair_enabled(int on) { g_stack_pair.store(on ? 1 : 0, std::memory_order_relaxed); }
+
+// epilogue variant of the CTA-pair kernel: -1 = per launch kind (forward: first version, backward: deferred-signal version), 0 / 1 = forced
+static std::atomic<int> g_stack_epilogue{-2};
+int stack_epilogue_choice() {
+    int v = g_stack_epilogue.load(std::memory_order_relaxed);
+    if (v < -1) {
+        const char* e = getenv("MSHGNN_STACK_EPILOGUE");
+        v = e ? (atoi(e) != 0 ? 1 : 0) : -1;
+        g_stack_epilogue.store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+void set_stack_epilogue_choice(int v) { g_stack_epilogue.store(v < 0 ? -1 : (v ? 1 : 0), std::memory_order_relaxed); }
+
 WsLayout ws_layout(const Plan& p, int64_t B, int train, int mode) {
     const bool tc = mode != MSHGNN_MODE_FP32;
     WsLayout w{};
     w.stack = tc && stack_enabled() && p.stack_infer.prog.n_phases > 0;
-    w.Bp = round_up(B < 1 ? 1 : B, TILE_M);
+    w.stack_pair = w.stack && stack_pair_enabled();
+    w.Bp = round_up(B < 1 ? 1 : B, w.stack_pair ? 2 * TILE_M : TILE_M);      // the CTA-pair kernel walks row tiles two at a time
     int ns = (int)((B + 511) / 512);
     w.n_splits = ns < 1 ? 1 : (ns > 64 ? 64 : ns);
     {   // tcgen05 reduce-GEMM: ~1024 rows per split (MSHGNN_DW_ROWS overrides for A/B runs) (fp32 accumulation in TMEM, splits summed in double), no empty split.

@@ -133,6 +133,7 @@ struct WsLayout {
     int64_t h16[MAX_LAYERS + 1][2], ct16[MAX_LAYERS][2], dh16[2][2], dc16[2][2], du16[2], w16[2];
     // stack mode (training, tensor-core modes): per-layer backward images, -1 when the ping-pong layout is used
     int stack = 0;
+    int stack_pair = 0;                // the stack launches use the CTA-pair kernel (Bp is a multiple of 256)
     int64_t dhL16[MAX_LAYERS + 1][2], dcL16[MAX_LAYERS + 1][2] /* index l + 1 */, duL16[MAX_LAYERS][2];
     int64_t stack_sync = -1;           // dependency counters of the stack kernel (uint32 [phases][row tiles]) + error word
     int64_t stack_sync_bytes = 0;
@@ -147,6 +148,10 @@ std::string build_plan(const mshgnn_desc* d, Plan& p);            // returns err
 WsLayout ws_layout(const Plan& p, int64_t B, int train, int mode);
 bool stack_enabled();                 // cross-layer stack kernel on (default) / off (MSHGNN_STACK=0 or mshgnn_set_option)
 void set_stack_enabled(int on);
+bool stack_pair_enabled();            // CTA-pair (cta_group::2) variant of the stack kernel on (default) / off (MSHGNN_STACK_2CTA=0)
+void set_stack_pair_enabled(int on);
+int stack_epilogue_choice();          // -1: per launch kind, 0 / 1: forced (MSHGNN_STACK_EPILOGUE, option "stack_epilogue")
+void set_stack_epilogue_choice(int v);
 std::string describe_plan(const Plan& p);
 
 }  // namespace mshgnn

@@ -80,14 +80,16 @@ class Base_Lightning(LightningModule):
             self.mse_loss = native_loss(self.model, y_pred, y, N.LOSS_MSE)
             with torch.no_grad():
                 b = self._fused.update(N.LOSS_MSE, y_pred.detach().reshape(-1), y, y_pred.numel(), 1)
-                self.rmse_loss, self.l1_loss = b[21], b[22]
+                b = b[21:23].clone()             # the fused buffer is overwritten by the next step: logged values must not alias it
+                self.rmse_loss, self.l1_loss = b[0], b[1]
         elif not self.regression and y_pred.is_cuda and y_pred.shape[1] == 8:
             # gradient-carrying CE from the fused loss head; accuracy / F1 / epoch states from ONE fused metrics call
             self.ce_loss = native_loss(self.model, y_pred, y, N.LOSS_CE2)
             with torch.no_grad():
                 b = self._fused.update(N.LOSS_CE2, y_pred.detach().reshape(-1, 2), y, y_pred.shape[0], 4)
-                self.acc = b[21]
-                self.f1_leg0, self.f1_leg1, self.f1_leg2, self.f1_leg3 = b[22], b[23], b[24], b[25]
+                b = b[21:26].clone()             # see above
+                self.acc = b[0]
+                self.f1_leg0, self.f1_leg1, self.f1_leg2, self.f1_leg3 = b[1], b[2], b[3], b[4]
         elif self.regression:
             # native fused MSE (gradient-carrying) + metric accumulation
             self.mse_loss = native_loss(self.model, y_pred, y, N.LOSS_MSE)
@@ -311,24 +313,76 @@ class HGNN_C2_Lightning_Reg(Base_Lightning):
     def step_helper_function(self, batch):
         return self._foot_step(batch, self.model.out_channels_per_foot * 4)
 
-    def training_step(self, batch, batch_idx):
+    # ---- world-frame epoch side (reference gnnLightning.py:L615-619, L701-711) ----
+    def log_losses_worldframe(self, step_name: str, on_step: bool):
+        self.log_losses(step_name, on_step)
+        for k, v in (("_MSE_loss_WorldFrame", self.mse_loss_worldframe), ("_RMSE_loss_WorldFrame", self.rmse_loss_worldframe),
+                     ("_L1_loss_WorldFrame", self.l1_loss_worldframe)):
+            self.log(step_name + k, v, on_step=on_step, on_epoch=not on_step)
+
+    def calculate_losses_epoch_worldframe(self) -> None:
+        self.calculate_losses_epoch()
+        self.mse_loss_worldframe = self.metric_mse_worldframe.compute()
+        self.rmse_loss_worldframe = self.metric_rmse_worldframe.compute()
+        self.l1_loss_worldframe = self.metric_l1_worldframe.compute()
+
+    def reset_all_metrics_worldframe(self) -> None:
+        self.reset_all_metrics()
+        for m in (self.metric_mse_worldframe, self.metric_rmse_worldframe, self.metric_l1_worldframe):
+            m.reset()
+
+    def _quat_of(self, batch):
+        if not hasattr(batch, "r_o") or batch.r_o is None:
+            raise ValueError("grf_body_to_world_frame=True needs the body orientation batch.r_o (x, y, z, w per graph)")
+        return batch.r_o.view(batch.batch_size, 4)
+
+    def _step(self, batch):
         y, y_pred = self.step_helper_function(batch)
         if self.body_to_world_frame:
-            self.calculate_losses_step_worldframe(y, y_pred, batch.r_o.view(batch.batch_size, 4))
+            self.calculate_losses_step_worldframe(y, y_pred, self._quat_of(batch))
         else:
             self.calculate_losses_step_original(y, y_pred)
-        self.log_losses("train", on_step=True)
         return self._loss()
+
+    def training_step(self, batch, batch_idx):
+        loss = self._step(batch)
+        if self.body_to_world_frame:
+            self.log_losses_worldframe("train", on_step=True)
+        else:
+            self.log_losses("train", on_step=True)
+        return loss
+
+    def _epoch_start(self):
+        if self.body_to_world_frame:
+            self.reset_all_metrics_worldframe()
+        else:
+            self.reset_all_metrics()
+
+    def _epoch_end(self, name):
+        if self.body_to_world_frame:
+            self.calculate_losses_epoch_worldframe()
+            self.log_losses_worldframe(name, on_step=False)
+        else:
+            self.calculate_losses_epoch()
+            self.log_losses(name, on_step=False)
+
+    def on_validation_epoch_start(self):
+        self._epoch_start()
 
     def validation_step(self, batch, batch_idx):
-        y, y_pred = self.step_helper_function(batch)
-        if self.body_to_world_frame:
-            self.calculate_losses_step_worldframe(y, y_pred, batch.r_o.view(batch.batch_size, 4))
-        else:
-            self.calculate_losses_step_original(y, y_pred)
-        return self._loss()
+        return self._step(batch)
 
-    test_step = validation_step
+    def on_validation_epoch_end(self):
+        self._epoch_end("val")
+
+    def on_test_epoch_start(self):
+        self._epoch_start()
+
+    def test_step(self, batch, batch_idx):
+        return self._step(batch)
+
+    def on_test_epoch_end(self):
+        self._epoch_end("test")
 
 
 # train_model / evaluate_model live next to the modules in the reference (gnnLightning.py:L913-1421)

@@ -264,13 +264,22 @@ def evaluate_model(path_to_checkpoint: Path, predict_dataset: WindowSubset, enab
     model.freeze()
     model.to(ds.device)
     model.model.validate_edges = "cached"
-    model.reset_all_metrics()
+    world = bool(getattr(model, "body_to_world_frame", False))
+    if world:
+        model.reset_all_metrics_worldframe()
+    else:
+        model.reset_all_metrics()
     preds, labels = [], []
     with torch.no_grad():
         for idx in _loader(predict_dataset, batch_size, False, None, None):
             batch = ds.batch(idx)
             labels_batch, y_pred = model.step_helper_function(batch)
-            if hasattr(model, "calculate_losses_step_original"):
+            if world:
+                # reference L1043-1045: world-frame metrics are what a body_to_world_frame model reports
+                if not hasattr(batch, "r_o") or batch.r_o is None:
+                    raise ValueError("grf_body_to_world_frame=True needs the body orientation r_o in every batch of predict_dataset")
+                model.calculate_losses_step_worldframe(labels_batch, y_pred, batch.r_o.view(batch.batch_size, 4), test_only_on_z)
+            elif hasattr(model, "calculate_losses_step_original"):
                 model.calculate_losses_step_original(labels_batch, y_pred)
             else:
                 model.calculate_losses_step(labels_batch, y_pred)
@@ -282,7 +291,9 @@ def evaluate_model(path_to_checkpoint: Path, predict_dataset: WindowSubset, enab
                 preds.append((p * w).sum(1)); labels.append((labels_batch.long() * w).sum(1))
             else:
                 preds.append(y_pred); labels.append(labels_batch)
-        if hasattr(model, "calculate_losses_epoch_original"):
+        if world:
+            model.calculate_losses_epoch_worldframe()
+        elif hasattr(model, "calculate_losses_epoch_original"):
             model.calculate_losses_epoch_original()
         else:
             model.calculate_losses_epoch()
@@ -290,4 +301,6 @@ def evaluate_model(path_to_checkpoint: Path, predict_dataset: WindowSubset, enab
     if not model.regression:
         avg = (model.f1_leg0 + model.f1_leg1 + model.f1_leg2 + model.f1_leg3) / 4.0
         return pred, lab, model.acc, model.f1_leg0, model.f1_leg1, model.f1_leg2, model.f1_leg3, avg
+    if world:
+        return pred, lab, model.mse_loss_worldframe, model.rmse_loss_worldframe, model.l1_loss_worldframe
     return pred, lab, model.mse_loss, model.rmse_loss, model.l1_loss

@@ -17,9 +17,11 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture
 def restore_stack_option():
-    before = N.get_option("stack")
+    before, before_pair, before_epi = N.get_option("stack"), N.get_option("stack_pair"), N.get_option("stack_epilogue")
     yield
     N.set_option("stack", before)
+    N.set_option("stack_pair", before_pair)
+    N.set_option("stack_epilogue", before_epi)
 
 
 def _step(nm, cfg, b):
@@ -74,6 +76,55 @@ def test_stack_kernel_is_bit_identical_to_the_per_layer_launches(name, B, layers
     print(f"stack[{name} B={B} L={layers}]: {launches_stack} launches per train step with the stack kernel, {launches_layer} per layer; "
           f"worst gradient difference between the two paths {worst:.1e}")
     assert launches_stack < launches_layer or layers < 2
+
+
+# CTA-pair kernel (csrc/kernels_stack2.cuh, cta_group::2 MMAs on two row tiles at once) against the one-CTA stack kernel: the same
+# products accumulate in the same order into the same kind of accumulator, so every bit must agree.  B = 129 / 385: the last
+# row-tile pair is half padding; 5000 graphs: 20 pairs; 1 graph: a single pair
+@pytest.mark.parametrize("name,B,layers,mode", [("mini_cheetah-k4-contact", 1, 3, "tc"), ("mini_cheetah-k4-contact", 129, 8, "tc"),
+                                                ("mini_cheetah-k4-contact", 5000, 8, "tc"), ("mini_cheetah-c2-contact", 385, 8, "tc"),
+                                                ("solo12-k4-com", 2100, 8, "tc"), ("mi-contact", 400, 8, "tc"),
+                                                ("mini_cheetah-k4-contact", 3300, 8, "tc1x")])
+def test_cta_pair_stack_kernel_is_bit_identical_to_the_one_cta_kernel(name, B, layers, mode, restore_stack_option):
+    cfg = CONFIGS[name]
+    b = make_batch(cfg, B, seed=B + 2).to("cuda:0")
+    nm = build_model(cfg, layers=layers, seed=3).set_mode(mode).to("cuda:0")
+    N.set_option("stack", 1)
+    res = []
+    for pair in (1, 0, 1):
+        N.set_option("stack_pair", pair)
+        if mode == "tc":
+            out, loss, g = _step(nm, cfg, b)
+        else:
+            out, loss, g = None, 0.0, {}
+        with torch.no_grad():
+            inf = nm(b.x_dict, b.edge_index_dict).clone()
+        torch.cuda.synchronize()
+        res.append((out, loss, g, inf))
+    for a, c in ((res[0], res[1]), (res[2], res[1])):
+        assert torch.equal(a[3], c[3])
+        if mode == "tc":
+            assert torch.equal(a[0], c[0]) and a[1] == c[1]
+            for k in a[2]:
+                assert torch.equal(a[2][k], c[2][k]), k
+
+
+@pytest.mark.parametrize("name,B", [("mini_cheetah-k4-contact", 2500), ("solo12-k4-com", 700)])
+def test_both_epilogue_variants_of_the_pair_kernel_give_the_same_bits(name, B, restore_stack_option):
+    """Option stack_epilogue: -1 picks per launch kind (forward 1, backward 0); forcing either must not change a bit."""
+    cfg = CONFIGS[name]
+    b = make_batch(cfg, B, seed=11).to("cuda:0")
+    nm = build_model(cfg, layers=8, seed=3).set_mode("tc").to("cuda:0")
+    N.set_option("stack", 1)
+    N.set_option("stack_pair", 1)
+    res = []
+    for epi in (-1, 0, 1):
+        N.set_option("stack_epilogue", epi)
+        res.append(_step(nm, cfg, b))
+    for r in res[1:]:
+        assert torch.equal(r[0], res[0][0]) and r[1] == res[0][1]
+        for k in r[2]:
+            assert torch.equal(r[2][k], res[0][2][k]), k
 
 
 def test_stack_kernel_single_pass_mode_is_bit_identical_too(restore_stack_option):
