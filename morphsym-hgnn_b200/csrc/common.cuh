@@ -78,7 +78,7 @@ struct StackItem {
     int tile;                         // first step (index relative to the program's first tile)
     int n_steps;                      // 1..3
     int out_slot;                     // node slot whose outputs (h / dh / dc) this item completes in its phase
-    int pad_;
+    int meta;                         // one byte per step: chunks | a_stage << 4 (so the scheduler warp needs no dependent load for them)
     unsigned long long dep_mask;      // node slots of the PREVIOUS phase (same row tile) that must be complete before it starts:
                                       // the slots it reads (operands, residual) and, where buffers ping-pong, the readers of the slot it overwrites
 };

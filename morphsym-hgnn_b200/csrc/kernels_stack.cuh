@@ -589,19 +589,20 @@ k_tc_stack(const __grid_constant__ TcMaps maps, const Tile* __restrict__ tiles, 
                 cur = (int)atomicAdd(args.next, 1u);
             }
             cur = __shfl_sync(0xffffffffu, cur, 0);
-            int4 a = make_int4(0, 0, 0, 0), b = make_int4(0, 0, 0, 0);
+            int4 a = make_int4(0, 0, 0, 0), b = make_int4(0, 0, 0, 0), cd = make_int4(0, 0, 0, 0), hd = make_int4(0, 0, 0, 0);
             if (cur < n_total) {
                 const ItemRef ir = args.chunked ? stack_decode_chunked(pg, NT, RC, cur) : stack_decode(pg, NT, RC, cur);
                 const StackItem it = items[ir.item];
-                int meta = 0;                             // per step one byte: chunks | a_stage << 4
-                for (int s = 0; s < it.n_steps && s < 4; ++s) meta |= (__ldg(&tiles[it.tile + s].n_chunks) | (__ldg(&tiles[it.tile + s].a_stage) << 4)) << (8 * s);
+                // descriptor loads first, dependency wait second: the two global round trips overlap
+                if (lane < SK_QCHUNKS) cd = stack_chunk_desc(tiles, it.tile, it.n_steps, it.meta, lane, br, Bp);
+                if (lane < it.n_steps * SK_HDR16) hd = __ldg(reinterpret_cast<const int4*>(tiles + it.tile + lane / SK_HDR16) + lane % SK_HDR16);
                 if (ir.phase > 0 && it.dep_mask)
                     SK_TIMED(1, stack_wait(args.sync + ((size_t)(ir.phase - 1) * NT + ir.row_tile) * args.n_slots, it.dep_mask, lane, err));
                 a = make_int4(ir.row_tile, ir.phase, it.tile, it.n_steps);
-                b = make_int4(meta, it.out_slot, 0, 0);
+                b = make_int4(it.meta, it.out_slot, 0, 0);
             }
-            if (lane < SK_QCHUNKS && a.w) q_chunk[n_pub % SK_QUEUE][lane] = stack_chunk_desc(tiles, a.z, a.w, b.x, lane, br, Bp);
-            if (lane < a.w * SK_HDR16) q_hdr[n_pub % SK_QUEUE][lane / SK_HDR16][lane % SK_HDR16] = __ldg(reinterpret_cast<const int4*>(tiles + a.z + lane / SK_HDR16) + lane % SK_HDR16);
+            if (lane < SK_QCHUNKS && a.w) q_chunk[n_pub % SK_QUEUE][lane] = cd;
+            if (lane < a.w * SK_HDR16) q_hdr[n_pub % SK_QUEUE][lane / SK_HDR16][lane % SK_HDR16] = hd;
             __syncwarp();
             for (int s = 0; s < a.w; ++s) stack_prefetch_step(*reinterpret_cast<const TileHdr*>(q_hdr[n_pub % SK_QUEUE][s]), bt, a.x * TILE_M, Bp, lane);
             if (lane == 0) {

@@ -175,31 +175,31 @@ k_tc_stack2(const __grid_constant__ TcMaps maps, const __grid_constant__ CUtenso
                 }
                 cur = __shfl_sync(0xffffffffu, cur, 0);
                 int4 a = make_int4(0, 0, 0, 0), b = make_int4(0, 0, 0, 0);
+                const int slot = n_pub % SK_QUEUE;
                 if (cur < n_total) {
                     const ItemRef ir = args.chunked ? stack_decode_chunked(pg, NP, RC2, cur) : stack_decode(pg, NP, RC2, cur);
                     const StackItem it = items[ir.item];
-                    int meta = 0;
-                    for (int s = 0; s < it.n_steps && s < 4; ++s) meta |= (__ldg(&tiles[it.tile + s].n_chunks) | (__ldg(&tiles[it.tile + s].a_stage) << 4)) << (8 * s);
+                    // descriptors first (they do not depend on the dependency; the slot is invisible until q_count moves),
+                    // dependency wait second: the global round trips and the remote stores overlap
+                    if (lane < SK_QCHUNKS) {
+                        const int4 d = stack_chunk_desc(tiles, it.tile, it.n_steps, it.meta, lane, br, Bp);
+                        const uint32_t qc = smem_u32(&q_chunk[slot][lane]);
+                        st_cluster_v4(map_to_cta(qc, 0), d);
+                        st_cluster_v4(map_to_cta(qc, 1), d);
+                    }
+                    if (lane < it.n_steps * SK_HDR16) {
+                        const int4 h = __ldg(reinterpret_cast<const int4*>(tiles + it.tile + lane / SK_HDR16) + lane % SK_HDR16);
+                        const uint32_t qh = smem_u32(&q_hdr[slot][lane / SK_HDR16][lane % SK_HDR16]);
+                        st_cluster_v4(map_to_cta(qh, 0), h);
+                        st_cluster_v4(map_to_cta(qh, 1), h);
+                    }
                     if (ir.phase > 0 && it.dep_mask) {
                         const uint32_t* ctr = args.sync + ((size_t)(ir.phase - 1) * NT + 2 * ir.row_tile) * args.n_slots;
                         stack_wait(ctr, it.dep_mask, lane, err);
                         stack_wait(ctr + args.n_slots, it.dep_mask, lane, err);
                     }
                     a = make_int4(2 * ir.row_tile, ir.phase, it.tile, it.n_steps);
-                    b = make_int4(meta, it.out_slot, 0, 0);
-                }
-                const int slot = n_pub % SK_QUEUE;
-                if (lane < SK_QCHUNKS && a.w) {
-                    const int4 d = stack_chunk_desc(tiles, a.z, a.w, b.x, lane, br, Bp);
-                    const uint32_t qc = smem_u32(&q_chunk[slot][lane]);
-                    st_cluster_v4(map_to_cta(qc, 0), d);
-                    st_cluster_v4(map_to_cta(qc, 1), d);
-                }
-                if (lane < a.w * SK_HDR16) {
-                    const int4 h = __ldg(reinterpret_cast<const int4*>(tiles + a.z + lane / SK_HDR16) + lane % SK_HDR16);
-                    const uint32_t qh = smem_u32(&q_hdr[slot][lane / SK_HDR16][lane % SK_HDR16]);
-                    st_cluster_v4(map_to_cta(qh, 0), h);
-                    st_cluster_v4(map_to_cta(qh, 1), h);
+                    b = make_int4(it.meta, it.out_slot, 0, 0);
                 }
                 asm volatile("fence.acq_rel.cluster;" ::: "memory");
                 __syncwarp();

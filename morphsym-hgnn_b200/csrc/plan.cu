@@ -101,6 +101,8 @@ static std::string build_stack_programs(Plan& p) {
         it.tile = (int)p.tiles.size() - st.tiles.begin; it.n_steps = (int)steps.size();
         const Tile& last = steps.back();
         it.out_slot = last.out_buf >= 0 ? last.out_slot : last.out2_slot;
+        it.meta = 0;
+        for (size_t s_ = 0; s_ < steps.size() && s_ < 4; ++s_) it.meta |= (steps[s_].n_chunks | (steps[s_].a_stage << 4)) << (8 * s_);
         unsigned long long rd = 0;
         for (const Tile& T : steps) {
             for (int c = 0; c < T.n_chunks; ++c)

@@ -116,10 +116,11 @@ def _load_adam_state(trainer: FusedTrainer, module, opt_state: dict, device) -> 
         off += k
 
 
-def _save_checkpoint(path: Path, module, trainer: FusedTrainer, epoch: int, global_step: int, dummy: dict) -> None:
+def _save_checkpoint(path: Path, module, trainer: FusedTrainer, epoch: int, global_step: int, dummy: dict, loop_state: dict = None) -> None:
     hp = {k: v for k, v in dict(module.hparams).items() if k not in ("dummy_batch", "activation_fn")}
     hp["dummy_batch"] = dummy
     torch.save({"epoch": epoch, "global_step": global_step, "pytorch-lightning_version": "mshgnn_b200",
+                "loop_state": loop_state,       # early-stopping / top-k bookkeeping and the shuffle generator (Lightning keeps them under "callbacks" / "loops")
                 "state_dict": {k: v.detach().cpu() for k, v in module.state_dict().items()},
                 "optimizer_states": [_adam_state(trainer, module)], "lr_schedulers": [], "hyper_parameters": hp,
                 "class": type(module).__name__}, str(path))
@@ -155,6 +156,9 @@ def train_model(train_dataset: WindowSubset, val_dataset: WindowSubset, test_dat
     model_type = fmts[0]
     if model_type not in _HGNN_FORMATS:
         raise ValueError("Invalid model type.")
+    if hidden_size != 128:
+        # the signature keeps the reference's default (10); the native plan is compiled for 128 hidden channels only
+        raise ValueError(f"hidden_size={hidden_size}: the B200-native path supports hidden_size=128 only (pass hidden_size=128)")
     if devices != 1:
         raise ValueError("train_model drives one GPU; launch one process per GPU and pass a process group to FusedTrainer for data parallelism")
     data_metadata = train_dataset.dataset.get_data_metadata()
@@ -200,10 +204,17 @@ def train_model(train_dataset: WindowSubset, val_dataset: WindowSubset, test_dat
         if ck.get("optimizer_states"):
             _load_adam_state(trainer, module, ck["optimizer_states"][0], ds.device)
         start_epoch, global_step = int(ck.get("epoch", -1)) + 1, int(ck.get("global_step", 0))
+        resumed = ck.get("loop_state")
+    else:
+        resumed = None
 
     dummy_plain = _plain_batch(ds.batch(dummy_idx[:min(20, dummy_idx.numel())]))
     saved: List[tuple] = []         # (epoch, monitor value, path)
     best_seen, bad_epochs = float("inf"), 0
+    if resumed:                     # early stopping, the top-k policy and the shuffle order continue where the run stopped
+        best_seen, bad_epochs = float(resumed["best_seen"]), int(resumed["bad_epochs"])
+        saved = [(int(e), float(v), Path(pth)) for e, v, pth in resumed["saved"] if Path(pth).exists()]
+        gen.set_state(resumed["generator_state"])
     loss = torch.zeros(())
     for epoch in range(start_epoch, epochs):
         module.train()
@@ -216,8 +227,11 @@ def train_model(train_dataset: WindowSubset, val_dataset: WindowSubset, test_dat
         logged.update(epoch=epoch, global_step=global_step, train_loss_last_step=_value(loss))
         log_f.write(json.dumps(logged) + "\n"); log_f.flush()
         name = f"epoch={epoch}-{monitor}={logged[monitor]:.5f}" + (f"-{second}={logged[second]:.5f}" if second in logged else "") + ".ckpt"
-        _save_checkpoint(path_to_save / name, module, trainer, epoch, global_step, dummy_plain)
         saved.append((epoch, logged[monitor], path_to_save / name))
+        better = logged[monitor] < best_seen
+        _save_checkpoint(path_to_save / name, module, trainer, epoch, global_step, dummy_plain,
+                         {"best_seen": min(best_seen, logged[monitor]), "bad_epochs": 0 if better else bad_epochs + 1,
+                          "saved": [(e, v, str(pth)) for e, v, pth in saved], "generator_state": gen.get_state()})
         # ModelCheckpoint(save_top_k=7, mode='min', monitor=monitor) + ModelCheckpoint(save_top_k=3, mode='max', monitor='epoch')
         keep = {s[2] for s in sorted(saved, key=lambda s: s[1])[:7]} | {s[2] for s in sorted(saved, key=lambda s: s[0])[-3:]}
         for s in saved:
