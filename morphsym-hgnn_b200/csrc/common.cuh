@@ -49,6 +49,7 @@ struct Chunk {
     int w16_row;     // tensor-core path: first row of this weight's 128x128 fp16 image (W for forward, W^T for dX)
 };
 
+constexpr int TILE_RES_PRIV = 1, TILE_OUT_PRIV = 2;
 // One 128-row x 128-col output tile of a row-GEMM launch.
 struct Tile {
     int n_chunks;
@@ -64,7 +65,7 @@ struct Tile {
     // chained steps of the cross-layer stack kernel (kernels_stack.cuh); zero in every per-layer launch table
     int a_stage;                      // chunk 0 reads its A operand from the staging tiles the previous step of the item left on chip
     int stage_out;                    // the epilogue leaves the (hi, lo) result in the staging tiles for the next step of the item
-    int pad_;
+    int priv;                         // stack programs only: TILE_RES_PRIV / TILE_OUT_PRIV (thread-private fp32 layout of residual-only tensors, kernels_stack.cuh)
     Chunk chunks[MAX_CHUNKS];
 };
 

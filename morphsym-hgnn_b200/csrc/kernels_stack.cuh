@@ -63,10 +63,12 @@ struct StackArgs {
     uint32_t* err;               // error word (a dependency wait timed out)
     uint32_t* next;              // work counter: the next item index to hand out (zeroed with the completion counters)
     unsigned long long* timing;  // TIMING instantiation only: per CTA 8 cycle counters (see k_tc_stack)
+    char* ws;                    // workspace base (thread-private fp32 tensors live in the image area of their buffer)
     int epilogue;                // CTA-pair kernel: 0 = epilogue with headers from the queue, deferred completion signal (backward: epilogue-bound,
                                  // -2..5 %); 1 = first version (forward: bound by the MMA side, where the longer scheduler chain of 0 costs 3 %)
     int debug;                   // ablation switches for timing experiments (MSHGNN_STACK_DEBUG; results are then garbage): 1 no A loads,
-                                 // 2 no W loads, 4 no MMAs, 8 epilogue reduced to its handshakes (CTA-pair kernel only)
+                                 // 2 no W loads, 4 no MMAs, 8 epilogue reduced to its handshakes, 16 completion signal at once, 32 barrier before every staging write,
+                                 // 64 no L1 prefetch, 256 no second output of two-output tiles, 512 no residuals (CTA-pair kernel only)
 };
 
 struct ItemRef { int phase, row_tile, item; };
@@ -190,7 +192,7 @@ __device__ __forceinline__ int4 stack_chunk_desc(const Tile* tiles, const int fi
 // header of a Tile (everything but the chunk list), fetched once per step into registers
 struct TileHdr {
     int n_chunks, out_buf, out_slot, bias_buf, bias_off, relu, posmask_buf, posmask_slot, res_buf, res_slot, mask_out_buf,
-        out2_buf, out2_slot, out2_mask_kind, out2_mask_buf, out2_mask_slot, mask_out_slot, a_stage, stage_out, pad_;
+        out2_buf, out2_slot, out2_mask_kind, out2_mask_buf, out2_mask_slot, mask_out_slot, a_stage, stage_out, priv;
 };
 static_assert(sizeof(TileHdr) == offsetof(Tile, chunks), "TileHdr must mirror the head of Tile");
 __device__ __forceinline__ TileHdr load_hdr(const Tile* t) {
@@ -236,10 +238,13 @@ __device__ __forceinline__ void stack_flush_signal(uint32_t*& pending) {
 }
 
 // One step of an item through one epilogue group (cf. tc_epilogue_q).  `sig`: completion counter of the item (last step only).
+// PRIV: the program has thread-private fp32 tensors (backward launches of the MS-HGNN models); the forward instantiation carries
+// none of that code - at the 96-register cap of a 608-thread CTA a few more live values cost every path 10 % and more.
+template <bool PRIV>
 __device__ __forceinline__ void stack_epilogue(const TileHdr& t, const BufTable& bt, const BufRows& br, const CUtensorMap* map_k,
                                                const uint32_t tmem_acc, const int row0, const int64_t B, const int64_t Bp,
                                                const int warp, const int lane, const int grp, const StackEpi es, uint32_t& res_count,
-                                               uint32_t* sig, uint32_t*& pending, unsigned long long* t_wait_acc = nullptr,
+                                               uint32_t* sig, uint32_t*& pending, char* const ws, unsigned long long* t_wait_acc = nullptr,
                                                const bool dbg_bare = false, const int dbg = 0) {
     const int q = warp & 3;                        // TMEM lane quarter this warp may access (hardware rule: warp index mod 4)
     const bool leader = q == 2 && lane == 0;       // first warp of the group (warps 2 + 4g .. 5 + 4g): warp index = 2 mod 4
@@ -249,7 +254,19 @@ __device__ __forceinline__ void stack_epilogue(const TileHdr& t, const BufTable&
     const bool all_live = (int64_t)row0 + TILE_M <= B;
     const uint32_t rsw = (uint32_t)((rl >> 1) & 3);     // SWIZZLE_64B: 16-byte chunk index ^= address bits [7, 9)
     const uint32_t tile = es.stg + (uint32_t)rl * 64u;
-    const bool has_out = t.out_buf >= 0, has_out2 = t.out2_buf >= 0, has_res = t.res_buf >= 0 && !dbg_bare;
+    // Thread-private fp32 tensors (Tile::priv): a [128 rows x 32 columns] quarter is stored as eight 2 KB chunks, chunk j = the
+    // 16 bytes (columns 4j .. 4j + 3) of every row - each thread owns 16 bytes of every chunk, a warp reads / writes 512
+    // contiguous bytes, and the quarter (16 KB, contiguous) comes back with ONE bulk copy.  The 64 KB of a (node slot, row tile)
+    // occupy the rows of the slot's hi image (quarters 0, 1) and lo image (quarters 2, 3).
+    const bool res_priv = PRIV && (t.priv & TILE_RES_PRIV) != 0, out_priv = PRIV && (t.priv & TILE_OUT_PRIV) != 0;
+    // (Reading a private residual straight into registers - eight coalesced 128-bit loads per thread instead of the bulk copy through
+    // the staging tiles - was measured: +10 % on the backward launch, and the 32 extra live registers at the 96-register cap cost the
+    // forward launch 12 % as well.)
+    auto priv_quarter = [&](const int buf, const int slot) -> char* {
+        return ws + ((size_t)((grp < 2 ? br.hi[buf] : br.lo[buf]) + (int)((int64_t)slot * Bp) + row0) << 8) + (size_t)(grp & 1) * 16384u;
+    };
+    const bool has_out = t.out_buf >= 0 && !out_priv, has_out2 = t.out2_buf >= 0 && !((dbg & 256) && t.out_buf >= 0), has_res = t.res_buf >= 0 && !dbg_bare && !(dbg & 512);
+    const bool res_staged = has_res;
     const bool want_mask = t.relu || t.mask_out_buf >= 0;
     const bool writes_stage = has_out || has_out2 || t.stage_out;
     const int col0 = grp * 32;
@@ -265,8 +282,14 @@ __device__ __forceinline__ void stack_epilogue(const TileHdr& t, const BufTable&
     }
 
     auto fetch_residual = [&]() {
-        const int r_hi = br.hi[t.res_buf] + (int)((int64_t)t.res_slot * Bp) + row0, r_lo = br.lo[t.res_buf] + (int)((int64_t)t.res_slot * Bp) + row0;
         mbar_expect_tx(es.res_bar, 2u * 8192u);
+        if (PRIV && res_priv) {
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(es.stg),
+                         "l"(priv_quarter(t.res_buf, t.res_slot)), "r"(16384u), "r"(es.res_bar)
+                         : "memory");
+            return;
+        }
+        const int r_hi = br.hi[t.res_buf] + (int)((int64_t)t.res_slot * Bp) + row0, r_lo = br.lo[t.res_buf] + (int)((int64_t)t.res_slot * Bp) + row0;
         tma_load_2d(es.stg, map_k, es.res_bar, col0, r_hi);
         tma_load_2d(es.stg + 8192, map_k, es.res_bar, col0, r_lo);
     };
@@ -274,7 +297,7 @@ __device__ __forceinline__ void stack_epilogue(const TileHdr& t, const BufTable&
         tma_store_wait_read();                     // the staging tiles may still feed this group's previous TMA stores
         // early fetch (hidden behind the MMAs of this step); the item is only published to this warp once its input
         // dependency - the residual is an output of the previous phase - has been seen satisfied by the producer warp
-        if (has_res && !t.a_stage) {
+        if (res_staged && !t.a_stage) {
             asm volatile("fence.proxy.async.global;" ::: "memory");
             fetch_residual();
         }
@@ -301,7 +324,7 @@ __device__ __forceinline__ void stack_epilogue(const TileHdr& t, const BufTable&
     tc_fence_before();
     mbar_arrive(es.free_bar);                      // this thread's part of the accumulator is in registers
     if (leader) stack_flush_signal(pending);       // the previous item's stores landed long ago
-    if (has_res) {
+    if (res_staged) {
         // chained step: the staging tiles were the A operand of THIS step's MMAs, which have completed by now
         if (t.a_stage && leader) fetch_residual();
         mbar_wait(es.res_bar, res_count & 1u);
@@ -331,12 +354,38 @@ __device__ __forceinline__ void stack_epilogue(const TileHdr& t, const BufTable&
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = ((pm >> j) & 1u) ? v[j] : 0.f;
     }
+    if (PRIV && has_res && res_priv && !(dbg & 2048)) {
+        // The quarter has been copied into shared memory and nothing reads it again: drop its (dirty) lines from L2 instead of
+        // letting them be written back - a residual-only dh is dead the moment it is consumed (1.07 GB of DRAM writes per step).
+        asm volatile("discard.global.L2 [%0], 128;" ::"l"(priv_quarter(t.res_buf, t.res_slot) + (size_t)rl * 128u) : "memory");
+    }
+    if (PRIV && has_res && res_priv) {
+        // fp32 residual: this thread's 16 bytes of each of the eight chunks; the chunks overlap OTHER threads' output bytes, so
+        // every thread of the group has to be done reading before the first staging write (barrier below)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint4 r = lds128(es.stg + (uint32_t)j * 2048u + (uint32_t)rl * 16u);
+            v[4 * j] += __uint_as_float(r.x); v[4 * j + 1] += __uint_as_float(r.y); v[4 * j + 2] += __uint_as_float(r.z); v[4 * j + 3] += __uint_as_float(r.w);
+        }
+    }
+    if (has_res && !res_priv) {
+        // image residual: read in place (the bytes this thread overwrites with its own result below)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const uint32_t a = tile + ((((uint32_t)g) ^ rsw) << 4);
+            join8_add(v + g * 8, lds128(a), lds128(a + 8192));
+        }
+    }
+    if (PRIV && out_priv) {
+        float4* const o = reinterpret_cast<float4*>(priv_quarter(t.out_buf, t.out_slot) + (size_t)rl * 16u);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j * 128] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
     // the leader has seen the previous stores of this group read the staging tiles (has_res: the residual has landed in them)
-    if (!has_res || (dbg & 32)) group_bar_sync(grp);
+    if (!has_res || res_priv || (dbg & 32)) group_bar_sync(grp);
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
         const uint32_t a = tile + ((((uint32_t)g) ^ rsw) << 4);
-        if (has_res) join8_add(v + g * 8, lds128(a), lds128(a + 8192));
         if (writes_stage) {
             uint4 hi, lo;
             split8(v + g * 8, hi, lo);
@@ -521,7 +570,7 @@ __device__ __forceinline__ void stack_epilogue_v1(const TileHdr& t, const BufTab
 // spend in each kind of wait into args.timing[blockIdx.x * 8 + {0: producer/ring slot, 1: producer/dependency, 2: MMA/operands,
 // 3: MMA/accumulator free, 4: MMA/staged operand, 5: epilogue group 0/accumulator, 6: kernel, 7: steps}].
 #define SK_TIMED(slot, stmt) do { if (TIMING) { const long long t0_ = clock64(); stmt; tim[slot] += (unsigned long long)(clock64() - t0_); } else { stmt; } } while (0)
-template <bool TIMING>
+template <bool TIMING, bool PRIV>
 __global__ void __launch_bounds__(SK_THREADS, 1)
 k_tc_stack(const __grid_constant__ TcMaps maps, const Tile* __restrict__ tiles, const StackItem* __restrict__ items,
            const __grid_constant__ StackArgs args, const BufTable bt, const BufRows br) {
@@ -740,8 +789,8 @@ k_tc_stack(const __grid_constant__ TcMaps maps, const Tile* __restrict__ tiles, 
                 const uint32_t a = k % SK_ACCS;
                 es.accum_bar = acc_full0 + 8 * a; es.free_bar = acc_free0 + 8 * a;
                 es.acc_parity = (k / SK_ACCS) & 1;
-                stack_epilogue(t, bt, br, &maps.k, tmem_base + a * 128, qa.x * TILE_M, B, Bp, warp, lane, grp, es, n_res,
-                               s == qa.w - 1 ? ctr : nullptr, pending, (TIMING && warp == 2 && lane == 0) ? &tim[5] : nullptr);
+                stack_epilogue<PRIV>(t, bt, br, &maps.k, tmem_base + a * 128, qa.x * TILE_M, B, Bp, warp, lane, grp, es, n_res,
+                                     s == qa.w - 1 ? ctr : nullptr, pending, args.ws, (TIMING && warp == 2 && lane == 0) ? &tim[5] : nullptr);
             }
         }
         if (sig_leader) { stack_flush_signal(pending); tma_store_wait_all(); }

@@ -106,6 +106,7 @@ __device__ __forceinline__ int ld_acquire_cluster(uint32_t saddr) {
     return v;
 }
 
+template <bool PRIV>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SK_THREADS, 1)
 k_tc_stack2(const __grid_constant__ TcMaps maps, const __grid_constant__ CUtensorMap map_w, const Tile* __restrict__ tiles,
             const StackItem* __restrict__ items, const __grid_constant__ StackArgs args, const BufTable bt, const BufRows br) {
@@ -356,12 +357,12 @@ k_tc_stack2(const __grid_constant__ TcMaps maps, const __grid_constant__ CUtenso
                 const uint32_t a = k % SK_ACCS;
                 es.accum_bar = acc_full0 + 8 * a; es.free_bar = acc_free0 + 8 * a;
                 es.acc_parity = (k / SK_ACCS) & 1;
-                if (args.epilogue == 1)
+                if (args.epilogue == 1 && !(PRIV && t.priv))     // the first version knows image tensors only
                     stack_epilogue_v1(load_hdr(tiles + qa.z + s), bt, br, &maps.k, tmem_base + a * 128, qa.x * TILE_M, B, Bp, warp, lane, grp, es, smem_u32(bias_s[grp]),
                                       n_res, s == qa.w - 1 ? ctr : nullptr);
                 else
-                    stack_epilogue(t, bt, br, &maps.k, tmem_base + a * 128, qa.x * TILE_M, B, Bp, warp, lane, grp, es, n_res, s == qa.w - 1 ? ctr : nullptr,
-                                   pending, nullptr, dbg_bare_epi, args.debug);
+                    stack_epilogue<PRIV>(t, bt, br, &maps.k, tmem_base + a * 128, qa.x * TILE_M, B, Bp, warp, lane, grp, es, n_res, s == qa.w - 1 ? ctr : nullptr,
+                                   pending, args.ws, nullptr, dbg_bare_epi, args.debug);
             }
         }
         if (sig_leader) { stack_flush_signal(pending); tma_store_wait_all(); }

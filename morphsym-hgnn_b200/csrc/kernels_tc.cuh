@@ -1461,10 +1461,11 @@ constexpr int ENCP_STAGES = 2;
 constexpr int ENCP_STAGE_BYTES = 6 * ENC_TILE_BYTES;          // 96 KB
 constexpr int ENCP_SMEM_BYTES = ENCP_STAGES * ENCP_STAGE_BYTES + 1024 + 256;
 constexpr uint32_t ENCP_TMEM_COLS = 256;
+constexpr int ENC_PF_BYTES = 1536;                      // first L2 prefetch request per feature row
 
 __global__ void __launch_bounds__(ENC_THREADS, 1)
 k_tc_encoder_pair(const __grid_constant__ EncMaps maps, const Tile* __restrict__ tiles, const BufTable bt, const BufRows br,
-                  const int64_t B, const int64_t Bp, const int x_f64, const int split) {
+                  const int64_t B, const int64_t Bp, const int x_f64, const int split, const int enc_prefetch) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ Tile t;
     __shared__ __align__(16) float bias_s[H];
@@ -1502,6 +1503,23 @@ k_tc_encoder_pair(const __grid_constant__ EncMaps maps, const Tile* __restrict__
     const int n_kb = (K + 63) / 64;
 
     if (warp == 0) {
+        // Optional (MSHGNN_ENC_PREFETCH=1, off by default) L2 prefetch of this CTA's feature rows as WHOLE-ROW bulk requests (one per
+        // graph row, up to 1.5 KB at a time).  Hypothesis tested in round 2: the loaders read the rows as 256-byte fragments, 14 KB
+        // apart, K block by K block, and DRAM serves that pattern badly (the weight-gradient kernel reads the same rows in 768-byte
+        // fragments at 3.8 TB/s).  Measured: 0.346 -> 0.388 ms, i.e. WORSE - fragment size is not what limits this kernel.
+        const Chunk& ch0 = t.chunks[0];
+        const bool pf_ok = enc_prefetch && !x_f64 && ((ch0.lda | ch0.a_off | K) & 3) == 0 && (reinterpret_cast<uintptr_t>(bt.p[ch0.a_buf]) & 15) == 0;
+        const float* xb = (const float*)bt.p[ch0.a_buf] + ch0.a_off;
+        const int row_bytes = K * 4;
+        auto prefetch_rows = [&](const int byte0, const int byte1, const int l0, const int lstep) {
+            if (byte1 <= byte0) return;
+            for (int r = l0; r < n_tiles * TILE_M; r += lstep) {
+                const int64_t row = (int64_t)row0 + r;
+                if (row >= B) break;
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char*>(xb + row * ch0.lda) + byte0), "r"(byte1 - byte0) : "memory");
+            }
+        };
+        if (pf_ok) prefetch_rows(0, row_bytes < ENC_PF_BYTES ? row_bytes : ENC_PF_BYTES, lane, 32);
         if (lane == 0) {
             const uint32_t tx_bytes = split ? 2 * ENC_TILE_BYTES : ENC_TILE_BYTES;
             const int wrow = t.chunks[0].w16_row;
@@ -1513,6 +1531,7 @@ k_tc_encoder_pair(const __grid_constant__ EncMaps maps, const Tile* __restrict__
                 mbar_expect_tx(fb, tx_bytes);
                 tma_load_2d(st + 4 * ENC_TILE_BYTES, &maps.w_hi, fb, i * 64, wrow);
                 if (split) tma_load_2d(st + 5 * ENC_TILE_BYTES, &maps.w_lo, fb, i * 64, wrow);
+                if (i == 1 && pf_ok) prefetch_rows(ENC_PF_BYTES, row_bytes, 0, 1);
             }
         }
     } else if (warp == 1) {

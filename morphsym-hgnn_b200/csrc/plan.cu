@@ -48,6 +48,7 @@ static Tile empty_tile() {
     t.out_buf = -1; t.out_slot = 0; t.bias_buf = -1; t.bias_off = 0; t.relu = 0;
     t.posmask_buf = -1; t.posmask_slot = 0; t.res_buf = -1; t.res_slot = 0; t.mask_out_buf = -1; t.mask_out_slot = 0;
     t.out2_buf = -1; t.out2_slot = 0; t.out2_mask_kind = MK_NONE; t.out2_mask_buf = -1; t.out2_mask_slot = 0;
+    t.priv = 0;
     return t;
 }
 
@@ -80,6 +81,12 @@ static bool emit_units(Plan& p, const std::vector<RPair>& prs, int K, int k0, in
 // activation / gradient buffers written by the phases of a stack program (as opposed to forward state a backward phase reads)
 static bool is_phase_buffer(int buf) {
     return (buf >= BUF_H0 && buf < BUF_H0 + MAX_LAYERS + 1) || (buf >= BUF_DHL0 && buf < BUF_DUL0 + MAX_LAYERS);
+}
+
+// MSHGNN_STACK_PRIVATE_DH=0: keep dh of every node as (hi, lo) images (A/B runs; read when a plan is created)
+static bool stack_private_dh() {
+    static const bool on = [] { const char* e = getenv("MSHGNN_STACK_PRIVATE_DH"); return !(e && !strcmp(e, "0")); }();
+    return on;
 }
 
 static std::string build_stack_programs(Plan& p) {
@@ -205,6 +212,17 @@ static std::string build_stack_programs(Plan& p) {
                     T.stage_out = 1; A.a_stage = 1; A.stage_out = 1; Bt.a_stage = 1;
                     emit(st, {T, A, Bt});
                 } else {
+                    // dh of a joint / foot node is read back ONLY as the pass-through residual of the same node one layer down (the
+                    // MMA operands are the masked dc images; only base nodes feed dh into base_transform's backward).  Such a dh is
+                    // kept as fp32 in a thread-private layout (kernels_stack.cuh): written straight from the epilogue's registers,
+                    // read back by one bulk copy - no (hi, lo) split, no second in-place pass through the staging tiles, and the
+                    // tile is left with ONE staged output (dc).  dh_L comes from the decoder kernel as images.
+                    if (p.morph_sym && stack_private_dh()) {
+                        const int slot = T.out_buf >= 0 ? T.out_slot : T.out2_slot;
+                        const bool base = p.slot_type[slot] == p.mlp_type;
+                        if (!base && T.out_buf == BUF_DHL0 + l && T.out2_buf >= 0) T.priv |= TILE_OUT_PRIV;
+                        if (!base && T.res_buf == BUF_DHL0 + l + 1 && l + 1 < p.L) T.priv |= TILE_RES_PRIV;
+                    }
                     emit(st, {T});
                 }
             }
@@ -619,18 +637,22 @@ bool stack_enabled() {
 }
 void set_stack_enabled(int on) { g_stack_on.store(on ? 1 : 0, std::memory_order_relaxed); }
 
-// CTA-pair variant of the stack kernel (kernels_stack2.cuh): on by default, MSHGNN_STACK_2CTA=0 / option "stack_pair" turn it off
+// CTA-pair variant of the stack kernel (kernels_stack2.cuh): 1 (default) = for batches of >= STACK_PAIR_MIN_GRAPHS graphs, 2 = always,
+// 0 = never (MSHGNN_STACK_2CTA / option "stack_pair").  Below ~6 K graphs a phase of a row chunk has fewer pair items than there are
+// CTA pairs to feed (8 pairs x 20 items against 74 pairs at 2048 graphs) and the one-CTA kernel is 5-10 % faster
+// (2048 graphs: 0.155 / 0.155 ms against 0.159 / 0.171; 4096: 0.214 / 0.251 against 0.215 / 0.268; 16384: 0.81 / 1.03 against 0.77 / 0.975).
+constexpr int64_t STACK_PAIR_MIN_GRAPHS = 6144;
 static std::atomic<int> g_stack_pair{-1};
-bool stack_pair_enabled() {
+int stack_pair_mode() {
     int v = g_stack_pair.load(std::memory_order_relaxed);
     if (v < 0) {
         const char* e = getenv("MSHGNN_STACK_2CTA");
-        v = !(e && !strcmp(e, "0"));
+        v = e ? (atoi(e) < 0 ? 0 : (atoi(e) > 2 ? 2 : atoi(e))) : 1;
         g_stack_pair.store(v, std::memory_order_relaxed);
     }
-    return v != 0;
+    return v;
 }
-void set_stack_pair_enabled(int on) { g_stack_pair.store(on ? 1 : 0, std::memory_order_relaxed); }
+void set_stack_pair_mode(int v) { g_stack_pair.store(v < 0 ? 0 : (v > 2 ? 2 : v), std::memory_order_relaxed); }
 
 // epilogue variant of the CTA-pair kernel: -1 = per launch kind (forward: first version, backward: deferred-signal version), 0 / 1 = forced
 static std::atomic<int> g_stack_epilogue{-2};
@@ -649,7 +671,7 @@ WsLayout ws_layout(const Plan& p, int64_t B, int train, int mode) {
     const bool tc = mode != MSHGNN_MODE_FP32;
     WsLayout w{};
     w.stack = tc && stack_enabled() && p.stack_infer.prog.n_phases > 0;
-    w.stack_pair = w.stack && stack_pair_enabled();
+    w.stack_pair = w.stack && (stack_pair_mode() == 2 || (stack_pair_mode() == 1 && B >= STACK_PAIR_MIN_GRAPHS));
     w.Bp = round_up(B < 1 ? 1 : B, w.stack_pair ? 2 * TILE_M : TILE_M);      // the CTA-pair kernel walks row tiles two at a time
     int ns = (int)((B + 511) / 512);
     w.n_splits = ns < 1 ? 1 : (ns > 64 ? 64 : ns);

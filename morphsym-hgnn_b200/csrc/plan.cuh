@@ -148,8 +148,8 @@ std::string build_plan(const mshgnn_desc* d, Plan& p);            // returns err
 WsLayout ws_layout(const Plan& p, int64_t B, int train, int mode);
 bool stack_enabled();                 // cross-layer stack kernel on (default) / off (MSHGNN_STACK=0 or mshgnn_set_option)
 void set_stack_enabled(int on);
-bool stack_pair_enabled();            // CTA-pair (cta_group::2) variant of the stack kernel on (default) / off (MSHGNN_STACK_2CTA=0)
-void set_stack_pair_enabled(int on);
+int stack_pair_mode();                // CTA-pair (cta_group::2) stack kernel: 1 = by batch size (default), 2 = always, 0 = never (MSHGNN_STACK_2CTA)
+void set_stack_pair_mode(int v);
 int stack_epilogue_choice();          // -1: per launch kind, 0 / 1: forced (MSHGNN_STACK_EPILOGUE, option "stack_epilogue")
 void set_stack_epilogue_choice(int v);
 std::string describe_plan(const Plan& p);

@@ -84,12 +84,19 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    try:
-        _build_if_needed()
-    except Exception as e:  # no nvcc on the box: a prebuilt .so must be there
-        if not os.path.exists(LIB_PATH):
-            raise RuntimeError(f"libmshgnn_b200.so is missing and could not be built: {e}") from e
-    L = C.CDLL(LIB_PATH)
+    override = os.environ.get("MSHGNN_LIB")      # measurement hook: load another build of the same ABI (same-box A/B of two commits)
+    if override:
+        if not os.path.exists(override):
+            raise RuntimeError(f"MSHGNN_LIB={override} does not exist")
+        path = override
+    else:
+        path = LIB_PATH
+        try:
+            _build_if_needed()
+        except Exception as e:  # no nvcc on the box: a prebuilt .so must be there
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(f"libmshgnn_b200.so is missing and could not be built: {e}") from e
+    L = C.CDLL(path)
     vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
     L.mshgnn_plan_create.argtypes = [C.POINTER(Desc), C.POINTER(vp)]; L.mshgnn_plan_create.restype = C.c_int
     L.mshgnn_plan_destroy.argtypes = [vp]; L.mshgnn_plan_destroy.restype = None
@@ -156,7 +163,7 @@ def launch_count() -> int:
 
 def set_option(name: str, value: int) -> None:
     """Library switches: 'stack' (1 = cross-layer persistent kernel for the layer loop, 0 = one launch per layer),
-    'stack_pair' (1 = CTA-pair stack kernel), 'stack_epilogue' (-1 = per launch kind, 0 / 1 = forced variant)."""
+    'stack_pair' (0 = never, 1 = CTA-pair stack kernel for batches >= 6144 graphs, 2 = always), 'stack_epilogue' (-1 = per launch kind, 0 / 1 = forced variant)."""
     check(lib().mshgnn_set_option(name.encode(), int(value)), "mshgnn_set_option")
 
 
