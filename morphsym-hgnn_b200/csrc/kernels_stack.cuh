@@ -213,6 +213,53 @@ struct StackEpi {
     uint32_t acc_parity;
 };
 
+// Accumulator -> value arithmetic of one thread's 32 columns, specialised on the (CTA-uniform) tile flags: with the flags as run-time
+// values the compiler predicates the per-element mask / ReLU code instead of branching around it - ~190 of the ~720 instructions of
+// a backward step were compare / select / min-max instructions of features the backward tiles do not have.
+template <bool BIAS, bool MASK, bool RELU>
+__device__ __forceinline__ unsigned epi_affine(const uint32_t (&raw)[32], float (&v)[32], const uint32_t bias_smem) {
+    unsigned mask = 0;
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (BIAS) asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(bias_smem + 16u * j4));
+        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int j = j4 * 4 + e;
+            float x = BIAS ? fmaf(__uint_as_float(raw[j]), TC_W_UNSCALE, bb[e]) : __uint_as_float(raw[j]) * TC_W_UNSCALE;
+            if (MASK && x > 0.f) mask |= 1u << j;
+            if (RELU) x = fmaxf(x, 0.f);
+            v[j] = x;
+        }
+    }
+    return mask;
+}
+__device__ __forceinline__ unsigned epi_affine_any(const bool has_bias, const bool want_mask, const bool relu, const uint32_t (&raw)[32], float (&v)[32],
+                                                   const uint32_t bias_smem) {
+    if (!has_bias && !want_mask && !relu) return epi_affine<false, false, false>(raw, v, bias_smem);      // backward tiles
+    if (has_bias && want_mask && relu) return epi_affine<true, true, true>(raw, v, bias_smem);            // training: conv, Linear + ReLU
+    if (has_bias && !want_mask && relu) return epi_affine<true, false, true>(raw, v, bias_smem);          // inference: the same
+    if (has_bias && !want_mask && !relu) return epi_affine<true, false, false>(raw, v, bias_smem);        // base-node conv, second Linear
+    // anything else (a stored mask without ReLU ...): flags as run-time values
+    unsigned mask = 0;
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has_bias) asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(bias_smem + 16u * j4));
+        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int j = j4 * 4 + e;
+            float x = fmaf(__uint_as_float(raw[j]), TC_W_UNSCALE, bb[e]);
+            if (want_mask && x > 0.f) mask |= 1u << j;
+            if (relu) x = fmaxf(x, 0.f);
+            v[j] = x;
+        }
+    }
+    return mask;
+}
+
 // L1 prefetches of what the epilogue of one step reads from global memory (bias quarter lines, stored ReLU bit masks of the
 // 128 rows): issued by the scheduler warp when the item is published, one or two items before the epilogue gets there.
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
@@ -331,25 +378,11 @@ __device__ __forceinline__ void stack_epilogue(const TileHdr& t, const BufTable&
         ++res_count;
     }
     float v[32];
-    unsigned mask = 0;
     if (has_bias) {
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(es.bias + 4u * lane), "f"(bias_l) : "memory");
         __syncwarp();
     }
-#pragma unroll
-    for (int j4 = 0; j4 < 8; ++j4) {
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (has_bias) asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(es.bias + 16u * j4));
-        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int j = j4 * 4 + e;
-            float x = fmaf(__uint_as_float(raw[j]), TC_W_UNSCALE, bb[e]);
-            if (want_mask && x > 0.f) mask |= 1u << j;
-            if (t.relu) x = fmaxf(x, 0.f);
-            v[j] = x;
-        }
-    }
+    const unsigned mask = epi_affine_any(has_bias, want_mask, t.relu != 0, raw, v, es.bias);
     if (t.posmask_buf >= 0) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = ((pm >> j) & 1u) ? v[j] : 0.f;
@@ -383,16 +416,32 @@ __device__ __forceinline__ void stack_epilogue(const TileHdr& t, const BufTable&
     }
     // the leader has seen the previous stores of this group read the staging tiles (has_res: the residual has landed in them)
     if (!has_res || res_priv || (dbg & 32)) group_bar_sync(grp);
+    if (writes_stage) {
+        const bool dead = !all_live && !live;       // rows [B, Bp) of every image stay zero
+        if (!has_out && has_out2) {
+            // the only staged output is the masked one: clear the masked-off columns as fp32 values (one select per element;
+            // clearing the packed fp16 lanes of the hi and the lo image afterwards cost ~ 3.5 instructions per element)
+            const uint32_t keep = dead ? 0u : m2;
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        const uint32_t a = tile + ((((uint32_t)g) ^ rsw) << 4);
-        if (writes_stage) {
-            uint4 hi, lo;
-            split8(v + g * 8, hi, lo);
-            if (!has_out && has_out2) { hi = mask8(hi, m2 >> (g * 8)); lo = mask8(lo, m2 >> (g * 8)); }
-            if (!all_live && !live) { hi = make_uint4(0u, 0u, 0u, 0u); lo = hi; }     // rows [B, Bp) of every image stay zero
-            sts128(a, hi);
-            sts128(a + 8192, lo);
+            for (int j = 0; j < 32; ++j) v[j] = ((keep >> j) & 1u) ? v[j] : 0.f;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const uint32_t a = tile + ((((uint32_t)g) ^ rsw) << 4);
+                uint4 hi, lo;
+                split8(v + g * 8, hi, lo);
+                sts128(a, hi);
+                sts128(a + 8192, lo);
+            }
+        } else {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const uint32_t a = tile + ((((uint32_t)g) ^ rsw) << 4);
+                uint4 hi, lo;
+                split8(v + g * 8, hi, lo);
+                if (dead) { hi = make_uint4(0u, 0u, 0u, 0u); lo = hi; }
+                sts128(a, hi);
+                sts128(a + 8192, lo);
+            }
         }
     }
     fence_proxy_async_smem();
@@ -491,21 +540,7 @@ __device__ __forceinline__ void stack_epilogue_v1(const TileHdr& t, const BufTab
         ++res_count;
     }
     float v[32];
-    unsigned mask = 0;
-#pragma unroll
-    for (int j4 = 0; j4 < 8; ++j4) {
-        float4 b4;
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(bias_smem + 16u * j4));
-        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int j = j4 * 4 + e;
-            float x = fmaf(__uint_as_float(raw[j]), TC_W_UNSCALE, bb[e]);
-            if (want_mask && x > 0.f) mask |= 1u << j;
-            if (t.relu) x = fmaxf(x, 0.f);
-            v[j] = x;
-        }
-    }
+    const unsigned mask = epi_affine_any(true, want_mask, t.relu != 0, raw, v, bias_smem);     // the bias quarter in shared memory is zero when the tile has none
     if (t.posmask_buf >= 0) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = ((pm >> j) & 1u) ? v[j] : 0.f;
