@@ -148,8 +148,12 @@ __device__ __forceinline__ void stack_wait(const uint32_t* ctr, const unsigned l
 }
 
 __device__ __forceinline__ void stack_signal(uint32_t* ctr) {
+    // one gpu-scope release: it is cumulative over everything that happens-before it (this thread's completed TMA stores, the other
+    // epilogue threads' global stores ordered by the group barrier).  A separate fence.acq_rel.gpu in front of it doubled the cost of
+    // what the stall profile shows as the single most expensive instruction of the backward launch (21 % + 5 % of the warp samples;
+    // train step 3.09 -> 3.03 ms).  Moving the release to a dedicated signal warp (mailboxes in shared memory, the group leader only
+    // posting the counter address) was measured afterwards: no further gain (3.05 ms against 3.03), dropped.
     asm volatile("fence.proxy.async.global;" ::: "memory");
-    asm volatile("fence.acq_rel.gpu;" ::: "memory");
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ctr), "r"(1u) : "memory");
 }
 
@@ -387,11 +391,8 @@ __device__ __forceinline__ void stack_epilogue(const TileHdr& t, const BufTable&
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = ((pm >> j) & 1u) ? v[j] : 0.f;
     }
-    if (PRIV && has_res && res_priv && !(dbg & 2048)) {
-        // The quarter has been copied into shared memory and nothing reads it again: drop its (dirty) lines from L2 instead of
-        // letting them be written back - a residual-only dh is dead the moment it is consumed (1.07 GB of DRAM writes per step).
-        asm volatile("discard.global.L2 [%0], 128;" ::"l"(priv_quarter(t.res_buf, t.res_slot) + (size_t)rl * 128u) : "memory");
-    }
+    // (discard.global.L2 of the consumed quarter - a residual-only dh is dead once read - was tried: ncu counted 2.11 GB of DRAM writes
+    // against 2.21 GB without it, and the CCTL + error-barrier sequence it compiles to held 9 % of the warp samples.  Dropped.)
     if (PRIV && has_res && res_priv) {
         // fp32 residual: this thread's 16 bytes of each of the eight chunks; the chunks overlap OTHER threads' output bytes, so
         // every thread of the group has to be done reading before the first staging write (barrier below)
