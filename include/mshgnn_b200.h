@@ -243,9 +243,8 @@ int mshgnn_check_edges(const mshgnn_plan* plan, int64_t B, const int64_t* const*
  * launch per layer.  It changes the workspace layout: query mshgnn_workspace_bytes again after switching.
  * Option "stack_pair" (MSHGNN_STACK_2CTA): the stack launches use the CTA-pair kernel (clusters of two CTAs,
  * tcgen05.mma.cta_group::2 on two row tiles at once; rows are then padded to a multiple of 256 - query the workspace size
- * again after switching): 1 (default) = for batches of >= 6144 graphs, 2 = always, 0 = never (the one-CTA stack kernel).  Option "stack_epilogue" (default -1, MSHGNN_STACK_EPILOGUE):
- * epilogue variant of the CTA-pair kernel, -1 = chosen per launch (forward 1, backward 0), 0 / 1 forced.  All three
- * choose between implementations that produce identical bits (tests/test_gpu_stack.py).
+ * again after switching): 1 (default) = for batches of >= 6144 graphs, 2 = always, 0 = never (the one-CTA stack kernel).
+ * Both choose between implementations that produce identical bits (tests/test_gpu_stack.py).
  * mshgnn_stack_status copies one word back (synchronising): *status_out = 1 when a dependency wait inside the last stack
  * launch on this workspace timed out (its results are then invalid); used by the tests. */
 int mshgnn_set_option(const char* name, int32_t value);

@@ -430,7 +430,6 @@ int launch_stack(int kind, const Plan& p, const Plan::Stack& sp, const WsLayout&
     a.ws = ws;
     static const int env_dbg = [] { const char* e = getenv("MSHGNN_STACK_DEBUG"); return e ? atoi(e) : 0; }();
     a.debug = env_dbg;
-    a.epilogue = stack_epilogue_choice() >= 0 ? stack_epilogue_choice() : (kind == K_STACK_FWD ? 1 : 0);
     if ((int64_t)sp.prog.n_phases * a.n_row_tiles * p.S + 2 > w.stack_sync_bytes / 4) return fail(MSHGNN_ERR_WORKSPACE, "internal: stack counters do not fit");
     int n_sm = 0, rc;
     if ((rc = sm_count(&n_sm))) return rc;
@@ -1027,14 +1026,12 @@ int mshgnn_set_option(const char* name, int32_t value) {
     if (!name) return fail(MSHGNN_ERR_ARG, "option name is NULL");
     if (!strcmp(name, "stack")) { set_stack_enabled(value); return 0; }
     if (!strcmp(name, "stack_pair")) { set_stack_pair_mode(value); return 0; }
-    if (!strcmp(name, "stack_epilogue")) { set_stack_epilogue_choice(value); return 0; }
     return fail(MSHGNN_ERR_ARG, "unknown option '%s'", name);
 }
 
 int32_t mshgnn_get_option(const char* name) {
     if (name && !strcmp(name, "stack")) return stack_enabled() ? 1 : 0;
     if (name && !strcmp(name, "stack_pair")) return stack_pair_mode();
-    if (name && !strcmp(name, "stack_epilogue")) return stack_epilogue_choice();
     return -1;
 }
 

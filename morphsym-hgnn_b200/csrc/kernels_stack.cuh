@@ -64,8 +64,6 @@ struct StackArgs {
     uint32_t* next;              // work counter: the next item index to hand out (zeroed with the completion counters)
     unsigned long long* timing;  // TIMING instantiation only: per CTA 8 cycle counters (see k_tc_stack)
     char* ws;                    // workspace base (thread-private fp32 tensors live in the image area of their buffer)
-    int epilogue;                // CTA-pair kernel: 0 = epilogue with headers from the queue, deferred completion signal (backward: epilogue-bound,
-                                 // -2..5 %); 1 = first version (forward: bound by the MMA side, where the longer scheduler chain of 0 costs 3 %)
     int debug;                   // ablation switches for timing experiments (MSHGNN_STACK_DEBUG; results are then garbage): 1 no A loads,
                                  // 2 no W loads, 4 no MMAs, 8 epilogue reduced to its handshakes, 16 completion signal at once, 32 barrier before every staging write,
                                  // 64 no L1 prefetch, 256 no second output of two-output tiles, 512 no residuals (CTA-pair kernel only)
@@ -481,125 +479,6 @@ __device__ __forceinline__ void stack_epilogue(const TileHdr& t, const BufTable&
         *(reinterpret_cast<uint32_t*>(bt.p[t.mask_out_buf]) + ((int64_t)t.mask_out_slot * Bp + row) * 4 + grp) = mask;
     if (leader && sig) pending = sig;              // published by stack_flush_signal (see there)
     if (leader && (dbg & 16)) stack_flush_signal(pending);
-}
-
-// Round-2 first version of the epilogue, kept for same-box A/B runs (MSHGNN_STACK_DEBUG bit 128): header from global memory,
-// bias through shared memory behind a step-start barrier, completion signal published at once.  `sig`: completion counter of the item (last step only).
-__device__ __forceinline__ void stack_epilogue_v1(const TileHdr& t, const BufTable& bt, const BufRows& br, const CUtensorMap* map_k,
-                                               const uint32_t tmem_acc, const int row0, const int64_t B, const int64_t Bp,
-                                               const int warp, const int lane, const int grp, const StackEpi es, const uint32_t bias_smem, uint32_t& res_count,
-                                               uint32_t* sig, unsigned long long* t_wait_acc = nullptr) {
-    const int q = warp & 3;                        // TMEM lane quarter this warp may access (hardware rule: warp index mod 4)
-    const bool leader = q == 2 && lane == 0;       // first warp of the group (warps 2 + 4g .. 5 + 4g): warp index = 2 mod 4
-    const int rl = q * 32 + lane;                  // row inside the tile
-    const int64_t row = (int64_t)row0 + rl;
-    const bool live = row < B;
-    const uint32_t rsw = (uint32_t)((rl >> 1) & 3);     // SWIZZLE_64B: 16-byte chunk index ^= address bits [7, 9)
-    const uint32_t tile = es.stg + (uint32_t)rl * 64u;
-    const bool has_out = t.out_buf >= 0, has_out2 = t.out2_buf >= 0, has_res = t.res_buf >= 0;
-    const bool want_mask = t.relu || t.mask_out_buf >= 0;
-    const bool writes_stage = has_out || has_out2 || t.stage_out;
-    const int col0 = grp * 32;
-
-    auto fetch_residual = [&]() {
-        const int r_hi = br.hi[t.res_buf] + (int)((int64_t)t.res_slot * Bp) + row0, r_lo = br.lo[t.res_buf] + (int)((int64_t)t.res_slot * Bp) + row0;
-        mbar_expect_tx(es.res_bar, 2u * 8192u);
-        tma_load_2d(es.stg, map_k, es.res_bar, col0, r_hi);
-        tma_load_2d(es.stg + 8192, map_k, es.res_bar, col0, r_lo);
-    };
-    if (leader) {
-        tma_store_wait_read();                     // the staging tiles may still feed this group's previous TMA stores
-        // early fetch (hidden behind the MMAs of this step); the item is only published to this warp once its input
-        // dependency - the residual is an output of the previous phase - has been seen satisfied by the producer warp
-        if (has_res && !t.a_stage) {
-            asm volatile("fence.proxy.async.global;" ::: "memory");
-            fetch_residual();
-        }
-    }
-    if (rl < 32) {
-        const float bv = t.bias_buf >= 0 ? __ldg((const float*)bt.p[t.bias_buf] + t.bias_off + col0 + rl) : 0.f;
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_smem + 4u * rl), "f"(bv) : "memory");
-    }
-    uint32_t pm = ~0u, m2 = ~0u;
-    if (live && t.posmask_buf >= 0) pm = __ldg(reinterpret_cast<const uint32_t*>(bt.p[t.posmask_buf]) + ((int64_t)t.posmask_slot * Bp + row) * 4 + grp);
-    if (live && has_out2 && t.out2_mask_kind == MK_BITS)
-        m2 = __ldg(reinterpret_cast<const uint32_t*>(bt.p[t.out2_mask_buf]) + ((int64_t)t.out2_mask_slot * Bp + row) * 4 + grp);
-    group_bar_sync(grp);
-
-    if (t_wait_acc) { const long long t0 = clock64(); mbar_wait(es.accum_bar, es.acc_parity); *t_wait_acc += (unsigned long long)(clock64() - t0); }
-    else mbar_wait(es.accum_bar, es.acc_parity);
-    tc_fence_after();
-    uint32_t raw[32];
-    tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + col0, raw);
-    tmem_ld_wait();
-    tc_fence_before();
-    mbar_arrive(es.free_bar);                      // this thread's part of the accumulator is in registers
-    if (has_res) {
-        // chained step: the staging tiles were the A operand of THIS step's MMAs, which have completed by now
-        if (t.a_stage && leader) fetch_residual();
-        mbar_wait(es.res_bar, res_count & 1u);
-        ++res_count;
-    }
-    float v[32];
-    const unsigned mask = epi_affine_any(true, want_mask, t.relu != 0, raw, v, bias_smem);     // the bias quarter in shared memory is zero when the tile has none
-    if (t.posmask_buf >= 0) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = ((pm >> j) & 1u) ? v[j] : 0.f;
-    }
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        const uint32_t a = tile + ((((uint32_t)g) ^ rsw) << 4);
-        if (has_res) join8_add(v + g * 8, lds128(a), lds128(a + 8192));
-        if (writes_stage) {
-            uint4 hi, lo;
-            split8(v + g * 8, hi, lo);
-            if (!has_out && has_out2) { hi = mask8(hi, m2 >> (g * 8)); lo = mask8(lo, m2 >> (g * 8)); }
-            if (!live) { hi = make_uint4(0u, 0u, 0u, 0u); lo = hi; }     // rows [B, Bp) of every image stay zero
-            sts128(a, hi);
-            sts128(a + 8192, lo);
-        }
-    }
-    fence_proxy_async_smem();
-    group_bar_sync(grp);
-    if (leader) {
-        const int ob = has_out ? t.out_buf : t.out2_buf, os = has_out ? t.out_slot : t.out2_slot;
-        if (ob >= 0) {
-            const int o = (int)((int64_t)os * Bp) + row0;
-            tma_store_2d(map_k, es.stg, col0, br.hi[ob] + o);
-            tma_store_2d(map_k, es.stg + 8192u, col0, br.lo[ob] + o);
-            tma_store_commit();
-        }
-        if (t.stage_out) mbar_arrive(es.stage_bar);        // this quarter of the next step's A operand is in place
-    }
-    if (has_out && has_out2) {
-        // second output = first output with the masked-off lanes cleared, made in place once the first store has read the tile
-        if (leader) tma_store_wait_read();
-        group_bar_sync(grp);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const uint32_t a = tile + ((((uint32_t)c) ^ rsw) << 4);
-            const uint32_t m = m2 >> (c * 8);
-            sts128(a, mask8(lds128(a), m));
-            sts128(a + 8192, mask8(lds128(a + 8192), m));
-        }
-        fence_proxy_async_smem();
-        group_bar_sync(grp);
-        if (leader) {
-            const int o = (int)((int64_t)t.out2_slot * Bp) + row0;
-            tma_store_2d(map_k, es.stg, col0, br.hi[t.out2_buf] + o);
-            tma_store_2d(map_k, es.stg + 8192u, col0, br.lo[t.out2_buf] + o);
-            tma_store_commit();
-        }
-    }
-    if (live && t.mask_out_buf >= 0)
-        *(reinterpret_cast<uint32_t*>(bt.p[t.mask_out_buf]) + ((int64_t)t.mask_out_slot * Bp + row) * 4 + grp) = mask;
-    if (leader && sig) {
-        // Publish the item as soon as its stores have landed.  (Deferring the signal to the next step of this CTA saved the
-        // store round trip here, but it added a whole item time to every dependency chain - the scheduler warps of the
-        // dependent items then waited for it two thirds of the time; the epilogue groups have the slack, the chains do not.)
-        tma_store_wait_all();
-        stack_signal(sig);
-    }
 }
 
 // TIMING = true is a diagnostic instantiation (MSHGNN_STACK_TIMING=1): the single-thread roles accumulate the cycles they

@@ -112,7 +112,6 @@ k_tc_stack2(const __grid_constant__ TcMaps maps, const __grid_constant__ CUtenso
             const StackItem* __restrict__ items, const __grid_constant__ StackArgs args, const BufTable bt, const BufRows br) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint32_t tmem_base_s;
-    __shared__ __align__(16) float bias_s[4][32];         // first-version epilogue (args.epilogue == 1): one quarter per group
     __shared__ __align__(16) float bias_w[16][32];        // one copy per epilogue warp
     __shared__ __align__(16) int4 q_ent[SK_QUEUE][2];     // written by the LEADER's scheduler warp (into both CTAs)
     __shared__ __align__(16) int4 q_chunk[SK_QUEUE][SK_QCHUNKS];   // operand rows of the item's chunks (stack_chunk_desc), same for both CTAs
@@ -357,10 +356,6 @@ k_tc_stack2(const __grid_constant__ TcMaps maps, const __grid_constant__ CUtenso
                 const uint32_t a = k % SK_ACCS;
                 es.accum_bar = acc_full0 + 8 * a; es.free_bar = acc_free0 + 8 * a;
                 es.acc_parity = (k / SK_ACCS) & 1;
-                if (args.epilogue == 1 && !(PRIV && t.priv))     // the first version knows image tensors only
-                    stack_epilogue_v1(load_hdr(tiles + qa.z + s), bt, br, &maps.k, tmem_base + a * 128, qa.x * TILE_M, B, Bp, warp, lane, grp, es, smem_u32(bias_s[grp]),
-                                      n_res, s == qa.w - 1 ? ctr : nullptr);
-                else
                     stack_epilogue<PRIV>(t, bt, br, &maps.k, tmem_base + a * 128, qa.x * TILE_M, B, Bp, warp, lane, grp, es, n_res, s == qa.w - 1 ? ctr : nullptr,
                                    pending, args.ws, nullptr, dbg_bare_epi, args.debug);
             }

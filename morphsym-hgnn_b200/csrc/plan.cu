@@ -654,19 +654,6 @@ int stack_pair_mode() {
 }
 void set_stack_pair_mode(int v) { g_stack_pair.store(v < 0 ? 0 : (v > 2 ? 2 : v), std::memory_order_relaxed); }
 
-// epilogue variant of the CTA-pair kernel: -1 = per launch kind (forward: first version, backward: deferred-signal version), 0 / 1 = forced
-static std::atomic<int> g_stack_epilogue{-2};
-int stack_epilogue_choice() {
-    int v = g_stack_epilogue.load(std::memory_order_relaxed);
-    if (v < -1) {
-        const char* e = getenv("MSHGNN_STACK_EPILOGUE");
-        v = e ? (atoi(e) != 0 ? 1 : 0) : -1;
-        g_stack_epilogue.store(v, std::memory_order_relaxed);
-    }
-    return v;
-}
-void set_stack_epilogue_choice(int v) { g_stack_epilogue.store(v < 0 ? -1 : (v ? 1 : 0), std::memory_order_relaxed); }
-
 WsLayout ws_layout(const Plan& p, int64_t B, int train, int mode) {
     const bool tc = mode != MSHGNN_MODE_FP32;
     WsLayout w{};

@@ -150,8 +150,6 @@ bool stack_enabled();                 // cross-layer stack kernel on (default) /
 void set_stack_enabled(int on);
 int stack_pair_mode();                // CTA-pair (cta_group::2) stack kernel: 1 = by batch size (default), 2 = always, 0 = never (MSHGNN_STACK_2CTA)
 void set_stack_pair_mode(int v);
-int stack_epilogue_choice();          // -1: per launch kind, 0 / 1: forced (MSHGNN_STACK_EPILOGUE, option "stack_epilogue")
-void set_stack_epilogue_choice(int v);
 std::string describe_plan(const Plan& p);
 
 }  // namespace mshgnn

@@ -163,7 +163,7 @@ def launch_count() -> int:
 
 def set_option(name: str, value: int) -> None:
     """Library switches: 'stack' (1 = cross-layer persistent kernel for the layer loop, 0 = one launch per layer),
-    'stack_pair' (0 = never, 1 = CTA-pair stack kernel for batches >= 6144 graphs, 2 = always), 'stack_epilogue' (-1 = per launch kind, 0 / 1 = forced variant)."""
+    'stack_pair' (0 = never, 1 = CTA-pair stack kernel for batches >= 6144 graphs, 2 = always)."""
     check(lib().mshgnn_set_option(name.encode(), int(value)), "mshgnn_set_option")
 
 

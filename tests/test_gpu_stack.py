@@ -17,11 +17,10 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture
 def restore_stack_option():
-    before, before_pair, before_epi = N.get_option("stack"), N.get_option("stack_pair"), N.get_option("stack_epilogue")
+    before, before_pair = N.get_option("stack"), N.get_option("stack_pair")
     yield
     N.set_option("stack", before)
     N.set_option("stack_pair", before_pair)
-    N.set_option("stack_epilogue", before_epi)
 
 
 def _step(nm, cfg, b):
@@ -107,24 +106,6 @@ def test_cta_pair_stack_kernel_is_bit_identical_to_the_one_cta_kernel(name, B, l
             assert torch.equal(a[0], c[0]) and a[1] == c[1]
             for k in a[2]:
                 assert torch.equal(a[2][k], c[2][k]), k
-
-
-@pytest.mark.parametrize("name,B", [("mini_cheetah-k4-contact", 2500), ("solo12-k4-com", 700)])
-def test_both_epilogue_variants_of_the_pair_kernel_give_the_same_bits(name, B, restore_stack_option):
-    """Option stack_epilogue: -1 picks per launch kind (forward 1, backward 0); forcing either must not change a bit."""
-    cfg = CONFIGS[name]
-    b = make_batch(cfg, B, seed=11).to("cuda:0")
-    nm = build_model(cfg, layers=8, seed=3).set_mode("tc").to("cuda:0")
-    N.set_option("stack", 1)
-    N.set_option("stack_pair", 2)
-    res = []
-    for epi in (-1, 0, 1):
-        N.set_option("stack_epilogue", epi)
-        res.append(_step(nm, cfg, b))
-    for r in res[1:]:
-        assert torch.equal(r[0], res[0][0]) and r[1] == res[0][1]
-        for k in r[2]:
-            assert torch.equal(r[2][k], res[0][2][k]), k
 
 
 def test_stack_kernel_single_pass_mode_is_bit_identical_too(restore_stack_option):
