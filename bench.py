@@ -483,9 +483,11 @@ def main():
                     "unit": "TFLOP/s", "frac": dom["frac_tensor_peak"], "traffic": t_dom,
                     "traffic_view": None if not t_dom else {
                         "dram_gbs": t_dom / (ms_launch * 1e-3) / 1e9, "frac_hbm_peak": t_dom / (ms_launch * 1e-3) / 1e9 / pk["hbm_gbs"],
-                        "note": "the layer kernels stream every activation slab (fp16 hi/lo pair = 4 B/element, 168 MB per layer > L2) through "
-                                "HBM once per launch; their ncu DRAM bytes / measured launch time sits much closer to the HBM roof than their "
-                                "algorithmic FLOPs sit to the tensor roof (SURVEY 8d counts zero mandatory bytes for a fused stack)"},
+                        "note": "ncu DRAM bytes of this kernel's launch (profiles/" + TRAFFIC_FILE + ") / measured launch time.  The cross-layer "
+                                "stack kernel keeps a row chunk's slabs in L2 between layers; what still reaches DRAM in a TRAINING launch is "
+                                "what the other pass needs (forward: h_l written once per layer; backward: h_l / masks read, dc_l written for "
+                                "the weight-gradient launch, dh_l of the residual chain written back although dead) - SURVEY 8d counts zero "
+                                "mandatory bytes for the layer stack of an inference forward"},
                     "peak_source": pk["src"] + " (bf16 dense, sustained)",
                     "launches_per_step": dom["launches_per_step"], "ms_per_launch": dom["ms_per_step"] / max(dom["launches_per_step"], 1),
                     "note": "algorithmic FLOPs per SURVEY 8d (one MAC per product; the fp32-class mode issues 3 fp16 MMAs per product, "
