@@ -251,14 +251,6 @@ int launch_tc_encoder(const Plan& p, const Launch& L, const WsLayout& w, const B
     }
     __half* e_hi = (__half*)(ws + w.wenc16[0]);
     __half* e_lo = (__half*)(ws + w.wenc16[1]);
-    {
-        ProfScope ps(K_DERIVE, st);
-        EncImgDesc ed;
-        ed.n_types = p.n_types;
-        for (int t = 0; t < p.n_types; ++t) { ed.w_off[t] = p.off_enc_w[t]; ed.K[t] = p.in_w[t]; }
-        k_derive_enc16<<<dim3(64, (unsigned)p.n_types), 256, 0, st>>>(params, ed, p.enc_kmax, e_hi, e_lo);
-        LAUNCH_CHECK();
-    }
     EncMaps maps;
     int rc;
     if ((rc = make_map_2d(&maps.w_hi, e_hi, (int64_t)p.n_types * H, p.enc_kmax, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
@@ -611,11 +603,11 @@ int mshgnn_forward(const mshgnn_plan* plan, int64_t B, const void* const* x, int
     for (int t = 0; t < p.n_types; ++t) bt.p[BUF_X0 + t] = (void*)x[t];
     const int xf64 = x_dtype == MSHGNN_F64;
 
-    {   // derived weights (transposes, root sums, bias sums) from the current parameters
+    if (mode == MSHGNN_MODE_FP32) {   // derived weights (transposes, root sums, bias sums) from the current parameters
         ProfScope ps(K_DERIVE, st);
-        const unsigned n_ops = mode == MSHGNN_MODE_FP32 ? (unsigned)p.derive_ops.size() : (unsigned)p.n_derive_bias;
+        const unsigned n_ops = (unsigned)p.derive_ops.size();
         if (n_ops > 0) {
-            dim3 grid(mode == MSHGNN_MODE_FP32 ? 16 : 1, n_ops);
+            dim3 grid(16, n_ops);
             k_derive<<<grid, 256, 0, st>>>(p.d_derive, params, (float*)bt.p[BUF_DERIVED]);
             LAUNCH_CHECK();
         }
@@ -636,13 +628,22 @@ int mshgnn_forward(const mshgnn_plan* plan, int64_t B, const void* const* x, int
         __half* w_hi = (__half*)((char*)workspace + w.w16[0]);
         __half* w_lo = (__half*)((char*)workspace + w.w16[1]);
         const int split = mode == MSHGNN_MODE_TC;
-        {
+        {   // bias sums, (hi, lo) weight images, encoder weight image, stack counters: one launch (k_fwd_prologue)
             ProfScope ps(K_DERIVE, st);
-            dim3 grid(8, (unsigned)p.derive16_ops.size());
-            k_derive16<<<grid, 256, 0, st>>>(p.d_derive16, params, w_hi, w_lo);
+            FwdPrologue fp;
+            fp.ops = p.d_derive; fp.n_bias = p.n_derive_bias;
+            fp.ops16 = p.d_derive16; fp.n16 = (int)p.derive16_ops.size();
+            fp.ed.n_types = p.n_types;
+            for (int t = 0; t < p.n_types; ++t) { fp.ed.w_off[t] = p.off_enc_w[t]; fp.ed.K[t] = p.in_w[t]; }
+            fp.kmax = p.enc_kmax;
+            fp.zero = w.stack ? (uint32_t*)((char*)workspace + w.stack_sync) : nullptr;
+            fp.zero_words = w.stack ? w.stack_sync_bytes / 4 : 0;
+            fp.zero_blocks = w.stack ? 16 : 0;
+            const unsigned blocks = (unsigned)(fp.n_bias + 8 * fp.n16 + 64 * p.n_types + fp.zero_blocks);
+            k_fwd_prologue<<<blocks, 256, 0, st>>>(fp, params, (float*)bt.p[BUF_DERIVED], w_hi, w_lo, (__half*)((char*)workspace + w.wenc16[0]),
+                                                    (__half*)((char*)workspace + w.wenc16[1]));
             LAUNCH_CHECK();
         }
-        if ((rc = stack_sync_reset(w, (char*)workspace, st))) return rc;
         if ((rc = launch_tc_encoder(p, train ? p.enc_train : p.enc_launch, w, bt, br, wm, (char*)workspace, params, B, xf64, split, st))) return rc;
         if (w.stack) {
             // all layers (conv + chained base_transform) in one persistent launch over L2-resident row chunks
@@ -736,8 +737,15 @@ int mshgnn_backward_staged(const mshgnn_plan* plan, int64_t B, const void* const
     float G = 1.f;
     if (tc) { int e = 0; std::frexp((double)(B * p.dec.n_dec), &e); G = (float)std::ldexp(1.0, e - 1); }
 
-    { ProfScope ps(K_MEMSET, st); CUDA_TRY(cudaMemsetAsync(grads, 0, (size_t)p.n_params * 4, st)); }
-    if (tc && (rc = stack_sync_reset(w, ws, st))) return rc;
+    if (tc && w.stack && (reinterpret_cast<uintptr_t>(grads) & 15) == 0) {
+        ProfScope ps(K_MEMSET, st);
+        const int64_t n4 = p.n_params / 4;
+        k_bwd_prologue<<<296, 256, 0, st>>>((float4*)grads, n4, grads + n4 * 4, (int)(p.n_params - n4 * 4), (uint32_t*)(ws + w.stack_sync), w.stack_sync_bytes / 4);
+        LAUNCH_CHECK();
+    } else {
+        { ProfScope ps(K_MEMSET, st); CUDA_TRY(cudaMemsetAsync(grads, 0, (size_t)p.n_params * 4, st)); }
+        if (tc && (rc = stack_sync_reset(w, ws, st))) return rc;
+    }
 
     {   // decoder backward: dH_L on the decoded slots (+ masked copy = dc_{L-1}), dW_dec, db_dec
         const int L = p.L;
@@ -799,7 +807,9 @@ int mshgnn_backward_staged(const mshgnn_plan* plan, int64_t B, const void* const
     auto reduce_layers = [&]() -> int {
         if (ngl > 0) {
             // 64 blocks per group = one element per thread: the groups of the shared base_transform weights sum up to 16 tasks x
-            // 16..64 splits per element, and that serial chain (not the 117 MB of partials) sets the launch time
+            // 16..64 splits per element, and that serial chain (not the 117 MB of partials) sets the launch time.  (Four lanes per
+            // element over the splits of a task, combined through shared memory, was measured: 2x SLOWER - the chain that matters is
+            // the one over the TASKS of a group, one load round trip each.)
             dim3 grid((unsigned)ngl, 64);
             ProfScope ps(K_REDUCE, st);
             k_reduce_partials<<<grid, 256, 0, st>>>(p.d_groups, part_w, part_b, w.segs, grads, 1.f / G);

@@ -1868,4 +1868,73 @@ k_derive16(const Derive16Op* __restrict__ ops, const float* __restrict__ params,
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// One launch for everything the tensor-core forward needs before its first GEMM (was k_derive + k_derive16 + k_derive_enc16 + a
+// memset: four launches of 5-16 us each, a quarter of the fixed tail of a 2048-graph step): blocks [0, n_bias) the derived bias
+// sums, [n_bias, + 8 n16) the (hi, lo) images of the 128x128 weights, [.., + 64 n_types) the encoder weight image, the rest zero the
+// completion counters of the stack kernel.
+// ------------------------------------------------------------------------------------------
+struct FwdPrologue {
+    const DeriveOp* ops; int n_bias;
+    const Derive16Op* ops16; int n16;
+    EncImgDesc ed; int kmax;
+    uint32_t* zero; int64_t zero_words; int zero_blocks;
+};
+__global__ void __launch_bounds__(256)
+k_fwd_prologue(const FwdPrologue a, const float* __restrict__ params, float* __restrict__ derived, __half* __restrict__ w_hi, __half* __restrict__ w_lo,
+               __half* __restrict__ e_hi, __half* __restrict__ e_lo) {
+    int b = blockIdx.x;
+    if (b < a.n_bias) {
+        const DeriveOp op = a.ops[b];
+        const int n = op.rows * op.cols;
+        for (int e = threadIdx.x; e < n; e += 256) {
+            int r, c;
+            if (op.transpose) { c = e / op.rows; r = e % op.rows; } else { r = e / op.cols; c = e % op.cols; }
+            float s = 0.f;
+            for (int i = 0; i < op.n_src; ++i) s += params[(int64_t)op.src_off[i] + (int64_t)r * op.cols + c];
+            derived[(int64_t)op.dst_off + e] = s;
+        }
+        return;
+    }
+    b -= a.n_bias;
+    if (b < 8 * a.n16) {
+        const Derive16Op op = a.ops16[b >> 3];
+        for (int e = (b & 7) * 256 + threadIdx.x; e < H * H; e += 8 * 256) {
+            const int r = e / H, c = e % H;
+            const int src = op.transpose ? (c * H + r) : e;
+            float s = 0.f;
+            for (int i = 0; i < op.n_src; ++i) s += params[(int64_t)op.src_off[i] + src];
+            s *= TC_W_SCALE;
+            const __half h = __float2half_rn(s);
+            w_hi[(int64_t)op.dst_row * H + e] = h;
+            w_lo[(int64_t)op.dst_row * H + e] = __float2half_rn((s - __half2float(h)) * TC_LO_SCALE);
+        }
+        return;
+    }
+    b -= 8 * a.n16;
+    if (b < 64 * a.ed.n_types) {
+        const int t = b >> 6, K = a.ed.K[t], row0 = t * H;
+        const int64_t w_off = a.ed.w_off[t];
+        for (int e = (b & 63) * 256 + threadIdx.x; e < H * a.kmax; e += 64 * 256) {
+            const int o = e / a.kmax, k = e % a.kmax;
+            const float s = k < K ? params[w_off + (int64_t)o * K + k] * TC_W_SCALE : 0.f;
+            const __half h = __float2half_rn(s);
+            e_hi[(int64_t)(row0 + o) * a.kmax + k] = h;
+            e_lo[(int64_t)(row0 + o) * a.kmax + k] = __float2half_rn((s - __half2float(h)) * TC_LO_SCALE);
+        }
+        return;
+    }
+    b -= 64 * a.ed.n_types;
+    for (int64_t i = (int64_t)b * 256 + threadIdx.x; i < a.zero_words; i += (int64_t)a.zero_blocks * 256) a.zero[i] = 0u;
+}
+
+// backward prologue: zero the flat gradient buffer (dead branches keep exact zeros) and the stack kernel's completion counters
+__global__ void __launch_bounds__(256)
+k_bwd_prologue(float4* __restrict__ grads4, const int64_t n4, float* __restrict__ grads_tail, const int n_tail, uint32_t* __restrict__ zero, const int64_t zero_words) {
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += stride) grads4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < zero_words; i += stride) zero[i] = 0u;
+    if (blockIdx.x == 0 && (int)threadIdx.x < n_tail) grads_tail[threadIdx.x] = 0.f;
+}
+
 }  // namespace mshgnn
