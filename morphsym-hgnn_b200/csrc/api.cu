@@ -662,9 +662,11 @@ int mshgnn_forward(const mshgnn_plan* plan, int64_t B, const void* const* x, int
         ProfScope ps(K_DEC_FWD, st);
         const bool tcm = mode != MSHGNN_MODE_FP32;
         const char* wsb = (const char*)workspace;
-        k_decoder_fwd<<<blocks, 256, 0, st>>>(p.dec, tcm ? nullptr : (const float*)bt.p[BUF_H0 + p.L],
-                                              tcm ? (const __half*)(wsb + w.h16[p.L][0]) : nullptr, tcm ? (const __half*)(wsb + w.h16[p.L][1]) : nullptr,
-                                              params, p.d_signs, out, B, w.Bp);
+#define MSHGNN_DEC_FWD(CM) k_decoder_fwd<CM><<<blocks, 256, 0, st>>>(p.dec, tcm ? nullptr : (const float*)bt.p[BUF_H0 + p.L], \
+                                              tcm ? (const __half*)(wsb + w.h16[p.L][0]) : nullptr, tcm ? (const __half*)(wsb + w.h16[p.L][1]) : nullptr, \
+                                              params, p.d_signs, out, B, w.Bp)
+        if (p.dec.C <= 2) MSHGNN_DEC_FWD(2); else if (p.dec.C <= 4) MSHGNN_DEC_FWD(4); else MSHGNN_DEC_FWD(8);
+#undef MSHGNN_DEC_FWD
         LAUNCH_CHECK();
     }
     return 0;
@@ -759,10 +761,12 @@ int mshgnn_backward_staged(const mshgnn_plan* plan, int64_t B, const void* const
         ProfScope ps(K_DEC_BWD, st);
         const int dhb = BUF_DHL0 + L, dcb = BUF_DCL0 + L - 1;
         const bool want_dh = p.morph_sym, want_dc = !p.morph_sym || p.dec_type != p.mlp_type;
-        k_decoder_bwd<<<DEC_BLOCKS, 256, 0, st>>>(p.dec, tc ? nullptr : (const float*)bt.p[BUF_H0 + L], tc ? bh.hi[BUF_H0 + L] : nullptr,
-                                                  tc ? bh.lo[BUF_H0 + L] : nullptr, params, p.d_signs, dout, tc ? nullptr : dh, tc ? nullptr : dc, mk, mbuf,
-                                                  dec_part, B, w.Bp, G, (tc && want_dh) ? bh.hi[dhb] : nullptr, (tc && want_dh) ? bh.lo[dhb] : nullptr,
-                                                  (tc && want_dc) ? bh.hi[dcb] : nullptr, (tc && want_dc) ? bh.lo[dcb] : nullptr);
+#define MSHGNN_DEC_BWD(CM) k_decoder_bwd<CM><<<DEC_BLOCKS, 256, 0, st>>>(p.dec, tc ? nullptr : (const float*)bt.p[BUF_H0 + L], tc ? bh.hi[BUF_H0 + L] : nullptr, \
+                                                  tc ? bh.lo[BUF_H0 + L] : nullptr, params, p.d_signs, dout, tc ? nullptr : dh, tc ? nullptr : dc, mk, mbuf, \
+                                                  dec_part, B, w.Bp, G, (tc && want_dh) ? bh.hi[dhb] : nullptr, (tc && want_dh) ? bh.lo[dhb] : nullptr, \
+                                                  (tc && want_dc) ? bh.hi[dcb] : nullptr, (tc && want_dc) ? bh.lo[dcb] : nullptr)
+        if (p.dec.C <= 2) MSHGNN_DEC_BWD(2); else if (p.dec.C <= 4) MSHGNN_DEC_BWD(4); else MSHGNN_DEC_BWD(8);
+#undef MSHGNN_DEC_BWD
         LAUNCH_CHECK();
         k_decoder_bwd_reduce<<<p.dec.C * H + p.dec.C, 256, 0, st>>>(p.dec, dec_part, DEC_BLOCKS, grads, 1.f / G);
         LAUNCH_CHECK();

@@ -435,6 +435,9 @@ k_derive(const DeriveOp* __restrict__ ops, const float* __restrict__ params, flo
 // ------------------------------------------------------------------------------------------
 // decoder: out[g*n_dec + j, c] = (h[slot_j][g] . Wdec[c] + b[c]) * sign[j*C + c]
 // ------------------------------------------------------------------------------------------
+// CMAX: compile-time bound of the decoder width (2 / 4 / 8): the weight rows are register arrays, and sized for 8 channels they cost the
+// 2-channel contact head 48 registers it never uses
+template <int CMAX>
 __global__ void __launch_bounds__(256)
 k_decoder_fwd(const DecoderDesc dd, const float* __restrict__ hslab, const __half* __restrict__ h_hi, const __half* __restrict__ h_lo,
               const float* __restrict__ params, const float* __restrict__ signs, float* __restrict__ out, const int64_t B, const int64_t Bp) {
@@ -442,17 +445,18 @@ k_decoder_fwd(const DecoderDesc dd, const float* __restrict__ hslab, const __hal
     const int64_t warp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int64_t n_rows = B * dd.n_dec;
     const int64_t stride = (int64_t)gridDim.x * 8;
-    float4 w[DEC_MAXC];
+    float4 w[CMAX];
 #pragma unroll
-    for (int c = 0; c < DEC_MAXC; ++c)
+    for (int c = 0; c < CMAX; ++c)
         w[c] = (c < dd.C) ? __ldg(reinterpret_cast<const float4*>(params + dd.w_off + c * H + lane * 4))
                           : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
     for (int64_t row = warp; row < n_rows; row += stride) {
         const int64_t g = row / dd.n_dec;
         const int j = (int)(row % dd.n_dec);
         const float4 h = load_h4(hslab, h_hi, h_lo, ((int64_t)dd.slots[j] * Bp + g) * H + lane * 4);
 #pragma unroll
-        for (int c = 0; c < DEC_MAXC; ++c) {
+        for (int c = 0; c < CMAX; ++c) {
             if (c >= dd.C) break;
             float s = h.x * w[c].x + h.y * w[c].y + h.z * w[c].z + h.w * w[c].w;
 #pragma unroll
@@ -468,6 +472,7 @@ k_decoder_fwd(const DecoderDesc dd, const float* __restrict__ hslab, const __hal
 
 // backward: dH[slot_j][g][:] = sum_c dout'[c] Wdec[c][:]   (written to dh_buf, masked copy to dc_buf)
 //           partial dWdec / db per block -> part[(block*(C*H + C))]
+template <int CMAX>
 __global__ void __launch_bounds__(256)
 k_decoder_bwd(const DecoderDesc dd, const float* __restrict__ hslab, const __half* __restrict__ h_hi, const __half* __restrict__ h_lo,
               const float* __restrict__ params,
@@ -475,21 +480,22 @@ k_decoder_bwd(const DecoderDesc dd, const float* __restrict__ hslab, const __hal
               float* __restrict__ dh, float* __restrict__ dc, const int mask_kind, const void* __restrict__ mask_buf,
               float* __restrict__ part, const int64_t B, const int64_t Bp, const float gscale,
               __half* __restrict__ dh_hi, __half* __restrict__ dh_lo, __half* __restrict__ dc_hi, __half* __restrict__ dc_lo) {
-    __shared__ float red[8][DEC_MAXC][H + 1];
-    __shared__ float redb[8][DEC_MAXC];
+    __shared__ float red[8][CMAX][H + 1];
+    __shared__ float redb[8][CMAX];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t warp = (int64_t)blockIdx.x * 8 + wid;
     const int64_t n_rows = B * dd.n_dec;
     const int64_t stride = (int64_t)gridDim.x * 8;
-    float4 w[DEC_MAXC], gw[DEC_MAXC];
-    float gb[DEC_MAXC];
+    float4 w[CMAX], gw[CMAX];
+    float gb[CMAX];
 #pragma unroll
-    for (int c = 0; c < DEC_MAXC; ++c) {
+    for (int c = 0; c < CMAX; ++c) {
         w[c] = (c < dd.C) ? __ldg(reinterpret_cast<const float4*>(params + dd.w_off + c * H + lane * 4))
                           : make_float4(0.f, 0.f, 0.f, 0.f);
         gw[c] = make_float4(0.f, 0.f, 0.f, 0.f);
         gb[c] = 0.f;
     }
+#pragma unroll 2
     for (int64_t row = warp; row < n_rows; row += stride) {
         const int64_t g = row / dd.n_dec;
         const int j = (int)(row % dd.n_dec);
@@ -497,7 +503,7 @@ k_decoder_bwd(const DecoderDesc dd, const float* __restrict__ hslab, const __hal
         const float4 h = load_h4(hslab, h_hi, h_lo, off);
         float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int c = 0; c < DEC_MAXC; ++c) {
+        for (int c = 0; c < CMAX; ++c) {
             if (c >= dd.C) break;
             float dv = __ldg(dout + row * dd.C + c) * gscale;
             if (dd.sign_off >= 0) dv *= __ldg(signs + dd.sign_off + j * dd.C + c);
@@ -530,7 +536,7 @@ k_decoder_bwd(const DecoderDesc dd, const float* __restrict__ hslab, const __hal
         }
     }
 #pragma unroll
-    for (int c = 0; c < DEC_MAXC; ++c) {
+    for (int c = 0; c < CMAX; ++c) {
         if (c >= dd.C) break;                  // only the decoder's C channels carry anything
         red[wid][c][lane * 4 + 0] = gw[c].x; red[wid][c][lane * 4 + 1] = gw[c].y;
         red[wid][c][lane * 4 + 2] = gw[c].z; red[wid][c][lane * 4 + 3] = gw[c].w;

@@ -141,7 +141,7 @@ struct WsLayout {
     int64_t total = 0;
 };
 
-constexpr int DEC_BLOCKS = 888;      // 148 SMs x 6 resident CTAs (33 KB of static shared memory each): one load in flight per warp, so latency is hidden by warps
+constexpr int DEC_BLOCKS = 1184;     // 148 SMs x 8 resident CTAs of the 2-channel instantiation (48 registers, 8 KB of shared memory; the 8-channel one: 2 per SM): one load in flight per warp, so latency is hidden by warps
 constexpr int LOSS_BLOCKS = 592;
 
 std::string build_plan(const mshgnn_desc* d, Plan& p);            // returns error text ("" = ok)
