@@ -145,6 +145,33 @@ __device__ __forceinline__ void stack_wait(const uint32_t* ctr, const unsigned l
     }
 }
 
+// The same wait on the counters of TWO row tiles (CTA-pair kernel) in one polling loop: one load round trip per poll instead of two
+// waits in series - the dependency wait sits on the scheduler warp's per-item chain (draw -> decode -> wait -> publish).
+__device__ __forceinline__ void stack_wait2(const uint32_t* ctr0, const uint32_t* ctr1, const unsigned long long mask, const int lane, uint32_t* err) {
+    unsigned spins = 0;
+    for (;;) {
+        bool ok = true;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int sl = lane + 32 * h;
+            if ((mask >> sl) & 1ull) {
+                uint32_t v0, v1;
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v0) : "l"(ctr0 + sl) : "memory");
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v1) : "l"(ctr1 + sl) : "memory");
+                ok = ok && v0 >= 4u && v1 >= 4u;
+            }
+        }
+        if (__all_sync(0xffffffffu, ok)) break;
+        ++spins;
+        if ((spins & 1023u) == 0) {
+            uint32_t e;
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(e) : "l"(err) : "memory");
+            if (e || spins >= SK_SPIN_LIMIT) { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(err), "r"(1u) : "memory"); break; }
+        }
+        __nanosleep(40);
+    }
+}
+
 __device__ __forceinline__ void stack_signal(uint32_t* ctr) {
     // one gpu-scope release: it is cumulative over everything that happens-before it (this thread's completed TMA stores, the other
     // epilogue threads' global stores ordered by the group barrier).  A separate fence.acq_rel.gpu in front of it doubled the cost of

@@ -195,8 +195,7 @@ k_tc_stack2(const __grid_constant__ TcMaps maps, const __grid_constant__ CUtenso
                     }
                     if (ir.phase > 0 && it.dep_mask) {
                         const uint32_t* ctr = args.sync + ((size_t)(ir.phase - 1) * NT + 2 * ir.row_tile) * args.n_slots;
-                        stack_wait(ctr, it.dep_mask, lane, err);
-                        stack_wait(ctr + args.n_slots, it.dep_mask, lane, err);
+                        stack_wait2(ctr, ctr + args.n_slots, it.dep_mask, lane, err);
                     }
                     a = make_int4(2 * ir.row_tile, ir.phase, it.tile, it.n_steps);
                     b = make_int4(it.meta, it.out_slot, 0, 0);
