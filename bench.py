@@ -309,10 +309,10 @@ def main():
                       "note": "per-rank compute of a 16384-graph global batch split over N GPUs, measured on this one GPU (no collective)"}
 
     # ---------------- end to end: pinned host buffers -> H2D -> train step -> D2H loss ----------------
-    e2e_ms = None
-    if not args.skip_e2e:
+    def e2e_leg(hb):
+        """ms for K steps: per step the pinned host batch `hb` -> H2D on a copy stream (double-buffered) -> train step -> D2H loss."""
         copy_stream = torch.cuda.Stream(dev)
-        bufs = [host.to(dev), host.to(dev)]
+        bufs = [hb.to(dev), hb.to(dev)]
         ready = [torch.cuda.Event(), torch.cuda.Event()]
         done = [torch.cuda.Event(), torch.cuda.Event()]
         loss_host = torch.empty(K + W, dtype=torch.float32).pin_memory()
@@ -321,11 +321,11 @@ def main():
             b = bufs[i % 2]
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(done[i % 2])          # the step that last read this buffer has finished
-                for k, v in host._x.items():
+                for k, v in hb._x.items():
                     b._x[k].copy_(v, non_blocking=True)
-                for k, v in host._edge_index.items():
+                for k, v in hb._edge_index.items():
                     b._edge_index[k].copy_(v, non_blocking=True)
-                b.y.copy_(host.y, non_blocking=True)
+                b.y.copy_(hb.y, non_blocking=True)
                 ready[i % 2].record(copy_stream)
 
         def e2e_loop(steps, base):
@@ -347,7 +347,19 @@ def main():
         e2e_loop(K, W)
         e1.record()
         barrier()
-        e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    e2e_ms = e2e_h_ms = None
+    h2d_bytes_h = None
+    if not args.skip_e2e:
+        e2e_ms = e2e_leg(host)
+        # the same leg with the node features stored as fp16 on the host (MSHGNN_F16, an input FORMAT: the kernels widen on load,
+        # results stay fp32; labels and edge_index unchanged) - half the bytes over PCIe.  Not the credited `e2e`: extra key.
+        host_h = type(host)({k: v.to(torch.float16) for k, v in host._x.items()}, dict(host._edge_index), host.y, host.batch_size).pin_memory()
+        h2d_bytes_h = sum(v.numel() * v.element_size() for v in host_h._x.values()) + \
+            sum(v.numel() * v.element_size() for v in host_h._edge_index.values()) + host_h.y.numel() * host_h.y.element_size()
+        e2e_h_ms = e2e_leg(host_h)
+        del host_h
 
     # ---------------- end to end through the device-side dataset ----------------
     # The raw sequence (what the reference keeps in host RAM as data.mat) is uploaded once; per step the host sends the
@@ -518,6 +530,9 @@ def main():
         "e2e": None if e2e_ms is None else {"value": total_graphs / (e2e_ms * 1e-3), "unit": "graphs/s", "ms_per_step": e2e_ms / K,
                                             "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                                             "note": "pinned host batch -> H2D (copy stream, double-buffered) -> train step -> D2H loss"},
+        "e2e_fp16_features": None if e2e_h_ms is None else {"value": total_graphs / (e2e_h_ms * 1e-3), "unit": "graphs/s", "ms_per_step": e2e_h_ms / K,
+                                                             "h2d_bytes_per_step": h2d_bytes_h, "d2h_bytes_per_step": 4,
+                                                             "note": "as e2e, host node features stored as fp16 (x_dtype MSHGNN_F16; lossy input format, arithmetic unchanged)"},
         "e2e_windowed": None if win_ms is None else dict(
             {"value": total_graphs / (win_ms * 1e-3), "unit": "graphs/s", "ms_per_step": win_ms / K, "h2d_bytes_per_step": B * 8,
              "d2h_bytes_per_step": 4,

@@ -38,6 +38,7 @@ extern "C" {
 #define MSHGNN_F32 0
 #define MSHGNN_F64 1
 #define MSHGNN_I64 2
+#define MSHGNN_F16 3   /* node features only (x_dtype of mshgnn_forward / mshgnn_backward): halves the host -> device bytes of a batch */
 
 /* arithmetic modes */
 #define MSHGNN_MODE_FP32   0   /* SIMT fp32 FMA everywhere: <=1e-4 parity mode              */

@@ -588,7 +588,7 @@ int mshgnn_forward(const mshgnn_plan* plan, int64_t B, const void* const* x, int
     if (!plan) return fail(MSHGNN_ERR_ARG, "plan is NULL");
     const Plan& p = plan->p;
     if (mode != MSHGNN_MODE_FP32 && mode != MSHGNN_MODE_TC && mode != MSHGNN_MODE_TC_1X) return fail(MSHGNN_ERR_ARG, "unknown mode %d", mode);
-    if (x_dtype != MSHGNN_F32 && x_dtype != MSHGNN_F64) return fail(MSHGNN_ERR_ARG, "x_dtype must be F32 or F64");
+    if (x_dtype != MSHGNN_F32 && x_dtype != MSHGNN_F64 && x_dtype != MSHGNN_F16) return fail(MSHGNN_ERR_ARG, "x_dtype must be F32, F64 or F16");
     if (!x || !params || !out) return fail(MSHGNN_ERR_ARG, "NULL argument");
     const WsLayout w = ws_layout(p, B, train, mode);
     int rc = check_common(plan, B, workspace, workspace_bytes, w);
@@ -601,7 +601,7 @@ int mshgnn_forward(const mshgnn_plan* plan, int64_t B, const void* const* x, int
     fill_bufs(p, w, (char*)workspace, bt);
     bt.p[BUF_PARAMS] = (void*)params;
     for (int t = 0; t < p.n_types; ++t) bt.p[BUF_X0 + t] = (void*)x[t];
-    const int xf64 = x_dtype == MSHGNN_F64;
+    const int xf64 = x_dtype == MSHGNN_F64 ? 1 : (x_dtype == MSHGNN_F16 ? 2 : 0);      // element-type code of the kernels (ld_x)
 
     if (mode == MSHGNN_MODE_FP32) {   // derived weights (transposes, root sums, bias sums) from the current parameters
         ProfScope ps(K_DERIVE, st);
@@ -709,7 +709,7 @@ int mshgnn_backward_staged(const mshgnn_plan* plan, int64_t B, const void* const
     if (!plan) return fail(MSHGNN_ERR_ARG, "plan is NULL");
     const Plan& p = plan->p;
     if (mode != MSHGNN_MODE_FP32 && mode != MSHGNN_MODE_TC && mode != MSHGNN_MODE_TC_1X) return fail(MSHGNN_ERR_ARG, "unknown mode %d", mode);
-    if (x_dtype != MSHGNN_F32 && x_dtype != MSHGNN_F64) return fail(MSHGNN_ERR_ARG, "x_dtype must be F32 or F64");
+    if (x_dtype != MSHGNN_F32 && x_dtype != MSHGNN_F64 && x_dtype != MSHGNN_F16) return fail(MSHGNN_ERR_ARG, "x_dtype must be F32, F64 or F16");
     if (!x || !params || !dout || !grads) return fail(MSHGNN_ERR_ARG, "NULL argument");
     const WsLayout w = ws_layout(p, B, 1, mode);
     int rc = check_common(plan, B, workspace, workspace_bytes, w);
@@ -721,7 +721,7 @@ int mshgnn_backward_staged(const mshgnn_plan* plan, int64_t B, const void* const
     bt.p[BUF_PARAMS] = (void*)params;
     bt.p[BUF_GRADS] = grads;
     for (int t = 0; t < p.n_types; ++t) { if (!x[t]) return fail(MSHGNN_ERR_ARG, "x[%d] is NULL", t); bt.p[BUF_X0 + t] = (void*)x[t]; }
-    const int xf64 = x_dtype == MSHGNN_F64;
+    const int xf64 = x_dtype == MSHGNN_F64 ? 1 : (x_dtype == MSHGNN_F16 ? 2 : 0);      // element-type code of the kernels (ld_x)
     char* ws = (char*)workspace;
     float* part_w = (float*)(ws + w.part_w);
     float* part_b = (float*)(ws + w.part_b);

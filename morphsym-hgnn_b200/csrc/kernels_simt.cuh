@@ -16,7 +16,9 @@
 
 namespace mshgnn {
 
+// node-feature element type of the caller's x tensors, as the kernels carry it ("x_f64" arguments): 0 fp32, 1 fp64, 2 fp16
 __device__ __forceinline__ float ld_x(const void* base, int dtype_f64, int64_t idx) {
+    if (dtype_f64 == 2) return __half2float(__ldg((const __half*)base + idx));
     return dtype_f64 ? (float)__ldg((const double*)base + idx) : __ldg((const float*)base + idx);
 }
 
@@ -73,7 +75,7 @@ __device__ __forceinline__ void rg_load(const Tile& t, const BufTable& bt, int c
                 const int64_t idx = row * (int64_t)ch.lda + ch.a_off + k;
                 const void* xb = bt.p[ch.a_buf];
                 const float* pf = (const float*)xb + idx;
-                if (!x_f64 && k + 3 < K && ((reinterpret_cast<uintptr_t>(pf) & 15) == 0)) {
+                if (x_f64 == 0 && k + 3 < K && ((reinterpret_cast<uintptr_t>(pf) & 15) == 0)) {
                     const float4 q = __ldg(reinterpret_cast<const float4*>(pf));
                     v0 = q.x; v1 = q.y; v2 = q.z; v3 = q.w;
                 } else {
@@ -268,7 +270,7 @@ __device__ __forceinline__ void rd_load(const RPair& p, const RTask& t, const Bu
                 const void* xb = bt.p[p.a_buf];
                 const float* pf = (const float*)xb + idx;
                 float v[4] = {0.f, 0.f, 0.f, 0.f};
-                if (!x_f64 && k + 3 < t.K && ((reinterpret_cast<uintptr_t>(pf) & 15) == 0)) {
+                if (x_f64 == 0 && k + 3 < t.K && ((reinterpret_cast<uintptr_t>(pf) & 15) == 0)) {
                     const float4 q = __ldg(reinterpret_cast<const float4*>(pf));
                     v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
                 } else {

@@ -1211,15 +1211,16 @@ struct XRows {
     int64_t lda;          // elements between the same node of consecutive graphs
     int a_off;            // element offset of the node inside a graph's block
     int K;
-    int f64;
-    int vec;              // widest aligned vector: fp32 4 / 2 / 1 elements, fp64 2 / 1 elements
+    int f64;              // element type: 0 fp32, 1 fp64, 2 fp16 (kernels_simt.cuh: ld_x)
+    int vec;              // widest aligned vector: fp32 / fp16 4 / 2 / 1 elements, fp64 2 / 1 elements
 };
 __device__ __forceinline__ XRows make_xrows(const void* base, int f64, int64_t lda, int a_off, int K) {
     XRows x;
     x.base = base; x.lda = lda; x.a_off = a_off; x.K = K; x.f64 = f64;
     const uintptr_t p = reinterpret_cast<uintptr_t>(base);
     const bool even = ((lda | a_off | K) & 1) == 0, quad = ((lda | a_off | K) & 3) == 0;
-    if (f64) x.vec = (even && (p & 15) == 0) ? 2 : 1;
+    if (f64 == 1) x.vec = (even && (p & 15) == 0) ? 2 : 1;
+    else if (f64 == 2) x.vec = (quad && (p & 7) == 0) ? 4 : ((even && (p & 3) == 0) ? 2 : 1);
     else x.vec = (quad && (p & 15) == 0) ? 4 : ((even && (p & 7) == 0) ? 2 : 1);
     return x;
 }
@@ -1263,7 +1264,34 @@ __device__ __forceinline__ void load_x_block(float4 (&v)[N], const XRows& x, con
     const int K = x.K;
     const int kc = k < K ? k : 0;
     const int c1 = min(kc + 1, K - 1), c2 = min(kc + 2, K - 1), c3 = min(kc + 3, K - 1);
-    if (!x.f64) {
+    if (x.f64 == 2) {
+        // fp16 features (MSHGNN_F16): 8-byte loads of four halves; the split to (hi, lo) images downstream is then exact (lo = 0)
+        const __half* b = (const __half*)x.base + x.a_off;
+        if (x.vec == 4) {
+#pragma unroll
+            for (int it = 0; it < N; ++it) {
+                const int64_t r = min(row_first + it * RS, row_last);
+                const uint2 q = __ldg(reinterpret_cast<const uint2*>(b + r * x.lda + kc));
+                const float2 lo2 = __half22float2(*reinterpret_cast<const __half2*>(&q.x)), hi2 = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
+                v[it] = make_float4(lo2.x, lo2.y, hi2.x, hi2.y);
+            }
+        } else if (x.vec == 2) {
+            const int kd = min(kc + 2, K - 2);
+#pragma unroll
+            for (int it = 0; it < N; ++it) {
+                const int64_t r = min(row_first + it * RS, row_last);
+                const float2 p = __half22float2(__ldg(reinterpret_cast<const __half2*>(b + r * x.lda + kc)));
+                const float2 q = __half22float2(__ldg(reinterpret_cast<const __half2*>(b + r * x.lda + kd)));
+                v[it] = make_float4(p.x, p.y, q.x, q.y);
+            }
+        } else {
+#pragma unroll
+            for (int it = 0; it < N; ++it) {
+                const __half* pr = b + min(row_first + it * RS, row_last) * x.lda;
+                v[it] = make_float4(__half2float(__ldg(pr + kc)), __half2float(__ldg(pr + c1)), __half2float(__ldg(pr + c2)), __half2float(__ldg(pr + c3)));
+            }
+        }
+    } else if (!x.f64) {
         const float* b = (const float*)x.base + x.a_off;
         if (x.vec == 4) {
 #pragma unroll

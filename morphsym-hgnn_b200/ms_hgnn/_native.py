@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_ROOT, "lib", "libmshgnn_b200.so")
 MAX_NODE_TYPES = 4
 MAX_EDGE_TYPES = 16
 
-F32, F64, I64 = 0, 1, 2
+F32, F64, I64, F16 = 0, 1, 2, 3
 MODE_FP32, MODE_TC, MODE_TC_1X = 0, 1, 2
 LOSS_MSE, LOSS_CE2 = 0, 1
 P_ENC_W, P_ENC_B, P_REL_W, P_REL_B, P_ROOT_W, P_MLP_W, P_MLP_B, P_DEC_W, P_DEC_B = range(9)

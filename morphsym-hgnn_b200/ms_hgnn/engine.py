@@ -40,9 +40,11 @@ def _dtype_code(t: torch.Tensor) -> int:
         return N.F32
     if t.dtype == torch.float64:
         return N.F64
+    if t.dtype == torch.float16:
+        return N.F16
     if t.dtype == torch.int64:
         return N.I64
-    raise TypeError(f"unsupported dtype {t.dtype} (float32, float64 or int64 expected)")
+    raise TypeError(f"unsupported dtype {t.dtype} (float32, float64, float16 features or int64 labels expected)")
 
 
 class Engine:

@@ -417,7 +417,8 @@ class NativeHGNN(nn.Module):
         else:
             out = eng.forward(xs, self._flat, train=False)
         out = self._finish(out, B)
-        return out if out.dtype == x0.dtype else out.to(x0.dtype)
+        # fp16 node features (MSHGNN_F16: half the host -> device bytes of a batch) are an INPUT format: results stay fp32
+        return out if (out.dtype == x0.dtype or x0.dtype == torch.float16) else out.to(x0.dtype)
 
 
 class _NativeLossFn(torch.autograd.Function):

@@ -30,7 +30,7 @@ def native_run(cfg, model, batch, x_dtype=torch.float32, mode="fp32"):
     B = b.batch_size
     eng = next(iter(model._engines.values()))
     kind = N.LOSS_CE2 if cfg.loss == "ce" else N.LOSS_MSE
-    loss, dout = eng.loss(out.detach().float().reshape(-1, eng.spec["out_channels"]).contiguous(), b.y.to(x_dtype), kind)
+    loss, dout = eng.loss(out.detach().float().reshape(-1, eng.spec["out_channels"]).contiguous(), b.y.to(torch.float32 if x_dtype == torch.float16 else x_dtype), kind)
     out.backward(dout.view_as(out).to(out.dtype))
     grads = {n: (p.grad.clone() if p.grad is not None else torch.zeros_like(p)) for n, p in model.named_parameters()}
     return out.detach(), loss.detach(), grads, model
@@ -73,6 +73,14 @@ def check_gradients(cfg, B, layers, x_dtype=torch.float32, mode="fp32", seed=Non
 @pytest.mark.parametrize("name,B,layers", CASES)
 def test_forward_loss_backward_parity(name, B, layers):
     check_gradients(CONFIGS[name], B, layers)
+
+
+@pytest.mark.parametrize("name,B,layers,mode", [("mini_cheetah-k4-contact", 200, 8, "tc"), ("a1-c2-grf", 64, 8, "tc"), ("solo12-k4-com", 257, 8, "tc"),
+                                                ("mini_cheetah-k4-contact", 64, 8, "fp32"), ("mi-grf", 20, 8, "fp32")])
+def test_fp16_node_features(name, B, layers, mode):
+    """x_dict in torch.float16 (MSHGNN_F16: an input FORMAT that halves the host -> device bytes of a batch; widths 900 / 300 / 450 / 6 /
+    2 / 1 cover the 8-, 4- and 2-byte load paths): same 1e-4 bound against the oracle run on the same fp16-rounded features."""
+    check_gradients(CONFIGS[name], B, layers, x_dtype=torch.float16, mode=mode)
 
 
 @pytest.mark.parametrize("name,B,layers", CASES)
