@@ -12,6 +12,7 @@
 
 #include "kernels_simt.cuh"
 #include "kernels_tc.cuh"
+#include "kernels_enc.cuh"
 #include "kernels_stack.cuh"
 #include "kernels_stack2.cuh"
 #include "plan.cuh"
@@ -244,10 +245,11 @@ int launch_tc_encoder(const Plan& p, const Launch& L, const WsLayout& w, const B
                       const float* params, int64_t B, int xf64, int split, cudaStream_t st) {
     if (L.count == 0) return 0;
     static std::atomic<bool> attr_set[64];
-    static const bool use_v1 = [] { const char* e = getenv("MSHGNN_ENCODER"); return e && !strcmp(e, "v1"); }();   // one row tile per CTA (A/B measurements)
+    static const int which = [] { const char* e = getenv("MSHGNN_ENCODER"); return !e ? 2 : (!strcmp(e, "v1") ? 1 : (!strcmp(e, "stream") ? 0 : 2)); }();   // default: k_tc_encoder_pair; "stream": persistent bulk-copy kernel (kernels_enc.cuh), "v1": one tile per CTA
     if (first_on_device(attr_set)) {
         CUDA_TRY(cudaFuncSetAttribute(k_tc_encoder, cudaFuncAttributeMaxDynamicSharedMemorySize, ENC_SMEM_BYTES));
         CUDA_TRY(cudaFuncSetAttribute(k_tc_encoder_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, ENCP_SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(k_tc_encoder_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, ENQ_SMEM_BYTES));
     }
     __half* e_hi = (__half*)(ws + w.wenc16[0]);
     __half* e_lo = (__half*)(ws + w.wenc16[1]);
@@ -256,12 +258,26 @@ int launch_tc_encoder(const Plan& p, const Launch& L, const WsLayout& w, const B
     if ((rc = make_map_2d(&maps.w_hi, e_hi, (int64_t)p.n_types * H, p.enc_kmax, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
     if ((rc = make_map_2d(&maps.w_lo, e_lo, (int64_t)p.n_types * H, p.enc_kmax, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
     maps.o = wm.tc.o;
+    // the persistent kernel copies row fragments with cp.async.bulk: fp32 features, every 64-column fragment 16-byte aligned
+    bool stream_ok = xf64 == 0 && L.count <= ENQ_MAX_SLOTS;
+    for (int i = 0; i < L.count && stream_ok; ++i) {
+        const Chunk& ch = p.tiles[L.begin + i].chunks[0];
+        stream_ok = enq_rows_ok(bt.p[ch.a_buf], ch.lda, ch.a_off, ch.K, ch.sign_off);
+    }
     ProfScope ps(K_ENC_FWD, st);
     const unsigned n_row_tiles = (unsigned)(w.Bp / TILE_M);
-    if (use_v1) k_tc_encoder<<<dim3(n_row_tiles, (unsigned)L.count), ENC_THREADS, ENC_SMEM_BYTES, st>>>(maps, p.d_tiles + L.begin, bt, br, B, w.Bp, xf64, split);
-    else {
+    if (which == 1) k_tc_encoder<<<dim3(n_row_tiles, (unsigned)L.count), ENC_THREADS, ENC_SMEM_BYTES, st>>>(maps, p.d_tiles + L.begin, bt, br, B, w.Bp, xf64, split);
+    else if (which == 2 || !stream_ok) {
         static const int pf = [] { const char* e = getenv("MSHGNN_ENC_PREFETCH"); return e ? atoi(e) : 0; }();     // 1: whole-row L2 prefetch of the feature rows (measured +12 % time: off)
         k_tc_encoder_pair<<<dim3((n_row_tiles + 1) / 2, (unsigned)L.count), ENC_THREADS, ENCP_SMEM_BYTES, st>>>(maps, p.d_tiles + L.begin, bt, br, B, w.Bp, xf64, split, pf);
+    } else {
+        // persistent kernel: one CTA per SM draws (node slot, row-tile pair) items from the counter the forward prologue zeroed
+        int n_sm = 0;
+        if ((rc = sm_count(&n_sm))) return rc;
+        const int64_t n_items = (int64_t)L.count * ((n_row_tiles + 1) / 2);
+        const unsigned grid = (unsigned)(n_items < n_sm ? n_items : n_sm);
+        static const int dbg = [] { const char* e = getenv("MSHGNN_ENC_DEBUG"); return e ? atoi(e) : 0; }();               // measurement switches (results are wrong when set)
+        k_tc_encoder_stream<<<grid, ENQ_THREADS, ENQ_SMEM_BYTES, st>>>(maps, p.d_tiles + L.begin, L.count, bt, br, B, w.Bp, split, (uint32_t*)(ws + w.enc_sync), dbg);
     }
     LAUNCH_CHECK();
     return 0;
@@ -639,6 +655,7 @@ int mshgnn_forward(const mshgnn_plan* plan, int64_t B, const void* const* x, int
             fp.zero = w.stack ? (uint32_t*)((char*)workspace + w.stack_sync) : nullptr;
             fp.zero_words = w.stack ? w.stack_sync_bytes / 4 : 0;
             fp.zero_blocks = w.stack ? 16 : 0;
+            fp.enc_sync = (uint32_t*)((char*)workspace + w.enc_sync);
             const unsigned blocks = (unsigned)(fp.n_bias + 8 * fp.n16 + 64 * p.n_types + fp.zero_blocks);
             k_fwd_prologue<<<blocks, 256, 0, st>>>(fp, params, (float*)bt.p[BUF_DERIVED], w_hi, w_lo, (__half*)((char*)workspace + w.wenc16[0]),
                                                     (__half*)((char*)workspace + w.wenc16[1]));

@@ -1907,11 +1907,13 @@ struct FwdPrologue {
     const Derive16Op* ops16; int n16;
     EncImgDesc ed; int kmax;
     uint32_t* zero; int64_t zero_words; int zero_blocks;
+    uint32_t* enc_sync;          // work counter of k_tc_encoder_stream
 };
 __global__ void __launch_bounds__(256)
 k_fwd_prologue(const FwdPrologue a, const float* __restrict__ params, float* __restrict__ derived, __half* __restrict__ w_hi, __half* __restrict__ w_lo,
                __half* __restrict__ e_hi, __half* __restrict__ e_lo) {
     int b = blockIdx.x;
+    if (b == 0 && threadIdx.x == 0 && a.enc_sync) *a.enc_sync = 0u;
     if (b < a.n_bias) {
         const DeriveOp op = a.ops[b];
         const int n = op.rows * op.cols;

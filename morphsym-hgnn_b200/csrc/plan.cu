@@ -809,6 +809,7 @@ WsLayout ws_layout(const Plan& p, int64_t B, int train, int mode) {
     }
     if (tc) {
         for (int i = 0; i < 2; ++i) w.wenc16[i] = take((int64_t)p.n_types * H * p.enc_kmax * 2);
+        w.enc_sync = take(256);
         if (train) {
             // row splits of the encoder weight gradient, fitted to whole waves like the layer-stack ones (16 units for the K4 model:
             // 512-row splits gave 64 CTAs on 148 SMs at 2048 graphs)

@@ -135,6 +135,7 @@ struct WsLayout {
     int stack = 0;
     int stack_pair = 0;                // the stack launches use the CTA-pair kernel (Bp is a multiple of 256)
     int64_t dhL16[MAX_LAYERS + 1][2], dcL16[MAX_LAYERS + 1][2] /* index l + 1 */, duL16[MAX_LAYERS][2];
+    int64_t enc_sync = -1;             // work counter of the persistent encoder (k_tc_encoder_stream), zeroed by the forward prologue
     int64_t stack_sync = -1;           // dependency counters of the stack kernel (uint32 [phases][row tiles]) + error word
     int64_t stack_sync_bytes = 0;
     int64_t stack_timing = -1;         // diagnostic cycle counters of the TIMING instantiation: [CTA][8] uint64
