@@ -205,6 +205,24 @@ int make_map_2d(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, in
     return 0;
 }
 
+// The caller's fp32 feature tensor x[B * nodes, K] of one node type as a (K, nodes, B) tensor, box = 64 columns x 1 node x 128 graphs:
+// one TMA request fetches the 256-byte fragments of a K block of 128 consecutive graphs of one node slot (k_tc_encoder_stream).
+int make_map_x3d(CUtensorMap* m, const void* base, int64_t B, int nodes, int K) {
+    EncodeTiledFn enc;
+    int rc = get_encode_fn(&enc);
+    if (rc) return rc;
+    static thread_local bool ctx_bound = false;
+    if (!ctx_bound) { CUDA_TRY(cudaFree(0)); ctx_bound = true; }
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)nodes, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)K * 4, (cuuint64_t)nodes * K * 4};
+    cuuint32_t box[3] = {64, 1, 128};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(MSHGNN_ERR_CUDA, "cuTensorMapEncodeTiled (features) failed with CUresult %d", (int)r);
+    return 0;
+}
+
 // The whole workspace as one [total/256 rows][128 fp16] tensor: every (hi, lo) image of every buffer (and the 128x128
 // weight images) is a row range of it, so three maps serve every tensor-core launch of a call.
 struct WsMaps {
@@ -245,7 +263,7 @@ int launch_tc_encoder(const Plan& p, const Launch& L, const WsLayout& w, const B
                       const float* params, int64_t B, int xf64, int split, cudaStream_t st) {
     if (L.count == 0) return 0;
     static std::atomic<bool> attr_set[64];
-    static const int which = [] { const char* e = getenv("MSHGNN_ENCODER"); return !e ? 2 : (!strcmp(e, "v1") ? 1 : (!strcmp(e, "stream") ? 0 : 2)); }();   // default: k_tc_encoder_pair; "stream": persistent bulk-copy kernel (kernels_enc.cuh), "v1": one tile per CTA
+    static const int which = [] { const char* e = getenv("MSHGNN_ENCODER"); return !e ? 0 : (!strcmp(e, "v1") ? 1 : (!strcmp(e, "pair") ? 2 : 0)); }();   // default: k_tc_encoder_pair; "stream": persistent bulk-copy kernel (kernels_enc.cuh), "v1": one tile per CTA
     if (first_on_device(attr_set)) {
         CUDA_TRY(cudaFuncSetAttribute(k_tc_encoder, cudaFuncAttributeMaxDynamicSharedMemorySize, ENC_SMEM_BYTES));
         CUDA_TRY(cudaFuncSetAttribute(k_tc_encoder_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, ENCP_SMEM_BYTES));
@@ -262,7 +280,7 @@ int launch_tc_encoder(const Plan& p, const Launch& L, const WsLayout& w, const B
     bool stream_ok = xf64 == 0 && L.count <= ENQ_MAX_SLOTS;
     for (int i = 0; i < L.count && stream_ok; ++i) {
         const Chunk& ch = p.tiles[L.begin + i].chunks[0];
-        stream_ok = enq_rows_ok(bt.p[ch.a_buf], ch.lda, ch.a_off, ch.K, ch.sign_off);
+        stream_ok = ch.a_buf >= BUF_X0 && ch.a_buf < BUF_X0 + p.n_types && enq_rows_ok(bt.p[ch.a_buf], ch.K, ch.sign_off);
     }
     ProfScope ps(K_ENC_FWD, st);
     const unsigned n_row_tiles = (unsigned)(w.Bp / TILE_M);
@@ -277,7 +295,14 @@ int launch_tc_encoder(const Plan& p, const Launch& L, const WsLayout& w, const B
         const int64_t n_items = (int64_t)L.count * ((n_row_tiles + 1) / 2);
         const unsigned grid = (unsigned)(n_items < n_sm ? n_items : n_sm);
         static const int dbg = [] { const char* e = getenv("MSHGNN_ENC_DEBUG"); return e ? atoi(e) : 0; }();               // measurement switches (results are wrong when set)
-        k_tc_encoder_stream<<<grid, ENQ_THREADS, ENQ_SMEM_BYTES, st>>>(maps, p.d_tiles + L.begin, L.count, bt, br, B, w.Bp, split, (uint32_t*)(ws + w.enc_sync), dbg);
+        EnqMaps em;
+        em.w_hi = maps.w_hi; em.w_lo = maps.w_lo; em.o = maps.o;
+        for (int t = 0; t < p.n_types; ++t) {
+            if (p.in_w[t] % 4 || (reinterpret_cast<uintptr_t>(bt.p[BUF_X0 + t]) & 15)) { em.x[t] = maps.o; continue; }      // no slot of this launch reads it (stream_ok)
+            if ((rc = make_map_x3d(&em.x[t], bt.p[BUF_X0 + t], B, p.nodes[t], p.in_w[t]))) return rc;
+        }
+        for (int t = p.n_types; t < 4; ++t) em.x[t] = maps.o;
+        k_tc_encoder_stream<<<grid, ENQ_THREADS, ENQ_SMEM_BYTES, st>>>(em, p.d_tiles + L.begin, L.count, (int)BUF_X0, bt, br, B, w.Bp, split, (uint32_t*)(ws + w.enc_sync), dbg);
     }
     LAUNCH_CHECK();
     return 0;

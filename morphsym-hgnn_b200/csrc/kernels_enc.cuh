@@ -12,10 +12,12 @@
 //  (one CTA per SM, dedicated epilogue warps, double-buffered accumulators) measured SLOWER (0.44 against 0.37 ms), and with the
 //  conversion and the MMAs switched off its loads alone still took 0.30 ms: the loads were the limit, not what surrounds them.
 //  Here the feature rows never pass through a scoreboard:
-//    * two producer warps (one per row tile) copy the 256-byte row fragments of a K block with cp.async.bulk straight into the
-//      operand stage: 128 rows x 256 B of raw fp32 land in the 32 KB that will hold the tile's (hi, lo) fp16 images.  Completion
-//      is a transaction count on an mbarrier per (stage, row tile) - ordered, per stage, no register is tied up while the bytes
-//      are in flight (64 KB per stage and SM);
+//    * a 3-D tensor map over every feature tensor x[B * nodes, K] (dims K, nodes, B; box 64 columns x 1 node x 128 graphs) lets
+//      ONE TMA request fetch the 128 row fragments of 256 bytes of a (row tile, K block): 32 KB of raw fp32 land in the 32 KB of
+//      the operand stage that will hold the tile's (hi, lo) fp16 images, columns >= K and graphs >= B arrive as zeros.
+//      Completion is a transaction count on an mbarrier per (stage, row tile) - ordered, per stage, no register is tied up while
+//      the bytes are in flight (64 KB per stage and SM).  (128 separate cp.async.bulk row copies per tile were measured first:
+//      0.43 ms, the copy engine's request rate - ~36 cycles per 256-byte copy - became the limit);
 //    * eight converter warps (two groups of 128 threads, one per row tile) wait for the landing barrier, read the raw tile into
 //      registers (16 x 16 bytes per thread), meet on a named barrier, and write the signed (hi, lo) split IN PLACE in the
 //      128B-swizzled K-major UMMA layout;
@@ -41,10 +43,16 @@ constexpr int ENQ_MAX_SLOTS = 32;
 constexpr int ENQ_ITEM_Q = 4;
 constexpr uint32_t ENQ_TMEM_COLS = 512;
 constexpr int ENQ_CONV_WARP0 = 4, ENQ_EPI_WARP0 = 12;
-constexpr int ENQ_ITEM_CONSUMERS = 1 + 2 + 8 + 4;            // MMA thread, producer warps, converter warps, epilogue warps
+constexpr int ENQ_ITEM_CONSUMERS = 1 + 8 + 4;                // MMA thread, converter warps, epilogue warps
 
 struct EnqSlot {
-    int a_buf, K, lda, a_off, sign_off, w16_row, n_kb, tile;
+    int xt, node, K, sign_off, w16_row, n_kb, tile, pad;     // xt: feature tensor (node type) of the slot, node: its node inside a graph
+};
+
+struct alignas(64) EnqMaps {
+    CUtensorMap w_hi, w_lo;      // encoder weight images, box 64 x 128, SWIZZLE_128B
+    CUtensorMap o;               // workspace images, box 64 x 128, SWIZZLE_128B (epilogue stores)
+    CUtensorMap x[4];             // caller's feature tensors as (K, nodes, B) fp32, box 64 x 1 x 128, no swizzle
 };
 
 struct alignas(16) EnqCtl {
@@ -58,13 +66,16 @@ struct alignas(16) EnqCtl {
 };
 static_assert(ENQ_TILE_REGION + sizeof(EnqCtl) <= ENQ_SMEM_BYTES, "encoder control block does not fit behind the tiles");
 
-// host-side test of what the bulk copies need: fp32 rows whose every 64-column fragment starts and ends on a 16-byte boundary
-inline bool enq_rows_ok(const void* base, int64_t lda, int a_off, int K, int sign_off) {
-    return (reinterpret_cast<uintptr_t>(base) & 15) == 0 && ((lda | a_off | K) & 3) == 0 && K >= 4 && (sign_off < 0 || (sign_off & 3) == 0);
+// host-side test of what the tensor maps need: fp32 rows of a 16-byte multiple on a 16-byte aligned base (and whole 4-column sign groups)
+inline bool enq_rows_ok(const void* base, int K, int sign_off) {
+    return (reinterpret_cast<uintptr_t>(base) & 15) == 0 && (K & 3) == 0 && K >= 4 && (sign_off < 0 || (sign_off & 3) == 0);
 }
 
-__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
 }
 
 // entry m of the item queue (every role reads the same sequence); warps release with one arrival
@@ -78,7 +89,7 @@ __device__ __forceinline__ int enq_take(EnqCtl& ctl, const int m, const bool who
 }
 
 __global__ void __launch_bounds__(ENQ_THREADS, 1)
-k_tc_encoder_stream(const __grid_constant__ EncMaps maps, const Tile* __restrict__ tiles, const int n_slots, const BufTable bt, const BufRows br,
+k_tc_encoder_stream(const __grid_constant__ EnqMaps maps, const Tile* __restrict__ tiles, const int n_slots, const int x_buf0 /*buffer id of the first feature tensor*/, const BufTable bt, const BufRows br,
                     const int64_t B, const int64_t Bp, const int split, uint32_t* __restrict__ counter,
                     const int dbg /*measurement switches: 1 no conversion, 2 no MMAs (results are wrong when set)*/) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -105,8 +116,8 @@ k_tc_encoder_stream(const __grid_constant__ EncMaps maps, const Tile* __restrict
             int rank = 0;
             for (int j = 0; j < n_slots; ++j) rank += (keys[j] > ch.K || (keys[j] == ch.K && j < tid)) ? 1 : 0;
             EnqSlot s;
-            s.a_buf = ch.a_buf; s.K = ch.K; s.lda = ch.lda; s.a_off = ch.a_off; s.sign_off = ch.sign_off; s.w16_row = ch.w16_row;
-            s.n_kb = (ch.K + 63) / 64; s.tile = tid;
+            s.xt = ch.a_buf - x_buf0; s.node = ch.a_off / ch.K; s.K = ch.K; s.sign_off = ch.sign_off; s.w16_row = ch.w16_row;
+            s.n_kb = (ch.K + 63) / 64; s.tile = tid; s.pad = 0;
             ctl.slots[rank] = s;
         }
     }
@@ -147,12 +158,25 @@ k_tc_encoder_stream(const __grid_constant__ EncMaps maps, const Tile* __restrict
                     publish(m + 1, id_next);                 // the producers open the next item while this one is still in the pipeline
                     const uint32_t id_after = id_next < (uint32_t)n_items ? atomicAdd(counter, 1u) : (uint32_t)n_items;
                     if (id_cur >= (uint32_t)n_items) break;
-                    const EnqSlot& sl = ctl.slots[(int)id_cur / n_pairs];
-                    const int wrow = sl.w16_row, n_kb = sl.n_kb;
+                    const int si = (int)id_cur / n_pairs;
+                    const EnqSlot& sl = ctl.slots[si];
+                    const int row0 = ((int)id_cur - si * n_pairs) * (2 * TILE_M);
+                    const bool two = (int64_t)row0 + TILE_M < Bp;
+                    const int wrow = sl.w16_row, n_kb = sl.n_kb, node = sl.node;
+                    const CUtensorMap* xm = &maps.x[sl.xt];
                     for (int i = 0; i < n_kb; ++i, ++kbi) {
                         const uint32_t s = kbi & 1u;
                         mbar_wait(empty0 + 8 * s, ((kbi >> 1) & 1u) ^ 1u);
                         const uint32_t st = smem_base + s * ENQ_STAGE_BYTES;
+                        // raw feature rows of both row tiles (graphs >= B and columns >= K are zero-filled by the TMA unit)
+                        const uint32_t lb = landed0 + 16 * s;
+                        mbar_expect_tx(lb, 2 * ENC_TILE_BYTES);
+                        tma_load_3d(st, xm, lb, i * 64, node, row0);
+                        if (two) {
+                            mbar_expect_tx(lb + 8, 2 * ENC_TILE_BYTES);
+                            tma_load_3d(st + 2 * ENC_TILE_BYTES, xm, lb + 8, i * 64, node, row0 + TILE_M);
+                        } else
+                            mbar_arrive(lb + 8);             // nothing to copy, but every barrier keeps one phase per K block
                         const uint32_t fb = full0 + 8 * s;
                         mbar_expect_tx(fb, tx_bytes);
                         tma_load_2d(st + 4 * ENC_TILE_BYTES, &maps.w_hi, fb, i * 64, wrow);
@@ -201,33 +225,6 @@ k_tc_encoder_stream(const __grid_constant__ EncMaps maps, const Tile* __restrict
                     umma_commit(acc_full0 + 8 * b);
                 }
             }
-        } else {
-            // ---------------- producers: warp 2 + g streams the raw rows of row tile g into the stages ----------------
-            const int g = warp - 2;
-            uint32_t kbi = 0;
-            for (int m = 0;; ++m) {
-                const int id = enq_take(ctl, m, true, lane);
-                if (id >= n_items) break;
-                const int si = id / n_pairs;
-                const int64_t row0 = (int64_t)(id - si * n_pairs) * (2 * TILE_M) + g * TILE_M;
-                const EnqSlot sl = ctl.slots[si];
-                const int n_rows = row0 >= B ? 0 : (int)(B - row0 < TILE_M ? B - row0 : TILE_M);       // rows [B, Bp) get no copy: the converters write zeros
-                const float* xb = reinterpret_cast<const float*>(bt.p[sl.a_buf]) + sl.a_off + row0 * sl.lda;
-                for (int i = 0; i < sl.n_kb; ++i, ++kbi) {
-                    const uint32_t s = kbi & 1u;
-                    mbar_wait(empty0 + 8 * s, ((kbi >> 1) & 1u) ^ 1u);
-                    const uint32_t lb = landed0 + 16 * s + 8 * g;
-                    if (n_rows == 0) {                       // second row tile of a one-tile item: nothing to copy, but every barrier keeps one phase per K block
-                        if (lane == 0) mbar_arrive(lb);
-                        continue;
-                    }
-                    const uint32_t nb = (uint32_t)(sl.K - i * 64 < 64 ? sl.K - i * 64 : 64) * 4u;
-                    if (lane == 0) mbar_expect_tx(lb, nb * (uint32_t)n_rows);
-                    __syncwarp();
-                    const uint32_t dst = smem_base + s * ENQ_STAGE_BYTES + (uint32_t)g * (2 * ENC_TILE_BYTES);
-                    for (int r = lane; r < n_rows; r += 32) bulk_load_1d(dst + (uint32_t)r * 256u, xb + (int64_t)r * sl.lda + i * 64, nb, lb);
-                }
-            }
         }
     } else if (warp < ENQ_EPI_WARP0) {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
@@ -244,12 +241,11 @@ k_tc_encoder_stream(const __grid_constant__ EncMaps maps, const Tile* __restrict
             const int si = id / n_pairs;
             const int64_t row0 = (int64_t)(id - si * n_pairs) * (2 * TILE_M) + g * TILE_M;
             const EnqSlot sl = ctl.slots[si];
-            const bool live = row0 < B;
-            const int n_rows = !live ? 0 : (int)(B - row0 < TILE_M ? B - row0 : TILE_M);
+            const bool live = row0 < Bp;
             for (int i = 0; i < sl.n_kb; ++i, ++kbi) {
                 const uint32_t s = kbi & 1u;
                 if (!live) {
-                    // nothing lands for this row tile: the producer's bare arrival says the stage has been released (one phase per K block on every barrier)
+                    // nothing lands for this row tile: the scheduler's bare arrival says the stage has been released (one phase per K block on every barrier)
                     mbar_wait(landed0 + 16 * s + 8 * g, (kbi >> 1) & 1u);
                     __syncwarp();
                     if (lane == 0) mbar_arrive(full0 + 8 * s);
@@ -268,14 +264,11 @@ k_tc_encoder_stream(const __grid_constant__ EncMaps maps, const Tile* __restrict
                 }
                 asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");       // every raw row of the tile is in registers: the images may overwrite them
                 if (!(dbg & 1)) {
-                    const bool kin = k < sl.K;                    // K % 4 == 0: a 4-column group is inside or outside as a whole
 #pragma unroll
                     for (int u = 0; u < 16; ++u) {
                         const int r = u * 8 + rsub;
-                        const bool in = kin && r < n_rows;        // nothing was copied there: stale shared memory, not zeros
-                        const float4 x = in ? v[u] : make_float4(0.f, 0.f, 0.f, 0.f);
                         const uint32_t off = (uint32_t)(r * 128 + ((((kq >> 1) ^ (r & 7))) << 4) + ((kq & 1) << 3));
-                        split_to_smem(st + off, st + ENC_TILE_BYTES + off, x, sg);
+                        split_to_smem(st + off, st + ENC_TILE_BYTES + off, v[u], sg);
                     }
                 }
                 fence_proxy_async_smem();
