@@ -91,7 +91,7 @@ __device__ __forceinline__ int enq_take(EnqCtl& ctl, const int m, const bool who
 __global__ void __launch_bounds__(ENQ_THREADS, 1)
 k_tc_encoder_stream(const __grid_constant__ EnqMaps maps, const Tile* __restrict__ tiles, const int n_slots, const int x_buf0 /*buffer id of the first feature tensor*/, const BufTable bt, const BufRows br,
                     const int64_t B, const int64_t Bp, const int split, uint32_t* __restrict__ counter,
-                    const int dbg /*measurement switches: 1 no conversion, 2 no MMAs (results are wrong when set)*/) {
+                    const int dbg /*measurement switches: 1 no conversion, 2 no MMAs, 4 no weight loads (results are wrong when set)*/) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -178,6 +178,7 @@ k_tc_encoder_stream(const __grid_constant__ EnqMaps maps, const Tile* __restrict
                         } else
                             mbar_arrive(lb + 8);             // nothing to copy, but every barrier keeps one phase per K block
                         const uint32_t fb = full0 + 8 * s;
+                        if (dbg & 4) { mbar_arrive(fb); continue; }
                         mbar_expect_tx(fb, tx_bytes);
                         tma_load_2d(st + 4 * ENC_TILE_BYTES, &maps.w_hi, fb, i * 64, wrow);
                         if (split) tma_load_2d(st + 5 * ENC_TILE_BYTES, &maps.w_lo, fb, i * 64, wrow);

@@ -1,5 +1,6 @@
-"""CPU restatement (numpy / torch fp64) of the reference's per-sample dataset path for the Mini Cheetah contact
-dataset, used as the checker of the device-side window builder.
+"""CPU restatement (numpy / torch fp64) of the reference's per-sample dataset paths - Mini Cheetah contact data
+(``sample``), quad-SDK A1 ground-reaction-force data (``sample_a1``), Solo12 centre-of-mass data (``sample_solo``) - used as
+the checker of the device-side window builder.
 
 TEST INFRASTRUCTURE ONLY: imported by tests/, bench.py's checker leg and __graft_entry__.smoke(); the product path
 (ms_hgnn.windows -> libmshgnn_b200.so) never imports it.
@@ -108,6 +109,111 @@ def sample(mat: Dict[str, np.ndarray], idx: int, model_type: str, T: int, normal
     for i in range(4):
         foot_x[i] = torch.cat([torch.tensor(np.asarray(feet[k])[:, 3 * i:3 * i + 3].flatten("F"), dtype=torch.float64) for k in range(2)])
     return base_x, joint_x, foot_x, torch.tensor(np.asarray(labels_sorted, dtype=np.float64), dtype=torch.float64)
+
+
+def sample_a1(mat: Dict[str, np.ndarray], idx: int, T: int, normalize: bool = True, grf_dimension: int = 1,
+              grf_body_to_world_frame: bool = False, symmetry_operator: Optional[str] = None, symmetry_mode: Optional[str] = None,
+              group: Optional[dict] = None):
+    """One entry of QuadSDKDataset_A1 with model_type 'heterogeneous_gnn_c2' -> (base_x, joint_x, foot_x, y, r_o or None).
+    Follows quadSDKDataset_Morph.py: load_data_at_dataset_seq_3d / load_data_at_dataset_seq L444-489 (label rotation by the last
+    orientation with scipy), load_data_sorted_c2 L100-174 (base tiling, identity URDF order L404-441, apply_symmetry L177-239, z-score
+    of base / joint arrays and of r_o), get_helper_heterogeneous_gnn_c2 L274-351 (widths flexibleDataset.py:L185-190: foot_x stays ones)."""
+    from scipy.spatial.transform import Rotation
+    lin_acc = np.array(mat["imu_acc"][idx:idx + T]).reshape(T, 3)
+    ang_vel = np.array(mat["imu_omega"][idx:idx + T]).reshape(T, 3)
+    j_p = np.array(mat["q"][idx:idx + T]).reshape(T, 12)
+    j_v = np.array(mat["qd"][idx:idx + T]).reshape(T, 12)
+    j_T = np.array(mat["tau"][idx:idx + T]).reshape(T, 12)
+    grfs = np.squeeze(np.array(mat["F"][idx:idx + T]).reshape(T, 12))[-1] if T > 1 else np.array(mat["F"][idx:idx + T]).reshape(12)
+    r_quat = np.array(mat["r_o"][idx:idx + T]).reshape(T, 4)
+    if grf_body_to_world_frame:
+        world_to_body_R = Rotation.from_quat(r_quat[-1])
+        grfs_T = np.array(grfs.reshape(4, 3), dtype=np.double).T
+        grfs = (world_to_body_R.as_matrix() @ grfs_T).T.flatten()
+    labels = grfs[[2, 5, 8, 11]] if grf_dimension == 1 else grfs
+    base = [np.tile(lin_acc, (1, 2)), np.tile(ang_vel, (1, 2))]
+    sym = symmetry_operator is not None
+    if sym:
+        base = [_act(base[0], group["permutation_Q_bs"], _coefficients(group, "reflection_Q_bs_lin", symmetry_mode), symmetry_operator),
+                _act(base[1], group["permutation_Q_bs"], _coefficients(group, "reflection_Q_bs_ang", symmetry_mode), symmetry_operator)]
+    order = np.arange(12, dtype=np.uint)                 # joint_node_indices_sorted for a1_pruned.urdf (identity)
+    joints = [a[:, order] for a in (j_p, j_v, j_T)]
+    if sym:
+        cj = _coefficients(group, "reflection_Q_js", symmetry_mode)
+        joints = [_act(a, group["permutation_Q_js"], cj, symmetry_operator) for a in joints]
+    foot_order = np.arange(4, dtype=np.uint)
+    if grf_dimension == 1:
+        labels_sorted = labels[foot_order]
+        if sym:
+            labels_sorted = _act(labels_sorted, group["permutation_Q_ls"], _coefficients(group, "reflection_Q_ls", symmetry_mode), symmetry_operator)
+    else:
+        labels_sorted = labels[[int(index * 3 + i) for index in foot_order for i in range(3)]]
+        if sym:
+            labels_sorted = _act(labels_sorted, group["permutation_Q_fs"], _coefficients(group, "reflection_Q_fs", symmetry_mode), symmetry_operator)
+    r_o = r_quat
+    if normalize:
+        if T <= 1:
+            raise ValueError("normalize needs history_length > 1 (the reference returns None arrays)")
+        base, joints, r_o = [zscore(a) for a in base], [zscore(a) for a in joints], zscore(r_quat)
+    base_x = torch.ones((2, 2 * 3 * T), dtype=torch.float64)
+    joint_x = torch.ones((12, 3 * T), dtype=torch.float64)
+    foot_x = torch.ones((4, 1), dtype=torch.float64)
+    for i in range(2):
+        base_x[i] = torch.cat([torch.tensor(np.asarray(base[k])[:, i * 3:(i + 1) * 3].flatten("F"), dtype=torch.float64) for k in range(2)])
+    for i in range(12):
+        joint_x[i] = torch.cat([torch.tensor(np.asarray(joints[k])[:, i].flatten("F"), dtype=torch.float64) for k in range(3)])
+    y = torch.tensor(np.asarray(labels_sorted, dtype=np.float64), dtype=torch.float64)
+    return base_x, joint_x, foot_x, y, (torch.tensor(np.asarray(r_o)[-1], dtype=torch.float64) if grf_body_to_world_frame else None)
+
+
+def sample_solo(mat: Dict[str, np.ndarray], idx: int, model_type: str, T: int, normalize: bool = True, joint_order=None):
+    """One entry of Solo12Dataset -> (base_x, joint_x, y).  Follows soloDataset.py: dataset-level standardisation L136-143 with the
+    stored statistics (Standarizer.transform L18-31), load_data_at_dataset_seq L382-401 (zero base inputs, label = last frame of Y),
+    load_data_sorted / _k4 / _c2 L332-380, L546-718 (base tiling, joint order, labels repeated per base node and interleaved
+    [lin | ang]), get_helper_heterogeneous_gnn L235-300.  joint_order = joint_node_indices_sorted (the Solo URDF is not in the tree)."""
+    nb = {"heterogeneous_gnn_k4_com": 4, "heterogeneous_gnn_c2_com": 2, "heterogeneous_gnn_s4_com": 1}[model_type]
+    X, Y = np.asarray(mat["X"], dtype=np.float64), np.asarray(mat["Y"], dtype=np.float64)
+    if normalize:
+        X, Y = (X - mat["x_mean"]) / mat["x_std"], (Y - mat["y_mean"]) / mat["y_std"]
+    j_p = X[:, :12][idx:idx + T].reshape(T, 12)
+    j_v = X[:, 12:][idx:idx + T].reshape(T, 12)
+    base_lin_vel = Y[:, :3][idx:idx + T].reshape(T, 3)
+    base_ang_vel = Y[:, 3:][idx:idx + T].reshape(T, 3)
+    labels = np.concatenate([base_lin_vel[-1], base_ang_vel[-1]])
+    lin_vel, ang_vel = np.zeros((T, 3)), np.zeros((T, 3))
+    if nb > 1:
+        lin_vel, ang_vel = np.tile(lin_vel, (1, nb)), np.tile(ang_vel, (1, nb))
+    order = np.arange(12) if joint_order is None else np.asarray(joint_order)
+    joints = [a[:, order] for a in (j_p, j_v)]
+    if nb == 1:
+        labels_sorted = labels
+    else:
+        lin, ang = np.tile(labels[:3], nb), np.tile(labels[3:], nb)
+        labels_sorted = [part[3 * i:3 * i + 3] for i in range(nb) for part in (lin, ang)]
+    base_x = torch.ones((nb, 6 * T), dtype=torch.float64)
+    joint_x = torch.ones((12, 2 * T), dtype=torch.float64)
+    base = [lin_vel, ang_vel]
+    for i in range(nb):
+        base_x[i] = torch.cat([torch.tensor(base[k][:, i * 3:(i + 1) * 3].flatten("F"), dtype=torch.float64) for k in range(2)])
+    for i in range(12):
+        joint_x[i] = torch.cat([torch.tensor(joints[k][:, i].flatten("F"), dtype=torch.float64) for k in range(2)])
+    return base_x, joint_x, torch.tensor(np.array(labels_sorted).reshape(-1), dtype=torch.float64)
+
+
+def synthetic_a1_mat(n_rows: int, seed: int = 0, dtype=np.float64) -> Dict[str, np.ndarray]:
+    """Random stand-in for the quad-SDK data.mat (keys and shapes of quadSDKDataset.py:L107-117); unit-ish quaternions."""
+    rng = np.random.default_rng(seed)
+    def walk(c, scale, offset):
+        return (offset + np.cumsum(rng.normal(0.0, scale, size=(n_rows, c)), axis=0) * 0.05 + rng.normal(0.0, scale, size=(n_rows, c))).astype(dtype)
+    q = walk(4, 0.05, np.array([0.02, -0.03, 0.1, 0.99]))
+    return {"imu_acc": walk(3, 1.0, np.array([0.0, 0.0, 9.8])), "imu_omega": walk(3, 0.3, 0.0), "q": walk(12, 0.2, 0.6), "qd": walk(12, 2.0, 0.0),
+            "tau": walk(12, 3.0, 0.0), "F": walk(12, 10.0, 30.0), "r_p": walk(3, 0.1, 0.3), "r_o": q, "timestamps": np.zeros((n_rows, 3), dtype=dtype)}
+
+
+def synthetic_solo_mat(n_rows: int, seed: int = 0) -> Dict[str, np.ndarray]:
+    rng = np.random.default_rng(seed)
+    X, Y = rng.normal(0.3, 1.5, size=(n_rows, 24)), rng.normal(-0.1, 0.7, size=(n_rows, 6))
+    return {"X": X, "Y": Y, "x_mean": X.mean(0), "x_std": X.std(0), "y_mean": Y.mean(0), "y_std": Y.std(0)}
 
 
 def batch(mat: Dict[str, np.ndarray], indices: List[int], model_type: str, T: int, **kw):

@@ -37,14 +37,107 @@ def interpret_table(spec: WindowSpec, seq: np.ndarray, lab: np.ndarray, starts):
         z = WO.zscore(w) if spec.normalize else w
         b = 0
         for t, (n, k) in enumerate(zip(spec.nodes, spec.blocks)):
-            rows = np.empty((n, k * spec.T))
+            L = spec.block_len[t]
+            rows = np.empty((n, k * L))
             for i in range(n):
                 for j in range(k):
-                    rows[i, j * spec.T:(j + 1) * spec.T] = np.asarray(z)[:, spec.block_col[b]] * spec.block_sign[b]
+                    c = spec.block_col[b]
+                    rows[i, j * L:(j + 1) * L] = np.asarray(z)[:, c] * spec.block_sign[b] if c >= 0 else float(spec.block_sign[b])
                     b += 1
             xs[t].append(rows)
         ys.append(lab[s + spec.T - 1, spec.label_col] * np.asarray(spec.label_sign))
     return [np.concatenate(v) for v in xs], np.concatenate(ys)
+
+
+A1_CASES = [(1, False, None), (3, False, None), (3, True, None), (1, True, "gs"), (3, True, "gs")]
+
+
+def _a1_kw(op):
+    if op is None:
+        return {}, {}
+    path = M.cfg_path("a1-c2")
+    return (dict(symmetry_operator=op, symmetry_mode="MorphSym", group_operator_path=path),
+            dict(symmetry_operator=op, symmetry_mode="MorphSym", group=M.load_group(path)))
+
+
+def _a1_oracle(mat, starts, spec_kw, orc_kw, dim, body, normalize=True, T=T):
+    parts = [WO.sample_a1(mat, int(i), T, normalize=normalize, grf_dimension=dim, grf_body_to_world_frame=body, **orc_kw) for i in starts]
+    xo = [torch.cat([p[k] for p in parts]).numpy() for k in range(3)]
+    yo = torch.cat([p[3] for p in parts]).numpy()
+    ro = torch.cat([p[4] for p in parts]).numpy() if body else None
+    return xo, yo, ro
+
+
+@pytest.mark.parametrize("dim,body,op", A1_CASES)
+def test_a1_tables_match_reference_restatement(dim, body, op):
+    """QuadSDKDataset_A1 / heterogeneous_gnn_c2 (BASELINE config a1-c2-grf: widths 900 / 450 / 1, 3-D body-frame GRF labels)."""
+    spec_kw, orc_kw = _a1_kw(op)
+    mat = WO.synthetic_a1_mat(400, seed=5)
+    spec = WindowSpec("heterogeneous_gnn_c2", T, True, dataset="a1", grf_dimension=dim, grf_body_to_world_frame=body, **spec_kw)
+    assert spec.widths == {"base": 900, "joint": 450, "foot": 1} and spec.n_labels == (4 if dim == 1 else 12)
+    seq, lab = spec.pack(mat, np.float64)
+    starts = [0, 7, 250]
+    xs, y = interpret_table(spec, seq, lab, starts)
+    xo, yo, ro = _a1_oracle(mat, starts, spec_kw, orc_kw, dim, body)
+    for k in range(3):
+        assert np.abs(xs[k] - xo[k]).max() <= 1e-12
+    assert np.abs(y - yo).max() <= 1e-9 * max(1.0, np.abs(yo).max())          # rotation: numpy formula vs scipy
+    if body:
+        r = xs[3].reshape(len(starts), 4, T)[:, :, -1].reshape(-1)
+        assert np.abs(r - ro).max() <= 1e-12
+
+
+@pytest.mark.parametrize("model_type,n_lab", [("heterogeneous_gnn_k4_com", 24), ("heterogeneous_gnn_c2_com", 12), ("heterogeneous_gnn_s4_com", 6)])
+@pytest.mark.parametrize("hist", [1, 3])
+def test_solo_tables_match_reference_restatement(model_type, n_lab, hist):
+    mat = WO.synthetic_solo_mat(60, seed=2)
+    order = [6, 7, 8, 0, 1, 2, 9, 10, 11, 3, 4, 5]
+    spec = WindowSpec(model_type, hist, True, dataset="solo12", joint_order=order)
+    assert spec.widths == {"base": 6 * hist, "joint": 2 * hist} and spec.n_labels == n_lab
+    seq, lab = spec.pack(mat, np.float64)
+    starts = [0, 11, 57]
+    xs, y = interpret_table(spec, seq, lab, starts)
+    parts = [WO.sample_solo(mat, i, model_type, hist, True, order) for i in starts]
+    for k in range(2):
+        assert np.abs(xs[k] - torch.cat([p[k] for p in parts]).numpy()).max() <= 1e-12
+    assert np.abs(y - torch.cat([p[2] for p in parts]).numpy()).max() <= 1e-12
+    with pytest.raises(ValueError):
+        WindowSpec(model_type, hist, True, dataset="solo12", symmetry_operator="gs")
+    with pytest.raises(ValueError):
+        WindowSpec("heterogeneous_gnn_k4", hist, True, dataset="solo12")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dim,body,op", A1_CASES)
+def test_a1_kernel_matches_oracle(dim, body, op):
+    spec_kw, orc_kw = _a1_kw(op)
+    mat = WO.synthetic_a1_mat(500, seed=6)
+    spec = WindowSpec("heterogeneous_gnn_c2", T, True, dataset="a1", grf_dimension=dim, grf_body_to_world_frame=body, **spec_kw)
+    ds = DeviceSequence(mat, spec, "cuda:0", torch.float64)
+    starts = [0, 3, 349, 120, 77]
+    b = ds.batch(torch.tensor(starts))
+    xo, yo, ro = _a1_oracle(mat, starts, spec_kw, orc_kw, dim, body)
+    for k, name in enumerate(("base", "joint", "foot")):
+        assert np.abs(b.x_dict[name].cpu().double().numpy() - xo[k]).max() <= 1e-6
+    assert np.abs(b.y.cpu().double().numpy() - yo).max() <= 1e-5 * max(1.0, np.abs(yo).max())
+    if body:
+        assert np.abs(b.r_o.cpu().double().numpy() - ro).max() <= 1e-6
+    else:
+        assert not hasattr(b, "r_o")
+
+
+@pytest.mark.gpu
+def test_solo_kernel_matches_oracle():
+    mat = WO.synthetic_solo_mat(300, seed=3)
+    for model_type in ("heterogeneous_gnn_k4_com", "heterogeneous_gnn_c2_com", "heterogeneous_gnn_s4_com"):
+        spec = WindowSpec(model_type, 1, True, dataset="solo12")
+        ds = DeviceSequence(mat, spec, "cuda:0", torch.float64)
+        starts = list(range(0, 300, 7))
+        b = ds.batch(torch.tensor(starts))
+        parts = [WO.sample_solo(mat, i, model_type, 1, True) for i in starts]
+        for k, name in enumerate(("base", "joint")):
+            assert np.abs(b.x_dict[name].cpu().double().numpy() - torch.cat([p[k] for p in parts]).numpy()).max() <= 1e-6
+        assert np.abs(b.y.cpu().double().numpy() - torch.cat([p[2] for p in parts]).numpy()).max() <= 1e-6
 
 
 def test_zscore_pinned_by_reference_golden_matrices():
