@@ -207,7 +207,7 @@ int make_map_2d(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, in
 
 // The caller's fp32 feature tensor x[B * nodes, K] of one node type as a (K, nodes, B) tensor, box = 64 columns x 1 node x 128 graphs:
 // one TMA request fetches the 256-byte fragments of a K block of 128 consecutive graphs of one node slot (k_tc_encoder_stream).
-int make_map_x3d(CUtensorMap* m, const void* base, int64_t B, int nodes, int K) {
+int make_map_x3d(CUtensorMap* m, const void* base, int64_t B, int nodes, int K, int box_rows = 128) {
     EncodeTiledFn enc;
     int rc = get_encode_fn(&enc);
     if (rc) return rc;
@@ -215,7 +215,7 @@ int make_map_x3d(CUtensorMap* m, const void* base, int64_t B, int nodes, int K) 
     if (!ctx_bound) { CUDA_TRY(cudaFree(0)); ctx_bound = true; }
     cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)nodes, (cuuint64_t)B};
     cuuint64_t strides[2] = {(cuuint64_t)K * 4, (cuuint64_t)nodes * K * 4};
-    cuuint32_t box[3] = {64, 1, 128};
+    cuuint32_t box[3] = {64, 1, (cuuint32_t)box_rows};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -870,14 +870,33 @@ int mshgnn_backward_staged(const mshgnn_plan* plan, int64_t B, const void* const
         if (layers_ready_event) CUDA_TRY(cudaEventRecord((cudaEvent_t)layers_ready_event, st));
         if (!p.enc_units.empty()) {
             static std::atomic<bool> attr_set[64];
-            if (first_on_device(attr_set)) CUDA_TRY(cudaFuncSetAttribute(k_tc_encoder_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, EDW_SMEM_BYTES));
+            if (first_on_device(attr_set)) {
+                CUDA_TRY(cudaFuncSetAttribute(k_tc_encoder_dw<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EDW_SMEM_BYTES));
+                CUDA_TRY(cudaFuncSetAttribute(k_tc_encoder_dw<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EDW_SMEM_BYTES));
+            }
+            // x rows by TMA (raw fp32 into the X operand area, converted in place) when every feature tensor allows it: fp32, 16-byte rows
+            // (measured, same box: 0.258-0.270 ms against 0.246-0.251 ms for the register-staged loaders - here the loads of a step are issued
+            // BEFORE its stage is free and nothing is pipelined across register sets, so the scoreboard effect of kernels_enc.cuh costs
+            // little, while a landing zone inside the stage serialises copy -> conversion -> MMA per stage.  Off unless MSHGNN_ENC_DW=tma.)
+            static const bool want_xt = [] { const char* e = getenv("MSHGNN_ENC_DW"); return e && !strcmp(e, "tma"); }();
+            bool xt = xf64 == 0 && want_xt;
+            for (const EncDwUnit& eu : p.enc_units)
+                if (xt) xt = eu.x_buf >= BUF_X0 && eu.x_buf < BUF_X0 + p.n_types && enq_rows_ok(bt.p[eu.x_buf], eu.K, 0);
+            EncXMaps xm;
+            for (int t = 0; t < 4; ++t) {
+                if (xt && t < p.n_types && p.in_w[t] % 4 == 0 && (reinterpret_cast<uintptr_t>(bt.p[BUF_X0 + t]) & 15) == 0) {
+                    if ((rc = make_map_x3d(&xm.x[t], bt.p[BUF_X0 + t], B, p.nodes[t], p.in_w[t], 64))) return rc;
+                } else xm.x[t] = wm.dw;
+            }
             float* pe_w = (float*)(ws + w.part_enc_w);
             float* pe_b = (float*)(ws + w.part_enc_b);
             {
                 ProfScope ps(K_DW_ENC, st);
                 dim3 grid((unsigned)p.enc_units.size(), (unsigned)w.n_splits_enc);
-                k_tc_encoder_dw<<<grid, ENC_THREADS, EDW_SMEM_BYTES, st>>>(wm.dw, p.d_enc_units, bt, br, B, w.Bp, w.rows_per_enc, w.n_splits_enc, xf64,
-                                                                           split, pe_w, pe_b);
+                if (xt) k_tc_encoder_dw<true><<<grid, ENC_THREADS, EDW_SMEM_BYTES, st>>>(wm.dw, xm, (int)BUF_X0, p.d_enc_units, bt, br, B, w.Bp, w.rows_per_enc, w.n_splits_enc, xf64,
+                                                                                         split, pe_w, pe_b);
+                else k_tc_encoder_dw<false><<<grid, ENC_THREADS, EDW_SMEM_BYTES, st>>>(wm.dw, xm, (int)BUF_X0, p.d_enc_units, bt, br, B, w.Bp, w.rows_per_enc, w.n_splits_enc, xf64,
+                                                                                       split, pe_w, pe_b);
                 LAUNCH_CHECK();
             }
             {

@@ -71,13 +71,6 @@ inline bool enq_rows_ok(const void* base, int K, int sign_off) {
     return (reinterpret_cast<uintptr_t>(base) & 15) == 0 && (K & 3) == 0 && K >= 4 && (sign_off < 0 || (sign_off & 3) == 0);
 }
 
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
-        "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-
 // entry m of the item queue (every role reads the same sequence); warps release with one arrival
 __device__ __forceinline__ int enq_take(EnqCtl& ctl, const int m, const bool whole_warp, const int lane) {
     const int q = m % ENQ_ITEM_Q;

@@ -1657,6 +1657,19 @@ k_tc_encoder_pair(const __grid_constant__ EncMaps maps, const Tile* __restrict__
 //  M = 128 output features (dpre images, MN-major via TMA like k_tc_reducegemm), N = 64*nkb input columns (the loaders
 //  write the split x rows as 64-column MN-major blocks, LBO = 8192 B), K = graph rows.  x is read exactly once per step
 //  over all units.  Accumulators: D0 [0,192) hi*hi, D1 [192,384) cross (x 2^11), D2 [384,400) / D3 [416,432) bias sums.
+// caller's feature tensors as (K, nodes, B) fp32 tensors, box 64 columns x 1 node x 64 graphs (no swizzle): one request lands the
+// 256-byte fragments of a 64-column block of 64 consecutive graphs of one node slot (see kernels_enc.cuh for why the feature rows
+// are kept off the register scoreboards)
+struct alignas(64) EncXMaps {
+    CUtensorMap x[4];
+};
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
 constexpr int EDW_STAGES = 2;
 constexpr int EDW_DC_BYTES = DW_IMG_BYTES;                 // 64 rows x 128 features fp16
 constexpr int EDW_X_BYTES = 3 * 64 * 128;                  // up to three 64-row x 64-column blocks
@@ -1664,8 +1677,12 @@ constexpr int EDW_STAGE_BYTES = 2 * EDW_DC_BYTES + 2 * EDW_X_BYTES;     // dC_hi
 constexpr int EDW_SMEM_BYTES = EDW_STAGES * EDW_STAGE_BYTES + DW_ONES_BYTES + 1024 + 256;
 constexpr int EDW_NMAX = 192;
 
+//  XT = true (fp32 features with 16-byte rows): the x rows of a step arrive by TMA as raw fp32 in the X operand area of the stage
+//  (64 rows x 64 columns x 4 B per block = the 16 KB its hi + lo images take) and the loader group converts them in place.
+template <bool XT>
 __global__ void __launch_bounds__(ENC_THREADS, 1)
-k_tc_encoder_dw(const __grid_constant__ CUtensorMap map, const EncDwUnit* __restrict__ units, const BufTable bt, const BufRows br,
+k_tc_encoder_dw(const __grid_constant__ CUtensorMap map, const __grid_constant__ EncXMaps xmaps, const int x_buf0, const EncDwUnit* __restrict__ units,
+                const BufTable bt, const BufRows br,
                 const int64_t B, const int64_t Bp, const int rows_per, const int n_splits, const int x_f64, const int split,
                 float* __restrict__ part_w, float* __restrict__ part_b) {
     extern __shared__ uint8_t smem_raw[];
@@ -1678,7 +1695,8 @@ k_tc_encoder_dw(const __grid_constant__ CUtensorMap map, const EncDwUnit* __rest
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* ones = smem + EDW_STAGES * EDW_STAGE_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(ones + DW_ONES_BYTES);
-    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + EDW_STAGES), accum_bar = smem_u32(bars + 2 * EDW_STAGES);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + EDW_STAGES), accum_bar = smem_u32(bars + 2 * EDW_STAGES),
+                   landed0 = smem_u32(bars + 2 * EDW_STAGES + 1);
     const uint32_t smem_base = smem_u32(smem);
 
     if (tid < (int)(sizeof(EncDwUnit) / 4)) reinterpret_cast<int*>(&u)[tid] = reinterpret_cast<const int*>(units + blockIdx.x)[tid];
@@ -1690,7 +1708,7 @@ k_tc_encoder_dw(const __grid_constant__ CUtensorMap map, const EncDwUnit* __rest
     for (int i = tid; i < DW_ONES_BYTES / 4; i += ENC_THREADS) reinterpret_cast<uint32_t*>(ones)[i] = 0x3C003C00u;
     fence_proxy_async_smem();
     if (tid == 0) {
-        for (int s = 0; s < EDW_STAGES; ++s) { mbar_init(full0 + 8 * s, 1 + ENC_LOADER_WARPS); mbar_init(empty0 + 8 * s, 1); }
+        for (int s = 0; s < EDW_STAGES; ++s) { mbar_init(full0 + 8 * s, 1 + ENC_LOADER_WARPS); mbar_init(empty0 + 8 * s, 1); mbar_init(landed0 + 8 * s, 1); }
         mbar_init(accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -1725,6 +1743,15 @@ k_tc_encoder_dw(const __grid_constant__ CUtensorMap map, const EncDwUnit* __rest
                 if (split) {
                     tma_load_2d(st + EDW_DC_BYTES, &map, fb, 0, br.lo[BUF_DC1_ID] + d_off);
                     tma_load_2d(st + EDW_DC_BYTES + EDW_DC_BYTES / 2, &map, fb, 64, br.lo[BUF_DC1_ID] + d_off);
+                }
+                if (XT) {
+                    // raw x rows of the step: graphs >= B and columns >= K arrive as zeros
+                    const int j = i / n_rb;
+                    const uint32_t lb = landed0 + 8 * s;
+                    mbar_expect_tx(lb, (uint32_t)nkb * 16384u);
+                    const CUtensorMap* xm = &xmaps.x[u.x_buf - x_buf0];
+                    const int node = u.a_off[j] / u.K;
+                    for (int jb = 0; jb < nkb; ++jb) tma_load_3d(st + 2 * EDW_DC_BYTES + jb * 16384, xm, lb, u.k0 + jb * 64, node, r0);
                 }
             }
         }
@@ -1770,10 +1797,25 @@ k_tc_encoder_dw(const __grid_constant__ CUtensorMap map, const EncDwUnit* __rest
             const int64_t r0 = r_begin + (int64_t)(i % n_rb) * DW_KB + rsub;
             const uint32_t st = smem_base + s * EDW_STAGE_BYTES + 2 * EDW_DC_BYTES;
             float4 v[3][8];
+            if (XT) {
+                mbar_wait(landed0 + 8 * s, (i / EDW_STAGES) & 1);
 #pragma unroll
-            for (int jb = 0; jb < 3; ++jb)
-                if (jb < nkb) load_x_block<8>(v[jb], xr, r0, B - 1, u.k0 + jb * 64 + kq * 4);
-            mbar_wait(empty0 + 8 * s, ((i / EDW_STAGES) & 1) ^ 1);
+                for (int jb = 0; jb < 3; ++jb)
+                    if (jb < nkb) {
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            const int r = it * 8 + rsub;
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[jb][it].x), "=f"(v[jb][it].y), "=f"(v[jb][it].z), "=f"(v[jb][it].w)
+                                         : "r"(st + (uint32_t)(jb * 16384 + r * 256 + kq * 16)));
+                        }
+                    }
+                asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");       // every raw row of the step is in registers: the images may overwrite them
+            } else {
+#pragma unroll
+                for (int jb = 0; jb < 3; ++jb)
+                    if (jb < nkb) load_x_block<8>(v[jb], xr, r0, B - 1, u.k0 + jb * 64 + kq * 4);
+                mbar_wait(empty0 + 8 * s, ((i / EDW_STAGES) & 1) ^ 1);
+            }
 #pragma unroll
             for (int jb = 0; jb < 3; ++jb)
                 if (jb < nkb) {
