@@ -292,7 +292,11 @@ int launch_tc_encoder(const Plan& p, const Launch& L, const WsLayout& w, const B
         // persistent kernel: one CTA per SM draws (node slot, row-tile pair) items from the counter the forward prologue zeroed
         int n_sm = 0;
         if ((rc = sm_count(&n_sm))) return rc;
-        const int64_t n_items = (int64_t)L.count * ((n_row_tiles + 1) / 2);
+        // two row tiles per item (they share every weight stage) only when that leaves every SM several items: at 2048 graphs 64 long and
+        // 96 short pair items on 148 SMs would make two long items the critical path (1.5 x the balanced time); single tiles balance
+        static const int force_tpi = [] { const char* e = getenv("MSHGNN_ENC_TPI"); return e ? atoi(e) : 0; }();
+        const int tpi = force_tpi == 1 || force_tpi == 2 ? force_tpi : ((int64_t)L.count * ((n_row_tiles + 1) / 2) >= 4 * (int64_t)n_sm ? 2 : 1);
+        const int64_t n_items = (int64_t)L.count * ((n_row_tiles + tpi - 1) / tpi);
         const unsigned grid = (unsigned)(n_items < n_sm ? n_items : n_sm);
         static const int dbg = [] { const char* e = getenv("MSHGNN_ENC_DEBUG"); return e ? atoi(e) : 0; }();               // measurement switches (results are wrong when set)
         EnqMaps em;
@@ -302,7 +306,7 @@ int launch_tc_encoder(const Plan& p, const Launch& L, const WsLayout& w, const B
             if ((rc = make_map_x3d(&em.x[t], bt.p[BUF_X0 + t], B, p.nodes[t], p.in_w[t]))) return rc;
         }
         for (int t = p.n_types; t < 4; ++t) em.x[t] = maps.o;
-        k_tc_encoder_stream<<<grid, ENQ_THREADS, ENQ_SMEM_BYTES, st>>>(em, p.d_tiles + L.begin, L.count, (int)BUF_X0, bt, br, B, w.Bp, split, (uint32_t*)(ws + w.enc_sync), dbg);
+        k_tc_encoder_stream<<<grid, ENQ_THREADS, ENQ_SMEM_BYTES, st>>>(em, p.d_tiles + L.begin, L.count, (int)BUF_X0, bt, br, B, w.Bp, split, (uint32_t*)(ws + w.enc_sync), tpi, dbg);
     }
     LAUNCH_CHECK();
     return 0;

@@ -83,7 +83,7 @@ __device__ __forceinline__ int enq_take(EnqCtl& ctl, const int m, const bool who
 
 __global__ void __launch_bounds__(ENQ_THREADS, 1)
 k_tc_encoder_stream(const __grid_constant__ EnqMaps maps, const Tile* __restrict__ tiles, const int n_slots, const int x_buf0 /*buffer id of the first feature tensor*/, const BufTable bt, const BufRows br,
-                    const int64_t B, const int64_t Bp, const int split, uint32_t* __restrict__ counter,
+                    const int64_t B, const int64_t Bp, const int split, uint32_t* __restrict__ counter, const int tpi /*row tiles per item: 1 or 2*/,
                     const int dbg /*measurement switches: 1 no conversion, 2 no MMAs, 4 no weight loads (results are wrong when set)*/) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const int tid = threadIdx.x;
@@ -92,7 +92,8 @@ k_tc_encoder_stream(const __grid_constant__ EnqMaps maps, const Tile* __restrict
     EnqCtl& ctl = *reinterpret_cast<EnqCtl*>(smem_raw + ENQ_TILE_REGION);
     const uint32_t full0 = smem_u32(&ctl.full[0]), empty0 = smem_u32(&ctl.empty[0]), landed0 = smem_u32(&ctl.landed[0][0]),
                    acc_full0 = smem_u32(&ctl.acc_full[0]), acc_free0 = smem_u32(&ctl.acc_free[0]);
-    const int n_pairs = (int)((Bp / TILE_M + 1) / 2);
+    const int n_pairs = (int)((Bp / TILE_M + tpi - 1) / tpi);        // items per node slot: tpi (1 or 2) row tiles each
+    const int item_rows = tpi * TILE_M;
     const int n_items = n_slots * n_pairs;
 
     if (smem_base & 1023u) __trap();                         // the swizzled tiles need the 1024-byte alignment (no static shared memory in this kernel)
@@ -153,8 +154,8 @@ k_tc_encoder_stream(const __grid_constant__ EnqMaps maps, const Tile* __restrict
                     if (id_cur >= (uint32_t)n_items) break;
                     const int si = (int)id_cur / n_pairs;
                     const EnqSlot& sl = ctl.slots[si];
-                    const int row0 = ((int)id_cur - si * n_pairs) * (2 * TILE_M);
-                    const bool two = (int64_t)row0 + TILE_M < Bp;
+                    const int row0 = ((int)id_cur - si * n_pairs) * item_rows;
+                    const bool two = tpi == 2 && (int64_t)row0 + TILE_M < Bp;
                     const int wrow = sl.w16_row, n_kb = sl.n_kb, node = sl.node;
                     const CUtensorMap* xm = &maps.x[sl.xt];
                     for (int i = 0; i < n_kb; ++i, ++kbi) {
@@ -188,8 +189,8 @@ k_tc_encoder_stream(const __grid_constant__ EnqMaps maps, const Tile* __restrict
                     const int id = enq_take(ctl, m, false, 0);
                     if (id >= n_items) break;
                     const int si = id / n_pairs;
-                    const int row0 = (id - si * n_pairs) * (2 * TILE_M);
-                    const int n_tiles = (int64_t)row0 + TILE_M < Bp ? 2 : 1;
+                    const int row0 = (id - si * n_pairs) * item_rows;
+                    const int n_tiles = (tpi == 2 && (int64_t)row0 + TILE_M < Bp) ? 2 : 1;
                     const int n_kb = ctl.slots[si].n_kb;
                     const uint32_t b = (uint32_t)m & 1u;
                     mbar_wait(acc_free0 + 8 * b, (((uint32_t)m >> 1) & 1u) ^ 1u);       // the epilogue has drained this accumulator pair
@@ -233,9 +234,9 @@ k_tc_encoder_stream(const __grid_constant__ EnqMaps maps, const Tile* __restrict
             const int id = enq_take(ctl, m, true, lane);
             if (id >= n_items) break;
             const int si = id / n_pairs;
-            const int64_t row0 = (int64_t)(id - si * n_pairs) * (2 * TILE_M) + g * TILE_M;
+            const int64_t row0 = (int64_t)(id - si * n_pairs) * item_rows + g * TILE_M;
             const EnqSlot sl = ctl.slots[si];
-            const bool live = row0 < Bp;
+            const bool live = g < tpi && row0 < Bp;
             for (int i = 0; i < sl.n_kb; ++i, ++kbi) {
                 const uint32_t s = kbi & 1u;
                 if (!live) {
@@ -279,8 +280,8 @@ k_tc_encoder_stream(const __grid_constant__ EnqMaps maps, const Tile* __restrict
             const int id = enq_take(ctl, m, true, lane);
             if (id >= n_items) break;
             const int si = id / n_pairs;
-            const int row0 = (id - si * n_pairs) * (2 * TILE_M);
-            const int n_tiles = (int64_t)row0 + TILE_M < Bp ? 2 : 1;
+            const int row0 = (id - si * n_pairs) * item_rows;
+            const int n_tiles = (tpi == 2 && (int64_t)row0 + TILE_M < Bp) ? 2 : 1;
             group_bar_sync(0);                                   // every warp is done with the previous item's tile
             {
                 const int* src = reinterpret_cast<const int*>(tiles + ctl.slots[si].tile);

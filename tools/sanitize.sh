@@ -37,8 +37,8 @@ torch.cuda.synchronize()
 print("windows", float(wb.x_dict["foot"].abs().mean()))
 PY
 # one-CTA stack kernel (these batches are below the CTA-pair threshold), then the CTA-pair kernel forced (MSHGNN_STACK_2CTA=2)
-for pair in 1 2; do
-for tool in memcheck racecheck; do
+for pair in ${SAN_PAIRS:-1 2}; do
+for tool in ${SAN_TOOLS:-memcheck racecheck}; do
   MSHGNN_STACK_2CTA=$pair timeout 1200 compute-sanitizer --tool $tool --print-limit 20 python /tmp/san.py > gpurun_out/sanitize_${tool}_pair$pair.log 2>&1
   echo "== $tool (MSHGNN_STACK_2CTA=$pair): $(grep -c 'ERROR SUMMARY' gpurun_out/sanitize_${tool}_pair$pair.log) summary lines"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|hazard|Invalid|loss|windows" gpurun_out/sanitize_${tool}_pair$pair.log | head -12
 done
