@@ -246,6 +246,11 @@ int mshgnn_check_edges(const mshgnn_plan* plan, int64_t B, const int64_t* const*
  * tcgen05.mma.cta_group::2 on two row tiles at once; rows are then padded to a multiple of 256 - query the workspace size
  * again after switching): 1 (default) = for batches of >= 6144 graphs, 2 = always, 0 = never (the one-CTA stack kernel).
  * Both choose between implementations that produce identical bits (tests/test_gpu_stack.py).
+ * Option "encoder" (MSHGNN_ENCODER=stream|v1|pair): kernel of the encoder forward: -1 (default) = the persistent TMA-fed kernel
+ * whenever the feature tensors allow it (fp32, 16-byte rows), 0 = the same, 1 = one row tile per CTA, 2 = two row tiles per CTA;
+ * "encoder_tpi" (MSHGNN_ENC_TPI): row tiles per work item of the persistent kernel, 0 = by batch size, 1, 2;
+ * "encoder_dw_tma" (MSHGNN_ENC_DW=tma): feature rows of the encoder weight gradient by TMA (1) or register-staged loads (0, default).
+ * All of them produce identical bits (tests/test_gpu_stack.py::test_encoder_kernels_are_bit_identical).
  * mshgnn_stack_status copies one word back (synchronising): *status_out = 1 when a dependency wait inside the last stack
  * launch on this workspace timed out (its results are then invalid); used by the tests. */
 int mshgnn_set_option(const char* name, int32_t value);

@@ -259,11 +259,16 @@ bool first_on_device(std::atomic<bool> (&flags)[MAX_DEVICES]) {
     return !flags[dev].exchange(true);
 }
 
+// encoder kernel choice: -1 = environment / default (persistent TMA-fed kernel when the inputs allow it), 0 persistent, 1 one tile per CTA, 2 two tiles per CTA;
+// rows tiles per item of the persistent kernel: 0 = by batch size, 1, 2 (mshgnn_set_option "encoder" / "encoder_tpi"; same-process A/B and bit-identity tests)
+static std::atomic<int> g_encoder_kernel{-1}, g_encoder_tpi{0}, g_encoder_dw_tma{-1};
+
 int launch_tc_encoder(const Plan& p, const Launch& L, const WsLayout& w, const BufTable& bt, const BufRows& br, const WsMaps& wm, char* ws,
                       const float* params, int64_t B, int xf64, int split, cudaStream_t st) {
     if (L.count == 0) return 0;
     static std::atomic<bool> attr_set[64];
-    static const int which = [] { const char* e = getenv("MSHGNN_ENCODER"); return !e ? 0 : (!strcmp(e, "v1") ? 1 : (!strcmp(e, "pair") ? 2 : 0)); }();   // default: k_tc_encoder_pair; "stream": persistent bulk-copy kernel (kernels_enc.cuh), "v1": one tile per CTA
+    static const int which_env = [] { const char* e = getenv("MSHGNN_ENCODER"); return !e ? 0 : (!strcmp(e, "v1") ? 1 : (!strcmp(e, "pair") ? 2 : 0)); }();   // default: k_tc_encoder_pair; "stream": persistent bulk-copy kernel (kernels_enc.cuh), "v1": one tile per CTA
+    const int which = g_encoder_kernel.load() >= 0 ? g_encoder_kernel.load() : which_env;
     if (first_on_device(attr_set)) {
         CUDA_TRY(cudaFuncSetAttribute(k_tc_encoder, cudaFuncAttributeMaxDynamicSharedMemorySize, ENC_SMEM_BYTES));
         CUDA_TRY(cudaFuncSetAttribute(k_tc_encoder_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, ENCP_SMEM_BYTES));
@@ -295,7 +300,8 @@ int launch_tc_encoder(const Plan& p, const Launch& L, const WsLayout& w, const B
         // two row tiles per item (they share every weight stage) only when that leaves every SM several items: at 2048 graphs 64 long and
         // 96 short pair items on 148 SMs would make two long items the critical path (1.5 x the balanced time); single tiles balance
         static const int force_tpi = [] { const char* e = getenv("MSHGNN_ENC_TPI"); return e ? atoi(e) : 0; }();
-        const int tpi = force_tpi == 1 || force_tpi == 2 ? force_tpi : ((int64_t)L.count * ((n_row_tiles + 1) / 2) >= 4 * (int64_t)n_sm ? 2 : 1);
+        const int opt_tpi = g_encoder_tpi.load() ? g_encoder_tpi.load() : force_tpi;
+        const int tpi = opt_tpi == 1 || opt_tpi == 2 ? opt_tpi : ((int64_t)L.count * ((n_row_tiles + 1) / 2) >= 4 * (int64_t)n_sm ? 2 : 1);
         const int64_t n_items = (int64_t)L.count * ((n_row_tiles + tpi - 1) / tpi);
         const unsigned grid = (unsigned)(n_items < n_sm ? n_items : n_sm);
         static const int dbg = [] { const char* e = getenv("MSHGNN_ENC_DEBUG"); return e ? atoi(e) : 0; }();               // measurement switches (results are wrong when set)
@@ -883,7 +889,7 @@ int mshgnn_backward_staged(const mshgnn_plan* plan, int64_t B, const void* const
             // BEFORE its stage is free and nothing is pipelined across register sets, so the scoreboard effect of kernels_enc.cuh costs
             // little, while a landing zone inside the stage serialises copy -> conversion -> MMA per stage.  Off unless MSHGNN_ENC_DW=tma.)
             static const bool want_xt = [] { const char* e = getenv("MSHGNN_ENC_DW"); return e && !strcmp(e, "tma"); }();
-            bool xt = xf64 == 0 && want_xt;
+            bool xt = xf64 == 0 && (g_encoder_dw_tma.load() >= 0 ? g_encoder_dw_tma.load() != 0 : want_xt);
             for (const EncDwUnit& eu : p.enc_units)
                 if (xt) xt = eu.x_buf >= BUF_X0 && eu.x_buf < BUF_X0 + p.n_types && enq_rows_ok(bt.p[eu.x_buf], eu.K, 0);
             EncXMaps xm;
@@ -1105,12 +1111,18 @@ int mshgnn_set_option(const char* name, int32_t value) {
     if (!name) return fail(MSHGNN_ERR_ARG, "option name is NULL");
     if (!strcmp(name, "stack")) { set_stack_enabled(value); return 0; }
     if (!strcmp(name, "stack_pair")) { set_stack_pair_mode(value); return 0; }
+    if (!strcmp(name, "encoder")) { g_encoder_kernel.store(value < 0 || value > 2 ? -1 : value); return 0; }
+    if (!strcmp(name, "encoder_tpi")) { g_encoder_tpi.store(value == 1 || value == 2 ? value : 0); return 0; }
+    if (!strcmp(name, "encoder_dw_tma")) { g_encoder_dw_tma.store(value < 0 ? -1 : (value ? 1 : 0)); return 0; }
     return fail(MSHGNN_ERR_ARG, "unknown option '%s'", name);
 }
 
 int32_t mshgnn_get_option(const char* name) {
     if (name && !strcmp(name, "stack")) return stack_enabled() ? 1 : 0;
     if (name && !strcmp(name, "stack_pair")) return stack_pair_mode();
+    if (name && !strcmp(name, "encoder")) return g_encoder_kernel.load();
+    if (name && !strcmp(name, "encoder_tpi")) return g_encoder_tpi.load();
+    if (name && !strcmp(name, "encoder_dw_tma")) return g_encoder_dw_tma.load();
     return -1;
 }
 

@@ -191,3 +191,27 @@ def test_cached_validation_checks_a_tensor_once():
         n0 = N.launch_count()
         nm(b.x_dict, fresh)
         assert N.launch_count() - n0 == a + 1
+
+
+@pytest.mark.parametrize("name,B", [("mini_cheetah-k4-contact", 2400), ("mini_cheetah-c2-contact", 1100), ("mini_cheetah-k4-contact", 96)])
+def test_encoder_kernels_are_bit_identical(name, B):
+    """Encoder forward: persistent TMA-fed kernel (one / two row tiles per item; 2400 and 1100 graphs end on a one-tile item and give
+    some CTAs several items) against the one-item-per-CTA kernels, and the encoder weight gradient with TMA-fed against register-staged
+    feature rows: same bits in the predictions, the loss and EVERY gradient (all variants accumulate the same products in the same
+    order; hgnn_k4.py:L159-160 and its autograd)."""
+    cfg = CONFIGS[name]
+    b = make_batch(cfg, B, seed=B + 7).to("cuda:0")
+    nm = build_model(cfg, layers=8, seed=5).set_mode("tc").to("cuda:0")
+    ref = None
+    try:
+        for enc, tpi, dw in ((2, 0, 0), (1, 0, 0), (0, 1, 0), (0, 2, 0), (0, 0, 1)):
+            N.set_option("encoder", enc); N.set_option("encoder_tpi", tpi); N.set_option("encoder_dw_tma", dw)
+            out, loss, g = _step(nm, cfg, b)
+            if ref is None:
+                ref = (out.clone(), loss, {k: v.clone() for k, v in g.items()})
+                continue
+            assert torch.equal(out, ref[0]) and loss == ref[1], (enc, tpi, dw)
+            for k in g:
+                assert torch.equal(g[k], ref[2][k]), (k, enc, tpi, dw)
+    finally:
+        N.set_option("encoder", -1); N.set_option("encoder_tpi", 0); N.set_option("encoder_dw_tma", -1)
