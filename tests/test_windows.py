@@ -289,3 +289,35 @@ def test_windowed_batch_feeds_the_model_like_a_host_batch():
         hb = host.to("cuda:0")
         y_host = nm(hb.x_dict, hb.edge_index_dict)
     assert torch.equal(y_dev, y_host)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg_name,dataset,model_type,hist,kw", [
+    ("a1-c2-grf", "a1", "heterogeneous_gnn_c2", T, dict(grf_dimension=3, grf_body_to_world_frame=True)),
+    ("solo12-k4-com", "solo12", "heterogeneous_gnn_k4_com", 1, {}),
+    ("solo-c2-com", "solo12", "heterogeneous_gnn_c2_com", 1, {})])
+def test_other_datasets_feed_their_models(cfg_name, dataset, model_type, hist, kw):
+    """The A1 and Solo12 window layouts line up with the models of the BASELINE configs that consume them (feature widths, label
+    count, edge template): one native train step on a windowed batch, loss equal to the oracle model's on the same tensors."""
+    from helpers import TOL_FP32, oracle_model, oracle_run
+    from ms_hgnn import _native as N
+    from ms_hgnn.synthetic import CONFIGS, HeteroBatch, build_model
+    cfg = CONFIGS[cfg_name]
+    mat = WO.synthetic_a1_mat(600, seed=8, dtype=np.float32) if dataset == "a1" else WO.synthetic_solo_mat(600, seed=8)
+    spec = WindowSpec(model_type, hist, True, dataset=dataset, **kw)
+    assert spec.widths == cfg.in_width and spec.n_labels == cfg.label_width
+    ds = DeviceSequence(mat, spec, "cuda:0", torch.float32)
+    idx = torch.randperm(len(ds), generator=torch.Generator().manual_seed(3))[:96]
+    b = ds.batch(idx)
+    om = oracle_model(cfg, layers=4, seed=1)
+    nm = build_model(cfg, layers=4, seed=2)
+    nm.load_state_dict({k: v.float() for k, v in om.state_dict().items()})
+    nm = nm.to("cuda:0")
+    out = nm(b.x_dict, b.edge_index_dict)
+    eng = nm._last_engine
+    loss, dout = eng.loss(out.detach().reshape(-1, eng.spec["out_channels"]).float().contiguous(), b.y, N.LOSS_MSE)
+    out.backward(dout.view_as(out).to(out.dtype))
+    host = HeteroBatch({k: v.cpu() for k, v in b.x_dict.items()}, {k: v.cpu() for k, v in b.edge_index_dict.items()}, b.y.cpu(), 96)
+    out_o, loss_o, _ = oracle_run(cfg, om, host)
+    assert abs(loss.item() - loss_o.item()) <= TOL_FP32 * abs(loss_o.item())
+    assert all(torch.isfinite(p.grad).all() for p in nm.parameters() if p.grad is not None)
