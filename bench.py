@@ -59,10 +59,23 @@ ALG = {
 TRAFFIC_FILE = "r2_dominant_traffic.json"   # ncu DRAM bytes of THIS round's kernels (tools/launch_traffic.py); keyed by kernel kind
 
 
+KERNEL_SWITCHES = ("MSHGNN_STACK", "MSHGNN_STACK_2CTA", "MSHGNN_ROWGEMM", "MSHGNN_ENCODER", "MSHGNN_ENC_TPI", "MSHGNN_ENC_DW", "MSHGNN_ENC_PF",
+                   "MSHGNN_ENC_DEBUG", "MSHGNN_STACK_DEBUG")
+
+
 def recorded_traffic():
-    """DRAM bytes from the committed ncu captures (profiles/): per launch of the dominant kernels and per train step."""
+    """DRAM bytes from the committed ncu captures (profiles/): per launch of the dominant kernels and per train step.  The capture belongs
+    to the DEFAULT kernel selection of this round: when a kernel switch of the library is set in the environment another kernel runs and
+    the recorded bytes are not its bytes - no traffic is reported then (stderr says why)."""
     p = os.path.join(ROOT, "profiles", TRAFFIC_FILE)
-    return json.load(open(p)) if os.path.exists(p) else {}
+    if not os.path.exists(p):
+        return {}
+    overridden = [k for k in KERNEL_SWITCHES if os.environ.get(k) not in (None, "")]
+    if overridden:
+        print(f"bench.py: {', '.join(overridden)} set - profiles/{TRAFFIC_FILE} was captured on the default kernels, roofline.traffic / hbm_step omitted",
+              file=sys.stderr)
+        return {}
+    return json.load(open(p))
 
 
 def peaks():
