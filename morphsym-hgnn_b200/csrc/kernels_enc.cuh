@@ -21,8 +21,9 @@
 //    * eight converter warps (two groups of 128 threads, one per row tile) wait for the landing barrier, read the raw tile into
 //      registers (16 x 16 bytes per thread), meet on a named barrier, and write the signed (hi, lo) split IN PLACE in the
 //      128B-swizzled K-major UMMA layout;
-//    * warp 0 = scheduler (items = node slot in descending-K order x pair of 128-row tiles, drawn from a global counter and
-//      published through a small shared-memory queue every role walks) + weight-tile TMA, warp 1 = MMA issuer;
+//    * warp 0 = scheduler (items = node slot in descending-K order x pair of 128-row tiles - single tiles when pairs would leave an SM
+//      fewer than four items, launch_tc_encoder - drawn from a global counter and published through a small shared-memory queue every
+//      role walks) + feature / weight-tile TMA, warp 1 = MMA issuer;
 //    * warps 12..15 only ever drain accumulators (tc_epilogue_alt, a private 32 KB staging pair, TMA stores); the accumulators
 //      are double-buffered in TMEM (2 items x 2 row tiles x 128 columns = all 512 columns), so the MMAs of item n + 1 run while
 //      item n is converted to (hi, lo) images and stored.
